@@ -1,0 +1,210 @@
+/*
+ * mpqe_b200 -- C ABI of the B200-native MPQE query-encoding hot path.
+ *
+ * The reference (dfdazac/mpqe) is pure Python: its "plugin boundary" for this path is the set of
+ * PyTorch / torch_geometric / torch_scatter library calls made from
+ *     mpqe/data_utils.py:377-409   (batch layout),
+ *     mpqe/encoders.py:29-45       (embedding gather + L2 normalise),
+ *     mpqe/model.py:269-305        (RGCNConv: per-edge transform, scatter-add, root, bias),
+ *     mpqe/model.py:380-398,497-515 (readouts),
+ *     mpqe/model.py:451-460,483-485 (cosine scoring, margin loss),
+ *     mpqe/utils.py:25-32          (percentile rank counts)
+ * and their autograd backward.  Every entry point below replaces one such group of calls and cites it.
+ *
+ * Conventions
+ *   - plain C: raw DEVICE pointers, explicit sizes, a `cudaStream_t` passed as `void*`; no torch types.
+ *   - all floating point data is fp32, ids are int64 (as in the reference), d (embedding width) must be 128.
+ *   - activations are row-major [B, slots, d] ("query-major": row b*slots+i, the reference's `x.reshape(-1, d)`).
+ *   - weight matrices are row-major [d_in, d_out] (the layout of `RGCNConv.basis[r]` / `.root`, model.py:244-249).
+ *   - functions never allocate, never synchronise the device and are re-entrant per stream; scratch memory is a
+ *     caller-provided workspace whose size comes from the matching *_workspace_bytes query.
+ *   - return value: 0 = ok; non-zero = error, text via mpqe_b200_last_error() (thread-local).
+ */
+#ifndef MPQE_B200_H_
+#define MPQE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define MPQE_API __attribute__((visibility("default")))
+#else
+#define MPQE_API
+#endif
+
+#define MPQE_D 128            /* embedding width the kernels are specialised for (train.py:19 default) */
+#define MPQE_MAX_GROUPS 8     /* formula groups fused into one launch */
+#define MPQE_MAX_TERMS 16     /* (edge + self-loop) terms per group */
+#define MPQE_MAX_SLOTS 8      /* output node slots per query */
+#define MPQE_MAX_DESTS 64     /* distinct weight matrices receiving a gradient in one launch */
+
+/* epilogues of the layer kernel */
+#define MPQE_EPI_NONE 0
+#define MPQE_EPI_RELU 1       /* F.relu between passes, model.py:437 */
+#define MPQE_EPI_MASK 2       /* multiply by (mask > 0): the ReLU backward */
+
+/* One term of a layer:  out[q, out_slot, :] += A[q, a_slot, :] @ M   with A = a + (q*a_slots + a_slot)*d.
+ * a_slots == 0 broadcasts one row to every query (variable-type embeddings, model.py:421).
+ * An edge e of the query template is the term (a_slot = src[e], M = basis[rel[e]], out_slot = dst[e]);
+ * the self-loop of node i is (a_slot = i, M = root, out_slot = i)  -- model.py:292-294, 301. */
+typedef struct {
+  const float* a;
+  const float* m;
+  int32_t a_slots;
+  int16_t a_slot;
+  int16_t out_slot;
+} mpqe_term_t;
+
+/* One formula group (all queries share one template, data_utils.py:293-311, 394-405). */
+typedef struct {
+  int64_t num_queries;
+  int32_t num_terms;
+  int32_t num_out_slots;                 /* output slots computed for this group */
+  mpqe_term_t terms[MPQE_MAX_TERMS];
+  float* out;                            /* [num_queries, out_slots, d] */
+  int32_t out_slots;                     /* slots per query in `out` (row stride / d) */
+  int32_t epilogue;                      /* MPQE_EPI_* */
+  const float* bias;                     /* [d] or NULL (model.py:303-304) */
+  float bias_scale[MPQE_MAX_SLOTS];      /* bias multiplier per out slot (n for a fused sum readout) */
+  int16_t out_slot_map[MPQE_MAX_SLOTS];  /* out slot j is stored at out[q, out_slot_map[j], :] */
+  const float* mask;                     /* EPI_MASK: [num_queries, mask_slots, d], slot = out_slot_map[j] */
+  int32_t mask_slots;
+  int32_t reserved;
+} mpqe_layer_group_t;
+
+/* One weight-gradient destination: dM = sum over every term (of every group) whose `m` equals `m_fwd` of
+ * A[:, a_slot]^T @ G[:, out_slot]   (autograd of bmm/index_select/matmul, model.py:292-294, 301). */
+typedef struct {
+  const float* m_fwd;
+  float* dm;              /* [d, d] */
+  int32_t accumulate;     /* 0: overwrite, 1: add to existing contents */
+  int32_t reserved;
+} mpqe_wgrad_dest_t;
+
+/* Per-group gradient operand for the weight-gradient kernel: G = g + (q*g_slots + slot_map[out_slot])*d. */
+typedef struct {
+  const float* g;
+  int32_t g_slots;                       /* 1 with slot_map all 0 broadcasts dq to all slots (sum readout) */
+  int16_t slot_map[MPQE_MAX_SLOTS];
+} mpqe_wgrad_operand_t;
+
+MPQE_API const char* mpqe_b200_last_error(void);
+MPQE_API int mpqe_b200_version(void);
+/* sizeof the ABI structs (0: term, 1: layer group, 2: wgrad dest, 3: wgrad operand) so bindings can self-check */
+MPQE_API int mpqe_b200_sizeof(int which);
+/* 1 if the library was built with the tcgen05 (sm_100a tensor core) layer kernels */
+MPQE_API int mpqe_b200_has_tcgen05(void);
+
+/* ---- a1: batch layout (data_utils.py:394-405 + PyG Batch.from_data_list) ---------------------------------
+ * edge_index[2, B*E], edge_type[B*E], batch[B*n] (all int64), bit-exact with the reference. */
+MPQE_API int mpqe_build_query_graph(int32_t n, int32_t E, const int32_t* tmpl_src_host, const int32_t* tmpl_dst_host,
+                           const int64_t* tmpl_rel_host, int64_t B,
+                           int64_t* edge_index, int64_t* edge_type, int64_t* batch, void* stream);
+
+/* Relation-sorted edge layout: perm = stable argsort of edge_type, seg_offsets[R+1] = exclusive histogram.
+ * (new artefact of the north star; CPU definition: torch.sort(edge_type, stable=True)). */
+MPQE_API size_t mpqe_relation_sort_workspace_bytes(int64_t num_edges, int32_t num_relations);
+MPQE_API int mpqe_relation_sort(const int64_t* edge_type, int64_t num_edges, int32_t num_relations,
+                       int64_t* perm, int64_t* seg_offsets, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a3/a4: embedding gather + L2 normalise (data_utils.py:35, utils.py:22, encoders.py:41-43) -------------
+ * row = id2row ? id2row[ids[i]] : ids[i];  out[i*out_stride .. +d] = table[row] / ||table[row]||  (no eps).
+ * inv_norm[i] (optional) receives 1/||row|| for the backward. */
+MPQE_API int mpqe_gather_normalize_fwd(const float* table, int64_t table_rows, const int64_t* id2row,
+                              const int64_t* ids, int64_t ids_stride, int64_t count,
+                              float* out, int64_t out_stride, float* inv_norm, void* stream);
+/* d(raw row) = (g - (g.y) y) * inv_norm, y = normalised row re-derived from the table;
+ * rows_out[i, :] and rows_id[i] (= table row) feed mpqe_sparse_rows_combine. */
+MPQE_API int mpqe_gather_normalize_bwd(const float* table, const int64_t* id2row, const int64_t* ids, int64_t ids_stride,
+                              int64_t count, const float* grad, int64_t grad_stride,
+                              float* rows_out, int64_t* rows_id, void* stream);
+/* a5 (model.py:418-422): x[b, i<a] = normalised anchor rows, x[b, i>=a] = mode_embeddings[var_ids[i-a]].
+ * tables/anchor ids are given per anchor slot. */
+MPQE_API int mpqe_broadcast_rows(const float* src, const int64_t* src_rows, int32_t num_rows,
+                        float* out, int64_t out_stride, int64_t count, void* stream);
+
+/* ---- a6-a9, a12: fused R-GCN layer / MLP layer (model.py:269-305, 435-441, 507-509) -----------------------
+ * For every group: out[q, j] = epilogue( sum_{terms t: out_slot==j} A_t[q] @ M_t + bias_scale[j]*bias ).
+ * With transposed matrices and swapped slots the same entry point computes the input gradient. */
+MPQE_API int mpqe_layer_forward(const mpqe_layer_group_t* groups_host, int32_t num_groups, int32_t use_tensor_cores,
+                       void* stream);
+
+/* Weight gradients of the same term lists (deterministic: fixed split over queries, ordered reduction). */
+MPQE_API size_t mpqe_layer_wgrad_workspace_bytes(int32_t num_dests, int32_t num_ctas_hint);
+MPQE_API int mpqe_layer_wgrad(const mpqe_layer_group_t* groups_host, const mpqe_wgrad_operand_t* grads_host,
+                     int32_t num_groups, const mpqe_wgrad_dest_t* dests_host, int32_t num_dests,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* Column sums: out[d] (+)= scale * sum over rows of src[r*stride .. +d], r in [0, rows): bias / mode-embedding grads. */
+MPQE_API size_t mpqe_colsum_workspace_bytes(int64_t rows);
+MPQE_API int mpqe_colsum(const float* src, int64_t rows, int64_t stride, float scale, float* out, int32_t accumulate,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* batched transpose of [count, d, d] (or one [rows, cols]) matrices */
+MPQE_API int mpqe_transpose(const float* src, float* dst, int64_t count, int32_t rows, int32_t cols, void* stream);
+
+/* ---- a11: max readout (model.py:383-385; torch_scatter.scatter_max) -------------------------------------
+ * q[b, c] = max_i z[b, i, c]; argmax[b, c] = smallest i attaining it (int64 node ROW b*n+i, like scatter_max). */
+MPQE_API int mpqe_max_readout_fwd(const float* z, int64_t B, int32_t n, float* q, int64_t* argmax, void* stream);
+/* g[b, i, c] = (argmax[b,c] == b*n+i) ? dq[b,c] : 0 */
+MPQE_API int mpqe_max_readout_bwd(const float* dq, const int64_t* argmax, int64_t B, int32_t n, float* g, void* stream);
+
+/* ---- a14/a15: cosine scoring + margin loss (model.py:451-452, 483-485) -----------------------------------
+ * y = normalised table row of each id; score = q.y / (max(||q||,1e-8) * max(||y||,1e-8)).
+ * ids_pos/ids_neg: [B]; loss[0] = mean(relu(margin - (pos - neg))). */
+MPQE_API size_t mpqe_margin_loss_workspace_bytes(int64_t B);
+MPQE_API int mpqe_cosine_margin_fwd(const float* q, int64_t B, const float* table, const int64_t* id2row,
+                           const int64_t* ids_pos, const int64_t* ids_neg, float margin,
+                           float* score_pos, float* score_neg, float* loss,
+                           void* workspace, size_t workspace_bytes, void* stream);
+/* backward of the above for upstream d(loss) = grad_loss[0] (device scalar):
+ * dq[B,d]; rows_out[2B,d] / rows_id[2B] = raw-row gradients of the positive (first B) and negative rows. */
+MPQE_API int mpqe_cosine_margin_bwd(const float* q, int64_t B, const float* table, const int64_t* id2row,
+                           const int64_t* ids_pos, const int64_t* ids_neg, float margin,
+                           const float* grad_loss, float* dq, float* rows_out, int64_t* rows_id, void* stream);
+/* eval scoring (model.py:451-460): candidate i belongs to query b with offsets[b] <= i < offsets[b+1]
+ * (the reference's repeat_interleave by neg_lengths); offsets == NULL means one candidate per query (count == B).
+ * scores[i] = cos(q[b], y(ids[i])). */
+MPQE_API int mpqe_cosine_scores(const float* q, int64_t B, const int64_t* offsets, const float* table, const int64_t* id2row,
+                       const int64_t* ids, int64_t count, float* scores, void* stream);
+/* backward of mpqe_cosine_scores for given d(scores): dq[B,d] (overwritten, or added to when accumulate != 0) sums
+ * each query's candidates in ascending order (bit-reproducible); rows_out[count,d] / rows_id[count] as above. */
+MPQE_API int mpqe_cosine_scores_bwd(const float* q, int64_t B, const int64_t* offsets, const float* table,
+                           const int64_t* id2row, const int64_t* ids, int64_t count, const float* grad_scores,
+                           float* dq, int32_t accumulate, float* rows_out, int64_t* rows_id, void* stream);
+
+/* ---- a17: rank counts (utils.py:25-32; scipy percentileofscore kind='rank') ------------------------------
+ * ragged negatives: left[b] = #(neg < pos[b]), right[b] = #(neg <= pos[b]) over neg[offsets[b]:offsets[b+1]]. */
+MPQE_API int mpqe_rank_counts_ragged(const float* pos, const float* neg, const int64_t* offsets, int64_t B,
+                            int64_t* left, int64_t* right, void* stream);
+/* full-entity ranking against one table shard (new; north star "full-entity ranking eval"):
+ * candidates = rows [row_begin, row_end) of `table`, score = cos(q[b], y(row)) as above;
+ * left/right are ACCUMULATED (zero them first) so shards can be chained or merged with an integer allreduce. */
+MPQE_API size_t mpqe_rank_counts_table_workspace_bytes(int64_t B, int64_t rows);
+MPQE_API int mpqe_rank_counts_table(const float* q, int64_t B, const float* pos, const float* table,
+                           int64_t row_begin, int64_t row_end, int64_t* left, int64_t* right,
+                           void* workspace, size_t workspace_bytes, int32_t use_tensor_cores, void* stream);
+
+/* ---- a16: row-sparse embedding gradients ----------------------------------------------------------------
+ * Combine `count` (row id, gradient row) pairs: unique_ids ascending, rows summed in ascending pair order
+ * (bit-reproducible).  num_unique is a device int64 scalar; outputs sized for `count` rows. */
+MPQE_API size_t mpqe_sparse_rows_workspace_bytes(int64_t count);
+MPQE_API int mpqe_sparse_rows_combine(const int64_t* rows_id, const float* rows, int64_t count, int64_t table_rows,
+                             int64_t* unique_ids, float* unique_rows, int64_t* num_unique,
+                             void* workspace, size_t workspace_bytes, void* stream);
+/* dense[ids[i], :] (+)= rows[i, :] for i < *num (ids unique) */
+MPQE_API int mpqe_scatter_rows(const int64_t* ids, const float* rows, const int64_t* num, int64_t max_count,
+                      float* dense, int32_t accumulate, void* stream);
+
+/* ---- optimiser (train.py:86-88, torch.optim.Adam defaults; caller of the hot path, row (f)) -------------- */
+MPQE_API int mpqe_adam_dense(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel,
+                    float lr, float beta1, float beta2, float eps, int32_t step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPQE_B200_H_ */

@@ -1,0 +1,73 @@
+// Shared helpers for the mpqe_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/mpqe_b200.h"
+
+namespace mpqe {
+
+constexpr int D = MPQE_D;  // embedding width (floats per row) = 512 B = one float4 per lane of a warp
+
+void set_error(const char* fmt, ...);
+
+#define MPQE_CHECK_ARG(cond, ...)      \
+  do {                                 \
+    if (!(cond)) {                     \
+      ::mpqe::set_error(__VA_ARGS__);  \
+      return 1;                        \
+    }                                  \
+  } while (0)
+
+#define MPQE_CHECK_LAUNCH(name)                                                        \
+  do {                                                                                 \
+    cudaError_t e__ = cudaGetLastError();                                              \
+    if (e__ != cudaSuccess) {                                                          \
+      ::mpqe::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));       \
+      return 2;                                                                        \
+    }                                                                                  \
+  } while (0)
+
+#define MPQE_CUDA(call)                                                                \
+  do {                                                                                 \
+    cudaError_t e__ = (call);                                                          \
+    if (e__ != cudaSuccess) {                                                          \
+      ::mpqe::set_error("%s failed: %s", #call, cudaGetErrorString(e__));              \
+      return 2;                                                                        \
+    }                                                                                  \
+  } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) {
+  return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+}
+
+// streaming 16-byte load that does not allocate in L1 (rows touched once)
+__device__ __forceinline__ float4 ldg_stream(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N));
+}
+
+}  // namespace mpqe

@@ -1,0 +1,332 @@
+// Integer kernels: batch layout, relation-sorted edge layout, and the row-sparse gradient combine.
+// All results are bit-exact and bit-reproducible (no floating-point atomics, stable sorts, ordered sums).
+//
+// Reference call sites (under /root/reference/mpqe/):
+//   data_utils.py:394-405 + PyG Batch.from_data_list     -> build_query_graph
+//   (new, north star) stable sort of edge_type           -> relation_sort
+//   autograd embedding_dense_backward    -> sparse_rows_combine / scatter_rows (row-sparse)
+#include "common.cuh"
+
+namespace mpqe {
+namespace {
+
+__global__ void build_query_graph_kernel(int n, int E, int64_t B, int4 src, int4 dst, longlong4 rel,
+                                         int64_t* __restrict__ edge_index, int64_t* __restrict__ edge_type,
+                                         int64_t* __restrict__ batch) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nE = B * E;
+  if (i < nE) {
+    const int64_t b = i / E;
+    const int e = (int)(i - b * E);
+    const int s = e == 0 ? src.x : e == 1 ? src.y : e == 2 ? src.z : src.w;
+    const int t = e == 0 ? dst.x : e == 1 ? dst.y : e == 2 ? dst.z : dst.w;
+    const int64_t r = e == 0 ? rel.x : e == 1 ? rel.y : e == 2 ? rel.z : rel.w;
+    edge_index[i] = b * n + s;
+    edge_index[nE + i] = b * n + t;
+    edge_type[i] = r;
+  }
+  if (i < B * n) batch[i] = i / n;
+}
+
+// ---- stable LSD radix pass (8-bit digit), one warp per chunk of SORT_CHUNK elements ------------------------
+constexpr int SORT_CHUNK = 1024;
+constexpr int SORT_WARPS = 8;
+constexpr int BINS = 256;
+
+__device__ __forceinline__ unsigned digit_of(uint32_t key, int shift) { return (key >> shift) & 0xffu; }
+
+// hist[bin * nchunks + chunk] = #elements of the chunk with that digit
+__global__ void __launch_bounds__(SORT_WARPS * 32) radix_hist_kernel(const uint32_t* __restrict__ keys, int64_t n,
+                                                                     int shift, int nchunks,
+                                                                     int32_t* __restrict__ hist) {
+  __shared__ int cnt[SORT_WARPS][BINS];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunk = blockIdx.x * SORT_WARPS + w;
+  for (int b = lane; b < BINS; b += 32) cnt[w][b] = 0;
+  __syncwarp();
+  if (chunk < nchunks) {
+    const int64_t i0 = (int64_t)chunk * SORT_CHUNK;
+    for (int r = 0; r < SORT_CHUNK; r += 32) {
+      const int64_t i = i0 + r + lane;
+      if (i < n) atomicAdd(&cnt[w][digit_of(keys[i], shift)], 1);
+    }
+    __syncwarp();
+    for (int b = lane; b < BINS; b += 32) hist[(int64_t)b * nchunks + chunk] = cnt[w][b];
+  }
+}
+
+// single-CTA exclusive scan (int32) of n entries; total written to *total (optional)
+__global__ void __launch_bounds__(1024) exclusive_scan_kernel(int32_t* __restrict__ data, int64_t n,
+                                                              int64_t* __restrict__ total) {
+  __shared__ int64_t part[1024];
+  const int t = threadIdx.x;
+  const int64_t per = (n + 1023) / 1024;
+  const int64_t i0 = per * t;
+  const int64_t i1 = i0 + per < n ? i0 + per : n;
+  int64_t s = 0;
+  for (int64_t i = i0; i < i1; ++i) s += data[i];
+  part[t] = s;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan of the per-thread sums
+    const int64_t v = t >= o ? part[t - o] : 0;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  int64_t run = t == 0 ? 0 : part[t - 1];
+  for (int64_t i = i0; i < i1; ++i) {
+    const int32_t v = data[i];
+    data[i] = (int32_t)run;
+    run += v;
+  }
+  if (total != nullptr && t == 1023) *total = part[1023];
+}
+
+// scatter: stable within chunk (lanes in order, rounds in order), chunks in order via the scanned histogram
+__global__ void __launch_bounds__(SORT_WARPS * 32) radix_scatter_kernel(
+    const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, int64_t n, int shift, int nchunks,
+    const int32_t* __restrict__ base, uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
+  __shared__ int run[SORT_WARPS][BINS];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunk = blockIdx.x * SORT_WARPS + w;
+  if (chunk >= nchunks) return;
+  for (int b = lane; b < BINS; b += 32) run[w][b] = base[(int64_t)b * nchunks + chunk];
+  __syncwarp();
+  const int64_t i0 = (int64_t)chunk * SORT_CHUNK;
+  for (int r = 0; r < SORT_CHUNK; r += 32) {
+    const int64_t i = i0 + r + lane;
+    const bool ok = i < n;
+    const uint32_t key = ok ? keys_in[i] : 0u;
+    const unsigned dg = ok ? digit_of(key, shift) : 0x100u + lane;  // inactive lanes match nobody
+    const unsigned peers = __match_any_sync(0xffffffffu, dg);
+    const int rank = __popc(peers & ((1u << lane) - 1u));
+    int pos = 0;
+    if (ok) pos = run[w][dg] + rank;
+    __syncwarp();
+    if (ok && rank == 0) run[w][dg] += __popc(peers);
+    __syncwarp();
+    if (ok) {
+      keys_out[pos] = key;
+      vals_out[pos] = vals_in != nullptr ? vals_in[i] : (uint32_t)i;
+    }
+  }
+}
+
+__global__ void narrow_keys_kernel(const int64_t* __restrict__ in, int64_t n, uint32_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (uint32_t)in[i];
+}
+
+__global__ void widen_vals_kernel(const uint32_t* __restrict__ in, int64_t n, int64_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (int64_t)in[i];
+}
+
+// seg_offsets[r] = first position in the sorted key array with key >= r  (binary search; r in [0, R])
+__global__ void segment_offsets_kernel(const uint32_t* __restrict__ sorted, int64_t n, int R,
+                                       int64_t* __restrict__ offsets) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > R) return;
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (sorted[mid] < (uint32_t)r) lo = mid + 1; else hi = mid;
+  }
+  offsets[r] = lo;
+}
+
+struct SortBuffers {
+  uint32_t *k0, *v0, *k1, *v1;
+  int32_t* hist;
+  int nchunks;
+  size_t bytes;
+};
+
+SortBuffers carve_sort(void* ws, int64_t n) {
+  SortBuffers s;
+  s.nchunks = (int)((n + SORT_CHUNK - 1) / SORT_CHUNK);
+  if (s.nchunks < 1) s.nchunks = 1;
+  size_t off = 0;
+  char* p = (char*)ws;
+  const size_t arr = align_up((size_t)(n > 0 ? n : 1) * sizeof(uint32_t), 256);
+  s.k0 = (uint32_t*)(p + off); off += arr;
+  s.v0 = (uint32_t*)(p + off); off += arr;
+  s.k1 = (uint32_t*)(p + off); off += arr;
+  s.v1 = (uint32_t*)(p + off); off += arr;
+  s.hist = (int32_t*)(p + off); off += align_up((size_t)BINS * s.nchunks * sizeof(int32_t), 256);
+  s.bytes = off;
+  return s;
+}
+
+// sorts (k0 -> result) with `passes` 8-bit digits; result ends in (*rk, *rv)
+int radix_sort(SortBuffers& s, int64_t n, int passes, cudaStream_t st, uint32_t** rk, uint32_t** rv) {
+  uint32_t *ki = s.k0, *vi = nullptr, *ko = s.k1, *vo = s.v1;
+  const int blocks = (s.nchunks + SORT_WARPS - 1) / SORT_WARPS;
+  for (int p = 0; p < passes; ++p) {
+    radix_hist_kernel<<<blocks, SORT_WARPS * 32, 0, st>>>(ki, n, 8 * p, s.nchunks, s.hist);
+    MPQE_CHECK_LAUNCH("radix_hist_kernel");
+    exclusive_scan_kernel<<<1, 1024, 0, st>>>(s.hist, (int64_t)BINS * s.nchunks, nullptr);
+    MPQE_CHECK_LAUNCH("exclusive_scan_kernel");
+    radix_scatter_kernel<<<blocks, SORT_WARPS * 32, 0, st>>>(ki, vi, n, 8 * p, s.nchunks, s.hist, ko, vo);
+    MPQE_CHECK_LAUNCH("radix_scatter_kernel");
+    uint32_t* tk = ki; ki = ko; ko = tk;
+    uint32_t* tv = (vi == nullptr) ? s.v0 : vi; vi = vo; vo = tv;
+  }
+  *rk = ki;
+  *rv = vi;
+  return 0;
+}
+
+int digits_for(int64_t max_key_exclusive) {
+  int passes = 1;
+  while (passes < 4 && (1ll << (8 * passes)) < max_key_exclusive) ++passes;
+  return passes;
+}
+
+// ---- row-sparse combine -----------------------------------------------------------------------------------
+__global__ void head_flags_kernel(const uint32_t* __restrict__ sorted, int64_t n, int32_t* __restrict__ flags) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flags[i] = (i == 0 || sorted[i] != sorted[i - 1]) ? 1 : 0;
+}
+
+// after the exclusive scan, uid[i] = (#heads before i); a head at i has unique index uid[i]
+__global__ void segment_starts_kernel(const uint32_t* __restrict__ sorted, const int32_t* __restrict__ uid, int64_t n,
+                                      int32_t* __restrict__ seg_start) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (i == 0 || sorted[i] != sorted[i - 1]) seg_start[uid[i]] = (int32_t)i;
+}
+
+__global__ void __launch_bounds__(256) segment_sum_kernel(const uint32_t* __restrict__ sorted_key,
+                                                          const uint32_t* __restrict__ sorted_val,
+                                                          const int32_t* __restrict__ seg_start,
+                                                          const int64_t* __restrict__ num_unique, int64_t n,
+                                                          const float* __restrict__ rows,
+                                                          int64_t* __restrict__ unique_ids,
+                                                          float* __restrict__ unique_rows) {
+  const int lane = threadIdx.x & 31;
+  const int64_t u = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int64_t nu = *num_unique;
+  if (u >= nu) return;
+  const int64_t i0 = seg_start[u];
+  const int64_t i1 = (u + 1 < nu) ? seg_start[u + 1] : n;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t i = i0; i < i1; ++i) {  // ascending pair index (the sort is stable): fixed summation order
+    const float4 v = *reinterpret_cast<const float4*>(rows + (int64_t)sorted_val[i] * D + lane * 4);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  *reinterpret_cast<float4*>(unique_rows + u * D + lane * 4) = acc;
+  if (lane == 0) unique_ids[u] = (int64_t)sorted_key[i0];
+}
+
+__global__ void __launch_bounds__(256) scatter_rows_kernel(const int64_t* __restrict__ ids,
+                                                           const float* __restrict__ rows,
+                                                           const int64_t* __restrict__ num, int64_t max_count,
+                                                           float* __restrict__ dense, int accumulate) {
+  const int lane = threadIdx.x & 31;
+  const int64_t u = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int64_t nu = num != nullptr ? *num : max_count;
+  if (u >= nu || u >= max_count) return;
+  float4 v = *reinterpret_cast<const float4*>(rows + u * D + lane * 4);
+  float4* dst = reinterpret_cast<float4*>(dense + ids[u] * D + lane * 4);
+  if (accumulate) {
+    const float4 o = *dst;
+    v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+  }
+  *dst = v;
+}
+
+inline unsigned blocks_for(int64_t n, int per) { return (unsigned)((n + per - 1) / per); }
+
+}  // namespace
+}  // namespace mpqe
+
+using namespace mpqe;
+
+extern "C" int mpqe_build_query_graph(int32_t n, int32_t E, const int32_t* tmpl_src_host, const int32_t* tmpl_dst_host,
+                                      const int64_t* tmpl_rel_host, int64_t B, int64_t* edge_index,
+                                      int64_t* edge_type, int64_t* batch, void* stream) {
+  MPQE_CHECK_ARG(n >= 1 && n <= MPQE_MAX_SLOTS && E >= 1 && E <= 4 && B >= 1, "mpqe_build_query_graph: bad shape");
+  MPQE_CHECK_ARG(tmpl_src_host && tmpl_dst_host && tmpl_rel_host && edge_index && edge_type && batch,
+                 "mpqe_build_query_graph: null argument");
+  int s[4] = {0, 0, 0, 0}, t[4] = {0, 0, 0, 0};
+  long long r[4] = {0, 0, 0, 0};
+  for (int e = 0; e < E; ++e) {
+    s[e] = tmpl_src_host[e];
+    t[e] = tmpl_dst_host[e];
+    r[e] = tmpl_rel_host[e];
+    MPQE_CHECK_ARG(s[e] >= 0 && s[e] < n && t[e] >= 0 && t[e] < n, "mpqe_build_query_graph: edge %d out of range", e);
+  }
+  const int64_t work = B * (E > n ? E : n);
+  build_query_graph_kernel<<<blocks_for(work, 256), 256, 0, (cudaStream_t)stream>>>(
+      n, E, B, make_int4(s[0], s[1], s[2], s[3]), make_int4(t[0], t[1], t[2], t[3]),
+      make_longlong4(r[0], r[1], r[2], r[3]), edge_index, edge_type, batch);
+  MPQE_CHECK_LAUNCH("build_query_graph_kernel");
+  return 0;
+}
+
+extern "C" size_t mpqe_relation_sort_workspace_bytes(int64_t num_edges, int32_t num_relations) {
+  (void)num_relations;
+  return carve_sort(nullptr, num_edges).bytes;
+}
+
+extern "C" int mpqe_relation_sort(const int64_t* edge_type, int64_t num_edges, int32_t num_relations, int64_t* perm,
+                                  int64_t* seg_offsets, void* workspace, size_t workspace_bytes, void* stream) {
+  MPQE_CHECK_ARG(edge_type && perm && seg_offsets && num_edges >= 1 && num_relations >= 1 && num_edges < (1ll << 31),
+                 "mpqe_relation_sort: bad argument");
+  SortBuffers s = carve_sort(workspace, num_edges);
+  MPQE_CHECK_ARG(workspace && workspace_bytes >= s.bytes, "mpqe_relation_sort: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  narrow_keys_kernel<<<blocks_for(num_edges, 256), 256, 0, st>>>(edge_type, num_edges, s.k0);
+  MPQE_CHECK_LAUNCH("narrow_keys_kernel");
+  uint32_t *rk, *rv;
+  if (radix_sort(s, num_edges, digits_for(num_relations), st, &rk, &rv)) return 2;
+  widen_vals_kernel<<<blocks_for(num_edges, 256), 256, 0, st>>>(rv, num_edges, perm);
+  MPQE_CHECK_LAUNCH("widen_vals_kernel");
+  segment_offsets_kernel<<<blocks_for(num_relations + 1, 256), 256, 0, st>>>(rk, num_edges, num_relations, seg_offsets);
+  MPQE_CHECK_LAUNCH("segment_offsets_kernel");
+  return 0;
+}
+
+extern "C" size_t mpqe_sparse_rows_workspace_bytes(int64_t count) {
+  const size_t n = (size_t)(count > 0 ? count : 1);
+  return carve_sort(nullptr, count).bytes + 2 * align_up(n * sizeof(int32_t), 256);
+}
+
+extern "C" int mpqe_sparse_rows_combine(const int64_t* rows_id, const float* rows, int64_t count, int64_t table_rows,
+                                        int64_t* unique_ids, float* unique_rows, int64_t* num_unique, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  MPQE_CHECK_ARG(rows_id && rows && unique_ids && unique_rows && num_unique && count >= 1 && count < (1ll << 31) &&
+                     table_rows >= 1 && table_rows < (1ll << 32),
+                 "mpqe_sparse_rows_combine: bad argument");
+  MPQE_CHECK_ARG(workspace && workspace_bytes >= mpqe_sparse_rows_workspace_bytes(count),
+                 "mpqe_sparse_rows_combine: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  SortBuffers s = carve_sort(workspace, count);
+  int32_t* uid = (int32_t*)((char*)workspace + s.bytes);
+  int32_t* seg_start = (int32_t*)((char*)uid + align_up((size_t)count * sizeof(int32_t), 256));
+  narrow_keys_kernel<<<blocks_for(count, 256), 256, 0, st>>>(rows_id, count, s.k0);
+  MPQE_CHECK_LAUNCH("narrow_keys_kernel");
+  uint32_t *rk, *rv;
+  if (radix_sort(s, count, digits_for(table_rows), st, &rk, &rv)) return 2;
+  head_flags_kernel<<<blocks_for(count, 256), 256, 0, st>>>(rk, count, uid);
+  MPQE_CHECK_LAUNCH("head_flags_kernel");
+  exclusive_scan_kernel<<<1, 1024, 0, st>>>(uid, count, num_unique);
+  MPQE_CHECK_LAUNCH("exclusive_scan_kernel");
+  segment_starts_kernel<<<blocks_for(count, 256), 256, 0, st>>>(rk, uid, count, seg_start);
+  MPQE_CHECK_LAUNCH("segment_starts_kernel");
+  segment_sum_kernel<<<blocks_for(count, 8), 256, 0, st>>>(rk, rv, seg_start, num_unique, count, rows, unique_ids,
+                                                         unique_rows);
+  MPQE_CHECK_LAUNCH("segment_sum_kernel");
+  return 0;
+}
+
+extern "C" int mpqe_scatter_rows(const int64_t* ids, const float* rows, const int64_t* num, int64_t max_count,
+                                 float* dense, int32_t accumulate, void* stream) {
+  MPQE_CHECK_ARG(ids && rows && dense && max_count >= 0, "mpqe_scatter_rows: bad argument");
+  if (max_count == 0) return 0;
+  scatter_rows_kernel<<<blocks_for(max_count, 8), 256, 0, (cudaStream_t)stream>>>(ids, rows, num, max_count, dense,
+                                                                               accumulate);
+  MPQE_CHECK_LAUNCH("scatter_rows_kernel");
+  return 0;
+}
