@@ -207,7 +207,13 @@ __global__ void __launch_bounds__(256) segment_sum_kernel(const uint32_t* __rest
   const int lane = threadIdx.x & 31;
   const int64_t u = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int64_t nu = *num_unique;
-  if (u >= nu) return;
+  if (u >= nu) {  // padding entries: a zero row at index 0, so fixed-size consumers need no host sync
+    if (u < n) {
+      *reinterpret_cast<float4*>(unique_rows + u * D + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (lane == 0) unique_ids[u] = 0;
+    }
+    return;
+  }
   const int64_t i0 = seg_start[u];
   const int64_t i1 = (u + 1 < nu) ? seg_start[u + 1] : n;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);

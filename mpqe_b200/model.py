@@ -1,0 +1,729 @@
+"""MPQE query encoder + scorer on B200: R-GCN over batched query graphs, readout, cosine scoring, margin loss.
+
+Mirror of the reference's `mpqe/model.py` R-GCN path (`RGCNConv` :206-310, `RGCNEncoderDecoder` :313-494,
+`MLPReadout` :497-515, `TargetMLPReadout` :518-553): same constructor arguments, attributes, state_dict names,
+`forward(...) -> scores` and `margin_loss(...) -> loss`, same exceptions.
+
+How it runs is different.  Every query of a batch shares one <=4-node template, so a layer pass is a short list
+of dense terms  out[:, dst] += h[:, src] @ W[rel]  (+ the self-loop term, bias, ReLU); `engine` turns a batch
+into such term lists and drives the fused CUDA layer kernel (`mpqe_layer_forward`) once per pass for ALL groups,
+with the readout folded into the last pass (sum: every term accumulates into one output row; target-message:
+only the target's terms are computed at all).  The backward is the same kernel on transposed matrices plus a
+deterministic weight-gradient kernel; entity-table gradients are row-sparse.  The reference instead gathers a
+d x d matrix per EDGE and runs bmm (:292-294), and runs the whole encoder twice per loss (:478-482); here the
+query embedding is computed once and scored against positives and negatives.
+"""
+import math
+import random
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .data_utils import QueryGraphBatch, RGCNQueryDataset, template_of
+from .encoders import DirectEncoder, table_gradient
+from .ops import D, EPI_MASK, EPI_NONE, EPI_RELU, Group, Term
+
+MLP_READOUTS = ('mlp', 'targetmlp', 'concat')
+
+
+def _uniform(size, tensor):
+    """PyG inits.uniform: U(+-1/sqrt(size)) (reference model.py:263-267)."""
+    if tensor is not None:
+        bound = 1.0 / math.sqrt(size)
+        tensor.data.uniform_(-bound, bound)
+
+
+class RGCNConv(nn.Module):
+    """Relational graph convolution  x'_i = x_i @ root + sum_{j ->r i} x_j @ W_r + bias  (aggr='add').
+
+    Parameters as in the reference: `basis [R | num_bases, in, out]`, `att [R, num_bases] | None`, `root [in, out]`,
+    `bias [out]`.  `forward(x, edge_index, edge_type)` takes either the reference's tensors plus `graph=` (the
+    `QueryGraphBatch` that produced them) or just a `QueryGraphBatch` as `edge_index`."""
+
+    def __init__(self, in_channels, out_channels, num_relations, num_bases, bias=True):
+        super(RGCNConv, self).__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.num_relations, self.num_bases = num_relations, num_bases
+        if num_bases == 0:
+            self.basis = nn.Parameter(torch.Tensor(num_relations, in_channels, out_channels))
+            self.att = None
+        else:
+            self.basis = nn.Parameter(torch.Tensor(num_bases, in_channels, out_channels))
+            self.att = nn.Parameter(torch.Tensor(num_relations, num_bases))
+        self.root = nn.Parameter(torch.Tensor(in_channels, out_channels))
+        if bias:
+            self.bias = nn.Parameter(torch.Tensor(out_channels))
+        else:
+            self.register_parameter('bias', None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        size = (self.num_relations if self.att is None else self.num_bases) * self.in_channels
+        _uniform(size, self.att)
+        _uniform(size, self.basis)
+        _uniform(size, self.root)
+        _uniform(size, self.bias)
+
+    def relation_weights(self):
+        """[R, in, out] weights; with a basis decomposition W_r = sum_b att[r, b] * basis[b] (model.py:281-284)."""
+        if self.att is None:
+            return self.basis
+        return torch.matmul(self.att, self.basis.view(self.num_bases, -1)).view(
+            self.num_relations, self.in_channels, self.out_channels)
+
+    def forward(self, x, edge_index, edge_type=None, edge_norm=None, graph=None):
+        if isinstance(edge_index, QueryGraphBatch):
+            graph = edge_index
+        if edge_norm is not None:
+            raise NotImplementedError('edge_norm is never passed by MPQE (model.py:436, 441)')
+        if graph is None:
+            raise NotImplementedError('RGCNConv on an arbitrary edge list needs the template that produced it: pass '
+                                      'graph=<QueryGraphBatch> (general graphs are outside the MPQE hot path)')
+        if self.in_channels != D or self.out_channels != D:
+            raise ValueError('kernels are specialised for %d channels' % D)
+        return _ConvFn.apply(x, self.relation_weights(), self.root, self.bias, graph)
+
+    def __repr__(self):
+        return '{}({}, {}, num_relations={})'.format(self.__class__.__name__, self.in_channels, self.out_channels,
+                                                     self.num_relations)
+
+
+def _conv_terms(t, rels, x, n, w, root):
+    terms = [Term(x, n, t.src[e], w[rels[e]], t.dst[e]) for e in range(t.num_edges)]
+    terms += [Term(x, n, i, root, i) for i in range(n)]
+    return terms
+
+
+class _ConvFn(torch.autograd.Function):
+    """One stand-alone layer pass over a template batch (the per-layer API of the reference's RGCNConv)."""
+
+    @staticmethod
+    def forward(ctx, x, w, root, bias, graph):
+        t, rels, B = graph.template, graph.edge_rel_ids, graph.num_graphs
+        n = t.num_nodes
+        with ops.device_guard(x.device):
+            x = x.contiguous()
+            out = torch.empty(B * n, D, dtype=torch.float32, device=x.device)
+            ops.layer_forward([Group(B, _conv_terms(t, rels, x, n, w, root), n, out, n, bias=bias)])
+        ctx.save_for_backward(x, w, root)
+        ctx.graph, ctx.has_bias = graph, bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w, root = ctx.saved_tensors
+        t, rels, B = ctx.graph.template, ctx.graph.edge_rel_ids, ctx.graph.num_graphs
+        n = t.num_nodes
+        with ops.device_guard(x.device):
+            g = g.contiguous()
+            wt, roott = ops.transpose(w), ops.transpose(root)
+            dx = torch.empty_like(x)
+            back = [Term(g, n, t.dst[e], wt[rels[e]], t.src[e]) for e in range(t.num_edges)]
+            back += [Term(g, n, i, roott, i) for i in range(n)]
+            ops.layer_forward([Group(B, back, n, dx, n)])
+            dw, droot = torch.zeros_like(w), torch.zeros_like(root)
+            fwd = Group(B, _conv_terms(t, rels, x, n, w, root), n, None, n)
+            dests = [(w[r], dw[r], 1) for r in sorted(set(rels))] + [(root, droot, 1)]
+            ops.layer_wgrad([fwd], [(g, n, list(range(n)))], dests)
+            dbias = None
+            if ctx.has_bias:
+                dbias = torch.empty(D, dtype=torch.float32, device=x.device)
+                ops.colsum(g, B * n, D, dbias)
+        return dx, dw, droot, dbias, None
+
+
+class MLPReadout(nn.Module):
+    """Linear-ReLU-Linear on every node, then scatter over each query's nodes (reference model.py:497-515).
+    Inside RGCNEncoderDecoder the arithmetic runs in the fused kernels; this module owns the parameters."""
+
+    def __init__(self, input_dim, output_dim, scatter_fn):
+        super(MLPReadout, self).__init__()
+        self.layers = nn.Sequential(nn.Linear(in_features=input_dim, out_features=output_dim), nn.ReLU(),
+                                    nn.Linear(in_features=output_dim, out_features=output_dim))
+        self.scatter_fn = scatter_fn
+
+
+class TargetMLPReadout(nn.Module):
+    """MLP on cat(target node, other node) for every non-target node, then scatter (reference model.py:518-553)."""
+
+    def __init__(self, dim, scatter_fn):
+        super(TargetMLPReadout, self).__init__()
+        self.layers = nn.Sequential(nn.Linear(in_features=2 * dim, out_features=dim), nn.ReLU(),
+                                    nn.Linear(in_features=dim, out_features=dim))
+        self.scatter_fn = scatter_fn
+
+
+# ===============================================================================================================
+# Engine: one formula group = one Job; passes of all jobs are launched together (<= MPQE_MAX_GROUPS per launch)
+# ===============================================================================================================
+class Job(object):
+    """One batch of queries of a single formula, ids already on the device."""
+
+    def __init__(self, template, edge_rels, var_rows, anchor_modes, target_mode, anchor_ids, num_passes):
+        self.t, self.rels, self.var_rows = template, tuple(edge_rels), var_rows
+        self.anchor_modes, self.target_mode = tuple(anchor_modes), target_mode
+        self.anchor_ids = anchor_ids                      # int64 [B, a] on device
+        self.B = int(anchor_ids.shape[0])
+        self.P = int(num_passes)
+        # filled by the engine
+        self.acts = None       # acts[p] = input of pass p, [B, n, D]
+        self.outs = None       # outs[p] = node slots computed by pass p
+        self.z = self.u = self.q = self.argmax = None
+        self.fwd_groups = None
+
+
+class Weights(object):
+    """Per-step views of the dense parameters in the layouts the kernels want."""
+
+    def __init__(self, model, need_grad):
+        self.w, self.root, self.bias = [], [], []
+        for layer in model.distinct_layers():
+            self.w.append(layer.relation_weights().contiguous())
+            self.root.append(layer.root)
+            self.bias.append(layer.bias)
+        self.mode_emb = model.mode_embeddings.weight
+        self.need_grad = need_grad
+        self.wt = self.roott = None
+        self.w1t = self.w1b = self.w2t = None
+        ro = model.readout if isinstance(model.readout, nn.Module) else None
+        self.ro = ro
+        if ro is not None:
+            lin1, lin2 = ro.layers[0], ro.layers[2]
+            self.w1, self.b1, self.w2, self.b2 = lin1.weight, lin1.bias, lin2.weight, lin2.bias
+            self.blocks = self.w1.shape[1] // D
+            self.w1t = ops.transpose(self.w1.contiguous())                     # [blocks*D, D]: block p = W1[:, pD:(p+1)D]^T
+            self.w2t = ops.transpose(self.w2.contiguous())
+        if need_grad:
+            self.wt = [ops.transpose(w) for w in self.w]
+            self.roott = [ops.transpose(r) for r in self.root]
+            if ro is not None:
+                self.w1b = ops.transpose(self.w1t.view(self.blocks, D, D))     # [blocks, D(u), D(h)] contiguous
+
+
+def _needed_slots(job, readout):
+    """outs[p]: node slots whose output pass p must produce (all, except for the target-message readout)."""
+    t, P = job.t, job.P
+    if readout != 'mp':
+        return [list(range(t.num_nodes)) for _ in range(P)]
+    need = {t.target_slot}
+    outs = [None] * P
+    for p in range(P - 1, -1, -1):
+        outs[p] = sorted(need)
+        need = need | {t.src[e] for e in range(t.num_edges) if t.dst[e] in need}
+    return outs
+
+
+class Engine(object):
+    def __init__(self, model):
+        self.m = model
+
+    # ---- forward ------------------------------------------------------------------------------------------
+    def build_inputs(self, jobs, W):
+        enc = self.m.enc
+        for job in jobs:
+            t, B, n = job.t, job.B, job.t.num_nodes
+            x = torch.empty(B, n, D, dtype=torch.float32, device=job.anchor_ids.device)
+            for i, mode in enumerate(job.anchor_modes):
+                ops.gather_normalize(enc.table(mode), enc.node_maps, job.anchor_ids, out=x, out_offset=i * D,
+                                     out_stride=n * D, ids_offset=i, ids_stride=t.num_anchors, count=B)
+            ops.broadcast_rows(W.mode_emb, job.var_rows, x, t.num_anchors * D, n * D, B)
+            job.acts = [x]
+
+    def layer_index(self, p, P):
+        if self.m.shared_layers:
+            return 0
+        return p if p < P - 1 else self.m.num_layers - 1
+
+    def pass_terms(self, job, p, W, outs):
+        """Forward terms of pass p restricted to the output slots `outs` (term.out_slot = index into outs)."""
+        t, n = job.t, job.t.num_nodes
+        li = self.layer_index(p, job.P)
+        x = job.acts[p]
+        pos = {s: k for k, s in enumerate(outs)}
+        terms = [Term(x, n, t.src[e], W.w[li][job.rels[e]], pos[t.dst[e]])
+                 for e in range(t.num_edges) if t.dst[e] in pos]
+        terms += [Term(x, n, s, W.root[li], pos[s]) for s in outs]
+        return terms, li
+
+    def encode(self, jobs, W):
+        """Runs every pass of every job; leaves job.q [B, D] (query embeddings)."""
+        readout = self.m.readout_str
+        self.build_inputs(jobs, W)
+        for job in jobs:
+            job.outs = _needed_slots(job, readout)
+            job.fwd_groups = [None] * job.P
+        max_p = max(job.P for job in jobs)
+        for p in range(max_p):
+            groups = []
+            for job in jobs:
+                if p >= job.P:
+                    continue
+                B, n = job.B, job.t.num_nodes
+                outs = job.outs[p]
+                terms, li = self.pass_terms(job, p, W, outs)
+                dev = job.anchor_ids.device
+                if p < job.P - 1:
+                    h = torch.empty(B, n, D, dtype=torch.float32, device=dev)
+                    g = Group(B, terms, len(outs), h, n, out_slot_map=outs, epilogue=EPI_RELU, bias=W.bias[li])
+                    job.acts.append(h)
+                elif readout in ('sum', 'mp'):
+                    # readout folded into the last pass: every term accumulates into the single output row
+                    for term in terms:
+                        term.out_slot = 0
+                    job.q = torch.empty(B, D, dtype=torch.float32, device=dev)
+                    g = Group(B, terms, 1, job.q, 1, out_slot_map=[0], bias=W.bias[li], bias_scale=[float(len(outs))])
+                else:
+                    job.z = torch.empty(B, n, D, dtype=torch.float32, device=dev)
+                    g = Group(B, terms, len(outs), job.z, n, out_slot_map=outs, bias=W.bias[li])
+                job.fwd_groups[p] = g
+                groups.append(g)
+            ops.layer_forward(groups)
+        if readout == 'max':
+            for job in jobs:
+                job.q, job.argmax = ops.max_readout(job.z, job.B, job.t.num_nodes)
+        elif readout in MLP_READOUTS:
+            self.mlp_readout(jobs, W)
+
+    def mlp_inputs(self, job):
+        """[(u slot k, [(tensor, slots, slot, block)])]: which rows feed MLP unit k, and through which W1 block."""
+        t, n = job.t, job.t.num_nodes
+        ro = self.m.readout_str
+        if ro == 'mlp':
+            return [[(job.z, n, j, 0)] for j in range(n)]
+        if ro == 'concat':
+            feats = job.acts[1:] + [job.z]
+            return [[(f, n, j, b) for b, f in enumerate(feats)] for j in range(n)]
+        others = [j for j in range(n) if j != t.target_slot]
+        return [[(job.z, n, t.target_slot, 0), (job.z, n, j, 1)] for j in others]
+
+    def mlp_readout(self, jobs, W):
+        g1, g2 = [], []
+        for job in jobs:
+            units = self.mlp_inputs(job)
+            nu = len(units)
+            dev = job.anchor_ids.device
+            terms = [Term(a, s, j, W.w1t[b * D:(b + 1) * D], k) for k, srcs in enumerate(units) for (a, s, j, b) in srcs]
+            job.u = torch.empty(job.B, nu, D, dtype=torch.float32, device=dev)
+            job.mlp1 = Group(job.B, terms, nu, job.u, nu, epilogue=EPI_RELU, bias=W.b1)
+            job.q = torch.empty(job.B, D, dtype=torch.float32, device=dev)
+            job.mlp2 = Group(job.B, [Term(job.u, nu, k, W.w2t, 0) for k in range(nu)], 1, job.q, 1, out_slot_map=[0],
+                             bias=W.b2, bias_scale=[float(nu)])
+            g1.append(job.mlp1)
+            g2.append(job.mlp2)
+        ops.layer_forward(g1)
+        ops.layer_forward(g2)
+
+    # ---- backward -----------------------------------------------------------------------------------------
+    def backward(self, jobs, W, dqs, G):
+        """dqs[i] = d loss / d job.q.  Accumulates dense gradients into `G` (a Grads) and row gradients into G.rows."""
+        readout = self.m.readout_str
+        # gradient wrt the last pass output, as (tensor, slots, slot_map over outs[P-1])
+        last = {}
+        if readout in ('sum', 'mp'):
+            for job, dq in zip(jobs, dqs):
+                last[job] = (dq, 1, [0] * len(job.outs[job.P - 1]))
+        elif readout == 'max':
+            for job, dq in zip(jobs, dqs):
+                n = job.t.num_nodes
+                last[job] = (ops.max_readout_bwd(dq, job.argmax, job.B, n), n, list(range(n)))
+        else:
+            self.mlp_backward(jobs, W, dqs, G, last)
+
+        cur = dict(last)  # job -> gradient operand of the pass being processed
+        max_p = max(job.P for job in jobs)
+        for p in range(max_p - 1, -1, -1):
+            active = [job for job in jobs if p < job.P]
+            # ---- weight / bias gradients of pass p (grouped by layer so destinations are unique per launch)
+            by_layer = {}
+            for job in active:
+                by_layer.setdefault(self.layer_index(p, job.P), []).append(job)
+            for li, ljobs in by_layer.items():
+                for i in range(0, len(ljobs), ops.MAX_GROUPS):
+                    chunk = ljobs[i:i + ops.MAX_GROUPS]
+                    rels = sorted({r for job in chunk for r in job.rels})
+                    dests = [(W.w[li][r], G.dw[li][r], 1) for r in rels] + [(W.root[li], G.droot[li], 1)]
+                    ops.layer_wgrad([job.fwd_groups[p] for job in chunk], [cur[job] for job in chunk], dests)
+                for job in ljobs:
+                    g, g_slots, smap = cur[job]
+                    if g_slots == 1:
+                        # sum readout: the bias was added once per node; target-message: once
+                        scale = float(job.fwd_groups[p].bias_scale[0])
+                        ops.colsum(g, job.B, D, G.dbias[li], scale=scale, accumulate=True)
+                    elif len(smap) == g_slots:
+                        ops.colsum(g, job.B * g_slots, D, G.dbias[li], accumulate=True)
+                    else:
+                        for s in smap:
+                            ops.colsum(g[:, s], job.B, g_slots * D, G.dbias[li], accumulate=True)
+            # ---- input gradients of pass p
+            groups, nxt = [], {}
+            for job in active:
+                t, n = job.t, job.t.num_nodes
+                g, g_slots, smap = cur[job]
+                li = self.layer_index(p, job.P)
+                outs = job.outs[p]
+                ins = job.outs[p - 1] if p > 0 else sorted(
+                    {t.src[e] for e in range(t.num_edges) if t.dst[e] in outs} | set(outs))
+                pos = {s: k for k, s in enumerate(ins)}
+                okey = {s: k for k, s in enumerate(outs)}
+                terms = [Term(g, g_slots, smap[okey[t.dst[e]]], W.wt[li][job.rels[e]], pos[t.src[e]])
+                         for e in range(t.num_edges) if t.dst[e] in okey and t.src[e] in pos]
+                terms += [Term(g, g_slots, smap[okey[s]], W.roott[li], pos[s]) for s in outs if s in pos]
+                if readout == 'concat' and p > 0:
+                    # h_p also feeds block p-1 of the concat MLP
+                    terms += [Term(job.du, n, j, W.w1b[p - 1], pos[j]) for j in range(n)]
+                dx = torch.empty(job.B, n, D, dtype=torch.float32, device=g.device)
+                if p > 0:
+                    groups.append(Group(job.B, terms, len(ins), dx, n, out_slot_map=ins, epilogue=EPI_MASK,
+                                        mask=job.acts[p], mask_slots=n))
+                else:
+                    groups.append(Group(job.B, terms, len(ins), dx, n, out_slot_map=ins))
+                nxt[job] = (dx, n, ins)
+            ops.layer_forward(groups)
+            for job in active:
+                dx, n, ins = nxt[job]
+                if p > 0:
+                    cur[job] = (dx, n, ins)
+                else:
+                    self.input_backward(job, dx, ins, G)
+
+    def input_backward(self, job, dx, ins, G):
+        """d loss / d x -> anchor table rows (through the normalisation) and variable-type embedding rows."""
+        t, n, B = job.t, job.t.num_nodes, job.B
+        enc = self.m.enc
+        for i, mode in enumerate(job.anchor_modes):
+            if i not in ins:
+                continue
+            rows, rows_id, off = G.rows.reserve(mode, B)
+            ops.gather_normalize_bwd(enc.table(mode), enc.node_maps, job.anchor_ids, dx, rows, rows_id,
+                                     grad_offset=i * D, grad_stride=n * D, ids_offset=i, ids_stride=t.num_anchors,
+                                     count=B, rows_offset=off)
+        for k, row in enumerate(job.var_rows_host):
+            s = t.num_anchors + k
+            if s in ins:
+                ops.colsum(dx[:, s], B, n * D, G.dmode[row], accumulate=True)
+
+    def mlp_backward(self, jobs, W, dqs, G, last):
+        """Backward of the MLP readouts; fills last[job] (gradient wrt the last R-GCN pass output) and job.du."""
+        ro = self.m.readout_str
+        g_du = []
+        for job, dq in zip(jobs, dqs):
+            nu = job.u.shape[1]
+            job.du = torch.empty_like(job.u)
+            # dU[:, k] = (dq @ W2) * (u > 0)       (W2 is stored [out, in] = the matrix this product needs)
+            g_du.append(Group(job.B, [Term(dq, 1, 0, W.w2, k) for k in range(nu)], nu, job.du, nu, epilogue=EPI_MASK,
+                              mask=job.u, mask_slots=nu))
+        ops.layer_forward(g_du)
+        for i in range(0, len(jobs), ops.MAX_GROUPS):
+            chunk = jobs[i:i + ops.MAX_GROUPS]
+            cdq = dqs[i:i + ops.MAX_GROUPS]
+            ops.layer_wgrad([job.mlp2 for job in chunk], [(dq, 1, [0]) for dq in cdq], [(W.w2t, G.dw2t, 1)])
+            dests = [(W.w1t[b * D:(b + 1) * D], G.dw1t[b * D:(b + 1) * D], 1) for b in range(W.blocks)]
+            ops.layer_wgrad([job.mlp1 for job in chunk],
+                            [(job.du, job.u.shape[1], list(range(job.u.shape[1]))) for job in chunk], dests)
+        g_last = []
+        for job, dq in zip(jobs, dqs):
+            nu, n, t = job.u.shape[1], job.t.num_nodes, job.t
+            ops.colsum(dq, job.B, D, G.db2, scale=float(nu), accumulate=True)
+            ops.colsum(job.du, job.B * nu, D, G.db1, accumulate=True)
+            gz = torch.empty(job.B, n, D, dtype=torch.float32, device=dq.device)
+            if ro == 'targetmlp':
+                others = [j for j in range(n) if j != t.target_slot]
+                terms = [Term(job.du, nu, k, W.w1b[0], t.target_slot) for k in range(nu)]
+                terms += [Term(job.du, nu, k, W.w1b[1], j) for k, j in enumerate(others)]
+            else:
+                terms = [Term(job.du, nu, j, W.w1b[W.blocks - 1], j) for j in range(n)]
+            g_last.append(Group(job.B, terms, n, gz, n))
+            last[job] = (gz, n, list(range(n)))
+        ops.layer_forward(g_last)
+
+
+class RowGrads(object):
+    """Collects (table row, gradient row) pairs per mode; capacities are known on the host before the backward."""
+
+    def __init__(self, capacities, device):
+        self.buf = {}
+        for mode, cap in capacities.items():
+            if cap > 0:
+                self.buf[mode] = [torch.empty(cap, D, dtype=torch.float32, device=device),
+                                  torch.empty(cap, dtype=torch.int64, device=device), 0]
+
+    def reserve(self, mode, count):
+        rows, ids, used = self.buf[mode]
+        assert used + count <= ids.numel()
+        self.buf[mode][2] = used + count
+        return rows, ids, used
+
+
+class Grads(object):
+    """Dense gradient buffers (zero-initialised, kernels accumulate) + the row-gradient collector."""
+
+    def __init__(self, model, W, row_capacities, device):
+        self.dw = [torch.zeros_like(w) for w in W.w]
+        self.droot = [torch.zeros_like(r) for r in W.root]
+        self.dbias = [torch.zeros(D, dtype=torch.float32, device=device) for _ in W.root]
+        self.dmode = torch.zeros_like(W.mode_emb)
+        if W.ro is not None:
+            self.dw1t, self.dw2t = torch.zeros_like(W.w1t), torch.zeros_like(W.w2t)
+            self.db1 = torch.zeros(D, dtype=torch.float32, device=device)
+            self.db2 = torch.zeros(D, dtype=torch.float32, device=device)
+        self.rows = RowGrads(row_capacities, device)
+
+
+# ===============================================================================================================
+class RGCNEncoderDecoder(nn.Module):
+    def __init__(self, graph, enc, readout='mp', scatter_op='add', dropout=0, weight_decay=1e-3, num_layers=3,
+                 shared_layers=True, adaptive=True):
+        super(RGCNEncoderDecoder, self).__init__()
+        self.enc = enc
+        self.graph = graph
+        self.emb_dim = graph.feature_dims[next(iter(graph.feature_dims))]
+        self.mode_embeddings = nn.Embedding(len(graph.mode_weights), self.emb_dim)
+        self.num_layers = num_layers
+        self.adaptive = adaptive
+        self.shared_layers = shared_layers
+        self.mode_ids = {mode: i for i, mode in enumerate(graph.mode_weights)}
+        self.rel_ids = {}
+        for r1 in graph.relations:
+            for r2 in graph.relations[r1]:
+                self.rel_ids[(r1, r2[1], r2[0])] = len(self.rel_ids)
+
+        self.layers = nn.ModuleList()
+        for i in range(num_layers):
+            if len(self.layers) == 0 or not shared_layers:
+                rgcn = RGCNConv(in_channels=self.emb_dim, out_channels=self.emb_dim,
+                                num_relations=len(graph.rel_edges), num_bases=0)
+            self.layers.append(rgcn)
+
+        if scatter_op not in ('add', 'max', 'mean'):
+            raise ValueError(f'Unknown scatter op {scatter_op}')
+        self.scatter_op = scatter_op
+        self.readout_str = readout
+        if readout == 'sum':
+            self.readout = self.sum_readout
+        elif readout == 'max':
+            self.readout = self.max_readout
+        elif readout == 'mlp':
+            self.readout = MLPReadout(self.emb_dim, self.emb_dim, scatter_op)
+        elif readout == 'targetmlp':
+            self.readout = TargetMLPReadout(self.emb_dim, scatter_op)
+        elif readout == 'concat':
+            self.readout = MLPReadout(self.emb_dim * num_layers, self.emb_dim, scatter_op)
+        elif readout == 'mp':
+            self.readout = self.target_message_readout
+        else:
+            raise ValueError(f'Unknown readout function {readout}')
+        if readout in MLP_READOUTS and scatter_op != 'add':
+            raise NotImplementedError('MLP readouts are fused with scatter_op="add" only (the reference default)')
+
+        self.dropout = nn.Dropout(dropout)  # constructed but never applied, as in the reference (model.py:377)
+        self.weight_decay = weight_decay
+        self.sparse_embedding_grad = getattr(enc, 'sparse_grad', False)
+        self._engine = Engine(self)
+        self._device_cache = {}
+
+    # The three named readouts stay callable with the reference's signature (model.py:380-398).
+    def sum_readout(self, embs, batch_idx=None, batch_size=None, num_nodes=None, **kwargs):
+        return embs.reshape(batch_size, num_nodes, -1).sum(dim=1) if batch_size else embs
+
+    def max_readout(self, embs, batch_idx=None, batch_size=None, num_nodes=None, **kwargs):
+        with ops.device_guard(embs.device):
+            return ops.max_readout(embs.contiguous(), batch_size, num_nodes)[0]
+
+    def target_message_readout(self, embs, batch_size, num_nodes, num_anchors, **kwargs):
+        return embs.reshape(batch_size, num_nodes, -1)[:, num_anchors]
+
+    def distinct_layers(self):
+        return [self.layers[0]] if self.shared_layers else list(self.layers)
+
+    # ---- job construction -----------------------------------------------------------------------------
+    def num_passes(self, formula):
+        if self.adaptive:
+            passes = RGCNQueryDataset.query_diameters[formula.query_type]
+            if passes > len(self.layers):
+                raise ValueError(f'RGCN is adaptive with {len(self.layers)} layers, but query requires {passes}.')
+            return passes
+        return self.num_layers
+
+    def make_job(self, formula, queries, anchor_ids=None, var_ids=None, q_graphs=None):
+        if self.emb_dim != D:
+            raise ValueError('kernels are specialised for embed_dim=%d' % D)
+        if self.readout_str == 'concat' and self.num_passes(formula) != self.num_layers:
+            raise ValueError('concat readout needs num_passes == num_layers (reference model.py:369-371 vs 443-445)')
+        device = self.mode_embeddings.weight.device
+        ops.device_guard(device)
+        if anchor_ids is None or var_ids is None or q_graphs is None:
+            anchor_ids, var_ids, q_graphs = RGCNQueryDataset.get_query_graph(formula, queries, self.rel_ids,
+                                                                             self.mode_ids)
+        q_graphs = q_graphs.to(device)
+        t = q_graphs.template if isinstance(q_graphs, QueryGraphBatch) else template_of(formula.query_type)
+        rels = q_graphs.edge_rel_ids
+        key = ('var', tuple(int(v) for v in var_ids.tolist()))
+        var_dev = self._device_cache.get(key)
+        if var_dev is None or var_dev.device != device:
+            var_dev = self._device_cache[key] = var_ids.to(device)
+        a_dev = anchor_ids.to(device=device, dtype=torch.int64, non_blocking=True).contiguous()
+        job = Job(t, rels, var_dev, formula.anchor_modes, formula.target_mode, a_dev, self.num_passes(formula))
+        job.var_rows_host = key[1]
+        return job
+
+    def _ids(self, nodes, device):
+        return self.enc.ids_on_device(nodes, device).reshape(-1)
+
+    def _params(self):
+        return [p for p in self.parameters()]
+
+    # ---- public API (reference model.py:400-494) ------------------------------------------------------
+    def forward(self, formula, queries, target_nodes, anchor_ids=None, var_ids=None, q_graphs=None,
+                neg_nodes=None, neg_lengths=None):
+        job = self.make_job(formula, queries, anchor_ids, var_ids, q_graphs)
+        device = job.anchor_ids.device
+        tgt = self._ids(target_nodes, device)
+        neg = offsets = None
+        if neg_nodes is not None:
+            neg = self._ids(neg_nodes, device)
+            lengths = torch.as_tensor(neg_lengths, dtype=torch.int64)
+            offsets = torch.zeros(lengths.numel() + 1, dtype=torch.int64)
+            offsets[1:] = torch.cumsum(lengths, 0)
+            offsets = offsets.to(device, non_blocking=True)
+        return _ScoresFn.apply(self, job, tgt, neg, offsets, *self._params())
+
+    def margin_loss(self, formula, queries, anchor_ids=None, var_ids=None, q_graphs=None, hard_negatives=False,
+                    margin=1):
+        if 'inter' not in formula.query_type and hard_negatives:
+            raise Exception('Hard negative examples can only be used with intersection queries')
+        elif hard_negatives:
+            neg_nodes = [random.choice(query.hard_neg_samples) for query in queries]
+        elif formula.query_type == '1-chain':
+            neg_nodes = [random.choice(self.graph.full_lists[formula.target_mode]) for _ in queries]
+        else:
+            neg_nodes = [random.choice(query.neg_samples) for query in queries]
+        return self.margin_loss_ids(formula, queries, [query.target_node for query in queries], neg_nodes,
+                                    anchor_ids, var_ids, q_graphs, margin)
+
+    def margin_loss_ids(self, formula, queries, target_nodes, neg_nodes, anchor_ids=None, var_ids=None,
+                        q_graphs=None, margin=1):
+        """margin_loss with the negatives chosen by the caller (tensors or lists of global node ids)."""
+        job = self.make_job(formula, queries, anchor_ids, var_ids, q_graphs)
+        device = job.anchor_ids.device
+        loss = _MarginLossFn.apply(self, [job], [self._ids(target_nodes, device)], [self._ids(neg_nodes, device)],
+                                   float(margin), *self._params())
+        if isinstance(self.readout, nn.Module) and self.weight_decay > 0:
+            l2_reg = 0
+            for param in self.readout.parameters():
+                l2_reg = l2_reg + torch.norm(param)
+            loss = loss + self.weight_decay * l2_reg
+        return loss
+
+    # ---- gradient plumbing shared by the autograd functions -------------------------------------------
+    def _row_capacities(self, jobs, extra):
+        cap = {}
+        for job in jobs:
+            for mode in job.anchor_modes:
+                cap[mode] = cap.get(mode, 0) + job.B
+        for mode, count in extra:
+            cap[mode] = cap.get(mode, 0) + count
+        return cap
+
+    def _collect_grads(self, W, G):
+        """Gradients in `self.parameters()` order."""
+        by_param = {}
+        for li, layer in enumerate(self.distinct_layers()):
+            if layer.att is None:
+                by_param[id(layer.basis)] = G.dw[li]
+            else:  # W_r = sum_b att[r,b] basis[b]
+                dw = G.dw[li].view(layer.num_relations, -1)
+                by_param[id(layer.att)] = dw @ layer.basis.view(layer.num_bases, -1).t()
+                by_param[id(layer.basis)] = (layer.att.t() @ dw).view_as(layer.basis)
+            by_param[id(layer.root)] = G.droot[li]
+            if layer.bias is not None:
+                by_param[id(layer.bias)] = G.dbias[li]
+        by_param[id(self.mode_embeddings.weight)] = G.dmode
+        if W.ro is not None:
+            by_param[id(W.w1)] = ops.transpose(G.dw1t)
+            by_param[id(W.w2)] = ops.transpose(G.dw2t)
+            by_param[id(W.b1)], by_param[id(W.b2)] = G.db1, G.db2
+        for mode, (rows, ids, used) in G.rows.buf.items():
+            table = self.enc.table(mode)
+            if used > 0:
+                by_param[id(table)] = table_gradient(table, ids[:used], rows[:used], self.sparse_embedding_grad)
+        return tuple(by_param.get(id(p)) for p in self.parameters())
+
+
+class _MarginLossFn(torch.autograd.Function):
+    """mean(relu(margin - (cos(q, target) - cos(q, negative)))) over one or more formula groups (summed)."""
+
+    @staticmethod
+    def forward(ctx, model, jobs, targets, negatives, margin, *params):
+        device = jobs[0].anchor_ids.device
+        need_grad = any(ctx.needs_input_grad)
+        with ops.device_guard(device):
+            W = Weights(model, need_grad)
+            model._engine.encode(jobs, W)
+            losses = []
+            for job, tgt, neg in zip(jobs, targets, negatives):
+                _, _, loss = ops.cosine_margin(job.q, model.enc.table(job.target_mode), model.enc.node_maps, tgt, neg,
+                                               margin)
+                losses.append(loss)
+            total = losses[0] if len(losses) == 1 else torch.stack(losses).sum()
+        ctx.model, ctx.jobs, ctx.W, ctx.margin = model, jobs, W, margin
+        ctx.targets, ctx.negatives = targets, negatives
+        return total
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        model, jobs, W = ctx.model, ctx.jobs, ctx.W
+        device = jobs[0].anchor_ids.device
+        with ops.device_guard(device):
+            cap = model._row_capacities(jobs, [(job.target_mode, 2 * job.B) for job in jobs])
+            G = Grads(model, W, cap, device)
+            gl = grad_loss.contiguous().reshape(1)
+            dqs = []
+            for job, tgt, neg in zip(jobs, ctx.targets, ctx.negatives):
+                rows, ids, off = G.rows.reserve(job.target_mode, 2 * job.B)
+                dqs.append(ops.cosine_margin_bwd(job.q, model.enc.table(job.target_mode), model.enc.node_maps, tgt, neg,
+                                                 ctx.margin, gl, rows, ids, rows_offset=off))
+            model._engine.backward(jobs, W, dqs, G)
+            grads = model._collect_grads(W, G)
+        return (None, None, None, None, None) + grads
+
+
+class _ScoresFn(torch.autograd.Function):
+    """scores = cat(cos(q, targets), cos(q[owner], negatives))  (reference model.py:451-460)."""
+
+    @staticmethod
+    def forward(ctx, model, job, tgt, neg, offsets, *params):
+        device = job.anchor_ids.device
+        need_grad = any(ctx.needs_input_grad)
+        table = model.enc.table(job.target_mode)
+        with ops.device_guard(device):
+            W = Weights(model, need_grad)
+            model._engine.encode([job], W)
+            total = job.B + (neg.numel() if neg is not None else 0)
+            scores = torch.empty(total, dtype=torch.float32, device=device)
+            ops.cosine_scores(job.q, table, model.enc.node_maps, tgt, out=scores)
+            if neg is not None and neg.numel() > 0:
+                ops.cosine_scores(job.q, table, model.enc.node_maps, neg, offsets=offsets, out=scores, out_offset=job.B)
+        ctx.model, ctx.job, ctx.W = model, job, W
+        ctx.tgt, ctx.neg, ctx.offsets = tgt, neg, offsets
+        return scores
+
+    @staticmethod
+    def backward(ctx, grad_scores):
+        model, job, W = ctx.model, ctx.job, ctx.W
+        device = job.anchor_ids.device
+        table = model.enc.table(job.target_mode)
+        nneg = ctx.neg.numel() if ctx.neg is not None else 0
+        with ops.device_guard(device):
+            G = Grads(model, W, model._row_capacities([job], [(job.target_mode, job.B + nneg)]), device)
+            gs = grad_scores.contiguous()
+            dq = torch.empty(job.B, D, dtype=torch.float32, device=device)
+            rows, ids, off = G.rows.reserve(job.target_mode, job.B)
+            ops.cosine_scores_bwd(job.q, table, model.enc.node_maps, ctx.tgt, None, gs, 0, dq, False, rows, ids, off)
+            if nneg > 0:
+                rows, ids, off = G.rows.reserve(job.target_mode, nneg)
+                ops.cosine_scores_bwd(job.q, table, model.enc.node_maps, ctx.neg, ctx.offsets, gs, job.B, dq, True,
+                                      rows, ids, off)
+            model._engine.backward([job], W, [dq], G)
+            grads = model._collect_grads(W, G)
+        return (None, None, None, None, None) + grads

@@ -1,0 +1,384 @@
+"""Tensor-level wrappers over the C ABI (`include/mpqe_b200.h`).
+
+PyTorch is used here only for device memory (caching allocator) and stream identity; every computation is a
+hand-written CUDA kernel behind `libmpqe_b200.so`.  There is no CPU or eager fallback: tensors must live on a
+CUDA device and the library must load, otherwise an exception is raised.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import D, EPI_MASK, EPI_NONE, EPI_RELU, MAX_DESTS, MAX_GROUPS, MAX_SLOTS, MAX_TERMS  # noqa: F401
+
+# use_tensor_cores: None -> tcgen05 path when the library has it and MPQE_TENSOR_CORES != 0
+_tc_default = None
+launch_count = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
+
+
+def _count(n=1):
+    global launch_count
+    launch_count += n
+
+
+def tensor_cores_default():
+    global _tc_default
+    if _tc_default is None:
+        import os
+        want = os.environ.get('MPQE_TENSOR_CORES', '1') != '0'
+        _tc_default = bool(want and _lib.load().mpqe_b200_has_tcgen05())
+    return _tc_default
+
+
+def set_tensor_cores(flag):
+    global _tc_default
+    if flag and not _lib.load().mpqe_b200_has_tcgen05():
+        raise _lib.MpqeError('library was built without the tcgen05 kernels')
+    _tc_default = bool(flag)
+
+
+def device_guard(device):
+    """Context manager selecting `device`; the single place that enforces "CUDA only, no CPU fallback"."""
+    device = torch.device(device)
+    if device.type != 'cuda':
+        raise _lib.MpqeError('mpqe_b200 runs on a CUDA device only (there is no CPU fallback); got %s' % device)
+    return torch.cuda.device(device)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _chk(t, dtype, name):
+    if not t.is_cuda:
+        raise _lib.MpqeError('%s must be a CUDA tensor (no CPU fallback)' % name)
+    if t.dtype != dtype:
+        raise _lib.MpqeError('%s must be %s, got %s' % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise _lib.MpqeError('%s must be contiguous' % name)
+    return t
+
+
+_ws = {}
+
+
+def workspace(nbytes, device, tag='ws'):
+    """Grow-only scratch buffer per (device, tag); kernels on one stream are ordered so reuse is safe."""
+    key = (device.index, tag, torch.cuda.current_stream().cuda_stream)
+    buf = _ws.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=device)
+        _ws[key] = buf
+    return buf
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Layer term lists
+# ---------------------------------------------------------------------------------------------------------------
+class Term(object):
+    """out[q, out_slot] += A[q, a_slot] @ M.  `a` is a [B, a_slots, D] tensor (a_slots = 0: one broadcast row set
+    [rows, D], a_slot selects the row), `m` a contiguous [D, D] tensor (view)."""
+    __slots__ = ('a', 'a_slots', 'a_slot', 'm', 'out_slot')
+
+    def __init__(self, a, a_slots, a_slot, m, out_slot):
+        self.a, self.a_slots, self.a_slot, self.m, self.out_slot = a, int(a_slots), int(a_slot), m, int(out_slot)
+
+
+class Group(object):
+    """One formula group of a layer launch (see mpqe_layer_group_t)."""
+
+    def __init__(self, num_queries, terms, num_out_slots, out, out_slots, out_slot_map=None, epilogue=EPI_NONE,
+                 bias=None, bias_scale=None, mask=None, mask_slots=0):
+        self.num_queries, self.terms, self.num_out_slots = int(num_queries), list(terms), int(num_out_slots)
+        self.out, self.out_slots = out, int(out_slots)
+        self.out_slot_map = list(out_slot_map) if out_slot_map is not None else list(range(num_out_slots))
+        self.epilogue, self.bias = epilogue, bias
+        self.bias_scale = list(bias_scale) if bias_scale is not None else [1.0] * num_out_slots
+        self.mask, self.mask_slots = mask, int(mask_slots)
+
+    def to_c(self):
+        if len(self.terms) > MAX_TERMS or self.num_out_slots > MAX_SLOTS:
+            raise _lib.MpqeError('group exceeds MPQE_MAX_TERMS / MPQE_MAX_SLOTS')
+        g = _lib.LayerGroup()
+        g.num_queries, g.num_terms, g.num_out_slots = self.num_queries, len(self.terms), self.num_out_slots
+        for i, t in enumerate(self.terms):
+            _chk(t.a, torch.float32, 'term.a')
+            _chk(t.m, torch.float32, 'term.m')
+            if t.m.numel() != D * D:
+                raise _lib.MpqeError('term matrix must be [%d,%d]' % (D, D))
+            g.terms[i].a, g.terms[i].m = t.a.data_ptr(), t.m.data_ptr()
+            g.terms[i].a_slots, g.terms[i].a_slot, g.terms[i].out_slot = t.a_slots, t.a_slot, t.out_slot
+        g.out = _chk(self.out, torch.float32, 'out').data_ptr() if self.out is not None else 0
+        g.out_slots, g.epilogue = self.out_slots, self.epilogue
+        g.bias = _chk(self.bias, torch.float32, 'bias').data_ptr() if self.bias is not None else 0
+        for j in range(self.num_out_slots):
+            g.bias_scale[j] = float(self.bias_scale[j])
+            g.out_slot_map[j] = int(self.out_slot_map[j])
+        g.mask = _chk(self.mask, torch.float32, 'mask').data_ptr() if self.mask is not None else 0
+        g.mask_slots = self.mask_slots
+        return g
+
+
+def layer_forward(groups, use_tensor_cores=None):
+    """mpqe_layer_forward over up to MPQE_MAX_GROUPS groups per launch."""
+    lib = _lib.load()
+    tc = tensor_cores_default() if use_tensor_cores is None else bool(use_tensor_cores)
+    for i in range(0, len(groups), MAX_GROUPS):
+        chunk = groups[i:i + MAX_GROUPS]
+        arr = (_lib.LayerGroup * len(chunk))(*[g.to_c() for g in chunk])
+        _lib.check(lib.mpqe_layer_forward(arr, len(chunk), int(tc), _stream()), 'mpqe_layer_forward')
+        _count()
+
+
+def layer_wgrad(groups, grad_operands, dests, ctas_hint=296):
+    """mpqe_layer_wgrad.  grad_operands[i] = (g tensor, g_slots, slot_map list) for groups[i];
+    dests = [(m_fwd tensor view, dm tensor view, accumulate)]."""
+    lib = _lib.load()
+    if len(groups) > MAX_GROUPS or len(dests) > MAX_DESTS:
+        raise _lib.MpqeError('too many groups / destinations for one wgrad launch')
+    garr = (_lib.LayerGroup * len(groups))(*[g.to_c() for g in groups])
+    oarr = (_lib.WgradOperand * len(groups))()
+    for i, (g, g_slots, slot_map) in enumerate(grad_operands):
+        oarr[i].g, oarr[i].g_slots = _chk(g, torch.float32, 'grad operand').data_ptr(), int(g_slots)
+        for j, s in enumerate(slot_map):
+            oarr[i].slot_map[j] = int(s)
+    darr = (_lib.WgradDest * len(dests))()
+    for j, (m_fwd, dm, acc) in enumerate(dests):
+        darr[j].m_fwd, darr[j].dm, darr[j].accumulate = m_fwd.data_ptr(), _chk(dm, torch.float32, 'dm').data_ptr(), int(acc)
+    dev = groups[0].terms[0].a.device
+    nbytes = lib.mpqe_layer_wgrad_workspace_bytes(len(dests), ctas_hint)
+    ws = workspace(nbytes, dev, 'wgrad')
+    _lib.check(lib.mpqe_layer_wgrad(garr, oarr, len(groups), darr, len(dests), _ptr(ws), ws.numel(), _stream()),
+               'mpqe_layer_wgrad')
+    _count(2)
+
+
+def colsum(src, rows, stride, out, scale=1.0, accumulate=False):
+    """out[D] (+)= scale * sum_r src.flat[r*stride : r*stride+D]; `src` may be an offset view into a larger buffer."""
+    lib = _lib.load()
+    nbytes = lib.mpqe_colsum_workspace_bytes(rows)
+    ws = workspace(nbytes, out.device, 'colsum')
+    _lib.check(lib.mpqe_colsum(C.c_void_p(src.data_ptr()), rows, stride, scale, _ptr(_chk(out, torch.float32, 'out')),
+                               int(accumulate), _ptr(ws), ws.numel(), _stream()), 'mpqe_colsum')
+    _count(2)
+
+
+def transpose(src, dst=None):
+    """[count, r, c] (or [r, c]) -> per-matrix transpose."""
+    lib = _lib.load()
+    _chk(src, torch.float32, 'src')
+    count = src.shape[0] if src.dim() == 3 else 1
+    r, c = src.shape[-2], src.shape[-1]
+    if dst is None:
+        dst = torch.empty(src.shape[:-2] + (c, r), dtype=torch.float32, device=src.device)
+    _lib.check(lib.mpqe_transpose(_ptr(src), _ptr(_chk(dst, torch.float32, 'dst')), count, r, c, _stream()),
+               'mpqe_transpose')
+    _count()
+    return dst
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Row kernels
+# ---------------------------------------------------------------------------------------------------------------
+def gather_normalize(table, id2row, ids, out=None, out_offset=0, out_stride=D, ids_offset=0, ids_stride=1,
+                     count=None, inv_norm=None):
+    """out.flat[out_offset + i*out_stride : +D] = normalised table[id2row[ids.flat[ids_offset + i*ids_stride]]]."""
+    lib = _lib.load()
+    _chk(table, torch.float32, 'table')
+    _chk(ids, torch.int64, 'ids')
+    if count is None:
+        count = ids.numel()
+    if out is None:
+        out = torch.empty(count, D, dtype=torch.float32, device=table.device)
+    _chk(out, torch.float32, 'out')
+    _lib.check(lib.mpqe_gather_normalize_fwd(
+        _ptr(table), table.shape[0], _ptr(id2row), C.c_void_p(ids.data_ptr() + 8 * ids_offset), ids_stride, count,
+        C.c_void_p(out.data_ptr() + 4 * out_offset), out_stride, _ptr(inv_norm), _stream()),
+        'mpqe_gather_normalize_fwd')
+    _count()
+    return out
+
+
+def gather_normalize_bwd(table, id2row, ids, grad, rows_out, rows_id, grad_offset=0, grad_stride=D, ids_offset=0,
+                         ids_stride=1, count=None, rows_offset=0):
+    lib = _lib.load()
+    if count is None:
+        count = ids.numel()
+    _lib.check(lib.mpqe_gather_normalize_bwd(
+        _ptr(table), _ptr(id2row), C.c_void_p(ids.data_ptr() + 8 * ids_offset), ids_stride, count,
+        C.c_void_p(grad.data_ptr() + 4 * grad_offset), grad_stride,
+        C.c_void_p(rows_out.data_ptr() + 4 * D * rows_offset), C.c_void_p(rows_id.data_ptr() + 8 * rows_offset),
+        _stream()), 'mpqe_gather_normalize_bwd')
+    _count()
+
+
+def broadcast_rows(src, src_rows, out, out_offset, out_stride, count):
+    lib = _lib.load()
+    _lib.check(lib.mpqe_broadcast_rows(_ptr(_chk(src, torch.float32, 'src')), _ptr(_chk(src_rows, torch.int64, 'rows')),
+                                       src_rows.numel(), C.c_void_p(out.data_ptr() + 4 * out_offset), out_stride,
+                                       count, _stream()), 'mpqe_broadcast_rows')
+    _count()
+
+
+def max_readout(z, B, n):
+    lib = _lib.load()
+    q = torch.empty(B, D, dtype=torch.float32, device=z.device)
+    arg = torch.empty(B, D, dtype=torch.int64, device=z.device)
+    _lib.check(lib.mpqe_max_readout_fwd(_ptr(_chk(z, torch.float32, 'z')), B, n, _ptr(q), _ptr(arg), _stream()),
+               'mpqe_max_readout_fwd')
+    _count()
+    return q, arg
+
+
+def max_readout_bwd(dq, argmax, B, n):
+    lib = _lib.load()
+    g = torch.empty(B, n, D, dtype=torch.float32, device=dq.device)
+    _lib.check(lib.mpqe_max_readout_bwd(_ptr(_chk(dq, torch.float32, 'dq')), _ptr(argmax), B, n, _ptr(g), _stream()),
+               'mpqe_max_readout_bwd')
+    _count()
+    return g
+
+
+def cosine_margin(q, table, id2row, ids_pos, ids_neg, margin):
+    lib = _lib.load()
+    B = q.shape[0]
+    dev = q.device
+    sp = torch.empty(B, dtype=torch.float32, device=dev)
+    sn = torch.empty(B, dtype=torch.float32, device=dev)
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    ws = workspace(lib.mpqe_margin_loss_workspace_bytes(B), dev, 'loss')
+    _lib.check(lib.mpqe_cosine_margin_fwd(_ptr(_chk(q, torch.float32, 'q')), B, _ptr(_chk(table, torch.float32, 'table')),
+                                          _ptr(id2row), _ptr(_chk(ids_pos, torch.int64, 'ids_pos')),
+                                          _ptr(_chk(ids_neg, torch.int64, 'ids_neg')), margin, _ptr(sp), _ptr(sn),
+                                          _ptr(loss), _ptr(ws), ws.numel(), _stream()), 'mpqe_cosine_margin_fwd')
+    _count(2)
+    return sp, sn, loss
+
+
+def cosine_margin_bwd(q, table, id2row, ids_pos, ids_neg, margin, grad_loss, rows_out, rows_id, rows_offset=0):
+    """rows_out/rows_id receive 2B entries starting at rows_offset."""
+    lib = _lib.load()
+    B = q.shape[0]
+    dq = torch.empty(B, D, dtype=torch.float32, device=q.device)
+    _lib.check(lib.mpqe_cosine_margin_bwd(_ptr(q), B, _ptr(table), _ptr(id2row), _ptr(ids_pos), _ptr(ids_neg), margin,
+                                          _ptr(_chk(grad_loss, torch.float32, 'grad_loss')), _ptr(dq),
+                                          C.c_void_p(rows_out.data_ptr() + 4 * D * rows_offset),
+                                          C.c_void_p(rows_id.data_ptr() + 8 * rows_offset), _stream()),
+               'mpqe_cosine_margin_bwd')
+    _count()
+    return dq
+
+
+def cosine_scores(q, table, id2row, ids, offsets=None, out=None, out_offset=0):
+    lib = _lib.load()
+    count = ids.numel()
+    if out is None:
+        out = torch.empty(count, dtype=torch.float32, device=q.device)
+    _lib.check(lib.mpqe_cosine_scores(_ptr(_chk(q, torch.float32, 'q')), q.shape[0], _ptr(offsets),
+                                      _ptr(_chk(table, torch.float32, 'table')), _ptr(id2row),
+                                      _ptr(_chk(ids, torch.int64, 'ids')), count,
+                                      C.c_void_p(out.data_ptr() + 4 * out_offset), _stream()), 'mpqe_cosine_scores')
+    _count()
+    return out
+
+
+def cosine_scores_bwd(q, table, id2row, ids, offsets, grad_scores, grad_offset, dq, accumulate, rows_out, rows_id,
+                      rows_offset=0):
+    lib = _lib.load()
+    _lib.check(lib.mpqe_cosine_scores_bwd(_ptr(q), q.shape[0], _ptr(offsets), _ptr(table), _ptr(id2row), _ptr(ids),
+                                          ids.numel(), C.c_void_p(grad_scores.data_ptr() + 4 * grad_offset), _ptr(dq),
+                                          int(accumulate), C.c_void_p(rows_out.data_ptr() + 4 * D * rows_offset),
+                                          C.c_void_p(rows_id.data_ptr() + 8 * rows_offset), _stream()),
+               'mpqe_cosine_scores_bwd')
+    _count()
+
+
+def rank_counts_ragged(pos, neg, offsets):
+    lib = _lib.load()
+    B = pos.numel()
+    left = torch.empty(B, dtype=torch.int64, device=pos.device)
+    right = torch.empty(B, dtype=torch.int64, device=pos.device)
+    _lib.check(lib.mpqe_rank_counts_ragged(_ptr(_chk(pos, torch.float32, 'pos')), _ptr(_chk(neg, torch.float32, 'neg')),
+                                           _ptr(_chk(offsets, torch.int64, 'offsets')), B, _ptr(left), _ptr(right),
+                                           _stream()), 'mpqe_rank_counts_ragged')
+    _count()
+    return left, right
+
+
+def rank_counts_table(q, pos, table, row_begin, row_end, left, right, use_tensor_cores=False):
+    """Accumulates into left/right (int64 [B])."""
+    lib = _lib.load()
+    B = q.shape[0]
+    nbytes = lib.mpqe_rank_counts_table_workspace_bytes(B, row_end - row_begin)
+    ws = workspace(nbytes, q.device, 'rank')
+    _lib.check(lib.mpqe_rank_counts_table(_ptr(_chk(q, torch.float32, 'q')), B, _ptr(_chk(pos, torch.float32, 'pos')),
+                                          _ptr(_chk(table, torch.float32, 'table')), row_begin, row_end,
+                                          _ptr(_chk(left, torch.int64, 'left')), _ptr(_chk(right, torch.int64, 'right')),
+                                          _ptr(ws), ws.numel(), int(use_tensor_cores), _stream()),
+               'mpqe_rank_counts_table')
+    _count(3)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Integer layout kernels
+# ---------------------------------------------------------------------------------------------------------------
+def build_query_graph(n, src, dst, rel, B, device):
+    lib = _lib.load()
+    E = len(src)
+    edge_index = torch.empty(2, B * E, dtype=torch.int64, device=device)
+    edge_type = torch.empty(B * E, dtype=torch.int64, device=device)
+    batch = torch.empty(B * n, dtype=torch.int64, device=device)
+    s = (C.c_int32 * E)(*src)
+    t = (C.c_int32 * E)(*dst)
+    r = (C.c_int64 * E)(*rel)
+    _lib.check(lib.mpqe_build_query_graph(n, E, s, t, r, B, _ptr(edge_index), _ptr(edge_type), _ptr(batch), _stream()),
+               'mpqe_build_query_graph')
+    _count()
+    return edge_index, edge_type, batch
+
+
+def relation_sort(edge_type, num_relations):
+    lib = _lib.load()
+    nE = edge_type.numel()
+    perm = torch.empty(nE, dtype=torch.int64, device=edge_type.device)
+    offsets = torch.empty(num_relations + 1, dtype=torch.int64, device=edge_type.device)
+    ws = workspace(lib.mpqe_relation_sort_workspace_bytes(nE, num_relations), edge_type.device, 'sort')
+    _lib.check(lib.mpqe_relation_sort(_ptr(_chk(edge_type, torch.int64, 'edge_type')), nE, num_relations, _ptr(perm),
+                                      _ptr(offsets), _ptr(ws), ws.numel(), _stream()), 'mpqe_relation_sort')
+    _count(6)
+    return perm, offsets
+
+
+def sparse_rows_combine(rows_id, rows, table_rows):
+    """(unique_ids[count], unique_rows[count, D], num_unique[1]); entries past num_unique are unspecified."""
+    lib = _lib.load()
+    count = rows_id.numel()
+    dev = rows.device
+    uid = torch.empty(count, dtype=torch.int64, device=dev)
+    urows = torch.empty(count, D, dtype=torch.float32, device=dev)
+    num = torch.empty(1, dtype=torch.int64, device=dev)
+    ws = workspace(lib.mpqe_sparse_rows_workspace_bytes(count), dev, 'sparse')
+    _lib.check(lib.mpqe_sparse_rows_combine(_ptr(_chk(rows_id, torch.int64, 'rows_id')),
+                                            _ptr(_chk(rows, torch.float32, 'rows')), count, table_rows, _ptr(uid),
+                                            _ptr(urows), _ptr(num), _ptr(ws), ws.numel(), _stream()),
+               'mpqe_sparse_rows_combine')
+    _count(10)
+    return uid, urows, num
+
+
+def scatter_rows(ids, rows, num, dense, accumulate=False):
+    lib = _lib.load()
+    _lib.check(lib.mpqe_scatter_rows(_ptr(ids), _ptr(rows), _ptr(num), ids.numel(), _ptr(_chk(dense, torch.float32, 'dense')),
+                                     int(accumulate), _stream()), 'mpqe_scatter_rows')
+    _count()
+
+
+def adam_dense(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step):
+    lib = _lib.load()
+    _lib.check(lib.mpqe_adam_dense(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(), lr, beta1,
+                                   beta2, eps, step, _stream()), 'mpqe_adam_dense')
+    _count()

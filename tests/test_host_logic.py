@@ -1,0 +1,120 @@
+"""Host-side orchestration (term lists, slot maps, gradient routing, autograd wiring) checked on CPU: the CUDA
+entry points are replaced by `tests/emulator.py`, the result is compared with the golden vectors and the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from mpqe_b200 import data_utils, ops
+from oracle import mpqe_oracle as O
+from tests import emulator
+from tests.helpers import GoldenCase, assert_close, golden_names
+from tests.model_utils import build_model, model_grads, oracle_loss_and_grads, queries_from_ids
+
+
+@pytest.fixture
+def emu(monkeypatch):
+    emulator.install(monkeypatch)
+
+
+@pytest.mark.parametrize('name', golden_names())
+def test_golden_through_host_logic(emu, name):
+    c = GoldenCase(name)
+    model = build_model(c.kg.raw(), c.cfg, c.params, 'cpu')
+    assert model.mode_ids == dict(c.mode_ids) and model.rel_ids == dict(c.rel_ids)
+    queries = queries_from_ids(c.query_type, c.rels, c.z['anchor_ids'], c.z['targets'])
+    formula = queries[0].formula
+    # integer layout
+    a_ids, var_ids, qg = data_utils.RGCNQueryDataset.get_query_graph(formula, queries, model.rel_ids, model.mode_ids)
+    assert np.array_equal(a_ids.numpy(), c.z['anchor_ids']) and np.array_equal(var_ids.numpy(), c.z['var_ids'])
+    assert np.array_equal(qg.edge_index.numpy(), c.z['edge_index'])
+    assert np.array_equal(qg.edge_type.numpy(), c.z['edge_type'])
+    assert np.array_equal(qg.batch.numpy(), c.z['batch'])
+    # eval-style scores
+    with torch.no_grad():
+        s = model.forward(formula, queries, c.z['targets'].tolist(), neg_nodes=c.z['eval_neg_nodes'].tolist(),
+                          neg_lengths=c.z['eval_neg_lengths'].tolist())
+    assert_close(s.numpy(), c.z['eval_scores'], 1e-4, 2e-6, 'scores')
+    # loss + gradients
+    model.zero_grad()
+    loss = model.margin_loss_ids(formula, queries, c.z['targets'].tolist(), c.z['train_neg_nodes'].tolist())
+    assert_close(loss.item(), c.z['loss'], 1e-5, 1e-6, 'loss')
+    loss.backward()
+    want = c.grads()
+    got = model_grads(model)
+    for k, g in want.items():
+        assert_close(got[k], g, 1e-3, 2e-5 * max(np.abs(g).max(), 1e-12), 'grad ' + k)
+
+
+@pytest.mark.parametrize('readout,num_layers,adaptive,shared', [
+    ('sum', 2, False, False), ('sum', 3, False, True), ('max', 2, False, False), ('mp', 3, True, False),
+    ('mp', 3, True, True), ('mp', 2, False, False), ('concat', 2, False, False), ('concat', 3, False, False),
+    ('mlp', 2, False, False), ('targetmlp', 2, False, False), ('sum', 1, False, False)])
+def test_all_types_vs_oracle(emu, readout, num_layers, adaptive, shared):
+    from mpqe_b200 import synthetic
+    kg = synthetic.make_kg('tiny', seed=5)
+    rels, _, node_maps = kg.raw()
+    cfg = O.Config(readout=readout, num_layers=num_layers, adaptive=adaptive, shared_layers=shared, weight_decay=1e-3)
+    params = O.init_params(rels, node_maps, cfg, d=128, seed=1)
+    mode_ids, rel_ids = O.schema_ids(rels)
+    id2row = O.id_to_row(node_maps)
+    qsets = synthetic.make_query_sets(kg, queries_per_formula=7, formulas_per_type=1, seed=2)
+    rng = np.random.RandomState(0)
+    for sparse in (False, True):
+        model = build_model(kg.raw(), cfg, params, 'cpu', sparse_grad=sparse)
+        for qt in synthetic.QUERY_TYPES:
+            frm_rels, raw = qsets[qt][0]
+            spec = O.formula_spec(qt, frm_rels)
+            parsed = [O.query_anchors_target(r[0]) for r in raw]
+            anchors = torch.tensor([p[2] for p in parsed])
+            targets = torch.tensor([p[3] for p in parsed])
+            negs = torch.tensor(node_maps[spec['target_mode']])[rng.randint(len(node_maps[spec['target_mode']]),
+                                                                            size=len(raw))]
+            want_loss, want = oracle_loss_and_grads(params, cfg, spec, anchors, rel_ids, mode_ids, id2row, targets,
+                                                    negs)
+            queries = queries_from_ids(qt, frm_rels, anchors, targets)
+            model.zero_grad()
+            loss = model.margin_loss_ids(queries[0].formula, queries, targets, negs)
+            assert_close(loss.item(), want_loss, 1e-5, 1e-6, qt + ' loss')
+            loss.backward()
+            got = model_grads(model)
+            for k, g in want.items():
+                assert_close(got[k], g, 1e-3, 2e-5 * max(np.abs(g).max(), 1e-12), '%s grad %s' % (qt, k))
+
+
+def test_adaptive_needs_enough_layers(emu):
+    from mpqe_b200 import synthetic
+    kg = synthetic.make_kg('tiny', seed=5)
+    rels, _, node_maps = kg.raw()
+    cfg = O.Config(readout='sum', num_layers=2, adaptive=True)
+    model = build_model(kg.raw(), cfg, O.init_params(rels, node_maps, cfg, seed=1), 'cpu')
+    frm_rels, raw = synthetic.make_query_sets(kg, 3, 1, seed=2, query_types=('3-chain',))['3-chain'][0]
+    parsed = [O.query_anchors_target(r[0]) for r in raw]
+    queries = queries_from_ids('3-chain', frm_rels, [p[2] for p in parsed], [p[3] for p in parsed])
+    with pytest.raises(ValueError, match='adaptive with 2 layers'):
+        model.margin_loss_ids(queries[0].formula, queries, [p[3] for p in parsed], [p[3] for p in parsed])
+    with pytest.raises(Exception, match='Hard negative'):
+        model.margin_loss(queries[0].formula, queries, hard_negatives=True)
+
+
+def test_unknown_readout_and_scatter():
+    from mpqe_b200 import synthetic
+    kg = synthetic.make_kg('tiny', seed=5)
+    rels, _, node_maps = kg.raw()
+    with pytest.raises(ValueError, match='Unknown readout'):
+        build_model(kg.raw(), O.Config(readout='nope'), {}, 'cpu')
+    with pytest.raises(ValueError, match='Unknown scatter op'):
+        build_model(kg.raw(), O.Config(readout='sum', scatter_op='prod'), {}, 'cpu')
+
+
+def test_no_cpu_fallback():
+    """Without the emulator the product refuses to run on CPU tensors."""
+    from mpqe_b200 import synthetic, _lib
+    kg = synthetic.make_kg('tiny', seed=5)
+    rels, _, node_maps = kg.raw()
+    cfg = O.Config(readout='sum', num_layers=2)
+    model = build_model(kg.raw(), cfg, O.init_params(rels, node_maps, cfg, seed=1), 'cpu')
+    frm_rels, raw = synthetic.make_query_sets(kg, 3, 1, seed=2, query_types=('2-inter',))['2-inter'][0]
+    parsed = [O.query_anchors_target(r[0]) for r in raw]
+    queries = queries_from_ids('2-inter', frm_rels, [p[2] for p in parsed], [p[3] for p in parsed])
+    with pytest.raises(_lib.MpqeError, match='no CPU fallback'):
+        model.margin_loss_ids(queries[0].formula, queries, [p[3] for p in parsed], [p[3] for p in parsed])
