@@ -1,0 +1,301 @@
+"""Each CUDA entry point against a CPU restatement on seeded inputs (run with -m gpu on the B200 box).
+Integer results must be bit-exact; fp32 results within the tolerance stated per test."""
+import numpy as np
+import pytest
+import torch
+
+from mpqe_b200 import ops
+from tests import emulator as E
+from tests.helpers import assert_close
+
+pytestmark = pytest.mark.gpu
+D = ops.D
+DEV = 'cuda:0'
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+def run_layer(groups_cpu, use_tc=False):
+    """groups given with CPU tensors -> run the same on GPU, return outputs."""
+    moved = {}
+
+    def mv(t):
+        if t is None:
+            return None
+        key = (t.untyped_storage().data_ptr(), t.storage_offset(), tuple(t.shape))
+        if key not in moved:
+            base_key = t.untyped_storage().data_ptr()
+            if base_key not in moved:
+                base = torch.empty(0)
+                base.set_(t.untyped_storage())
+                moved[base_key] = base.to(DEV)
+            moved[key] = moved[base_key].as_strided(t.shape, t.stride(), t.storage_offset())
+        return moved[key]
+
+    gg = []
+    for g in groups_cpu:
+        terms = [ops.Term(mv(t.a), t.a_slots, t.a_slot, mv(t.m), t.out_slot) for t in g.terms]
+        gg.append(ops.Group(g.num_queries, terms, g.num_out_slots, mv(g.out), g.out_slots, g.out_slot_map, g.epilogue,
+                            mv(g.bias), g.bias_scale, mv(g.mask), g.mask_slots))
+    return gg
+
+
+@pytest.mark.parametrize('B', [1, 63, 64, 65, 300, 4096])
+@pytest.mark.parametrize('epi', [ops.EPI_NONE, ops.EPI_RELU, ops.EPI_MASK])
+def test_layer_forward_matches_cpu(B, epi):
+    n = 4
+    x = rnd(B, n, D, seed=1)
+    w = rnd(5, D, D, seed=2, scale=0.05)
+    bias = rnd(D, seed=3)
+    mask = rnd(B, n, D, seed=4)
+    out = torch.full((B, n, D), float('nan'))
+    terms = [ops.Term(x, n, 0, w[0], 3), ops.Term(x, n, 1, w[1], 3), ops.Term(x, n, 2, w[2], 3),
+             ops.Term(x, n, 3, w[4], 3), ops.Term(x, n, 0, w[4], 0), ops.Term(x, n, 1, w[4], 1),
+             ops.Term(x, n, 2, w[4], 2)]
+    g = ops.Group(B, terms, n, out, n, epilogue=epi, bias=bias, bias_scale=[1, 1, 1, 2.0],
+                  mask=mask if epi == ops.EPI_MASK else None, mask_slots=n)
+    E.layer_forward([g])
+    gg = run_layer([g])
+    gg[0].out.fill_(float('nan'))
+    ops.layer_forward(gg, use_tensor_cores=False)
+    # fp32 tolerance: K=128..512 products of O(1)*O(0.05) -> abs error ~1e-6
+    assert_close(gg[0].out.cpu().numpy(), out.numpy(), 1e-5, 2e-5, 'layer out')
+
+
+def test_layer_forward_multi_group_slot_maps_and_broadcast():
+    B1, B2 = 130, 70
+    x1, x2 = rnd(B1, 3, D, seed=1), rnd(B2, 2, D, seed=2)
+    vrow = rnd(4, D, seed=3)
+    w = rnd(3, D, D, seed=4, scale=0.05)
+    bias = rnd(D, seed=5)
+    out1 = torch.zeros(B1, 1, D)
+    out2 = torch.full((B2, 4, D), 7.0)
+    g1 = ops.Group(B1, [ops.Term(x1, 3, j, w[j], 0) for j in range(3)] + [ops.Term(vrow, 0, 2, w[0], 0)], 1, out1, 1,
+                   bias=bias, bias_scale=[3.0])
+    g2 = ops.Group(B2, [ops.Term(x2, 2, 0, w[1], 0), ops.Term(x2, 2, 1, w[2], 1)], 2, out2, 4, out_slot_map=[3, 1],
+                   epilogue=ops.EPI_RELU)
+    E.layer_forward([g1, g2])
+    gg = run_layer([g1, g2])
+    gg[0].out.zero_()
+    gg[1].out.fill_(7.0)
+    ops.layer_forward(gg, use_tensor_cores=False)
+    assert_close(gg[0].out.cpu().numpy(), out1.numpy(), 1e-5, 2e-5, 'group 1')
+    assert_close(gg[1].out.cpu().numpy(), out2.numpy(), 1e-5, 2e-5, 'group 2 (untouched slots keep 7.0)')
+
+
+@pytest.mark.parametrize('B', [5, 64, 1000, 5000])
+def test_layer_wgrad_matches_cpu_and_is_deterministic(B):
+    n = 3
+    x = rnd(B, n, D, seed=1)
+    g = rnd(B, n, D, seed=2)
+    dq = rnd(B, D, seed=5)
+    w = rnd(3, D, D, seed=3)
+    grp = ops.Group(B, [ops.Term(x, n, 0, w[0], 2), ops.Term(x, n, 1, w[0], 2), ops.Term(x, n, 2, w[2], 2),
+                        ops.Term(x, n, 0, w[2], 0), ops.Term(x, n, 1, w[2], 1)], n, None, n)
+    grp2 = ops.Group(B, [ops.Term(x, n, 1, w[1], 0), ops.Term(x, n, 2, w[2], 0)], 1, None, 1)
+    dm = torch.zeros(3, D, D)
+    dm[1] = 1.0
+    E.layer_wgrad([grp, grp2], [(g, n, [0, 1, 2]), (dq, 1, [0])], [(w[0], dm[0], 0), (w[1], dm[1], 1), (w[2], dm[2], 0)])
+    xs, gs, dqs, ws = x.to(DEV), g.to(DEV), dq.to(DEV), w.to(DEV)
+    gg = ops.Group(B, [ops.Term(xs, n, 0, ws[0], 2), ops.Term(xs, n, 1, ws[0], 2), ops.Term(xs, n, 2, ws[2], 2),
+                       ops.Term(xs, n, 0, ws[2], 0), ops.Term(xs, n, 1, ws[2], 1)], n, None, n)
+    gg2 = ops.Group(B, [ops.Term(xs, n, 1, ws[1], 0), ops.Term(xs, n, 2, ws[2], 0)], 1, None, 1)
+    outs = []
+    for _ in range(2):
+        dmd = torch.zeros(3, D, D, device=DEV)
+        dmd[1] = 1.0
+        ops.layer_wgrad([gg, gg2], [(gs, n, [0, 1, 2]), (dqs, 1, [0])],
+                        [(ws[0], dmd[0], 0), (ws[1], dmd[1], 1), (ws[2], dmd[2], 0)])
+        outs.append(dmd.cpu())
+    scale = float(dm.abs().max())
+    assert_close(outs[0].numpy(), dm.numpy(), 1e-4, 1e-5 * scale, 'dM')
+    assert torch.equal(outs[0], outs[1]), 'weight gradient must be bit-reproducible'
+
+
+def test_colsum_and_transpose():
+    src = rnd(1000, 3, D, seed=1)
+    out = torch.ones(D)
+    E.colsum(src[:, 1], 1000, 3 * D, out, scale=2.0, accumulate=True)
+    s = src.to(DEV)
+    o = torch.ones(D, device=DEV)
+    ops.colsum(s[:, 1], 1000, 3 * D, o, scale=2.0, accumulate=True)
+    assert_close(o.cpu().numpy(), out.numpy(), 1e-5, 1e-4, 'colsum')
+    m = rnd(5, D, 2 * D, seed=2)
+    assert torch.equal(ops.transpose(m.to(DEV)).cpu(), m.transpose(1, 2).contiguous())
+    m2 = rnd(37, 91, seed=3)
+    assert torch.equal(ops.transpose(m2.to(DEV)).cpu(), m2.t().contiguous())
+
+
+def test_gather_normalize_fwd_bwd():
+    table = rnd(50, D, seed=1, scale=1.0 / D)
+    id2row = torch.randperm(200, generator=torch.Generator().manual_seed(0)) % 50
+    ids = torch.randint(0, 200, (33, 2), generator=torch.Generator().manual_seed(1))
+    out = torch.zeros(33, 3, D)
+    E.gather_normalize(table, id2row, ids, out=out, out_offset=D, out_stride=3 * D, ids_offset=1, ids_stride=2, count=33)
+    od = torch.zeros(33, 3, D, device=DEV)
+    ops.gather_normalize(table.to(DEV), id2row.to(DEV), ids.to(DEV), out=od, out_offset=D, out_stride=3 * D,
+                         ids_offset=1, ids_stride=2, count=33)
+    assert_close(od.cpu().numpy(), out.numpy(), 2e-6, 1e-7, 'normalised rows')
+    assert torch.equal(od[:, 0].cpu(), torch.zeros(33, D))
+    grad = rnd(33, 3, D, seed=2)
+    rows, rid = torch.zeros(40, D), torch.zeros(40, dtype=torch.int64)
+    E.gather_normalize_bwd(table, id2row, ids, grad, rows, rid, grad_offset=D, grad_stride=3 * D, ids_offset=1,
+                           ids_stride=2, count=33, rows_offset=7)
+    rows_d, rid_d = torch.zeros(40, D, device=DEV), torch.zeros(40, dtype=torch.int64, device=DEV)
+    ops.gather_normalize_bwd(table.to(DEV), id2row.to(DEV), ids.to(DEV), grad.to(DEV), rows_d, rid_d, grad_offset=D,
+                             grad_stride=3 * D, ids_offset=1, ids_stride=2, count=33, rows_offset=7)
+    assert torch.equal(rid_d.cpu(), rid)
+    assert_close(rows_d.cpu().numpy(), rows.numpy(), 1e-4, 1e-3, 'row grads')  # rows are O(100): abs tol scaled
+
+
+def test_max_readout_ties_pick_smallest_node():
+    B, n = 70, 4
+    z = torch.relu(rnd(B, n, D, seed=1))  # exact zeros -> real ties
+    z[:, 2] = z[:, 1]                     # and duplicated rows
+    q, arg = E.max_readout(z, B, n)
+    qd, argd = ops.max_readout(z.to(DEV), B, n)
+    assert torch.equal(qd.cpu(), q)
+    assert torch.equal(argd.cpu(), arg), 'argmax must be bit-exact (smallest node row among maxima)'
+    dq = rnd(B, D, seed=2)
+    assert torch.equal(ops.max_readout_bwd(dq.to(DEV), argd, B, n).cpu(), E.max_readout_bwd(dq, arg, B, n))
+
+
+def test_cosine_margin_fwd_bwd():
+    B = 77
+    table = rnd(60, D, seed=1, scale=1.0 / D)
+    q = rnd(B, D, seed=2)
+    q[3] = 0  # zero query embedding -> eps clamp path
+    ip = torch.randint(0, 60, (B,), generator=torch.Generator().manual_seed(3))
+    ineg = torch.randint(0, 60, (B,), generator=torch.Generator().manual_seed(4))
+    sp, sn, loss = E.cosine_margin(q, table, None, ip, ineg, 1.0)
+    spd, snd, lossd = ops.cosine_margin(q.to(DEV), table.to(DEV), None, ip.to(DEV), ineg.to(DEV), 1.0)
+    assert_close(spd.cpu().numpy(), sp.numpy(), 1e-5, 1e-6, 'pos scores')
+    assert_close(snd.cpu().numpy(), sn.numpy(), 1e-5, 1e-6, 'neg scores')
+    assert_close(lossd.item(), loss.item(), 1e-6, 1e-6, 'loss')
+    gl = torch.tensor([0.7])
+    rows, rid = torch.zeros(2 * B, D), torch.zeros(2 * B, dtype=torch.int64)
+    dq = E.cosine_margin_bwd(q, table, None, ip, ineg, 1.0, gl, rows, rid)
+    rows_d, rid_d = torch.zeros(2 * B, D, device=DEV), torch.zeros(2 * B, dtype=torch.int64, device=DEV)
+    dqd = ops.cosine_margin_bwd(q.to(DEV), table.to(DEV), None, ip.to(DEV), ineg.to(DEV), 1.0, gl.to(DEV), rows_d, rid_d)
+    assert torch.equal(rid_d.cpu(), rid)
+    assert_close(dqd.cpu().numpy(), dq.numpy(), 1e-4, 1e-7, 'dq')
+    assert_close(rows_d.cpu().numpy(), rows.numpy(), 1e-4, 1e-5, 'row grads')
+
+
+def test_cosine_scores_ragged_and_rank_counts():
+    B = 41
+    table = rnd(80, D, seed=1, scale=1.0 / D)
+    q = rnd(B, D, seed=2)
+    lengths = torch.randint(0, 9, (B,), generator=torch.Generator().manual_seed(5))
+    offsets = torch.zeros(B + 1, dtype=torch.int64)
+    offsets[1:] = torch.cumsum(lengths, 0)
+    ids = torch.randint(0, 80, (int(offsets[-1]),), generator=torch.Generator().manual_seed(6))
+    s = E.cosine_scores(q, table, None, ids, offsets)
+    sd = ops.cosine_scores(q.to(DEV), table.to(DEV), None, ids.to(DEV), offsets.to(DEV))
+    assert_close(sd.cpu().numpy(), s.numpy(), 1e-5, 1e-6, 'ragged scores')
+    pos = rnd(B, seed=7, scale=0.1)
+    neg = sd.cpu()
+    neg[::5] = pos[E._owner(offsets, neg.numel(), B)][::5]  # exact ties
+    lt, le = E.rank_counts_ragged(pos, neg, offsets)
+    ltd, led = ops.rank_counts_ragged(pos.to(DEV), neg.to(DEV), offsets.to(DEV))
+    assert torch.equal(ltd.cpu(), lt) and torch.equal(led.cpu(), le), 'rank counts must be bit-exact'
+    # backward
+    gs = rnd(B + ids.numel(), seed=8)
+    dq = torch.zeros(B, D)
+    rows, rid = torch.zeros(ids.numel(), D), torch.zeros(ids.numel(), dtype=torch.int64)
+    E.cosine_scores_bwd(q, table, None, ids, offsets, gs, B, dq, False, rows, rid)
+    dqd = torch.zeros(B, D, device=DEV)
+    rows_d = torch.zeros(ids.numel(), D, device=DEV)
+    rid_d = torch.zeros(ids.numel(), dtype=torch.int64, device=DEV)
+    ops.cosine_scores_bwd(q.to(DEV), table.to(DEV), None, ids.to(DEV), offsets.to(DEV), gs.to(DEV), B, dqd, False,
+                          rows_d, rid_d)
+    assert torch.equal(rid_d.cpu(), rid)
+    assert_close(dqd.cpu().numpy(), dq.numpy(), 1e-4, 1e-6, 'dq')
+    assert_close(rows_d.cpu().numpy(), rows.numpy(), 1e-4, 1e-5, 'rows')
+
+
+@pytest.mark.parametrize('qt', ['1-chain', '2-chain', '3-chain', '2-inter', '3-inter', '3-inter_chain',
+                                '3-chain_inter'])
+def test_query_graph_layout_bit_exact(qt):
+    from mpqe_b200.data_utils import template_of
+    t = template_of(qt)
+    rel = [11, 3, 7][:t.num_edges]
+    for B in (1, 5, 513):
+        ei, et, b = E.build_query_graph(t.num_nodes, t.src, t.dst, rel, B, None)
+        eid, etd, bd = ops.build_query_graph(t.num_nodes, t.src, t.dst, rel, B, torch.device(DEV))
+        assert torch.equal(eid.cpu(), ei) and torch.equal(etd.cpu(), et) and torch.equal(bd.cpu(), b)
+
+
+@pytest.mark.parametrize('n,R', [(1, 3), (100, 7), (5000, 78), (300000, 300), (70000, 70000)])
+def test_relation_sort_bit_exact(n, R):
+    et = torch.randint(0, R, (n,), generator=torch.Generator().manual_seed(n))
+    perm, off = E.relation_sort(et, R)
+    pd, od = ops.relation_sort(et.to(DEV), R)
+    assert torch.equal(pd.cpu(), perm), 'stable permutation must be bit-exact'
+    assert torch.equal(od.cpu(), off)
+
+
+@pytest.mark.parametrize('count,table_rows', [(1, 10), (64, 5), (3000, 400), (100000, 372584), (50000, 3)])
+def test_sparse_rows_combine(count, table_rows):
+    ids = torch.randint(0, table_rows, (count,), generator=torch.Generator().manual_seed(count))
+    rows = rnd(count, D, seed=9)
+    uid, urows, num = E.sparse_rows_combine(ids, rows, table_rows)
+    outs = []
+    for _ in range(2):
+        uidd, urowsd, numd = ops.sparse_rows_combine(ids.to(DEV), rows.to(DEV), table_rows)
+        outs.append(urowsd.cpu())
+    k = int(num)
+    assert int(numd) == k
+    assert torch.equal(uidd.cpu()[:k], uid[:k]), 'unique ids (sorted) must be bit-exact'
+    assert torch.equal(uidd.cpu()[k:], torch.zeros(count - k, dtype=torch.int64))
+    assert torch.equal(outs[0][k:], torch.zeros(count - k, D))
+    assert_close(outs[0][:k].numpy(), urows[:k].numpy(), 1e-5, 1e-4 * max(1.0, count / table_rows / 10), 'summed rows')
+    assert torch.equal(outs[0], outs[1]), 'combine must be bit-reproducible'
+    dense = torch.zeros(table_rows, D, device=DEV)
+    ops.scatter_rows(uidd, urowsd, numd, dense)
+    ref = torch.zeros(table_rows, D).index_add(0, ids, rows)
+    assert_close(dense.cpu().numpy(), ref.numpy(), 1e-5, 1e-4 * max(1.0, count / table_rows / 10), 'dense scatter')
+
+
+@pytest.mark.parametrize('B,N', [(5, 100), (130, 1000), (64, 20000)])
+def test_rank_counts_table_sandwich(B, N):
+    table = rnd(N, D, seed=1, scale=1.0 / D)
+    q = rnd(B, D, seed=2)
+    tgt = torch.randint(0, N, (B,), generator=torch.Generator().manual_seed(3))
+    qd, td = q.to(DEV), table.to(DEV)
+    pos = ops.cosine_scores(qd, td, None, tgt.to(DEV))
+    left = torch.zeros(B, dtype=torch.int64, device=DEV)
+    right = torch.zeros(B, dtype=torch.int64, device=DEV)
+    half = N // 3
+    ops.rank_counts_table(qd, pos, td, 0, half, left, right)      # two shards chained = one table
+    ops.rank_counts_table(qd, pos, td, half, N, left, right)
+    # float64 scores on the CPU bracket the fp32 ones: counts must lie between the counts at pos -/+ tol
+    y = table.double() / table.double().norm(dim=1, keepdim=True)
+    s = (q.double() / q.double().norm(dim=1, keepdim=True)) @ y.t()
+    p = pos.cpu().double().unsqueeze(1)
+    tol = 2e-6
+    lo_lt, hi_lt = (s < p - tol).sum(1), (s < p + tol).sum(1)
+    lo_le, hi_le = (s <= p - tol).sum(1), (s <= p + tol).sum(1)
+    l, r = left.cpu(), right.cpu()
+    assert bool(((l >= lo_lt) & (l <= hi_lt)).all()) and bool(((r >= lo_le) & (r <= hi_le)).all())
+    assert bool((r >= l).all()) and bool((r <= N).all())
+    # the positive itself is a candidate: it can never be counted as strictly lower than itself by a wide margin
+    exact = ((l == (s < p).sum(1)) & (r == (s <= p).sum(1))).float().mean()
+    assert exact > 0.5
+
+
+def test_adam_matches_torch():
+    p = rnd(1000, seed=1)
+    ref = torch.nn.Parameter(p.clone())
+    opt = torch.optim.Adam([ref], lr=0.01)
+    pd = p.to(DEV)
+    m, v = torch.zeros_like(pd), torch.zeros_like(pd)
+    for step in range(1, 4):
+        g = rnd(1000, seed=10 + step)
+        ref.grad = g.clone()
+        opt.step()
+        ops.adam_dense(pd, g.to(DEV), m, v, 0.01, 0.9, 0.999, 1e-8, step)
+    assert_close(pd.cpu().numpy(), ref.detach().numpy(), 1e-5, 1e-6, 'adam')

