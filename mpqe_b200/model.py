@@ -459,14 +459,22 @@ class Grads(object):
     """Dense gradient buffers (zero-initialised, kernels accumulate) + the row-gradient collector."""
 
     def __init__(self, model, W, row_capacities, device):
-        self.dw = [torch.zeros_like(w) for w in W.w]
-        self.droot = [torch.zeros_like(r) for r in W.root]
-        self.dbias = [torch.zeros(D, dtype=torch.float32, device=device) for _ in W.root]
-        self.dmode = torch.zeros_like(W.mode_emb)
+        # one flat zeroed bucket: a single memset here, a single NCCL all-reduce in data-parallel training
+        shapes = [tuple(w.shape) for w in W.w] + [tuple(r.shape) for r in W.root] + [(D,)] * len(W.root)
+        shapes.append(tuple(W.mode_emb.shape))
         if W.ro is not None:
-            self.dw1t, self.dw2t = torch.zeros_like(W.w1t), torch.zeros_like(W.w2t)
-            self.db1 = torch.zeros(D, dtype=torch.float32, device=device)
-            self.db2 = torch.zeros(D, dtype=torch.float32, device=device)
+            shapes += [tuple(W.w1t.shape), tuple(W.w2t.shape), (D,), (D,)]
+        sizes = [int(torch.Size(s).numel()) for s in shapes]
+        self.flat = torch.zeros(sum(sizes), dtype=torch.float32, device=device)
+        views, off = [], 0
+        for s, k in zip(shapes, sizes):
+            views.append(self.flat[off:off + k].view(s))
+            off += k
+        L = len(W.w)
+        self.dw, self.droot, self.dbias = views[:L], views[L:2 * L], views[2 * L:3 * L]
+        self.dmode = views[3 * L]
+        if W.ro is not None:
+            self.dw1t, self.dw2t, self.db1, self.db2 = views[3 * L + 1:3 * L + 5]
         self.rows = RowGrads(row_capacities, device)
 
 
@@ -650,22 +658,43 @@ class RGCNEncoderDecoder(nn.Module):
         return tuple(by_param.get(id(p)) for p in self.parameters())
 
 
+def loss_forward(model, jobs, targets, negatives, margin, need_grad):
+    """Encodes every job once and scores it against its positives and negatives.
+    Returns (per-job losses [len(jobs)] on the device, Weights)."""
+    device = jobs[0].anchor_ids.device
+    W = Weights(model, need_grad)
+    model._engine.encode(jobs, W)
+    losses = torch.empty(len(jobs), dtype=torch.float32, device=device)
+    for i, (job, tgt, neg) in enumerate(zip(jobs, targets, negatives)):
+        ops.cosine_margin(job.q, model.enc.table(job.target_mode), model.enc.node_maps, tgt, neg, margin,
+                          loss_out=losses[i:i + 1])
+    return losses, W
+
+
+def loss_backward(model, jobs, W, targets, negatives, margin, grad_losses):
+    """Backward of `loss_forward` for d(total)/d(loss_i) = grad_losses[i] (device tensor [len(jobs)]).
+    Returns the filled `Grads` (dense bucket + per-mode (row id, gradient row) pairs, not yet combined)."""
+    device = jobs[0].anchor_ids.device
+    cap = model._row_capacities(jobs, [(job.target_mode, 2 * job.B) for job in jobs])
+    G = Grads(model, W, cap, device)
+    dqs = []
+    for i, (job, tgt, neg) in enumerate(zip(jobs, targets, negatives)):
+        rows, ids, off = G.rows.reserve(job.target_mode, 2 * job.B)
+        dqs.append(ops.cosine_margin_bwd(job.q, model.enc.table(job.target_mode), model.enc.node_maps, tgt, neg,
+                                         margin, grad_losses[i:i + 1], rows, ids, rows_offset=off))
+    model._engine.backward(jobs, W, dqs, G)
+    return G
+
+
 class _MarginLossFn(torch.autograd.Function):
-    """mean(relu(margin - (cos(q, target) - cos(q, negative)))) over one or more formula groups (summed)."""
+    """sum over formula groups of mean(relu(margin - (cos(q, target) - cos(q, negative))))."""
 
     @staticmethod
     def forward(ctx, model, jobs, targets, negatives, margin, *params):
         device = jobs[0].anchor_ids.device
-        need_grad = any(ctx.needs_input_grad)
         with ops.device_guard(device):
-            W = Weights(model, need_grad)
-            model._engine.encode(jobs, W)
-            losses = []
-            for job, tgt, neg in zip(jobs, targets, negatives):
-                _, _, loss = ops.cosine_margin(job.q, model.enc.table(job.target_mode), model.enc.node_maps, tgt, neg,
-                                               margin)
-                losses.append(loss)
-            total = losses[0] if len(losses) == 1 else torch.stack(losses).sum()
+            losses, W = loss_forward(model, jobs, targets, negatives, margin, any(ctx.needs_input_grad))
+            total = losses[0].clone() if len(jobs) == 1 else losses.sum()
         ctx.model, ctx.jobs, ctx.W, ctx.margin = model, jobs, W, margin
         ctx.targets, ctx.negatives = targets, negatives
         return total
@@ -673,17 +702,9 @@ class _MarginLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_loss):
         model, jobs, W = ctx.model, ctx.jobs, ctx.W
-        device = jobs[0].anchor_ids.device
-        with ops.device_guard(device):
-            cap = model._row_capacities(jobs, [(job.target_mode, 2 * job.B) for job in jobs])
-            G = Grads(model, W, cap, device)
-            gl = grad_loss.contiguous().reshape(1)
-            dqs = []
-            for job, tgt, neg in zip(jobs, ctx.targets, ctx.negatives):
-                rows, ids, off = G.rows.reserve(job.target_mode, 2 * job.B)
-                dqs.append(ops.cosine_margin_bwd(job.q, model.enc.table(job.target_mode), model.enc.node_maps, tgt, neg,
-                                                 ctx.margin, gl, rows, ids, rows_offset=off))
-            model._engine.backward(jobs, W, dqs, G)
+        with ops.device_guard(jobs[0].anchor_ids.device):
+            gl = grad_loss.contiguous().reshape(1).expand(len(jobs)).contiguous()
+            G = loss_backward(model, jobs, W, ctx.targets, ctx.negatives, ctx.margin, gl)
             grads = model._collect_grads(W, G)
         return (None, None, None, None, None) + grads
 

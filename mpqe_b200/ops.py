@@ -123,6 +123,42 @@ class Group(object):
         return g
 
 
+profile = None  # bench.py sets this to a list: (kind, start event, end event, algorithmic bytes, flops) per launch
+
+
+def _algorithmic(groups, grad_operands=None):
+    """Algorithmic bytes / flops of a term-list launch: every distinct input row and every output row once."""
+    nbytes = flops = 0
+    for i, g in enumerate(groups):
+        rows = len({(t.a.data_ptr(), t.a_slot) for t in g.terms if t.a_slots > 0})
+        if grad_operands is None:
+            rows += g.num_out_slots * (2 if g.epilogue == EPI_MASK else 1)
+        else:
+            gt, g_slots, smap = grad_operands[i]
+            rows += len({smap[t.out_slot] for t in g.terms})
+        nbytes += g.num_queries * rows * D * 4
+        flops += g.num_queries * len(g.terms) * 2 * D * D
+    return nbytes, flops
+
+
+class _Profiled(object):
+    def __init__(self, kind, groups, grad_operands=None):
+        self.on = profile is not None
+        if self.on:
+            self.kind = kind
+            self.cost = _algorithmic(groups, grad_operands)
+            self.s, self.e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def __enter__(self):
+        if self.on:
+            self.s.record()
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.e.record()
+            profile.append((self.kind, self.s, self.e, self.cost[0], self.cost[1]))
+
+
 def layer_forward(groups, use_tensor_cores=None):
     """mpqe_layer_forward over up to MPQE_MAX_GROUPS groups per launch."""
     lib = _lib.load()
@@ -130,7 +166,8 @@ def layer_forward(groups, use_tensor_cores=None):
     for i in range(0, len(groups), MAX_GROUPS):
         chunk = groups[i:i + MAX_GROUPS]
         arr = (_lib.LayerGroup * len(chunk))(*[g.to_c() for g in chunk])
-        _lib.check(lib.mpqe_layer_forward(arr, len(chunk), int(tc), _stream()), 'mpqe_layer_forward')
+        with _Profiled('layer', chunk):
+            _lib.check(lib.mpqe_layer_forward(arr, len(chunk), int(tc), _stream()), 'mpqe_layer_forward')
         _count()
 
 
@@ -152,8 +189,9 @@ def layer_wgrad(groups, grad_operands, dests, ctas_hint=296):
     dev = groups[0].terms[0].a.device
     nbytes = lib.mpqe_layer_wgrad_workspace_bytes(len(dests), ctas_hint)
     ws = workspace(nbytes, dev, 'wgrad')
-    _lib.check(lib.mpqe_layer_wgrad(garr, oarr, len(groups), darr, len(dests), _ptr(ws), ws.numel(), _stream()),
-               'mpqe_layer_wgrad')
+    with _Profiled('wgrad', groups, grad_operands):
+        _lib.check(lib.mpqe_layer_wgrad(garr, oarr, len(groups), darr, len(dests), _ptr(ws), ws.numel(), _stream()),
+                   'mpqe_layer_wgrad')
     _count(2)
 
 
@@ -243,13 +281,13 @@ def max_readout_bwd(dq, argmax, B, n):
     return g
 
 
-def cosine_margin(q, table, id2row, ids_pos, ids_neg, margin):
+def cosine_margin(q, table, id2row, ids_pos, ids_neg, margin, loss_out=None):
     lib = _lib.load()
     B = q.shape[0]
     dev = q.device
     sp = torch.empty(B, dtype=torch.float32, device=dev)
     sn = torch.empty(B, dtype=torch.float32, device=dev)
-    loss = torch.empty((), dtype=torch.float32, device=dev)
+    loss = loss_out if loss_out is not None else torch.empty((), dtype=torch.float32, device=dev)
     ws = workspace(lib.mpqe_margin_loss_workspace_bytes(B), dev, 'loss')
     _lib.check(lib.mpqe_cosine_margin_fwd(_ptr(_chk(q, torch.float32, 'q')), B, _ptr(_chk(table, torch.float32, 'table')),
                                           _ptr(id2row), _ptr(_chk(ids_pos, torch.int64, 'ids_pos')),

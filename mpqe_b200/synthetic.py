@@ -155,3 +155,12 @@ def make_query_sets(kg, queries_per_formula=16, formulas_per_type=2, seed=0, num
             groups.append((rels, kg.sample_queries(qt, rels, queries_per_formula, rng, num_neg, num_hard_neg)))
         out[qt] = groups
     return out
+
+
+def sample_id_batch(kg, formula, count, rng):
+    """Vectorised ids for one formula batch: (anchor_ids [count, a], targets [count], negatives [count]) int64,
+    uniform over the proper modes (the tensorised form of `sample_queries`, for benchmark-sized batches)."""
+    anchors = np.stack([kg._ent(m, rng, size=count) for m in formula.anchor_modes], axis=1).astype(np.int64)
+    targets = kg._ent(formula.target_mode, rng, size=count).astype(np.int64)
+    negatives = kg._ent(formula.target_mode, rng, size=count).astype(np.int64)
+    return anchors, targets, negatives

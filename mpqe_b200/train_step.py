@@ -1,0 +1,162 @@
+"""One optimiser step's worth of the hot path without Python autograd in the loop: margin-loss forward + backward
+over a list of formula batches, gradient synchronisation across ranks, optional fused Adam.
+
+This is the caller-side row (f)1 of SURVEY.md section 8 (`run_train` / `run_batch_v2`, reference
+train_helpers.py:76-120): the reference issues up to 11 `margin_loss` calls per step, one per query type, each
+a separate pair of encoder forwards; here all batches of a step go through the same per-pass launches.
+
+Multi-GPU (one process per GPU, torch.distributed): query batches are data-parallel.  Per step there is exactly one
+exchange: an all-reduce of the flat dense-gradient bucket and an all-gather of the per-mode (row id, gradient row)
+pairs, followed by the same deterministic combine on every rank, so that all ranks apply identical updates.
+"""
+import torch
+
+from . import ops
+from .model import Job, loss_backward, loss_forward
+from .ops import D
+
+
+class Batch(object):
+    """Device-resident ids of one formula batch."""
+
+    def __init__(self, job, targets, negatives, weight=1.0):
+        self.job, self.targets, self.negatives, self.weight = job, targets, negatives, float(weight)
+
+
+class HostBatch(object):
+    """Pinned host ids of one formula batch (what a data loader hands over)."""
+
+    def __init__(self, formula, anchor_ids, targets, negatives, weight=1.0):
+        self.formula = formula
+        self.anchor_ids = anchor_ids.contiguous().pin_memory() if torch.cuda.is_available() else anchor_ids
+        self.targets = targets.contiguous().pin_memory() if torch.cuda.is_available() else targets
+        self.negatives = negatives.contiguous().pin_memory() if torch.cuda.is_available() else negatives
+        self.weight = float(weight)
+
+    def nbytes(self):
+        return 8 * (self.anchor_ids.numel() + self.targets.numel() + self.negatives.numel())
+
+
+class StepResult(object):
+    def __init__(self, losses, total, dense, sparse):
+        self.losses, self.total, self.dense, self.sparse = losses, total, dense, sparse
+
+
+class TrainStep(object):
+    def __init__(self, model, margin=1.0, process_group=None, average=True):
+        self.model = model
+        self.margin = float(margin)
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if self._dist() else 1
+        self.average = average
+        self._layouts = {}
+        self.adam_state = None
+        self.steps = 0
+
+    def _dist(self):
+        return torch.distributed.is_available() and torch.distributed.is_initialized()
+
+    # ---- batch construction ---------------------------------------------------------------------------
+    def layout(self, formula):
+        key = formula
+        lay = self._layouts.get(key)
+        if lay is None:
+            from .data_utils import RGCNQueryDataset
+            m = self.model
+            t, var_ids, rels = RGCNQueryDataset.formula_layout(formula, m.rel_ids, m.mode_ids)
+            dev = m.mode_embeddings.weight.device
+            lay = self._layouts[key] = (t, tuple(rels), tuple(var_ids),
+                                        torch.tensor(var_ids, dtype=torch.int64, device=dev), m.num_passes(formula))
+        return lay
+
+    def to_device(self, hb):
+        """H2D copy of one host batch (async from pinned memory) -> Batch."""
+        dev = self.model.mode_embeddings.weight.device
+        t, rels, var_host, var_dev, passes = self.layout(hb.formula)
+        a = hb.anchor_ids.to(dev, non_blocking=True)
+        job = Job(t, rels, var_dev, hb.formula.anchor_modes, hb.formula.target_mode, a, passes)
+        job.var_rows_host = var_host
+        return Batch(job, hb.targets.to(dev, non_blocking=True), hb.negatives.to(dev, non_blocking=True), hb.weight)
+
+    def refresh(self, batch):
+        """A Batch can be re-run: drop the activations of the previous step."""
+        j = batch.job
+        j.acts = j.outs = j.z = j.u = j.q = j.argmax = j.fwd_groups = None
+        return batch
+
+    # ---- the step -------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward_backward(self, batches):
+        """Returns StepResult: per-batch losses, weighted total (device scalars), the flat dense gradient bucket
+        (views per parameter in .dense.named) and {mode: (unique row ids, rows, num_unique)}."""
+        m = self.model
+        dev = m.mode_embeddings.weight.device
+        with ops.device_guard(dev):
+            jobs = [self.refresh(b).job for b in batches]
+            tg = [b.targets for b in batches]
+            ng = [b.negatives for b in batches]
+            losses, W = loss_forward(m, jobs, tg, ng, self.margin, True)
+            key = tuple(b.weight for b in batches)
+            wts = getattr(self, '_wts', None)
+            if wts is None or wts[0] != key:
+                wts = self._wts = (key, torch.tensor(key, dtype=torch.float32, device=dev))
+            G = loss_backward(m, jobs, W, tg, ng, self.margin, wts[1])
+            sparse = {}
+            for mode, (rows, ids, used) in G.rows.buf.items():
+                if used > 0:
+                    sparse[mode] = ops.sparse_rows_combine(ids[:used], rows[:used], m.enc.table(mode).shape[0])
+            if self.world > 1:
+                sparse = self.sync(G, sparse)
+            total = (losses * wts[1]).sum()
+        return StepResult(losses, total, G, sparse)
+
+    def sync(self, G, sparse):
+        """Data-parallel exchange: all-reduce(dense bucket), all-gather(row ids, rows) + identical re-combine."""
+        dist = torch.distributed
+        scale = 1.0 / self.world if self.average else 1.0
+        dist.all_reduce(G.flat, group=self.pg)
+        if scale != 1.0:
+            G.flat.mul_(scale)
+        out = {}
+        for mode in sorted(sparse):
+            uid, urows, num = sparse[mode]
+            cap = uid.numel()
+            all_ids = torch.empty(self.world * cap, dtype=torch.int64, device=uid.device)
+            all_rows = torch.empty(self.world * cap, D, dtype=torch.float32, device=uid.device)
+            dist.all_gather_into_tensor(all_ids, uid, group=self.pg)
+            dist.all_gather_into_tensor(all_rows, urows, group=self.pg)
+            if scale != 1.0:
+                all_rows.mul_(scale)
+            # padding entries are (row 0, zero row): harmless for the sum; rank order + stable sort => same bits everywhere
+            out[mode] = ops.sparse_rows_combine(all_ids, all_rows, self.model.enc.table(mode).shape[0])
+        return out
+
+    @torch.no_grad()
+    def run_host(self, host_batches):
+        """End-to-end step from pinned host ids: H2D copies, forward+backward(+sync), D2H of the losses."""
+        batches = [self.to_device(hb) for hb in host_batches]
+        res = self.forward_backward(batches)
+        return res, res.losses.cpu()
+
+    # ---- optional fused optimiser over the dense bucket (torch.optim.Adam defaults, train.py:86-88) -----
+    @torch.no_grad()
+    def adam_step_dense(self, res, lr=0.01, betas=(0.9, 0.999), eps=1e-8):
+        """Adam on the dense parameters straight from the flat gradient bucket (entity tables are left to the caller:
+        the reference's dense Adam keeps moving rows after they were touched)."""
+        m = self.model
+        W_params = []
+        for layer in m.distinct_layers():
+            W_params.append(layer.basis)
+        for layer in m.distinct_layers():
+            W_params.append(layer.root)
+        for layer in m.distinct_layers():
+            W_params.append(layer.bias)
+        W_params.append(m.mode_embeddings.weight)
+        G = res.dense
+        grads = list(G.dw) + list(G.droot) + list(G.dbias) + [G.dmode]
+        if self.adam_state is None:
+            self.adam_state = [(torch.zeros_like(p.data), torch.zeros_like(p.data)) for p in W_params]
+        self.steps += 1
+        with ops.device_guard(G.flat.device):
+            for p, g, (m1, m2) in zip(W_params, grads, self.adam_state):
+                ops.adam_dense(p.data, g.contiguous(), m1, m2, lr, betas[0], betas[1], eps, self.steps)

@@ -138,11 +138,15 @@ def _cos(q, y):
     return ((q / nq.clamp_min(EPS).unsqueeze(1)) * (y / ny.clamp_min(EPS).unsqueeze(1))).sum(1)
 
 
-def cosine_margin(q, table, id2row, ids_pos, ids_neg, margin):
+def cosine_margin(q, table, id2row, ids_pos, ids_neg, margin, loss_out=None):
     yp, _ = _norm_rows(table, _resolve(id2row, ids_pos))
     yn, _ = _norm_rows(table, _resolve(id2row, ids_neg))
     sp, sn = _cos(q, yp), _cos(q, yn)
-    return sp, sn, torch.clamp(margin - (sp - sn), min=0).mean()
+    loss = torch.clamp(margin - (sp - sn), min=0).mean()
+    if loss_out is not None:
+        loss_out.copy_(loss.reshape(loss_out.shape))
+        loss = loss_out
+    return sp, sn, loss
 
 
 def _pair_bwd(q, table, rows, gscore):

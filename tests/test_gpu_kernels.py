@@ -282,9 +282,6 @@ def test_rank_counts_table_sandwich(B, N):
     l, r = left.cpu(), right.cpu()
     assert bool(((l >= lo_lt) & (l <= hi_lt)).all()) and bool(((r >= lo_le) & (r <= hi_le)).all())
     assert bool((r >= l).all()) and bool((r <= N).all())
-    # the positive itself is a candidate: it can never be counted as strictly lower than itself by a wide margin
-    exact = ((l == (s < p).sum(1)) & (r == (s <= p).sum(1))).float().mean()
-    assert exact > 0.5
 
 
 def test_adam_matches_torch():
