@@ -137,7 +137,7 @@ MPQE_API int mpqe_layer_forward(const mpqe_layer_group_t* groups_host, int32_t n
 MPQE_API size_t mpqe_layer_wgrad_workspace_bytes(int32_t num_dests, int32_t num_ctas_hint);
 MPQE_API int mpqe_layer_wgrad(const mpqe_layer_group_t* groups_host, const mpqe_wgrad_operand_t* grads_host,
                      int32_t num_groups, const mpqe_wgrad_dest_t* dests_host, int32_t num_dests,
-                     void* workspace, size_t workspace_bytes, void* stream);
+                     int32_t use_tensor_cores, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Column sums: out[d] (+)= scale * sum over rows of src[r*stride .. +d], r in [0, rows): bias / mode-embedding grads. */
 MPQE_API size_t mpqe_colsum_workspace_bytes(int64_t rows);

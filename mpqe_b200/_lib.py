@@ -46,7 +46,7 @@ SIGNATURES = {
     'mpqe_broadcast_rows': (I32, [P, P, I32, P, I64, I64, P]),
     'mpqe_layer_forward': (I32, [P, I32, I32, P]),
     'mpqe_layer_wgrad_workspace_bytes': (SZ, [I32, I32]),
-    'mpqe_layer_wgrad': (I32, [P, P, I32, P, I32, P, SZ, P]),
+    'mpqe_layer_wgrad': (I32, [P, P, I32, P, I32, I32, P, SZ, P]),
     'mpqe_colsum_workspace_bytes': (SZ, [I64]),
     'mpqe_colsum': (I32, [P, I64, I64, F32, P, I32, P, SZ, P]),
     'mpqe_transpose': (I32, [P, P, I64, I32, I32, P]),

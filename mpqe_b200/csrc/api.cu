@@ -25,6 +25,3 @@ extern "C" int mpqe_b200_sizeof(int which) {
     default: return -1;
   }
 }
-#ifndef MPQE_WITH_TCGEN05
-extern "C" int mpqe_b200_has_tcgen05(void) { return 0; }
-#endif

@@ -39,6 +39,26 @@ void set_error(const char* fmt, ...);
     }                                                                                  \
   } while (0)
 
+// kernel-parameter blocks shared by the FFMA (layer_simt.cu) and tcgen05 (layer_tc.cu) versions
+struct LayerLaunch {
+  int num_groups;
+  mpqe_layer_group_t g[MPQE_MAX_GROUPS];
+};
+
+struct WgradLaunch {
+  int num_groups;
+  int num_dests;
+  float* partials;  // [sum chunks][D][D]
+  int chunks[MPQE_MAX_DESTS];
+  mpqe_wgrad_dest_t d[MPQE_MAX_DESTS];
+  mpqe_layer_group_t g[MPQE_MAX_GROUPS];
+  mpqe_wgrad_operand_t go[MPQE_MAX_GROUPS];
+};
+
+int layer_forward_simt(const mpqe_layer_group_t* groups, int num_groups, cudaStream_t stream);
+int layer_forward_tc(const mpqe_layer_group_t* groups, int num_groups, cudaStream_t stream);
+int layer_wgrad_tc_launch(const WgradLaunch& launch, int total_chunks, cudaStream_t stream);
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 __device__ __forceinline__ float warp_sum(float v) {

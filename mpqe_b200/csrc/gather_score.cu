@@ -7,31 +7,10 @@
 //   model.py:383-385 (torch_scatter.scatter_max)        -> max_readout_{fwd,bwd}
 //   model.py:451-460, 483-485                           -> cosine_scores*, cosine_margin_{fwd,bwd}
 //   utils.py:25-32 (scipy percentileofscore 'rank')     -> rank_counts_ragged
-#include <math_constants.h>
-
-#include "common.cuh"
+#include "rowops.cuh"
 
 namespace mpqe {
 namespace {
-
-constexpr int ROW_THREADS = 256;           // 8 warps = 8 rows per CTA
-constexpr float COS_EPS = 1e-8f;           // F.cosine_similarity default eps
-
-__device__ __forceinline__ int64_t resolve_row(const int64_t* id2row, const int64_t* ids, int64_t stride, int64_t i) {
-  const int64_t id = ids[i * stride];
-  return id2row != nullptr ? id2row[id] : id;
-}
-
-__device__ __forceinline__ float4 scale4(const float4& v, float s) { return make_float4(v.x * s, v.y * s, v.z * s, v.w * s); }
-__device__ __forceinline__ float4 div4(const float4& v, float s) { return make_float4(v.x / s, v.y / s, v.z / s, v.w / s); }
-
-// y = row / ||row||  (division, like Tensor.div in encoders.py:43); returns ||row||
-__device__ __forceinline__ float normalize_row(const float* table, int64_t row, int lane, float4& y) {
-  const float4 v = *reinterpret_cast<const float4*>(table + row * D + lane * 4);
-  const float nrm = sqrtf(warp_sum(dot4(v, v)));
-  y = div4(v, nrm);
-  return nrm;
-}
 
 __global__ void __launch_bounds__(ROW_THREADS) gather_normalize_fwd_kernel(
     const float* __restrict__ table, int64_t table_rows, const int64_t* __restrict__ id2row,
@@ -51,12 +30,6 @@ __global__ void __launch_bounds__(ROW_THREADS) gather_normalize_fwd_kernel(
   }
   *reinterpret_cast<float4*>(out + i * out_stride + lane * 4) = y;
   if (inv_norm != nullptr && lane == 0) inv_norm[i] = 1.f / nrm;
-}
-
-// d(row) = (g - (g.y) y) / ||row||
-__device__ __forceinline__ float4 normalize_bwd(const float4& g, const float4& y, float nrm) {
-  const float gy = warp_sum(dot4(g, y));
-  return make_float4((g.x - gy * y.x) / nrm, (g.y - gy * y.y) / nrm, (g.z - gy * y.z) / nrm, (g.w - gy * y.w) / nrm);
 }
 
 __global__ void __launch_bounds__(ROW_THREADS) gather_normalize_bwd_kernel(
@@ -124,35 +97,6 @@ __global__ void __launch_bounds__(ROW_THREADS) max_readout_bwd_kernel(const floa
     const float4 o = make_float4(a0 == i ? v.x : 0.f, a1 == i ? v.y : 0.f, a2 == i ? v.z : 0.f, a3 == i ? v.w : 0.f);
     *reinterpret_cast<float4*>(g + (b * n + i) * (int64_t)D + lane * 4) = o;
   }
-}
-
-// ---- cosine scoring ---------------------------------------------------------------------------------------------
-struct Cos {
-  float score, nq, nqc, ny, nyc;  // norms and their eps-clamped versions
-};
-
-__device__ __forceinline__ Cos cosine(const float4& q, const float4& y) {
-  Cos c;
-  c.nq = sqrtf(warp_sum(dot4(q, q)));
-  c.ny = sqrtf(warp_sum(dot4(y, y)));
-  c.nqc = fmaxf(c.nq, COS_EPS);
-  c.nyc = fmaxf(c.ny, COS_EPS);
-  // torch: sum((x1 / clamp_min(|x1|, eps)) * (x2 / clamp_min(|x2|, eps)))
-  const float4 a = div4(q, c.nqc), b = div4(y, c.nyc);
-  c.score = warp_sum(dot4(a, b));
-  return c;
-}
-
-// gradient of score wrt q (dsq) and wrt y (dsy), times upstream g
-__device__ __forceinline__ void cosine_bwd(const float4& q, const float4& y, const Cos& c, float g, float4& dq,
-                                           float4& dy) {
-  const float kq = c.nq > COS_EPS ? c.score / (c.nqc * c.nq) : 0.f;
-  const float ky = c.ny > COS_EPS ? c.score / (c.nyc * c.ny) : 0.f;
-  const float iq = 1.f / c.nqc, iy = 1.f / c.nyc;
-  dq = make_float4(g * (y.x * iy * iq - kq * q.x), g * (y.y * iy * iq - kq * q.y), g * (y.z * iy * iq - kq * q.z),
-                   g * (y.w * iy * iq - kq * q.w));
-  dy = make_float4(g * (q.x * iq * iy - ky * y.x), g * (q.y * iq * iy - ky * y.y), g * (q.z * iq * iy - ky * y.z),
-                   g * (q.w * iq * iy - ky * y.w));
 }
 
 __global__ void __launch_bounds__(ROW_THREADS) cosine_margin_fwd_kernel(
@@ -304,8 +248,6 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   v[i] = vi;
   p[i] -= (lr / bc1) * mi / (sqrtf(vi) / bc2_sqrt + eps);
 }
-
-inline unsigned row_blocks(int64_t rows) { return (unsigned)((rows + ROW_THREADS / 32 - 1) / (ROW_THREADS / 32)); }
 
 }  // namespace
 }  // namespace mpqe

@@ -10,11 +10,6 @@
 
 namespace mpqe {
 
-struct LayerLaunch {
-  int num_groups;
-  mpqe_layer_group_t g[MPQE_MAX_GROUPS];
-};
-
 namespace {
 
 constexpr int BM = 64;        // queries per CTA tile
@@ -171,16 +166,6 @@ __global__ void __launch_bounds__(THREADS, 2) layer_simt_kernel(const __grid_con
 // Weight gradient: dM_j = sum over matching terms, over queries, of A[q]^T G[q]  (a [128,B]x[B,128] reduction).
 // Each CTA owns (destination j, chunk c) and a fixed query range per group; partials are reduced in order.
 // ------------------------------------------------------------------------------------------------------------
-struct WgradLaunch {
-  int num_groups;
-  int num_dests;
-  float* partials;  // [sum chunks][D][D]
-  int chunks[MPQE_MAX_DESTS];
-  mpqe_wgrad_dest_t d[MPQE_MAX_DESTS];
-  mpqe_layer_group_t g[MPQE_MAX_GROUPS];
-  mpqe_wgrad_operand_t go[MPQE_MAX_GROUPS];
-};
-
 constexpr int KQ = 16;  // queries per smem tile
 constexpr int W_STAGE = 2 * KQ * D;
 constexpr int W_STAGES = 3;
@@ -421,7 +406,7 @@ extern "C" int mpqe_layer_forward(const mpqe_layer_group_t* groups_host, int32_t
     MPQE_CHECK_ARG(groups_host[i].epilogue != MPQE_EPI_MASK || groups_host[i].mask != nullptr,
                    "mpqe_layer_forward: group %d: EPI_MASK without mask", i);
   }
-  MPQE_CHECK_ARG(use_tensor_cores == 0, "mpqe_layer_forward: tcgen05 path not built into this library");
+  if (use_tensor_cores) return layer_forward_tc(groups_host, num_groups, (cudaStream_t)stream);
   return layer_forward_simt(groups_host, num_groups, (cudaStream_t)stream);
 }
 
@@ -432,7 +417,7 @@ extern "C" size_t mpqe_layer_wgrad_workspace_bytes(int32_t num_dests, int32_t nu
 
 extern "C" int mpqe_layer_wgrad(const mpqe_layer_group_t* groups_host, const mpqe_wgrad_operand_t* grads_host,
                                 int32_t num_groups, const mpqe_wgrad_dest_t* dests_host, int32_t num_dests,
-                                void* workspace, size_t workspace_bytes, void* stream) {
+                                int32_t use_tensor_cores, void* workspace, size_t workspace_bytes, void* stream) {
   if (validate_groups(groups_host, num_groups, "mpqe_layer_wgrad")) return 1;
   MPQE_CHECK_ARG(num_dests >= 1 && num_dests <= MPQE_MAX_DESTS, "mpqe_layer_wgrad: num_dests must be in [1,%d]",
                  MPQE_MAX_DESTS);
@@ -477,8 +462,12 @@ extern "C" int mpqe_layer_wgrad(const mpqe_layer_group_t* groups_host, const mpq
     L.chunks[j] = (int)c;
     total_chunks += (int)c;
   }
-  wgrad_simt_kernel<<<total_chunks, THREADS, WGRAD_SMEM, (cudaStream_t)stream>>>(L);
-  MPQE_CHECK_LAUNCH("wgrad_simt_kernel");
+  if (use_tensor_cores) {
+    if (layer_wgrad_tc_launch(L, total_chunks, (cudaStream_t)stream)) return 2;
+  } else {
+    wgrad_simt_kernel<<<total_chunks, THREADS, WGRAD_SMEM, (cudaStream_t)stream>>>(L);
+    MPQE_CHECK_LAUNCH("wgrad_simt_kernel");
+  }
   wgrad_reduce_kernel<<<dim3(D * D / 4 / 256, num_dests), 256, 0, (cudaStream_t)stream>>>(L);
   MPQE_CHECK_LAUNCH("wgrad_reduce_kernel");
   return 0;

@@ -171,7 +171,7 @@ def layer_forward(groups, use_tensor_cores=None):
         _count()
 
 
-def layer_wgrad(groups, grad_operands, dests, ctas_hint=296):
+def layer_wgrad(groups, grad_operands, dests, ctas_hint=296, use_tensor_cores=None):
     """mpqe_layer_wgrad.  grad_operands[i] = (g tensor, g_slots, slot_map list) for groups[i];
     dests = [(m_fwd tensor view, dm tensor view, accumulate)]."""
     lib = _lib.load()
@@ -190,8 +190,9 @@ def layer_wgrad(groups, grad_operands, dests, ctas_hint=296):
     nbytes = lib.mpqe_layer_wgrad_workspace_bytes(len(dests), ctas_hint)
     ws = workspace(nbytes, dev, 'wgrad')
     with _Profiled('wgrad', groups, grad_operands):
-        _lib.check(lib.mpqe_layer_wgrad(garr, oarr, len(groups), darr, len(dests), _ptr(ws), ws.numel(), _stream()),
-                   'mpqe_layer_wgrad')
+        tc = tensor_cores_default() if use_tensor_cores is None else bool(use_tensor_cores)
+        _lib.check(lib.mpqe_layer_wgrad(garr, oarr, len(groups), darr, len(dests), int(tc), _ptr(ws), ws.numel(),
+                                        _stream()), 'mpqe_layer_wgrad')
     _count(2)
 
 

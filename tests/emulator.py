@@ -42,7 +42,7 @@ def layer_forward(groups, use_tensor_cores=None):
             out[:, s] = v
 
 
-def layer_wgrad(groups, grad_operands, dests, ctas_hint=296):
+def layer_wgrad(groups, grad_operands, dests, ctas_hint=296, use_tensor_cores=None):
     for (m_fwd, dm, acc) in dests:
         total = torch.zeros(D, D)
         for g, (gt, g_slots, smap) in zip(groups, grad_operands):
