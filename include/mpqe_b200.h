@@ -94,7 +94,8 @@ typedef struct {
 
 MPQE_API const char* mpqe_b200_last_error(void);
 MPQE_API int mpqe_b200_version(void);
-/* sizeof the ABI structs (0: term, 1: layer group, 2: wgrad dest, 3: wgrad operand) so bindings can self-check */
+/* sizeof the ABI structs (0: term, 1: layer group, 2: wgrad dest, 3: wgrad operand, 4: gather item, 5: margin item,
+ * 6: colsum item) so bindings can self-check */
 MPQE_API int mpqe_b200_sizeof(int which);
 /* 1 if the library was built with the tcgen05 (sm_100a tensor core) layer kernels */
 MPQE_API int mpqe_b200_has_tcgen05(void);
@@ -176,6 +177,70 @@ MPQE_API int mpqe_cosine_scores(const float* q, int64_t B, const int64_t* offset
 MPQE_API int mpqe_cosine_scores_bwd(const float* q, int64_t B, const int64_t* offsets, const float* table,
                            const int64_t* id2row, const int64_t* ids, int64_t count, const float* grad_scores,
                            float* dq, int32_t accumulate, float* rows_out, int64_t* rows_id, void* stream);
+
+/* ---- multi-item launches: every formula group of a training step in one kernel ------------------------------
+ * Same arithmetic per row as the single-item entry points above; the work items travel in the kernel parameters. */
+#define MPQE_MAX_GATHER_ITEMS 32
+#define MPQE_MAX_MARGIN_ITEMS 8
+#define MPQE_MAX_COLSUM_ITEMS 64
+
+/* One (group, node slot) of the input build (model.py:418-421) or of its backward.
+ * forward : out[i*out_stride .. +d] = normalize ? table[row]/||table[row]|| : table[row],
+ *           row = id2row ? id2row[ids[i*ids_stride]] : ids[i*ids_stride]   (ids_stride 0 broadcasts one row)
+ * backward: rows_out[i] = normalise-backward of grad[i*grad_stride .. +d], rows_id[i] = row + id_offset */
+typedef struct {
+  const float* table;
+  int64_t table_rows;
+  const int64_t* id2row;
+  const int64_t* ids;
+  int64_t ids_stride;
+  int64_t count;
+  float* out;
+  int64_t out_stride;
+  const float* grad;
+  int64_t grad_stride;
+  float* rows_out;
+  int64_t* rows_id;
+  int64_t id_offset;
+  int32_t normalize;
+  int32_t reserved;
+} mpqe_gather_item_t;
+MPQE_API int mpqe_gather_multi(const mpqe_gather_item_t* items_host, int32_t n, int32_t backward, void* stream);
+
+/* One formula group of the margin loss (model.py:451-452, 483-485); fields as mpqe_cosine_margin_{fwd,bwd}.
+ * hinge is a [B] scratch array; id_offset is added to the emitted table row ids. */
+typedef struct {
+  const float* q;
+  int64_t B;
+  const float* table;
+  const int64_t* id2row;
+  const int64_t* ids_pos;
+  const int64_t* ids_neg;
+  float* score_pos; /* optional */
+  float* score_neg; /* optional */
+  float* hinge;
+  float* loss;
+  const float* grad_loss;
+  float* dq;
+  float* rows_out;
+  int64_t* rows_id;
+  int64_t id_offset;
+} mpqe_margin_item_t;
+MPQE_API int mpqe_cosine_margin_multi(const mpqe_margin_item_t* items_host, int32_t n, float margin, int32_t backward,
+                                      void* stream);
+
+/* dst[d] += scale * sum over rows of src[r*stride .. +d], items applied in order (bit-reproducible). */
+typedef struct {
+  const float* src;
+  int64_t rows;
+  int64_t stride;
+  float* dst;
+  float scale;
+  int32_t reserved;
+} mpqe_colsum_item_t;
+MPQE_API size_t mpqe_colsum_multi_workspace_bytes(const mpqe_colsum_item_t* items_host, int32_t n);
+MPQE_API int mpqe_colsum_multi(const mpqe_colsum_item_t* items_host, int32_t n, void* workspace, size_t workspace_bytes,
+                               void* stream);
 
 /* ---- a17: rank counts (utils.py:25-32; scipy percentileofscore kind='rank') ------------------------------
  * ragged negatives: left[b] = #(neg < pos[b]), right[b] = #(neg <= pos[b]) over neg[offsets[b]:offsets[b+1]]. */

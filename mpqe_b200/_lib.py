@@ -30,6 +30,28 @@ class WgradOperand(C.Structure):
     _fields_ = [('g', C.c_void_p), ('g_slots', C.c_int32), ('slot_map', C.c_int16 * MAX_SLOTS)]
 
 
+class GatherItem(C.Structure):
+    _fields_ = [('table', C.c_void_p), ('table_rows', C.c_int64), ('id2row', C.c_void_p), ('ids', C.c_void_p),
+                ('ids_stride', C.c_int64), ('count', C.c_int64), ('out', C.c_void_p), ('out_stride', C.c_int64),
+                ('grad', C.c_void_p), ('grad_stride', C.c_int64), ('rows_out', C.c_void_p), ('rows_id', C.c_void_p),
+                ('id_offset', C.c_int64), ('normalize', C.c_int32), ('reserved', C.c_int32)]
+
+
+class MarginItem(C.Structure):
+    _fields_ = [('q', C.c_void_p), ('B', C.c_int64), ('table', C.c_void_p), ('id2row', C.c_void_p),
+                ('ids_pos', C.c_void_p), ('ids_neg', C.c_void_p), ('score_pos', C.c_void_p), ('score_neg', C.c_void_p),
+                ('hinge', C.c_void_p), ('loss', C.c_void_p), ('grad_loss', C.c_void_p), ('dq', C.c_void_p),
+                ('rows_out', C.c_void_p), ('rows_id', C.c_void_p), ('id_offset', C.c_int64)]
+
+
+class ColsumItem(C.Structure):
+    _fields_ = [('src', C.c_void_p), ('rows', C.c_int64), ('stride', C.c_int64), ('dst', C.c_void_p),
+                ('scale', C.c_float), ('reserved', C.c_int32)]
+
+
+MAX_GATHER_ITEMS, MAX_MARGIN_ITEMS, MAX_COLSUM_ITEMS = 32, 8, 64
+ABI_STRUCTS = (Term, LayerGroup, WgradDest, WgradOperand, GatherItem, MarginItem, ColsumItem)
+
 P, I32, I64, F32, SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
 
 # name -> (restype, argtypes); mirrors include/mpqe_b200.h one to one (tests/test_abi.py checks both directions)
@@ -64,6 +86,10 @@ SIGNATURES = {
     'mpqe_sparse_rows_combine': (I32, [P, P, I64, I64, P, P, P, P, SZ, P]),
     'mpqe_scatter_rows': (I32, [P, P, P, I64, P, I32, P]),
     'mpqe_adam_dense': (I32, [P, P, P, P, I64, F32, F32, F32, F32, I32, P]),
+    'mpqe_gather_multi': (I32, [P, I32, I32, P]),
+    'mpqe_cosine_margin_multi': (I32, [P, I32, F32, I32, P]),
+    'mpqe_colsum_multi_workspace_bytes': (SZ, [P, I32]),
+    'mpqe_colsum_multi': (I32, [P, I32, P, SZ, P]),
 }
 
 _lib = None
@@ -86,7 +112,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    for which, struct in enumerate((Term, LayerGroup, WgradDest, WgradOperand)):
+    for which, struct in enumerate(ABI_STRUCTS):
         if lib.mpqe_b200_sizeof(which) != C.sizeof(struct):
             raise MpqeError('ABI mismatch: %s is %d bytes in python, %d in the library'
                             % (struct.__name__, C.sizeof(struct), lib.mpqe_b200_sizeof(which)))

@@ -22,6 +22,9 @@ extern "C" int mpqe_b200_sizeof(int which) {
     case 1: return (int)sizeof(mpqe_layer_group_t);
     case 2: return (int)sizeof(mpqe_wgrad_dest_t);
     case 3: return (int)sizeof(mpqe_wgrad_operand_t);
+    case 4: return (int)sizeof(mpqe_gather_item_t);
+    case 5: return (int)sizeof(mpqe_margin_item_t);
+    case 6: return (int)sizeof(mpqe_colsum_item_t);
     default: return -1;
   }
 }

@@ -100,10 +100,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
-// instruction descriptor: c=f32, a=b=tf32, N=128, M=128; bit15/16 = A/B are MN-major
-constexpr uint32_t IDESC_BASE = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
-constexpr uint32_t IDESC_A_K_B_MN = IDESC_BASE | (1u << 16);
-constexpr uint32_t IDESC_A_MN_B_MN = IDESC_BASE | (1u << 15) | (1u << 16);
+// instruction descriptor: c=f32, a=b=tf32 (both K-major: bits 15/16 clear), N=128, M=128
+constexpr uint32_t IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
 __device__ __forceinline__ void split_tf32(const float4& x, float4& hi, float4& lo) {
   uint32_t h0, h1, h2, h3;
@@ -115,11 +113,12 @@ __device__ __forceinline__ void split_tf32(const float4& x, float4& hi, float4& 
   lo = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
 }
 
-// K-major operand tile [128 rows][32 k]: element (row, k) at (row/8)*1024 + (k/4)*128 + (row%8)*16 + (k%4)*4 bytes.
-//   descriptor for k-step j (k = 8j..8j+7): start + j*256, LBO = 128 (next 4 k), SBO = 1024 (next 8 rows)
-// MN-major operand tile [32 k][128 mn]: element (k, mn) at (k/8)*4096 + (mn/4)*128 + (k%8)*16 + (mn%4)*4 bytes.
-//   descriptor for k-step j: start + j*4096, SBO = 128 (next 4 mn), LBO = 4096 (next 8 k)
-// Each warp instruction below writes 512 contiguous bytes.
+// Every operand tile is K-major [128 rows][32 k]: element (row, k) at (row/8)*1024 + (k/4)*128 + (row%8)*16 + (k%4)*4
+// bytes; descriptor for k-step j (k = 8j..8j+7): start + j*256, LBO = 128 (next 4 k), SBO = 1024 (next 8 rows).
+// (Probed on B200 with tests/tc_probe.cu: K-major no-swizzle tf32 operands are exact, MN-major ones yield zeros.)
+// Sources whose contiguous dimension is the tile's ROW dimension (weight matrices [k][n], and both operands of the
+// weight gradient) are transposed on the way into shared memory with 4-byte stores whose component order is rotated
+// per lane so that each warp instruction hits 32 distinct banks.
 
 struct Frag {  // one pipeline stage worth of one operand, per thread
   float4 v[4];
@@ -149,25 +148,38 @@ __device__ __forceinline__ void store_kmajor(const Frag& f, uint8_t* hi_tile, ui
     *reinterpret_cast<float4*>(lo_tile + off) = lo;
   }
 }
-// MN-major tile from a row-major [k][128] source with row pitch `pitch` floats: idx -> k block idx/8, mn block idx%8
-__device__ __forceinline__ void load_mnmajor(Frag& f, const float* src, int64_t pitch, int warp, int lane) {
+// Transposing stage: source is row-major [32 k][128 mn] (pitch floats between k rows); the tile wants mn as rows.
+//   instr t = warp*4+i: k half = t&1, mn4 pair = t>>1;  lane: k = 16*(t&1) + 4*r + (lane&3), r = (lane>>2)&3,
+//   mn4 = 2*(t>>1) + (lane>>4).  Loads: 32 contiguous bytes per k row (full sectors).
+__device__ __forceinline__ void load_transposed(Frag& f, const float* src, int64_t pitch, int k_valid, int warp,
+                                                int lane) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int idx = warp * 4 + i;
-    const int k = (idx >> 3) * 8 + (lane & 7);
-    const int mn4 = (idx & 7) * 4 + (lane >> 3);
-    f.v[i] = *reinterpret_cast<const float4*>(src + k * pitch + mn4 * 4);
+    const int t = warp * 4 + i;
+    const int k = 16 * (t & 1) + 4 * ((lane >> 2) & 3) + (lane & 3);
+    const int mn4 = 2 * (t >> 1) + (lane >> 4);
+    f.v[i] = k < k_valid ? *reinterpret_cast<const float4*>(src + k * pitch + mn4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
-__device__ __forceinline__ void store_mnmajor(const Frag& f, uint8_t* hi_tile, uint8_t* lo_tile, int warp, int lane) {
+__device__ __forceinline__ void store_transposed(const Frag& f, uint8_t* hi_tile, uint8_t* lo_tile, int warp, int lane) {
+  const int r = (lane >> 2) & 3;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int idx = warp * 4 + i;
-    const int off = (idx >> 3) * 4096 + ((idx & 7) * 4 + (lane >> 3)) * 128 + (lane & 7) * 16;
+    const int t = warp * 4 + i;
+    const int k = 16 * (t & 1) + 4 * r + (lane & 3);
+    const int mn4 = 2 * (t >> 1) + (lane >> 4);
     float4 hi, lo;
     split_tf32(f.v[i], hi, lo);
-    *reinterpret_cast<float4*>(hi_tile + off) = hi;
-    *reinterpret_cast<float4*>(lo_tile + off) = lo;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = (j + r) & 3;  // rotated component order: bank = ((mn%8)*4 + k%4) is distinct across the warp
+      const int mn = mn4 * 4 + c;
+      const int off = (mn >> 3) * 1024 + (k >> 2) * 128 + (mn & 7) * 16 + (k & 3) * 4;
+      const float h = c == 0 ? hi.x : c == 1 ? hi.y : c == 2 ? hi.z : hi.w;
+      const float l = c == 0 ? lo.x : c == 1 ? lo.y : c == 2 ? lo.z : lo.w;
+      *reinterpret_cast<float*>(hi_tile + off) = h;
+      *reinterpret_cast<float*>(lo_tile + off) = l;
+    }
   }
 }
 
@@ -183,18 +195,16 @@ __device__ __forceinline__ uint8_t* align_1024(uint8_t* p) {
   return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023));
 }
 
-// issue the 3xTF32 products of one stage: 4 k-steps x (hi*hi, lo*hi, hi*lo)
+// issue the 3xTF32 products of one stage: 4 k-steps x (lo*hi, hi*lo, hi*hi), small products first
 __device__ __forceinline__ void issue_stage(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
-                                            bool a_kmajor, uint32_t idesc, bool first) {
+                                            bool first) {
 #pragma unroll
   for (int j = 0; j < KC / 8; ++j) {
-    const uint32_t aoff = a_kmajor ? j * 256 : j * 4096;
-    const uint32_t albo = a_kmajor ? 128 : 4096, asbo = a_kmajor ? 1024 : 128;
-    const uint64_t dah = make_desc(a_hi + aoff, albo, asbo), dal = make_desc(a_lo + aoff, albo, asbo);
-    const uint64_t dbh = make_desc(b_hi + j * 4096, 4096, 128), dbl = make_desc(b_lo + j * 4096, 4096, 128);
-    umma_tf32(tmem_d, dal, dbh, idesc, (first && j == 0) ? 0u : 1u);  // small products first
-    umma_tf32(tmem_d, dah, dbl, idesc, 1u);
-    umma_tf32(tmem_d, dah, dbh, idesc, 1u);
+    const uint64_t dah = make_desc(a_hi + j * 256, 128, 1024), dal = make_desc(a_lo + j * 256, 128, 1024);
+    const uint64_t dbh = make_desc(b_hi + j * 256, 128, 1024), dbl = make_desc(b_lo + j * 256, 128, 1024);
+    umma_tf32(tmem_d, dal, dbh, IDESC_TF32, (first && j == 0) ? 0u : 1u);
+    umma_tf32(tmem_d, dah, dbl, IDESC_TF32, 1u);
+    umma_tf32(tmem_d, dah, dbh, IDESC_TF32, 1u);
   }
 }
 
@@ -238,7 +248,7 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc_kernel(const __grid_const
     const mpqe_term_t& T = G.terms[sh.term[step / (D / KC)]];
     const int kc = (step % (D / KC)) * KC;
     load_kmajor(fa, T, q0, B, kc, warp, lane);
-    load_mnmajor(fb, T.m + (int64_t)kc * D, D, warp, lane);
+    load_transposed(fb, T.m + (int64_t)kc * D, D, KC, warp, lane);
   };
   if (nsteps > 0) load_step(0);
   for (int step = 0; step < nsteps; ++step) {
@@ -246,14 +256,14 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc_kernel(const __grid_const
     uint8_t* st = smem + s * STAGE_BYTES;
     if (u > 0) mbar_wait(smem_u32(&sh.empty[s]), (u - 1) & 1);  // MMAs that read this stage have completed
     store_kmajor(fa, st, st + TILE_BYTES, warp, lane);
-    store_mnmajor(fb, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, warp, lane);
+    store_transposed(fb, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, warp, lane);
     if (step + 1 < nsteps) load_step(step + 1);  // global loads of the next stage fly while this one is multiplied
     fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
       const uint32_t a = smem_u32(st);
-      issue_stage(tmem, a, a + TILE_BYTES, a + 2 * TILE_BYTES, a + 3 * TILE_BYTES, true, IDESC_A_K_B_MN, step == 0);
+      issue_stage(tmem, a, a + TILE_BYTES, a + 2 * TILE_BYTES, a + 3 * TILE_BYTES, step == 0);
       umma_commit(smem_u32(&sh.empty[s]));
       if (step == nsteps - 1) umma_commit(smem_u32(&sh.done));
     }
@@ -305,7 +315,7 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc_kernel(const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Weight gradient on tensor cores: dM = sum_q A[q]^T G[q]; both operands are MN-major (features contiguous).
+// Weight gradient on tensor cores: dM = sum_q A[q]^T G[q]; both operands are transposed into K-major tiles.
 // ------------------------------------------------------------------------------------------------------------
 struct WgradIter {
   int g, t;
@@ -331,19 +341,6 @@ __device__ __forceinline__ bool wgrad_seek(const WgradLaunch& L, const float* m_
     }
   }
   return false;
-}
-
-// 32 query rows x 128 features, zero beyond qe; idx -> k(block of 8 queries) idx/8, feature block idx%8
-__device__ __forceinline__ void load_rows_mn(Frag& f, const float* base, int64_t slots, int slot, int64_t q0, int64_t qe,
-                                             int warp, int lane) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int idx = warp * 4 + i;
-    const int64_t q = q0 + (idx >> 3) * 8 + (lane & 7);
-    const int mn4 = (idx & 7) * 4 + (lane >> 3);
-    f.v[i] = q < qe ? *reinterpret_cast<const float4*>(base + (q * slots + slot) * (int64_t)D + mn4 * 4)
-                    : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
 }
 
 __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_constant__ WgradLaunch L) {
@@ -378,8 +375,10 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
     const mpqe_layer_group_t& G = L.g[it.g];
     const mpqe_term_t& T = G.terms[it.t];
     const mpqe_wgrad_operand_t& O = L.go[it.g];
-    load_rows_mn(fa, T.a, T.a_slots, T.a_slot, it.q, it.qe, warp, lane);
-    load_rows_mn(fb, O.g, O.g_slots, O.slot_map[T.out_slot], it.q, it.qe, warp, lane);
+    const int valid = (int)(it.qe - it.q < KC ? it.qe - it.q : KC);
+    load_transposed(fa, T.a + (it.q * T.a_slots + T.a_slot) * (int64_t)D, (int64_t)T.a_slots * D, valid, warp, lane);
+    const int gs = O.slot_map[T.out_slot];
+    load_transposed(fb, O.g + (it.q * O.g_slots + gs) * (int64_t)D, (int64_t)O.g_slots * D, valid, warp, lane);
     it.q += KC;
     if (it.q >= it.qe) {
       ++it.t;
@@ -393,8 +392,8 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
     const int s = step % STAGES, u = step / STAGES;
     uint8_t* st = smem + s * STAGE_BYTES;
     if (u > 0) mbar_wait(smem_u32(&sh.empty[s]), (u - 1) & 1);
-    store_mnmajor(fa, st, st + TILE_BYTES, warp, lane);
-    store_mnmajor(fb, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, warp, lane);
+    store_transposed(fa, st, st + TILE_BYTES, warp, lane);
+    store_transposed(fb, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, warp, lane);
     have = more;
     if (have) load_next();
     fence_proxy_async();
@@ -402,7 +401,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
     if (tid == 0) {
       tc_fence_after();
       const uint32_t a = smem_u32(st);
-      issue_stage(tmem, a, a + TILE_BYTES, a + 2 * TILE_BYTES, a + 3 * TILE_BYTES, false, IDESC_A_MN_B_MN, step == 0);
+      issue_stage(tmem, a, a + TILE_BYTES, a + 2 * TILE_BYTES, a + 3 * TILE_BYTES, step == 0);
       umma_commit(smem_u32(&sh.empty[s]));
       if (!have) umma_commit(smem_u32(&sh.done));
     }

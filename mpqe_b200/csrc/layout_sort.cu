@@ -28,76 +28,92 @@ __global__ void build_query_graph_kernel(int n, int E, int64_t B, int4 src, int4
   if (i < B * n) batch[i] = i / n;
 }
 
-// ---- stable LSD radix pass (8-bit digit), one warp per chunk of SORT_CHUNK elements ------------------------
-constexpr int SORT_CHUNK = 1024;
+// ---- stable LSD radix sort: digits of up to 10 bits, one WARP per chunk of 256 keys --------------------------
+// Per pass: (1) per-chunk digit histogram, (2) exclusive scan of the [bin][chunk] table, done as one warp per bin
+// row + one small block over the bin totals, (3) stable scatter (lane order inside a round via match_any, rounds and
+// chunks in order).  Small chunks keep >= 500 warps busy at the ~1e5 keys of a training step.
+constexpr int SORT_CHUNK = 256;
 constexpr int SORT_WARPS = 8;
-constexpr int BINS = 256;
+constexpr int MAX_BINS = 1024;
 
-__device__ __forceinline__ unsigned digit_of(uint32_t key, int shift) { return (key >> shift) & 0xffu; }
+__device__ __forceinline__ unsigned digit_of(uint32_t key, int shift, unsigned mask) { return (key >> shift) & mask; }
 
-// hist[bin * nchunks + chunk] = #elements of the chunk with that digit
 __global__ void __launch_bounds__(SORT_WARPS * 32) radix_hist_kernel(const uint32_t* __restrict__ keys, int64_t n,
-                                                                     int shift, int nchunks,
+                                                                     int shift, int bins, int nchunks,
                                                                      int32_t* __restrict__ hist) {
-  __shared__ int cnt[SORT_WARPS][BINS];
+  __shared__ int cnt[SORT_WARPS][MAX_BINS];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunk = blockIdx.x * SORT_WARPS + w;
-  for (int b = lane; b < BINS; b += 32) cnt[w][b] = 0;
+  for (int b = lane; b < bins; b += 32) cnt[w][b] = 0;
   __syncwarp();
   if (chunk < nchunks) {
     const int64_t i0 = (int64_t)chunk * SORT_CHUNK;
+#pragma unroll
     for (int r = 0; r < SORT_CHUNK; r += 32) {
       const int64_t i = i0 + r + lane;
-      if (i < n) atomicAdd(&cnt[w][digit_of(keys[i], shift)], 1);
+      if (i < n) atomicAdd(&cnt[w][digit_of(keys[i], shift, bins - 1)], 1);
     }
     __syncwarp();
-    for (int b = lane; b < BINS; b += 32) hist[(int64_t)b * nchunks + chunk] = cnt[w][b];
+    for (int b = lane; b < bins; b += 32) hist[(int64_t)b * nchunks + chunk] = cnt[w][b];
   }
 }
 
-// single-CTA exclusive scan (int32) of n entries; total written to *total (optional)
-__global__ void __launch_bounds__(1024) exclusive_scan_kernel(int32_t* __restrict__ data, int64_t n,
-                                                              int64_t* __restrict__ total) {
-  __shared__ int64_t part[1024];
+// one warp per bin: exclusive scan of the bin's per-chunk counts, total to bin_total[bin]
+__global__ void __launch_bounds__(256) radix_row_scan_kernel(int32_t* __restrict__ hist, int bins, int nchunks,
+                                                             int32_t* __restrict__ bin_total) {
+  const int lane = threadIdx.x & 31;
+  const int bin = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (bin >= bins) return;
+  int32_t* row = hist + (int64_t)bin * nchunks;
+  int run = 0;
+  for (int c0 = 0; c0 < nchunks; c0 += 32) {
+    const int c = c0 + lane;
+    const int v = c < nchunks ? row[c] : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (c < nchunks) row[c] = run + incl - v;
+    run += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (lane == 0) bin_total[bin] = run;
+}
+
+// single block: exclusive scan of the (<= 1024) bin totals, in place
+__global__ void __launch_bounds__(MAX_BINS) radix_bin_scan_kernel(int32_t* __restrict__ bin_total, int bins) {
+  __shared__ int s[MAX_BINS];
   const int t = threadIdx.x;
-  const int64_t per = (n + 1023) / 1024;
-  const int64_t i0 = per * t;
-  const int64_t i1 = i0 + per < n ? i0 + per : n;
-  int64_t s = 0;
-  for (int64_t i = i0; i < i1; ++i) s += data[i];
-  part[t] = s;
+  const int v = t < bins ? bin_total[t] : 0;
+  s[t] = v;
   __syncthreads();
-  for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan of the per-thread sums
-    const int64_t v = t >= o ? part[t - o] : 0;
+  for (int o = 1; o < MAX_BINS; o <<= 1) {
+    const int a = t >= o ? s[t - o] : 0;
     __syncthreads();
-    part[t] += v;
+    s[t] += a;
     __syncthreads();
   }
-  int64_t run = t == 0 ? 0 : part[t - 1];
-  for (int64_t i = i0; i < i1; ++i) {
-    const int32_t v = data[i];
-    data[i] = (int32_t)run;
-    run += v;
-  }
-  if (total != nullptr && t == 1023) *total = part[1023];
+  if (t < bins) bin_total[t] = s[t] - v;
 }
 
-// scatter: stable within chunk (lanes in order, rounds in order), chunks in order via the scanned histogram
 __global__ void __launch_bounds__(SORT_WARPS * 32) radix_scatter_kernel(
-    const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, int64_t n, int shift, int nchunks,
-    const int32_t* __restrict__ base, uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
-  __shared__ int run[SORT_WARPS][BINS];
+    const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, int64_t n, int shift, int bins,
+    int nchunks, const int32_t* __restrict__ hist, const int32_t* __restrict__ bin_base,
+    uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
+  __shared__ int run[SORT_WARPS][MAX_BINS];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunk = blockIdx.x * SORT_WARPS + w;
   if (chunk >= nchunks) return;
-  for (int b = lane; b < BINS; b += 32) run[w][b] = base[(int64_t)b * nchunks + chunk];
+  for (int b = lane; b < bins; b += 32) run[w][b] = bin_base[b] + hist[(int64_t)b * nchunks + chunk];
   __syncwarp();
   const int64_t i0 = (int64_t)chunk * SORT_CHUNK;
+#pragma unroll 1
   for (int r = 0; r < SORT_CHUNK; r += 32) {
     const int64_t i = i0 + r + lane;
     const bool ok = i < n;
     const uint32_t key = ok ? keys_in[i] : 0u;
-    const unsigned dg = ok ? digit_of(key, shift) : 0x100u + lane;  // inactive lanes match nobody
+    const unsigned dg = ok ? digit_of(key, shift, bins - 1) : 0x10000u + lane;  // inactive lanes match nobody
     const unsigned peers = __match_any_sync(0xffffffffu, dg);
     const int rank = __popc(peers & ((1u << lane) - 1u));
     int pos = 0;
@@ -137,7 +153,7 @@ __global__ void segment_offsets_kernel(const uint32_t* __restrict__ sorted, int6
 
 struct SortBuffers {
   uint32_t *k0, *v0, *k1, *v1;
-  int32_t* hist;
+  int32_t *hist, *bin_total;
   int nchunks;
   size_t bytes;
 };
@@ -153,21 +169,29 @@ SortBuffers carve_sort(void* ws, int64_t n) {
   s.v0 = (uint32_t*)(p + off); off += arr;
   s.k1 = (uint32_t*)(p + off); off += arr;
   s.v1 = (uint32_t*)(p + off); off += arr;
-  s.hist = (int32_t*)(p + off); off += align_up((size_t)BINS * s.nchunks * sizeof(int32_t), 256);
+  s.hist = (int32_t*)(p + off); off += align_up((size_t)MAX_BINS * s.nchunks * sizeof(int32_t), 256);
+  s.bin_total = (int32_t*)(p + off); off += align_up((size_t)MAX_BINS * sizeof(int32_t), 256);
   s.bytes = off;
   return s;
 }
 
-// sorts (k0 -> result) with `passes` 8-bit digits; result ends in (*rk, *rv)
-int radix_sort(SortBuffers& s, int64_t n, int passes, cudaStream_t st, uint32_t** rk, uint32_t** rv) {
+// sorts k0 by the low `key_bits` bits; result ends in (*rk, *rv)
+int radix_sort(SortBuffers& s, int64_t n, int key_bits, cudaStream_t st, uint32_t** rk, uint32_t** rv) {
+  if (key_bits < 1) key_bits = 1;
+  const int passes = (key_bits + 9) / 10;
+  const int digit_bits = (key_bits + passes - 1) / passes;
+  const int bins = 1 << digit_bits;
   uint32_t *ki = s.k0, *vi = nullptr, *ko = s.k1, *vo = s.v1;
   const int blocks = (s.nchunks + SORT_WARPS - 1) / SORT_WARPS;
   for (int p = 0; p < passes; ++p) {
-    radix_hist_kernel<<<blocks, SORT_WARPS * 32, 0, st>>>(ki, n, 8 * p, s.nchunks, s.hist);
+    radix_hist_kernel<<<blocks, SORT_WARPS * 32, 0, st>>>(ki, n, digit_bits * p, bins, s.nchunks, s.hist);
     MPQE_CHECK_LAUNCH("radix_hist_kernel");
-    exclusive_scan_kernel<<<1, 1024, 0, st>>>(s.hist, (int64_t)BINS * s.nchunks, nullptr);
-    MPQE_CHECK_LAUNCH("exclusive_scan_kernel");
-    radix_scatter_kernel<<<blocks, SORT_WARPS * 32, 0, st>>>(ki, vi, n, 8 * p, s.nchunks, s.hist, ko, vo);
+    radix_row_scan_kernel<<<(bins + 7) / 8, 256, 0, st>>>(s.hist, bins, s.nchunks, s.bin_total);
+    MPQE_CHECK_LAUNCH("radix_row_scan_kernel");
+    radix_bin_scan_kernel<<<1, MAX_BINS, 0, st>>>(s.bin_total, bins);
+    MPQE_CHECK_LAUNCH("radix_bin_scan_kernel");
+    radix_scatter_kernel<<<blocks, SORT_WARPS * 32, 0, st>>>(ki, vi, n, digit_bits * p, bins, s.nchunks, s.hist,
+                                                            s.bin_total, ko, vo);
     MPQE_CHECK_LAUNCH("radix_scatter_kernel");
     uint32_t* tk = ki; ki = ko; ko = tk;
     uint32_t* tv = (vi == nullptr) ? s.v0 : vi; vi = vo; vo = tv;
@@ -177,13 +201,40 @@ int radix_sort(SortBuffers& s, int64_t n, int passes, cudaStream_t st, uint32_t*
   return 0;
 }
 
-int digits_for(int64_t max_key_exclusive) {
-  int passes = 1;
-  while (passes < 4 && (1ll << (8 * passes)) < max_key_exclusive) ++passes;
-  return passes;
+int bits_for(int64_t max_key_exclusive) {
+  int bits = 1;
+  while (bits < 32 && (1ll << bits) < max_key_exclusive) ++bits;
+  return bits;
 }
 
 // ---- row-sparse combine -----------------------------------------------------------------------------------
+// single-CTA exclusive scan (int32) of n entries; total written to *total
+__global__ void __launch_bounds__(1024) exclusive_scan_kernel(int32_t* __restrict__ data, int64_t n,
+                                                              int64_t* __restrict__ total) {
+  __shared__ int64_t part[1024];
+  const int t = threadIdx.x;
+  const int64_t per = (n + 1023) / 1024;
+  const int64_t i0 = per * t;
+  const int64_t i1 = i0 + per < n ? i0 + per : n;
+  int64_t s = 0;
+  for (int64_t i = i0; i < i1; ++i) s += data[i];
+  part[t] = s;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const int64_t v = t >= o ? part[t - o] : 0;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  int64_t run = t == 0 ? 0 : part[t - 1];
+  for (int64_t i = i0; i < i1; ++i) {
+    const int32_t v = data[i];
+    data[i] = (int32_t)run;
+    run += v;
+  }
+  if (total != nullptr && t == 1023) *total = part[1023];
+}
+
 __global__ void head_flags_kernel(const uint32_t* __restrict__ sorted, int64_t n, int32_t* __restrict__ flags) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) flags[i] = (i == 0 || sorted[i] != sorted[i - 1]) ? 1 : 0;
@@ -286,7 +337,7 @@ extern "C" int mpqe_relation_sort(const int64_t* edge_type, int64_t num_edges, i
   narrow_keys_kernel<<<blocks_for(num_edges, 256), 256, 0, st>>>(edge_type, num_edges, s.k0);
   MPQE_CHECK_LAUNCH("narrow_keys_kernel");
   uint32_t *rk, *rv;
-  if (radix_sort(s, num_edges, digits_for(num_relations), st, &rk, &rv)) return 2;
+  if (radix_sort(s, num_edges, bits_for(num_relations), st, &rk, &rv)) return 2;
   widen_vals_kernel<<<blocks_for(num_edges, 256), 256, 0, st>>>(rv, num_edges, perm);
   MPQE_CHECK_LAUNCH("widen_vals_kernel");
   segment_offsets_kernel<<<blocks_for(num_relations + 1, 256), 256, 0, st>>>(rk, num_edges, num_relations, seg_offsets);
@@ -314,7 +365,7 @@ extern "C" int mpqe_sparse_rows_combine(const int64_t* rows_id, const float* row
   narrow_keys_kernel<<<blocks_for(count, 256), 256, 0, st>>>(rows_id, count, s.k0);
   MPQE_CHECK_LAUNCH("narrow_keys_kernel");
   uint32_t *rk, *rv;
-  if (radix_sort(s, count, digits_for(table_rows), st, &rk, &rv)) return 2;
+  if (radix_sort(s, count, bits_for(table_rows), st, &rk, &rv)) return 2;
   head_flags_kernel<<<blocks_for(count, 256), 256, 0, st>>>(rk, count, uid);
   MPQE_CHECK_LAUNCH("head_flags_kernel");
   exclusive_scan_kernel<<<1, 1024, 0, st>>>(uid, count, num_unique);

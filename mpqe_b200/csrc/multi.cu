@@ -1,0 +1,295 @@
+// Multi-item versions of the HBM-bound row kernels: one launch serves every formula group of a training step.
+//
+// A step touches up to 7 query types x (<=3 anchor slots + <=3 variable slots + positive + negative rows); launching
+// one small kernel per (group, slot) made the step launch-bound (166 launches / 3.6 ms in the first B200 profile,
+// profiles/r01_launches_simt_v1.csv).  Here the per-(group, slot) work items travel in the kernel parameter block
+// and every warp finds its item from a prefix over the item counts.  Arithmetic per row is identical to the
+// single-item kernels in gather_score.cu (shared device code in rowops.cuh); reference call sites as listed there.
+#include "rowops.cuh"
+
+namespace mpqe {
+namespace {
+
+struct GatherLaunch {
+  int n;
+  mpqe_gather_item_t it[MPQE_MAX_GATHER_ITEMS];
+};
+struct MarginLaunch {
+  int n;
+  float margin;
+  mpqe_margin_item_t it[MPQE_MAX_MARGIN_ITEMS];
+};
+struct ColsumLaunch {
+  int n;
+  float* partials;  // [total blocks][D]
+  float* totals;    // [n][D]
+  mpqe_colsum_item_t it[MPQE_MAX_COLSUM_ITEMS];
+};
+
+template <class Launch>
+__device__ __forceinline__ bool find_item(const Launch& L, int64_t w, int& item, int64_t& local) {
+  for (int i = 0; i < L.n; ++i) {
+    const int64_t c = L.it[i].count;
+    if (w < c) {
+      item = i;
+      local = w;
+      return true;
+    }
+    w -= c;
+  }
+  return false;
+}
+
+__global__ void __launch_bounds__(ROW_THREADS) gather_fwd_multi_kernel(const __grid_constant__ GatherLaunch L) {
+  const int lane = threadIdx.x & 31;
+  int item;
+  int64_t i;
+  if (!find_item(L, (int64_t)blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5), item, i)) return;
+  const mpqe_gather_item_t& T = L.it[item];
+  const int64_t row = resolve_row(T.id2row, T.ids, T.ids_stride, i);
+  float4 y;
+  if (row < 0 || row >= T.table_rows) {
+    y = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F);
+  } else if (T.normalize) {
+    normalize_row(T.table, row, lane, y);
+  } else {
+    y = *reinterpret_cast<const float4*>(T.table + row * D + lane * 4);
+  }
+  *reinterpret_cast<float4*>(T.out + i * T.out_stride + lane * 4) = y;
+}
+
+__global__ void __launch_bounds__(ROW_THREADS) gather_bwd_multi_kernel(const __grid_constant__ GatherLaunch L) {
+  const int lane = threadIdx.x & 31;
+  int item;
+  int64_t i;
+  if (!find_item(L, (int64_t)blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5), item, i)) return;
+  const mpqe_gather_item_t& T = L.it[item];
+  const int64_t row = resolve_row(T.id2row, T.ids, T.ids_stride, i);
+  float4 y;
+  const float nrm = normalize_row(T.table, row, lane, y);
+  const float4 g = *reinterpret_cast<const float4*>(T.grad + i * T.grad_stride + lane * 4);
+  *reinterpret_cast<float4*>(T.rows_out + i * D + lane * 4) = normalize_bwd(g, y, nrm);
+  if (lane == 0) T.rows_id[i] = row + T.id_offset;
+}
+
+template <class Launch>
+__device__ __forceinline__ bool find_query(const Launch& L, int64_t w, int& item, int64_t& local) {
+  for (int i = 0; i < L.n; ++i) {
+    const int64_t c = L.it[i].B;
+    if (w < c) {
+      item = i;
+      local = w;
+      return true;
+    }
+    w -= c;
+  }
+  return false;
+}
+
+__global__ void __launch_bounds__(ROW_THREADS) margin_fwd_multi_kernel(const __grid_constant__ MarginLaunch L) {
+  const int lane = threadIdx.x & 31;
+  int item;
+  int64_t b;
+  if (!find_query(L, (int64_t)blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5), item, b)) return;
+  const mpqe_margin_item_t& T = L.it[item];
+  const float4 qv = *reinterpret_cast<const float4*>(T.q + b * D + lane * 4);
+  float4 yp, yn;
+  normalize_row(T.table, resolve_row(T.id2row, T.ids_pos, 1, b), lane, yp);
+  normalize_row(T.table, resolve_row(T.id2row, T.ids_neg, 1, b), lane, yn);
+  const float sp = cosine(qv, yp).score, sn = cosine(qv, yn).score;
+  if (lane == 0) {
+    if (T.score_pos != nullptr) T.score_pos[b] = sp;
+    if (T.score_neg != nullptr) T.score_neg[b] = sn;
+    T.hinge[b] = fmaxf(L.margin - (sp - sn), 0.f);
+  }
+}
+
+// deterministic mean per item: fixed strided partials per thread + fixed tree (same order as the single-item kernel)
+__global__ void __launch_bounds__(1024) margin_mean_multi_kernel(const __grid_constant__ MarginLaunch L) {
+  __shared__ float s[1024];
+  const mpqe_margin_item_t& T = L.it[blockIdx.x];
+  float acc = 0.f;
+  for (int64_t i = threadIdx.x; i < T.B; i += 1024) acc += T.hinge[i];
+  s[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) T.loss[0] = s[0] / (float)T.B;
+}
+
+__global__ void __launch_bounds__(ROW_THREADS) margin_bwd_multi_kernel(const __grid_constant__ MarginLaunch L) {
+  const int lane = threadIdx.x & 31;
+  int item;
+  int64_t b;
+  if (!find_query(L, (int64_t)blockIdx.x * (ROW_THREADS / 32) + (threadIdx.x >> 5), item, b)) return;
+  const mpqe_margin_item_t& T = L.it[item];
+  const int64_t B = T.B;
+  const float4 qv = *reinterpret_cast<const float4*>(T.q + b * D + lane * 4);
+  const int64_t rp = resolve_row(T.id2row, T.ids_pos, 1, b), rn = resolve_row(T.id2row, T.ids_neg, 1, b);
+  float4 yp, yn;
+  const float np_ = normalize_row(T.table, rp, lane, yp);
+  const float nn_ = normalize_row(T.table, rn, lane, yn);
+  const Cos cp = cosine(qv, yp), cn = cosine(qv, yn);
+  const float active = (L.margin - (cp.score - cn.score)) >= 0.f ? 1.f : 0.f;
+  const float g = active * T.grad_loss[0] / (float)B;
+  float4 dqp, dyp, dqn, dyn;
+  cosine_bwd(qv, yp, cp, -g, dqp, dyp);
+  cosine_bwd(qv, yn, cn, g, dqn, dyn);
+  *reinterpret_cast<float4*>(T.dq + b * D + lane * 4) =
+      make_float4(dqp.x + dqn.x, dqp.y + dqn.y, dqp.z + dqn.z, dqp.w + dqn.w);
+  *reinterpret_cast<float4*>(T.rows_out + b * D + lane * 4) = normalize_bwd(dyp, yp, np_);
+  *reinterpret_cast<float4*>(T.rows_out + (B + b) * D + lane * 4) = normalize_bwd(dyn, yn, nn_);
+  if (lane == 0) {
+    T.rows_id[b] = rp + T.id_offset;
+    T.rows_id[B + b] = rn + T.id_offset;
+  }
+}
+
+// ---- column sums of many sources in three launches ------------------------------------------------------------
+constexpr int CS_ROWS = 128;  // rows per CTA (8 warps x 16 rows)
+
+__device__ __forceinline__ int64_t cs_blocks(int64_t rows) { return (rows + CS_ROWS - 1) / CS_ROWS; }
+
+__global__ void __launch_bounds__(256) colsum_partial_multi_kernel(const __grid_constant__ ColsumLaunch L) {
+  __shared__ float4 red[8][32];
+  int64_t blk = blockIdx.x;
+  int item = 0;
+  for (; item < L.n - 1; ++item) {
+    const int64_t nb = cs_blocks(L.it[item].rows);
+    if (blk < nb) break;
+    blk -= nb;
+  }
+  const mpqe_colsum_item_t& T = L.it[item];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r0 = blk * CS_ROWS;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int k = 0; k < CS_ROWS / 8; ++k) {  // fixed row order per warp, fixed warp order below: bit-reproducible
+    const int64_t r = r0 + warp + 8 * k;
+    if (r < T.rows) {
+      const float4 v = *reinterpret_cast<const float4*>(T.src + r * T.stride + lane * 4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  red[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0) {
+    float4 s = red[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) {
+      const float4 v = red[w][lane];
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    *reinterpret_cast<float4*>(L.partials + (int64_t)blockIdx.x * D + lane * 4) = s;
+  }
+}
+
+__global__ void __launch_bounds__(128) colsum_item_multi_kernel(const __grid_constant__ ColsumLaunch L) {
+  const int item = blockIdx.x;
+  int64_t base = 0;
+  for (int i = 0; i < item; ++i) base += cs_blocks(L.it[i].rows);
+  const int64_t nb = cs_blocks(L.it[item].rows);
+  float s = 0.f;
+  for (int64_t b = 0; b < nb; ++b) s += L.partials[(base + b) * D + threadIdx.x];
+  L.totals[(int64_t)item * D + threadIdx.x] = s * L.it[item].scale;
+}
+
+__global__ void __launch_bounds__(128) colsum_apply_multi_kernel(const __grid_constant__ ColsumLaunch L) {
+  for (int i = 0; i < L.n; ++i)  // item order: several items may accumulate into the same destination
+    L.it[i].dst[threadIdx.x] += L.totals[(int64_t)i * D + threadIdx.x];
+}
+
+}  // namespace
+}  // namespace mpqe
+
+using namespace mpqe;
+
+extern "C" int mpqe_gather_multi(const mpqe_gather_item_t* items_host, int32_t n, int32_t backward, void* stream) {
+  MPQE_CHECK_ARG(items_host != nullptr && n >= 1 && n <= MPQE_MAX_GATHER_ITEMS, "mpqe_gather_multi: n must be in [1,%d]",
+                 MPQE_MAX_GATHER_ITEMS);
+  static thread_local GatherLaunch L;
+  L.n = n;
+  int64_t total = 0;
+  for (int i = 0; i < n; ++i) {
+    const mpqe_gather_item_t& T = items_host[i];
+    MPQE_CHECK_ARG(T.table && T.ids && T.count >= 0 && T.ids_stride >= 0, "mpqe_gather_multi: item %d: bad argument", i);
+    if (backward)
+      MPQE_CHECK_ARG(T.grad && T.rows_out && T.rows_id && T.grad_stride >= D, "mpqe_gather_multi: item %d: bad bwd argument", i);
+    else
+      MPQE_CHECK_ARG(T.out && T.out_stride >= D, "mpqe_gather_multi: item %d: bad fwd argument", i);
+    L.it[i] = T;
+    total += T.count;
+  }
+  if (total == 0) return 0;
+  if (backward)
+    gather_bwd_multi_kernel<<<row_blocks(total), ROW_THREADS, 0, (cudaStream_t)stream>>>(L);
+  else
+    gather_fwd_multi_kernel<<<row_blocks(total), ROW_THREADS, 0, (cudaStream_t)stream>>>(L);
+  MPQE_CHECK_LAUNCH("gather_multi_kernel");
+  return 0;
+}
+
+extern "C" int mpqe_cosine_margin_multi(const mpqe_margin_item_t* items_host, int32_t n, float margin, int32_t backward,
+                                        void* stream) {
+  MPQE_CHECK_ARG(items_host != nullptr && n >= 1 && n <= MPQE_MAX_MARGIN_ITEMS,
+                 "mpqe_cosine_margin_multi: n must be in [1,%d]", MPQE_MAX_MARGIN_ITEMS);
+  static thread_local MarginLaunch L;
+  L.n = n;
+  L.margin = margin;
+  int64_t total = 0;
+  for (int i = 0; i < n; ++i) {
+    const mpqe_margin_item_t& T = items_host[i];
+    MPQE_CHECK_ARG(T.q && T.table && T.ids_pos && T.ids_neg && T.B >= 1, "mpqe_cosine_margin_multi: item %d: bad argument", i);
+    if (backward)
+      MPQE_CHECK_ARG(T.grad_loss && T.dq && T.rows_out && T.rows_id, "mpqe_cosine_margin_multi: item %d: bad bwd argument", i);
+    else
+      MPQE_CHECK_ARG(T.hinge && T.loss, "mpqe_cosine_margin_multi: item %d: bad fwd argument", i);
+    L.it[i] = T;
+    total += T.B;
+  }
+  if (backward) {
+    margin_bwd_multi_kernel<<<row_blocks(total), ROW_THREADS, 0, (cudaStream_t)stream>>>(L);
+    MPQE_CHECK_LAUNCH("margin_bwd_multi_kernel");
+  } else {
+    margin_fwd_multi_kernel<<<row_blocks(total), ROW_THREADS, 0, (cudaStream_t)stream>>>(L);
+    MPQE_CHECK_LAUNCH("margin_fwd_multi_kernel");
+    margin_mean_multi_kernel<<<n, 1024, 0, (cudaStream_t)stream>>>(L);
+    MPQE_CHECK_LAUNCH("margin_mean_multi_kernel");
+  }
+  return 0;
+}
+
+extern "C" size_t mpqe_colsum_multi_workspace_bytes(const mpqe_colsum_item_t* items_host, int32_t n) {
+  size_t blocks = 0;
+  for (int i = 0; i < n; ++i) blocks += (size_t)((items_host[i].rows + CS_ROWS - 1) / CS_ROWS);
+  return (blocks + (size_t)n + 1) * D * sizeof(float);
+}
+
+extern "C" int mpqe_colsum_multi(const mpqe_colsum_item_t* items_host, int32_t n, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  MPQE_CHECK_ARG(items_host != nullptr && n >= 1 && n <= MPQE_MAX_COLSUM_ITEMS, "mpqe_colsum_multi: n must be in [1,%d]",
+                 MPQE_MAX_COLSUM_ITEMS);
+  MPQE_CHECK_ARG(workspace && workspace_bytes >= mpqe_colsum_multi_workspace_bytes(items_host, n),
+                 "mpqe_colsum_multi: workspace too small");
+  static thread_local ColsumLaunch L;
+  L.n = n;
+  int64_t blocks = 0;
+  for (int i = 0; i < n; ++i) {
+    const mpqe_colsum_item_t& T = items_host[i];
+    MPQE_CHECK_ARG(T.src && T.dst && T.rows >= 1 && T.stride >= D && T.stride % 4 == 0,
+                   "mpqe_colsum_multi: item %d: bad argument", i);
+    L.it[i] = T;
+    blocks += (T.rows + CS_ROWS - 1) / CS_ROWS;
+  }
+  L.partials = (float*)workspace;
+  L.totals = L.partials + blocks * D;
+  colsum_partial_multi_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(L);
+  MPQE_CHECK_LAUNCH("colsum_partial_multi_kernel");
+  colsum_item_multi_kernel<<<n, 128, 0, (cudaStream_t)stream>>>(L);
+  MPQE_CHECK_LAUNCH("colsum_item_multi_kernel");
+  colsum_apply_multi_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(L);
+  MPQE_CHECK_LAUNCH("colsum_apply_multi_kernel");
+  return 0;
+}

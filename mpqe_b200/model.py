@@ -220,15 +220,21 @@ class Engine(object):
 
     # ---- forward ------------------------------------------------------------------------------------------
     def build_inputs(self, jobs, W):
+        """x[b, i<a] = normalised anchor rows, x[b, i>=a] = variable-type embedding rows (reference model.py:418-421):
+        one multi-item launch for every (job, node slot)."""
         enc = self.m.enc
+        items = []
         for job in jobs:
             t, B, n = job.t, job.B, job.t.num_nodes
             x = torch.empty(B, n, D, dtype=torch.float32, device=job.anchor_ids.device)
             for i, mode in enumerate(job.anchor_modes):
-                ops.gather_normalize(enc.table(mode), enc.node_maps, job.anchor_ids, out=x, out_offset=i * D,
-                                     out_stride=n * D, ids_offset=i, ids_stride=t.num_anchors, count=B)
-            ops.broadcast_rows(W.mode_emb, job.var_rows, x, t.num_anchors * D, n * D, B)
+                items.append(ops.GatherItem(enc.table(mode), enc.node_maps, job.anchor_ids, B, ids_offset=i,
+                                            ids_stride=t.num_anchors, out=x, out_offset=i * D, out_stride=n * D))
+            for k in range(t.num_vars):
+                items.append(ops.GatherItem(W.mode_emb, None, job.var_rows, B, ids_offset=k, ids_stride=0, out=x,
+                                            out_offset=(t.num_anchors + k) * D, out_stride=n * D, normalize=False))
             job.acts = [x]
+        ops.gather_multi(items)
 
     def layer_index(self, p, P):
         if self.m.shared_layers:
@@ -349,12 +355,12 @@ class Engine(object):
                     if g_slots == 1:
                         # sum readout: the bias was added once per node; target-message: once
                         scale = float(job.fwd_groups[p].bias_scale[0])
-                        ops.colsum(g, job.B, D, G.dbias[li], scale=scale, accumulate=True)
+                        G.colsum(g, job.B, D, G.dbias[li], scale)
                     elif len(smap) == g_slots:
-                        ops.colsum(g, job.B * g_slots, D, G.dbias[li], accumulate=True)
+                        G.colsum(g, job.B * g_slots, D, G.dbias[li])
                     else:
                         for s in smap:
-                            ops.colsum(g[:, s], job.B, g_slots * D, G.dbias[li], accumulate=True)
+                            G.colsum(g[:, s], job.B, g_slots * D, G.dbias[li])
             # ---- input gradients of pass p
             groups, nxt = [], {}
             for job in active:
@@ -386,6 +392,7 @@ class Engine(object):
                     cur[job] = (dx, n, ins)
                 else:
                     self.input_backward(job, dx, ins, G)
+        G.flush()
 
     def input_backward(self, job, dx, ins, G):
         """d loss / d x -> anchor table rows (through the normalisation) and variable-type embedding rows."""
@@ -394,14 +401,14 @@ class Engine(object):
         for i, mode in enumerate(job.anchor_modes):
             if i not in ins:
                 continue
-            rows, rows_id, off = G.rows.reserve(mode, B)
-            ops.gather_normalize_bwd(enc.table(mode), enc.node_maps, job.anchor_ids, dx, rows, rows_id,
-                                     grad_offset=i * D, grad_stride=n * D, ids_offset=i, ids_stride=t.num_anchors,
-                                     count=B, rows_offset=off)
+            rows, rows_id, off, id_off = G.rows.reserve(mode, B)
+            G.gathers.append(ops.GatherItem(enc.table(mode), enc.node_maps, job.anchor_ids, B, ids_offset=i,
+                                            ids_stride=t.num_anchors, grad=dx, grad_offset=i * D, grad_stride=n * D,
+                                            rows_out=rows, rows_id=rows_id, rows_offset=off, id_offset=id_off))
         for k, row in enumerate(job.var_rows_host):
             s = t.num_anchors + k
             if s in ins:
-                ops.colsum(dx[:, s], B, n * D, G.dmode[row], accumulate=True)
+                G.colsum(dx[:, s], B, n * D, G.dmode[row])
 
     def mlp_backward(self, jobs, W, dqs, G, last):
         """Backward of the MLP readouts; fills last[job] (gradient wrt the last R-GCN pass output) and job.du."""
@@ -424,8 +431,8 @@ class Engine(object):
         g_last = []
         for job, dq in zip(jobs, dqs):
             nu, n, t = job.u.shape[1], job.t.num_nodes, job.t
-            ops.colsum(dq, job.B, D, G.db2, scale=float(nu), accumulate=True)
-            ops.colsum(job.du, job.B * nu, D, G.db1, accumulate=True)
+            G.colsum(dq, job.B, D, G.db2, float(nu))
+            G.colsum(job.du, job.B * nu, D, G.db1)
             gz = torch.empty(job.B, n, D, dtype=torch.float32, device=dq.device)
             if ro == 'targetmlp':
                 others = [j for j in range(n) if j != t.target_slot]
@@ -439,26 +446,38 @@ class Engine(object):
 
 
 class RowGrads(object):
-    """Collects (table row, gradient row) pairs per mode; capacities are known on the host before the backward."""
+    """Collects (table row, gradient row) pairs; capacities are known on the host before the backward.
+    Per mode by default; with `table_offsets` ({mode: first global row}) all modes share ONE buffer and the kernels
+    emit global row ids (mode offset + row), so a step needs a single sort/combine and a single all-gather."""
 
-    def __init__(self, capacities, device):
+    def __init__(self, capacities, device, table_offsets=None):
         self.buf = {}
+        self.table_offsets = table_offsets
+        if table_offsets is not None:
+            cap = sum(capacities.values())
+            self.shared = [torch.empty(cap, D, dtype=torch.float32, device=device),
+                           torch.empty(cap, dtype=torch.int64, device=device), 0]
+            return
         for mode, cap in capacities.items():
             if cap > 0:
                 self.buf[mode] = [torch.empty(cap, D, dtype=torch.float32, device=device),
                                   torch.empty(cap, dtype=torch.int64, device=device), 0]
 
     def reserve(self, mode, count):
-        rows, ids, used = self.buf[mode]
+        """(rows buffer, ids buffer, first entry, offset the kernel adds to the row ids)."""
+        entry = self.shared if self.table_offsets is not None else self.buf[mode]
+        rows, ids, used = entry
         assert used + count <= ids.numel()
-        self.buf[mode][2] = used + count
-        return rows, ids, used
+        entry[2] = used + count
+        return rows, ids, used, (self.table_offsets[mode] if self.table_offsets is not None else 0)
 
 
 class Grads(object):
     """Dense gradient buffers (zero-initialised, kernels accumulate) + the row-gradient collector."""
 
-    def __init__(self, model, W, row_capacities, device):
+    def __init__(self, model, W, row_capacities, device, table_offsets=None):
+        self.device = device
+        self.colsums, self.gathers, self.keep = [], [], []
         # one flat zeroed bucket: a single memset here, a single NCCL all-reduce in data-parallel training
         shapes = [tuple(w.shape) for w in W.w] + [tuple(r.shape) for r in W.root] + [(D,)] * len(W.root)
         shapes.append(tuple(W.mode_emb.shape))
@@ -475,7 +494,18 @@ class Grads(object):
         self.dmode = views[3 * L]
         if W.ro is not None:
             self.dw1t, self.dw2t, self.db1, self.db2 = views[3 * L + 1:3 * L + 5]
-        self.rows = RowGrads(row_capacities, device)
+        self.rows = RowGrads(row_capacities, device, table_offsets)
+
+    def colsum(self, src, rows, stride, dst, scale=1.0):
+        """Deferred dst += scale * column-sum(src): all of a backward's reductions run in one multi-item launch."""
+        self.colsums.append(ops.ColsumItem(src, rows, stride, dst, scale))
+
+    def flush(self):
+        if self.gathers:
+            ops.gather_multi(self.gathers, backward=True)
+        if self.colsums:
+            ops.colsum_multi(self.colsums, self.device)
+        self.colsums, self.gathers = [], []
 
 
 # ===============================================================================================================
@@ -665,23 +695,31 @@ def loss_forward(model, jobs, targets, negatives, margin, need_grad):
     W = Weights(model, need_grad)
     model._engine.encode(jobs, W)
     losses = torch.empty(len(jobs), dtype=torch.float32, device=device)
+    hinge = torch.empty(sum(job.B for job in jobs), dtype=torch.float32, device=device)
+    items, off = [], 0
     for i, (job, tgt, neg) in enumerate(zip(jobs, targets, negatives)):
-        ops.cosine_margin(job.q, model.enc.table(job.target_mode), model.enc.node_maps, tgt, neg, margin,
-                          loss_out=losses[i:i + 1])
+        items.append(ops.MarginItem(job.q, model.enc.table(job.target_mode), model.enc.node_maps, tgt, neg,
+                                    hinge=hinge[off:off + job.B], loss=losses[i:i + 1]))
+        off += job.B
+    ops.cosine_margin_multi(items, margin)
     return losses, W
 
 
-def loss_backward(model, jobs, W, targets, negatives, margin, grad_losses):
+def loss_backward(model, jobs, W, targets, negatives, margin, grad_losses, table_offsets=None):
     """Backward of `loss_forward` for d(total)/d(loss_i) = grad_losses[i] (device tensor [len(jobs)]).
-    Returns the filled `Grads` (dense bucket + per-mode (row id, gradient row) pairs, not yet combined)."""
+    Returns the filled `Grads` (dense bucket + (row id, gradient row) pairs, not yet combined)."""
     device = jobs[0].anchor_ids.device
     cap = model._row_capacities(jobs, [(job.target_mode, 2 * job.B) for job in jobs])
-    G = Grads(model, W, cap, device)
-    dqs = []
+    G = Grads(model, W, cap, device, table_offsets)
+    dqs, items = [], []
     for i, (job, tgt, neg) in enumerate(zip(jobs, targets, negatives)):
-        rows, ids, off = G.rows.reserve(job.target_mode, 2 * job.B)
-        dqs.append(ops.cosine_margin_bwd(job.q, model.enc.table(job.target_mode), model.enc.node_maps, tgt, neg,
-                                         margin, grad_losses[i:i + 1], rows, ids, rows_offset=off))
+        rows, ids, off, id_off = G.rows.reserve(job.target_mode, 2 * job.B)
+        dq = torch.empty(job.B, D, dtype=torch.float32, device=device)
+        items.append(ops.MarginItem(job.q, model.enc.table(job.target_mode), model.enc.node_maps, tgt, neg,
+                                    grad_loss=grad_losses[i:i + 1], dq=dq, rows_out=rows, rows_id=ids, rows_offset=off,
+                                    id_offset=id_off))
+        dqs.append(dq)
+    ops.cosine_margin_multi(items, margin, backward=True)
     model._engine.backward(jobs, W, dqs, G)
     return G
 
@@ -739,10 +777,10 @@ class _ScoresFn(torch.autograd.Function):
             G = Grads(model, W, model._row_capacities([job], [(job.target_mode, job.B + nneg)]), device)
             gs = grad_scores.contiguous()
             dq = torch.empty(job.B, D, dtype=torch.float32, device=device)
-            rows, ids, off = G.rows.reserve(job.target_mode, job.B)
+            rows, ids, off, _ = G.rows.reserve(job.target_mode, job.B)
             ops.cosine_scores_bwd(job.q, table, model.enc.node_maps, ctx.tgt, None, gs, 0, dq, False, rows, ids, off)
             if nneg > 0:
-                rows, ids, off = G.rows.reserve(job.target_mode, nneg)
+                rows, ids, off, _ = G.rows.reserve(job.target_mode, nneg)
                 ops.cosine_scores_bwd(job.q, table, model.enc.node_maps, ctx.neg, ctx.offsets, gs, job.B, dq, True,
                                       rows, ids, off)
             model._engine.backward([job], W, [dq], G)

@@ -421,3 +421,96 @@ def adam_dense(param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step):
     _lib.check(lib.mpqe_adam_dense(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(), lr, beta1,
                                    beta2, eps, step, _stream()), 'mpqe_adam_dense')
     _count()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Multi-item launches (one kernel for every formula group of a step)
+# ---------------------------------------------------------------------------------------------------------------
+def _addr(t, elem_offset=0):
+    return t.data_ptr() + elem_offset * t.element_size() if t is not None else 0
+
+
+class GatherItem(object):
+    """One (group, node slot) work item of `gather_multi` (see mpqe_gather_item_t); tensors + element offsets."""
+
+    def __init__(self, table, id2row, ids, count, ids_offset=0, ids_stride=1, out=None, out_offset=0, out_stride=D,
+                 grad=None, grad_offset=0, grad_stride=D, rows_out=None, rows_id=None, rows_offset=0, id_offset=0,
+                 normalize=True):
+        self.table, self.id2row, self.ids, self.count = table, id2row, ids, int(count)
+        self.ids_offset, self.ids_stride = int(ids_offset), int(ids_stride)
+        self.out, self.out_offset, self.out_stride = out, int(out_offset), int(out_stride)
+        self.grad, self.grad_offset, self.grad_stride = grad, int(grad_offset), int(grad_stride)
+        self.rows_out, self.rows_id, self.rows_offset = rows_out, rows_id, int(rows_offset)
+        self.id_offset, self.normalize = int(id_offset), bool(normalize)
+
+    def to_c(self):
+        it = _lib.GatherItem()
+        it.table, it.table_rows, it.id2row = _addr(self.table), self.table.shape[0], _addr(self.id2row)
+        it.ids, it.ids_stride, it.count = _addr(self.ids, self.ids_offset), self.ids_stride, self.count
+        it.out, it.out_stride = _addr(self.out, self.out_offset), self.out_stride
+        it.grad, it.grad_stride = _addr(self.grad, self.grad_offset), self.grad_stride
+        it.rows_out, it.rows_id = _addr(self.rows_out, self.rows_offset * D), _addr(self.rows_id, self.rows_offset)
+        it.id_offset, it.normalize = self.id_offset, int(self.normalize)
+        return it
+
+
+def gather_multi(items, backward=False):
+    lib = _lib.load()
+    for i in range(0, len(items), _lib.MAX_GATHER_ITEMS):
+        chunk = items[i:i + _lib.MAX_GATHER_ITEMS]
+        arr = (_lib.GatherItem * len(chunk))(*[it.to_c() for it in chunk])
+        _lib.check(lib.mpqe_gather_multi(arr, len(chunk), int(backward), _stream()), 'mpqe_gather_multi')
+        _count()
+
+
+class MarginItem(object):
+    """One formula group of `cosine_margin_multi` (see mpqe_margin_item_t)."""
+
+    def __init__(self, q, table, id2row, ids_pos, ids_neg, hinge=None, loss=None, grad_loss=None, dq=None,
+                 rows_out=None, rows_id=None, rows_offset=0, id_offset=0):
+        self.q, self.table, self.id2row, self.ids_pos, self.ids_neg = q, table, id2row, ids_pos, ids_neg
+        self.hinge, self.loss, self.grad_loss, self.dq = hinge, loss, grad_loss, dq
+        self.rows_out, self.rows_id, self.rows_offset, self.id_offset = rows_out, rows_id, int(rows_offset), int(id_offset)
+
+    def to_c(self):
+        it = _lib.MarginItem()
+        it.q, it.B, it.table, it.id2row = _addr(self.q), self.q.shape[0], _addr(self.table), _addr(self.id2row)
+        it.ids_pos, it.ids_neg = _addr(self.ids_pos), _addr(self.ids_neg)
+        it.score_pos = it.score_neg = 0
+        it.hinge, it.loss, it.grad_loss, it.dq = _addr(self.hinge), _addr(self.loss), _addr(self.grad_loss), _addr(self.dq)
+        it.rows_out, it.rows_id = _addr(self.rows_out, self.rows_offset * D), _addr(self.rows_id, self.rows_offset)
+        it.id_offset = self.id_offset
+        return it
+
+
+def cosine_margin_multi(items, margin, backward=False):
+    lib = _lib.load()
+    for i in range(0, len(items), _lib.MAX_MARGIN_ITEMS):
+        chunk = items[i:i + _lib.MAX_MARGIN_ITEMS]
+        arr = (_lib.MarginItem * len(chunk))(*[it.to_c() for it in chunk])
+        _lib.check(lib.mpqe_cosine_margin_multi(arr, len(chunk), margin, int(backward), _stream()),
+                   'mpqe_cosine_margin_multi')
+        _count(1 if backward else 2)
+
+
+class ColsumItem(object):
+    """dst[D] += scale * sum_r src.flat[r*stride : r*stride+D]  (src may be an offset view into a larger buffer)."""
+
+    def __init__(self, src, rows, stride, dst, scale=1.0):
+        self.src, self.rows, self.stride, self.dst, self.scale = src, int(rows), int(stride), dst, float(scale)
+
+    def to_c(self):
+        it = _lib.ColsumItem()
+        it.src, it.rows, it.stride, it.dst, it.scale = self.src.data_ptr(), self.rows, self.stride, self.dst.data_ptr(), self.scale
+        return it
+
+
+def colsum_multi(items, device):
+    """Applies every item in order (3 launches per <=64 items)."""
+    lib = _lib.load()
+    for i in range(0, len(items), _lib.MAX_COLSUM_ITEMS):
+        chunk = items[i:i + _lib.MAX_COLSUM_ITEMS]
+        arr = (_lib.ColsumItem * len(chunk))(*[it.to_c() for it in chunk])
+        ws = workspace(lib.mpqe_colsum_multi_workspace_bytes(arr, len(chunk)), device, 'colsum')
+        _lib.check(lib.mpqe_colsum_multi(arr, len(chunk), _ptr(ws), ws.numel(), _stream()), 'mpqe_colsum_multi')
+        _count(3)

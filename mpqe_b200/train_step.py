@@ -52,6 +52,12 @@ class TrainStep(object):
         self._layouts = {}
         self.adam_state = None
         self.steps = 0
+        # all entity tables as one id space: global row = table_offsets[mode] + row
+        self.table_offsets, off = {}, 0
+        for mode, module in model.enc.feature_modules.items():
+            self.table_offsets[mode] = off
+            off += module.weight.shape[0]
+        self.total_rows = off
 
     def _dist(self):
         return torch.distributed.is_available() and torch.distributed.is_initialized()
@@ -88,7 +94,8 @@ class TrainStep(object):
     @torch.no_grad()
     def forward_backward(self, batches):
         """Returns StepResult: per-batch losses, weighted total (device scalars), the flat dense gradient bucket
-        (views per parameter in .dense.named) and {mode: (unique row ids, rows, num_unique)}."""
+        (`.dense.flat`, views per parameter in `.dense`) and the row-sparse entity gradient
+        `.sparse = (unique global row ids, summed rows, num_unique)` with global row = table_offsets[mode] + row."""
         m = self.model
         dev = m.mode_embeddings.weight.device
         with ops.device_guard(dev):
@@ -100,11 +107,9 @@ class TrainStep(object):
             wts = getattr(self, '_wts', None)
             if wts is None or wts[0] != key:
                 wts = self._wts = (key, torch.tensor(key, dtype=torch.float32, device=dev))
-            G = loss_backward(m, jobs, W, tg, ng, self.margin, wts[1])
-            sparse = {}
-            for mode, (rows, ids, used) in G.rows.buf.items():
-                if used > 0:
-                    sparse[mode] = ops.sparse_rows_combine(ids[:used], rows[:used], m.enc.table(mode).shape[0])
+            G = loss_backward(m, jobs, W, tg, ng, self.margin, wts[1], self.table_offsets)
+            rows, ids, used = G.rows.shared
+            sparse = ops.sparse_rows_combine(ids[:used], rows[:used], self.total_rows)
             if self.world > 1:
                 sparse = self.sync(G, sparse)
             total = (losses * wts[1]).sum()
@@ -117,19 +122,16 @@ class TrainStep(object):
         dist.all_reduce(G.flat, group=self.pg)
         if scale != 1.0:
             G.flat.mul_(scale)
-        out = {}
-        for mode in sorted(sparse):
-            uid, urows, num = sparse[mode]
-            cap = uid.numel()
-            all_ids = torch.empty(self.world * cap, dtype=torch.int64, device=uid.device)
-            all_rows = torch.empty(self.world * cap, D, dtype=torch.float32, device=uid.device)
-            dist.all_gather_into_tensor(all_ids, uid, group=self.pg)
-            dist.all_gather_into_tensor(all_rows, urows, group=self.pg)
-            if scale != 1.0:
-                all_rows.mul_(scale)
-            # padding entries are (row 0, zero row): harmless for the sum; rank order + stable sort => same bits everywhere
-            out[mode] = ops.sparse_rows_combine(all_ids, all_rows, self.model.enc.table(mode).shape[0])
-        return out
+        uid, urows, num = sparse
+        cap = uid.numel()
+        all_ids = torch.empty(self.world * cap, dtype=torch.int64, device=uid.device)
+        all_rows = torch.empty(self.world * cap, D, dtype=torch.float32, device=uid.device)
+        dist.all_gather_into_tensor(all_ids, uid, group=self.pg)
+        dist.all_gather_into_tensor(all_rows, urows, group=self.pg)
+        if scale != 1.0:
+            all_rows.mul_(scale)
+        # padding entries are (row 0, zero row): harmless for the sum; rank order + stable sort => same bits everywhere
+        return ops.sparse_rows_combine(all_ids, all_rows, self.total_rows)
 
     @torch.no_grad()
     def run_host(self, host_batches):

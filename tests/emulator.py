@@ -258,6 +258,39 @@ def install(monkeypatch):
     for name in ('layer_forward', 'layer_wgrad', 'colsum', 'transpose', 'gather_normalize', 'gather_normalize_bwd',
                  'broadcast_rows', 'max_readout', 'max_readout_bwd', 'cosine_margin', 'cosine_margin_bwd',
                  'cosine_scores', 'cosine_scores_bwd', 'rank_counts_ragged', 'rank_counts_table',
-                 'build_query_graph', 'relation_sort', 'sparse_rows_combine', 'scatter_rows'):
+                 'build_query_graph', 'relation_sort', 'sparse_rows_combine', 'scatter_rows', 'gather_multi',
+                 'cosine_margin_multi', 'colsum_multi'):
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(ops, 'device_guard', lambda device: contextlib.nullcontext())
+
+
+def gather_multi(items, backward=False):
+    for it in items:
+        if backward:
+            gather_normalize_bwd(it.table, it.id2row, it.ids, it.grad, it.rows_out, it.rows_id, it.grad_offset,
+                                 it.grad_stride, it.ids_offset, max(it.ids_stride, 1), it.count, it.rows_offset)
+            it.rows_id[it.rows_offset:it.rows_offset + it.count] += it.id_offset
+        elif it.normalize:
+            gather_normalize(it.table, it.id2row, it.ids, it.out, it.out_offset, it.out_stride, it.ids_offset,
+                             it.ids_stride, it.count)
+        else:  # plain row copy; ids_stride 0 broadcasts one row
+            row = it.ids.reshape(-1)[it.ids_offset]
+            view = torch.as_strided(it.out, (it.count, D), (it.out_stride, 1), it.out.storage_offset() + it.out_offset)
+            view.copy_(it.table[row].unsqueeze(0).expand(it.count, D))
+
+
+def cosine_margin_multi(items, margin, backward=False):
+    for it in items:
+        if backward:
+            dq = cosine_margin_bwd(it.q, it.table, it.id2row, it.ids_pos, it.ids_neg, margin, it.grad_loss, it.rows_out,
+                                   it.rows_id, it.rows_offset)
+            it.dq.copy_(dq)
+            B = it.q.shape[0]
+            it.rows_id[it.rows_offset:it.rows_offset + 2 * B] += it.id_offset
+        else:
+            cosine_margin(it.q, it.table, it.id2row, it.ids_pos, it.ids_neg, margin, loss_out=it.loss)
+
+
+def colsum_multi(items, device):
+    for it in items:
+        colsum(it.src, it.rows, it.stride, it.dst, it.scale, True)

@@ -35,7 +35,7 @@ def test_every_declared_symbol_is_exported_and_bound():
 def test_struct_sizes_match():
     build.build()
     lib = _lib.load()
-    for which, struct in enumerate((_lib.Term, _lib.LayerGroup, _lib.WgradDest, _lib.WgradOperand)):
+    for which, struct in enumerate(_lib.ABI_STRUCTS):
         assert lib.mpqe_b200_sizeof(which) == ctypes.sizeof(struct)
 
 

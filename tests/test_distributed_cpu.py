@@ -48,7 +48,8 @@ def _worker(rank, world, port, out):
     host = [HostBatch(f, torch.from_numpy(a), torch.from_numpy(t), torch.from_numpy(n)) for f, (a, t, n) in
             zip(formulas, ids)]
     res = ts.forward_backward([ts.to_device(hb) for hb in host])
-    sparse = {m: (u[:int(k)].clone(), r[:int(k)].clone()) for m, (u, r, k) in res.sparse.items()}
+    u, r, k = res.sparse
+    sparse = {'all': (u[:int(k)].clone(), r[:int(k)].clone())}
     torch.save({'flat': res.dense.flat.clone(), 'sparse': sparse, 'losses': res.losses.clone()}, out % rank)
     dist.destroy_process_group()
 
@@ -74,7 +75,7 @@ def test_two_rank_gradients_equal_single_rank(tmp_path, monkeypatch):
     res = ts.forward_backward([ts.to_device(hb) for hb in host])
     np.testing.assert_allclose(r0['flat'].numpy(), res.dense.flat.numpy(), rtol=1e-4,
                                atol=1e-6 * float(res.dense.flat.abs().max()))
-    for m, (u, r, k) in res.sparse.items():
+    for m, (u, r, k) in {'all': res.sparse}.items():
         k = int(k)
         ids_dp, rows_dp = r0['sparse'][m]
         nz = rows_dp.abs().sum(1) > 0          # the DP union may carry the padding id 0 with a zero row
