@@ -5,26 +5,33 @@
 // lines replaced are /root/reference/mpqe/model.py:292-294 (index_select + bmm), :277 (gather + scatter_add),
 // :301-304 (root, bias), :437 (relu) and their autograd.
 //
-// Data path (per CTA, 256 threads, 1 CTA / SM):
-//   global fp32 --ld.global.v4--> registers --split hi/lo--> st.shared.v4 in the UMMA canonical NO-SWIZZLE layout
-//   (8x16-byte core matrices, written 512 contiguous bytes per warp instruction: no bank conflicts)
-//   --fence.proxy.async + barrier--> one thread issues tcgen05.mma.kind::tf32 (M=128, N=128, K=8) x 3 products
-//   --tcgen05.commit--> mbarrier frees the smem stage; after the last term: tcgen05.ld 32x32b -> epilogue -> global.
-// The operands are staged by the threads rather than by TMA because every element has to pass through registers
-// once anyway to be split into its hi/lo TF32 parts.
+// Persistent, warp-specialised CTAs (one per SM, 13 warps):
+//   warps 4-11  producers : global fp32 --ld.global.v4--> registers --split hi/lo--> st.shared in the UMMA canonical
+//                           K-major no-swizzle layout --fence.proxy.async--> mbarrier full[stage]
+//   warp  12    MMA issuer: waits full[stage], issues 12 x tcgen05.mma.kind::tf32 (M=128, N=128, K=8),
+//                           tcgen05.commit -> empty[stage]; after a unit's last stage commit -> acc_full[buffer]
+//   warps 0-3   epilogue  : waits acc_full, tcgen05.ld 32x32b (one accumulator row per thread), bias / relu / mask,
+//                           global stores, arrives acc_empty  (two 128-column TMEM accumulators ping-pong, so the
+//                           epilogue of unit u overlaps the main loop of unit u+1)
+// The operands are staged by threads rather than by TMA because every element has to pass through registers once
+// anyway to be split into its hi/lo TF32 parts (and half of them need a transpose on the way).
 #include "common.cuh"
 
 namespace mpqe {
 
 namespace {
 
-constexpr int THREADS = 256;
-constexpr int BM = 128;              // rows (queries) per CTA = UMMA M
+constexpr int EPI_WARPS = 4;
+constexpr int PROD_WARPS = 8;
+constexpr int PROD_THREADS = PROD_WARPS * 32;
+constexpr int MMA_WARP = EPI_WARPS + PROD_WARPS;
+constexpr int THREADS = (MMA_WARP + 1) * 32;   // 416
+constexpr int BM = 128;              // rows per unit = UMMA M
 constexpr int KC = 32;               // k per pipeline stage = 4 UMMA k-steps of 8
 constexpr int STAGES = 3;
 constexpr int TILE_BYTES = BM * KC * 4;          // 16 KB: one operand tile (hi or lo)
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;      // A_hi, A_lo, B_hi, B_lo
-constexpr int TMEM_COLS = 128;
+constexpr int TMEM_COLS = 256;                   // two 128-column fp32 accumulators
 constexpr size_t TC_SMEM = size_t(STAGES) * STAGE_BYTES + 1024;  // + alignment slack
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------
@@ -32,6 +39,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -115,21 +125,22 @@ __device__ __forceinline__ void split_tf32(const float4& x, float4& hi, float4& 
 
 // Every operand tile is K-major [128 rows][32 k]: element (row, k) at (row/8)*1024 + (k/4)*128 + (row%8)*16 + (k%4)*4
 // bytes; descriptor for k-step j (k = 8j..8j+7): start + j*256, LBO = 128 (next 4 k), SBO = 1024 (next 8 rows).
-// (Probed on B200 with tests/tc_probe.cu: K-major no-swizzle tf32 operands are exact, MN-major ones yield zeros.)
+// (Probed on B200 with tests/tc_probe.cu: K-major tf32 operands are exact with and without the 128-byte swizzle and
+// run at the same ~160 cycles per 128x128x8 MMA; MN-major no-swizzle tf32 operands yield zeros.)
 // Sources whose contiguous dimension is the tile's ROW dimension (weight matrices [k][n], and both operands of the
 // weight gradient) are transposed on the way into shared memory with 4-byte stores whose component order is rotated
 // per lane so that each warp instruction hits 32 distinct banks.
 
-struct Frag {  // one pipeline stage worth of one operand, per thread
+struct Frag {  // one pipeline stage worth of one operand, per producer thread
   float4 v[4];
 };
 
-// rows = queries (K-major A): idx = warp*4+i -> row group idx/2, k half idx%2
-__device__ __forceinline__ void load_kmajor(Frag& f, const mpqe_term_t& T, int64_t q0, int64_t B, int kc, int warp,
+// rows = queries (K-major source): idx = pw*4+i -> row group idx/2, k half idx%2   (pw = producer warp 0..7)
+__device__ __forceinline__ void load_kmajor(Frag& f, const mpqe_term_t& T, int64_t q0, int64_t B, int kc, int pw,
                                             int lane) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int idx = warp * 4 + i;
+    const int idx = pw * 4 + i;
     const int row = (idx >> 1) * 8 + (lane & 7);
     const int kq = (idx & 1) * 4 + (lane >> 3);
     int64_t q = q0 + row;
@@ -137,10 +148,10 @@ __device__ __forceinline__ void load_kmajor(Frag& f, const mpqe_term_t& T, int64
     f.v[i] = *reinterpret_cast<const float4*>(T.a + (q * T.a_slots + T.a_slot) * (int64_t)D + kc + kq * 4);
   }
 }
-__device__ __forceinline__ void store_kmajor(const Frag& f, uint8_t* hi_tile, uint8_t* lo_tile, int warp, int lane) {
+__device__ __forceinline__ void store_kmajor(const Frag& f, uint8_t* hi_tile, uint8_t* lo_tile, int pw, int lane) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int idx = warp * 4 + i;
+    const int idx = pw * 4 + i;
     const int off = (idx >> 1) * 1024 + ((idx & 1) * 4 + (lane >> 3)) * 128 + (lane & 7) * 16;
     float4 hi, lo;
     split_tf32(f.v[i], hi, lo);
@@ -149,23 +160,23 @@ __device__ __forceinline__ void store_kmajor(const Frag& f, uint8_t* hi_tile, ui
   }
 }
 // Transposing stage: source is row-major [32 k][128 mn] (pitch floats between k rows); the tile wants mn as rows.
-//   instr t = warp*4+i: k half = t&1, mn4 pair = t>>1;  lane: k = 16*(t&1) + 4*r + (lane&3), r = (lane>>2)&3,
+//   instr t = pw*4+i: k half = t&1, mn4 pair = t>>1;  lane: k = 16*(t&1) + 4*r + (lane&3), r = (lane>>2)&3,
 //   mn4 = 2*(t>>1) + (lane>>4).  Loads: 32 contiguous bytes per k row (full sectors).
-__device__ __forceinline__ void load_transposed(Frag& f, const float* src, int64_t pitch, int k_valid, int warp,
+__device__ __forceinline__ void load_transposed(Frag& f, const float* src, int64_t pitch, int k_valid, int pw,
                                                 int lane) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int t = warp * 4 + i;
+    const int t = pw * 4 + i;
     const int k = 16 * (t & 1) + 4 * ((lane >> 2) & 3) + (lane & 3);
     const int mn4 = 2 * (t >> 1) + (lane >> 4);
     f.v[i] = k < k_valid ? *reinterpret_cast<const float4*>(src + k * pitch + mn4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
-__device__ __forceinline__ void store_transposed(const Frag& f, uint8_t* hi_tile, uint8_t* lo_tile, int warp, int lane) {
+__device__ __forceinline__ void store_transposed(const Frag& f, uint8_t* hi_tile, uint8_t* lo_tile, int pw, int lane) {
   const int r = (lane >> 2) & 3;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int t = warp * 4 + i;
+    const int t = pw * 4 + i;
     const int k = 16 * (t & 1) + 4 * r + (lane & 3);
     const int mn4 = 2 * (t >> 1) + (lane >> 4);
     float4 hi, lo;
@@ -184,20 +195,39 @@ __device__ __forceinline__ void store_transposed(const Frag& f, uint8_t* hi_tile
 }
 
 struct TcShared {
+  uint64_t full[STAGES];
   uint64_t empty[STAGES];
-  uint64_t done;
+  uint64_t acc_full[2];
+  uint64_t acc_empty[2];
   uint32_t tmem_base;
-  int term[MPQE_MAX_TERMS];
-  int nterms;
 };
 
 __device__ __forceinline__ uint8_t* align_1024(uint8_t* p) {
   return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023));
 }
 
+__device__ __forceinline__ void setup(TcShared& sh, int warp, int tid) {
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&sh.full[s]), PROD_THREADS);
+      mbar_init(smem_u32(&sh.empty[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&sh.acc_full[b]), 1);
+      mbar_init(smem_u32(&sh.acc_empty[b]), EPI_WARPS * 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&sh.tmem_base), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+}
+
 // issue the 3xTF32 products of one stage: 4 k-steps x (lo*hi, hi*lo, hi*hi), small products first
-__device__ __forceinline__ void issue_stage(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
-                                            bool first) {
+__device__ __forceinline__ void issue_stage(uint32_t tmem_d, uint32_t stage_addr, bool first) {
+  const uint32_t a_hi = stage_addr, a_lo = stage_addr + TILE_BYTES, b_hi = stage_addr + 2 * TILE_BYTES,
+                 b_lo = stage_addr + 3 * TILE_BYTES;
 #pragma unroll
   for (int j = 0; j < KC / 8; ++j) {
     const uint64_t dah = make_desc(a_hi + j * 256, 128, 1024), dal = make_desc(a_lo + j * 256, 128, 1024);
@@ -208,12 +238,40 @@ __device__ __forceinline__ void issue_stage(uint32_t tmem_d, uint32_t a_hi, uint
   }
 }
 
-__global__ void __launch_bounds__(THREADS, 1) layer_tc_kernel(const __grid_constant__ LayerLaunch L) {
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ TcShared sh;
-  uint8_t* smem = align_1024(smem_raw);
+// MMA-issuer role, shared by both kernels: consumes `nsteps` stages for the unit with per-CTA index `uc`
+__device__ __forceinline__ void mma_unit(TcShared& sh, uint32_t smem_base, uint32_t tmem, int uc, int nsteps,
+                                         uint32_t& it) {
+  const int ab = uc & 1, use = uc >> 1;
+  if (use > 0) mbar_wait(smem_u32(&sh.acc_empty[ab]), (use - 1) & 1);   // epilogue drained this accumulator
+  tc_fence_after();
+  for (int step = 0; step < nsteps; ++step, ++it) {
+    const int s = it % STAGES;
+    mbar_wait(smem_u32(&sh.full[s]), (it / STAGES) & 1);
+    tc_fence_after();
+    issue_stage(tmem + ab * 128, smem_base + s * STAGE_BYTES, step == 0);
+    umma_commit(smem_u32(&sh.empty[s]));                                // frees the stage when the MMAs have read it
+  }
+  umma_commit(smem_u32(&sh.acc_full[ab]));                              // accumulator complete
+}
 
-  int unit = blockIdx.x;
+// producer-side stage acquisition: stage index + wait until the MMAs that read it last have completed
+__device__ __forceinline__ uint8_t* acquire_stage(TcShared& sh, uint8_t* smem, uint32_t it) {
+  const int s = it % STAGES;
+  const uint32_t use = it / STAGES;
+  if (use > 0) mbar_wait(smem_u32(&sh.empty[s]), (use - 1) & 1);
+  return smem + s * STAGE_BYTES;
+}
+__device__ __forceinline__ void publish_stage(TcShared& sh, uint32_t it) {
+  fence_proxy_async();                                                  // generic-proxy stores -> async proxy (UMMA)
+  mbar_arrive(smem_u32(&sh.full[it % STAGES]));
+}
+
+struct UnitInfo {
+  int gi, slot;
+  int64_t q0;
+};
+
+__device__ __forceinline__ UnitInfo decode_unit(const LayerLaunch& L, int unit) {
   int gi = 0;
   for (; gi < L.num_groups - 1; ++gi) {
     const int tiles = int((L.g[gi].num_queries + BM - 1) / BM);
@@ -221,92 +279,130 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc_kernel(const __grid_const
     if (unit < units) break;
     unit -= units;
   }
-  const mpqe_layer_group_t& G = L.g[gi];
-  const int slot = unit % G.num_out_slots;
-  const int64_t q0 = int64_t(unit / G.num_out_slots) * BM;
-  const int64_t B = G.num_queries;
+  UnitInfo u;
+  u.gi = gi;
+  u.slot = unit % L.g[gi].num_out_slots;
+  u.q0 = int64_t(unit / L.g[gi].num_out_slots) * BM;
+  return u;
+}
+
+__device__ __forceinline__ uint32_t term_mask(const mpqe_layer_group_t& G, int slot) {
+  uint32_t m = 0;
+  for (int t = 0; t < G.num_terms; ++t)
+    if (G.terms[t].out_slot == slot) m |= 1u << t;
+  return m;
+}
+
+__global__ void __launch_bounds__(THREADS, 1) layer_tc_kernel(const __grid_constant__ LayerLaunch L, int total_units) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ TcShared sh;
+  uint8_t* smem = align_1024(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-  if (tid == 0) {
-    int n = 0;
-    for (int t = 0; t < G.num_terms; ++t)
-      if (G.terms[t].out_slot == slot) sh.term[n++] = t;
-    sh.nterms = n;
-    for (int s = 0; s < STAGES; ++s) mbar_init(smem_u32(&sh.empty[s]), 1);
-    mbar_init(smem_u32(&sh.done), 1);
-    fence_barrier_init();
-  }
-  if (warp == 0) tmem_alloc(smem_u32(&sh.tmem_base), TMEM_COLS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
+  setup(sh, warp, tid);
   const uint32_t tmem = sh.tmem_base;
-  const int nsteps = sh.nterms * (D / KC);
 
-  Frag fa, fb;
-  auto load_step = [&](int step) {
-    const mpqe_term_t& T = G.terms[sh.term[step / (D / KC)]];
-    const int kc = (step % (D / KC)) * KC;
-    load_kmajor(fa, T, q0, B, kc, warp, lane);
-    load_transposed(fb, T.m + (int64_t)kc * D, D, KC, warp, lane);
-  };
-  if (nsteps > 0) load_step(0);
-  for (int step = 0; step < nsteps; ++step) {
-    const int s = step % STAGES, u = step / STAGES;
-    uint8_t* st = smem + s * STAGE_BYTES;
-    if (u > 0) mbar_wait(smem_u32(&sh.empty[s]), (u - 1) & 1);  // MMAs that read this stage have completed
-    store_kmajor(fa, st, st + TILE_BYTES, warp, lane);
-    store_transposed(fb, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, warp, lane);
-    if (step + 1 < nsteps) load_step(step + 1);  // global loads of the next stage fly while this one is multiplied
-    fence_proxy_async();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t a = smem_u32(st);
-      issue_stage(tmem, a, a + TILE_BYTES, a + 2 * TILE_BYTES, a + 3 * TILE_BYTES, step == 0);
-      umma_commit(smem_u32(&sh.empty[s]));
-      if (step == nsteps - 1) umma_commit(smem_u32(&sh.done));
-    }
-  }
-
-  // ---- epilogue: TMEM -> registers -> bias / relu / mask -> global -------------------------------------------
-  if (nsteps > 0) {
-    mbar_wait(smem_u32(&sh.done), 0);
-    tc_fence_after();
-  }
-  const int row = (warp & 3) * 32 + lane;          // TMEM lane = tile row; a warp may only touch its own 32 lanes
-  const int64_t q = q0 + row;
-  const int oslot = G.out_slot_map[slot];
-  const float bscale = G.bias != nullptr ? G.bias_scale[slot] : 0.f;
-#pragma unroll 1
-  for (int half = 0; half < 2; ++half) {
-    const int c0 = (warp >> 2) * 64 + half * 32;
-    uint32_t v[32];
-    if (nsteps > 0) {
-      tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + c0, v);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = 0u;
-    }
-    if (q < B) {
-      float* orow = G.out + (q * G.out_slots + oslot) * (int64_t)D + c0;
-      const float* mrow = G.epilogue == MPQE_EPI_MASK ? G.mask + (q * G.mask_slots + oslot) * (int64_t)D + c0 : nullptr;
-#pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        float4 o = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
-                               __uint_as_float(v[i + 3]));
-        if (G.bias != nullptr) {
-          const float4 b = *reinterpret_cast<const float4*>(G.bias + c0 + i);
-          o.x += bscale * b.x; o.y += bscale * b.y; o.z += bscale * b.z; o.w += bscale * b.w;
-        }
-        if (G.epilogue == MPQE_EPI_RELU) {
-          o = make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
-        } else if (G.epilogue == MPQE_EPI_MASK) {
-          const float4 m = *reinterpret_cast<const float4*>(mrow + i);
-          o = make_float4(m.x > 0.f ? o.x : 0.f, m.y > 0.f ? o.y : 0.f, m.z > 0.f ? o.z : 0.f, m.w > 0.f ? o.w : 0.f);
-        }
-        *reinterpret_cast<float4*>(orow + i) = o;
+  if (warp >= EPI_WARPS && warp < MMA_WARP) {
+    // ===== producers =====
+    const int pw = warp - EPI_WARPS;
+    uint32_t it = 0;
+    Frag fa, fb;
+    // iterator over (unit, term, k chunk)
+    int unit = blockIdx.x;
+    UnitInfo U = decode_unit(L, unit < total_units ? unit : 0);
+    uint32_t mask = unit < total_units ? term_mask(L.g[U.gi], U.slot) : 0u;
+    int kc = 0;
+    auto advance = [&]() {  // moves to the next (term, k chunk), crossing units; returns false when all work is done
+      kc += KC;
+      if (kc < D) return true;
+      kc = 0;
+      mask &= mask - 1;
+      while (mask == 0) {
+        unit += gridDim.x;
+        if (unit >= total_units) return false;
+        U = decode_unit(L, unit);
+        mask = term_mask(L.g[U.gi], U.slot);
       }
+      return true;
+    };
+    auto load = [&]() {
+      const mpqe_layer_group_t& G = L.g[U.gi];
+      const mpqe_term_t& T = G.terms[__ffs(mask) - 1];
+      load_kmajor(fa, T, U.q0, G.num_queries, kc, pw, lane);
+      load_transposed(fb, T.m + (int64_t)kc * D, D, KC, pw, lane);
+    };
+    bool have = unit < total_units;
+    while (have && mask == 0) {  // (a unit without terms contributes no stages)
+      unit += gridDim.x;
+      have = unit < total_units;
+      if (have) {
+        U = decode_unit(L, unit);
+        mask = term_mask(L.g[U.gi], U.slot);
+      }
+    }
+    if (have) load();
+    while (have) {
+      uint8_t* st = acquire_stage(sh, smem, it);
+      store_kmajor(fa, st, st + TILE_BYTES, pw, lane);
+      store_transposed(fb, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, pw, lane);
+      have = advance();
+      if (have) load();          // the next stage's global loads fly while this stage is published and multiplied
+      publish_stage(sh, it);
+      ++it;
+    }
+  } else if (warp == MMA_WARP) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      int uc = 0;
+      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++uc) {
+        const UnitInfo U = decode_unit(L, unit);
+        const int nsteps = __popc(term_mask(L.g[U.gi], U.slot)) * (D / KC);
+        mma_unit(sh, smem_u32(smem), tmem, uc, nsteps, it);
+      }
+    }
+  } else {
+    // ===== epilogue: one accumulator row per thread =====
+    int uc = 0;
+    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++uc) {
+      const UnitInfo U = decode_unit(L, unit);
+      const mpqe_layer_group_t& G = L.g[U.gi];
+      const int nsteps = __popc(term_mask(G, U.slot)) * (D / KC);
+      const int ab = uc & 1;
+      mbar_wait(smem_u32(&sh.acc_full[ab]), (uc >> 1) & 1);
+      tc_fence_after();
+      const int64_t q = U.q0 + warp * 32 + lane;
+      const int oslot = G.out_slot_map[U.slot];
+      const float bscale = G.bias != nullptr ? G.bias_scale[U.slot] : 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < D; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + ab * 128 + c0, v);
+        if (q < G.num_queries) {
+          float* orow = G.out + (q * G.out_slots + oslot) * (int64_t)D + c0;
+          const float* mrow =
+              G.epilogue == MPQE_EPI_MASK ? G.mask + (q * G.mask_slots + oslot) * (int64_t)D + c0 : nullptr;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            float4 o = nsteps > 0 ? make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]),
+                                                __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]))
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (G.bias != nullptr) {
+              const float4 b = *reinterpret_cast<const float4*>(G.bias + c0 + i);
+              o.x += bscale * b.x; o.y += bscale * b.y; o.z += bscale * b.z; o.w += bscale * b.w;
+            }
+            if (G.epilogue == MPQE_EPI_RELU) {
+              o = make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
+            } else if (G.epilogue == MPQE_EPI_MASK) {
+              const float4 m = *reinterpret_cast<const float4*>(mrow + i);
+              o = make_float4(m.x > 0.f ? o.x : 0.f, m.y > 0.f ? o.y : 0.f, m.z > 0.f ? o.z : 0.f,
+                              m.w > 0.f ? o.w : 0.f);
+            }
+            *reinterpret_cast<float4*>(orow + i) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(&sh.acc_empty[ab]));
     }
   }
   tc_fence_before();
@@ -316,6 +412,7 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc_kernel(const __grid_const
 
 // ------------------------------------------------------------------------------------------------------------
 // Weight gradient on tensor cores: dM = sum_q A[q]^T G[q]; both operands are transposed into K-major tiles.
+// unit = (destination, chunk); its stages are the 32-query tiles of every matching (group, term).
 // ------------------------------------------------------------------------------------------------------------
 struct WgradIter {
   int g, t;
@@ -343,96 +440,120 @@ __device__ __forceinline__ bool wgrad_seek(const WgradLaunch& L, const float* m_
   return false;
 }
 
-__global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_constant__ WgradLaunch L) {
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ TcShared sh;
-  uint8_t* smem = align_1024(smem_raw);
-  int unit = blockIdx.x;
-  int j = 0;
+__device__ __forceinline__ void decode_wgrad_unit(const WgradLaunch& L, int unit, int& j, int& c) {
+  j = 0;
   for (; j < L.num_dests - 1; ++j) {
     if (unit < L.chunks[j]) break;
     unit -= L.chunks[j];
   }
-  const int c = unit, chunks = L.chunks[j];
-  const float* m_fwd = L.d[j].m_fwd;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  c = unit;
+}
 
-  if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) mbar_init(smem_u32(&sh.empty[s]), 1);
-    mbar_init(smem_u32(&sh.done), 1);
-    fence_barrier_init();
+__device__ __forceinline__ int wgrad_unit_steps(const WgradLaunch& L, int j, int c) {
+  int steps = 0;
+  for (int g = 0; g < L.num_groups; ++g) {
+    int64_t qb, qe;
+    chunk_range(L.g[g].num_queries, L.chunks[j], c, qb, qe);
+    const int tiles = (int)((qe - qb + KC - 1) / KC);
+    for (int t = 0; t < L.g[g].num_terms; ++t)
+      if (L.g[g].terms[t].m == L.d[j].m_fwd) steps += tiles;
   }
-  if (warp == 0) tmem_alloc(smem_u32(&sh.tmem_base), TMEM_COLS);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
+  return steps;
+}
+
+__global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_constant__ WgradLaunch L, int total_units) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ TcShared sh;
+  uint8_t* smem = align_1024(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  setup(sh, warp, tid);
   const uint32_t tmem = sh.tmem_base;
 
-  WgradIter it{0, 0, 0, 0};
-  bool more = wgrad_seek(L, m_fwd, chunks, c, it);
-  Frag fa, fb;
-  auto load_next = [&]() {  // loads the tile the iterator points at, then advances it
-    const mpqe_layer_group_t& G = L.g[it.g];
-    const mpqe_term_t& T = G.terms[it.t];
-    const mpqe_wgrad_operand_t& O = L.go[it.g];
-    const int valid = (int)(it.qe - it.q < KC ? it.qe - it.q : KC);
-    load_transposed(fa, T.a + (it.q * T.a_slots + T.a_slot) * (int64_t)D, (int64_t)T.a_slots * D, valid, warp, lane);
-    const int gs = O.slot_map[T.out_slot];
-    load_transposed(fb, O.g + (it.q * O.g_slots + gs) * (int64_t)D, (int64_t)O.g_slots * D, valid, warp, lane);
-    it.q += KC;
-    if (it.q >= it.qe) {
-      ++it.t;
-      more = wgrad_seek(L, m_fwd, chunks, c, it);
+  if (warp >= EPI_WARPS && warp < MMA_WARP) {
+    const int pw = warp - EPI_WARPS;
+    uint32_t it = 0;
+    Frag fa, fb;
+    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+      int j, c;
+      decode_wgrad_unit(L, unit, j, c);
+      WgradIter wi{0, 0, 0, 0};
+      bool more = wgrad_seek(L, L.d[j].m_fwd, L.chunks[j], c, wi);
+      auto load_next = [&]() {  // loads the tile the iterator points at, then advances it
+        const mpqe_layer_group_t& G = L.g[wi.g];
+        const mpqe_term_t& T = G.terms[wi.t];
+        const mpqe_wgrad_operand_t& O = L.go[wi.g];
+        const int valid = (int)(wi.qe - wi.q < KC ? wi.qe - wi.q : KC);
+        load_transposed(fa, T.a + (wi.q * T.a_slots + T.a_slot) * (int64_t)D, (int64_t)T.a_slots * D, valid, pw, lane);
+        const int gs = O.slot_map[T.out_slot];
+        load_transposed(fb, O.g + (wi.q * O.g_slots + gs) * (int64_t)D, (int64_t)O.g_slots * D, valid, pw, lane);
+        wi.q += KC;
+        if (wi.q >= wi.qe) {
+          ++wi.t;
+          more = wgrad_seek(L, L.d[j].m_fwd, L.chunks[j], c, wi);
+        }
+      };
+      bool have = more;
+      if (have) load_next();
+      while (have) {
+        uint8_t* st = acquire_stage(sh, smem, it);
+        store_transposed(fa, st, st + TILE_BYTES, pw, lane);
+        store_transposed(fb, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, pw, lane);
+        have = more;
+        if (have) load_next();
+        publish_stage(sh, it);
+        ++it;
+      }
     }
-  };
-  bool have = more;
-  if (have) load_next();
-  int step = 0;
-  while (have) {
-    const int s = step % STAGES, u = step / STAGES;
-    uint8_t* st = smem + s * STAGE_BYTES;
-    if (u > 0) mbar_wait(smem_u32(&sh.empty[s]), (u - 1) & 1);
-    store_transposed(fa, st, st + TILE_BYTES, warp, lane);
-    store_transposed(fb, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, warp, lane);
-    have = more;
-    if (have) load_next();
-    fence_proxy_async();
-    __syncthreads();
-    if (tid == 0) {
+  } else if (warp == MMA_WARP) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      int uc = 0;
+      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++uc) {
+        int j, c;
+        decode_wgrad_unit(L, unit, j, c);
+        mma_unit(sh, smem_u32(smem), tmem, uc, wgrad_unit_steps(L, j, c), it);
+      }
+    }
+  } else {
+    int uc = 0;
+    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++uc) {
+      int j, c;
+      decode_wgrad_unit(L, unit, j, c);
+      const int nsteps = wgrad_unit_steps(L, j, c);
+      const int ab = uc & 1;
+      mbar_wait(smem_u32(&sh.acc_full[ab]), (uc >> 1) & 1);
       tc_fence_after();
-      const uint32_t a = smem_u32(st);
-      issue_stage(tmem, a, a + TILE_BYTES, a + 2 * TILE_BYTES, a + 3 * TILE_BYTES, step == 0);
-      umma_commit(smem_u32(&sh.empty[s]));
-      if (!have) umma_commit(smem_u32(&sh.done));
-    }
-    ++step;
-  }
-  if (step > 0) {
-    mbar_wait(smem_u32(&sh.done), 0);
-    tc_fence_after();
-  }
-  int pbase = 0;
-  for (int jj = 0; jj < j; ++jj) pbase += L.chunks[jj];
-  float* P = L.partials + (int64_t)(pbase + c) * D * D;
-  const int row = (warp & 3) * 32 + lane;
+      float* P = L.partials + (int64_t)unit * D * D;   // units are numbered destination-major, chunk-minor
+      const int row = warp * 32 + lane;
 #pragma unroll 1
-  for (int half = 0; half < 2; ++half) {
-    const int c0 = (warp >> 2) * 64 + half * 32;
-    uint32_t v[32];
-    if (step > 0) {
-      tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + c0, v);
-    } else {
+      for (int c0 = 0; c0 < D; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + ab * 128 + c0, v);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = 0u;
+        for (int i = 0; i < 32; i += 4)
+          *reinterpret_cast<float4*>(P + row * D + c0 + i) =
+              nsteps > 0 ? make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
+                                       __uint_as_float(v[i + 3]))
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(&sh.acc_empty[ab]));
     }
-#pragma unroll
-    for (int i = 0; i < 32; i += 4)
-      *reinterpret_cast<float4*>(P + row * D + c0 + i) =
-          make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+int num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
 }
 
 }  // namespace
@@ -452,7 +573,8 @@ int layer_forward_tc(const mpqe_layer_group_t* groups, int num_groups, cudaStrea
     units += (groups[i].num_queries + BM - 1) / BM * groups[i].num_out_slots;
   }
   MPQE_CHECK_ARG(units < (1ll << 31), "mpqe_layer_forward: too many tiles");
-  layer_tc_kernel<<<(unsigned)units, THREADS, TC_SMEM, stream>>>(L);
+  const int grid = units < num_sms() ? (int)units : num_sms();
+  layer_tc_kernel<<<grid, THREADS, TC_SMEM, stream>>>(L, (int)units);
   MPQE_CHECK_LAUNCH("layer_tc_kernel");
   return 0;
 }
@@ -464,7 +586,8 @@ int layer_wgrad_tc_launch(const WgradLaunch& launch, int total_chunks, cudaStrea
     MPQE_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
     configured = true;
   }
-  wgrad_tc_kernel<<<total_chunks, THREADS, TC_SMEM, stream>>>(launch);
+  const int grid = total_chunks < num_sms() ? total_chunks : num_sms();
+  wgrad_tc_kernel<<<grid, THREADS, TC_SMEM, stream>>>(launch, total_chunks);
   MPQE_CHECK_LAUNCH("wgrad_tc_kernel");
   return 0;
 }

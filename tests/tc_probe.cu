@@ -22,12 +22,14 @@
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t version) {
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t version,
+                                              uint32_t layout_type = 0) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3fff);
   d |= (uint64_t)((lbo >> 4) & 0x3fff) << 16;
   d |= (uint64_t)((sbo >> 4) & 0x3fff) << 32;
   d |= (uint64_t)(version & 3) << 46;
+  d |= (uint64_t)(layout_type & 7) << 61;
   return d;
 }
 
@@ -38,6 +40,8 @@ struct Params {
   int ksteps;
   int use_mask_form;        // CUTLASS 4-register disable_output_lane form
   int version;
+  int layout_type;          // 0 none, 2 = SWIZZLE_128B
+  int repeat;               // timing: issue the k-step sequence this many times
 };
 
 __global__ void __launch_bounds__(128) probe_kernel(const uint8_t* a_img, const uint8_t* b_img, int a_bytes, int b_bytes,
@@ -65,12 +69,15 @@ __global__ void __launch_bounds__(128) probe_kernel(const uint8_t* a_img, const 
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_base;
+  long long t0 = 0;
   if (tid == 0) {
     info[0] = tmem;
+    t0 = clock64();
+    for (int rep = 0; rep < P.repeat; ++rep)
     for (int j = 0; j < P.ksteps; ++j) {
-      const uint64_t da = make_desc(smem_u32(sa) + j * P.a_step, P.a_lbo, P.a_sbo, P.version);
-      const uint64_t db = make_desc(smem_u32(sb) + j * P.b_step, P.b_lbo, P.b_sbo, P.version);
-      const uint32_t acc = j > 0 ? 1u : 0u;
+      const uint64_t da = make_desc(smem_u32(sa) + j * P.a_step, P.a_lbo, P.a_sbo, P.version, P.layout_type);
+      const uint64_t db = make_desc(smem_u32(sb) + j * P.b_step, P.b_lbo, P.b_sbo, P.version, P.layout_type);
+      const uint32_t acc = (j > 0 || rep > 0) ? 1u : 0u;
       if (P.use_mask_form) {
         asm volatile(
             "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -97,7 +104,11 @@ __global__ void __launch_bounds__(128) probe_kernel(const uint8_t* a_img, const 
         : "r"(smem_u32(&bar)), "r"(0)
         : "memory");
   }
-  if (tid == 0) info[1] = ok;
+  if (tid == 0) {
+    info[1] = ok;
+    const long long t1 = clock64();
+    info[2] = (uint32_t)(t1 - t0);
+  }
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const int row = warp * 32 + lane;
   for (int c0 = 0; c0 < 128; c0 += 32) {
@@ -126,6 +137,9 @@ static int off_kmajor(int r, int k, int lbo, int sbo) { return (r / 8) * sbo + (
 // MN-major tile [k][mn=128], element (k,mn) -> byte offset
 static int off_mnmajor(int k, int mn, int lbo, int sbo) { return (mn / 4) * sbo + (k / 8) * lbo + (k % 8) * 16 + (mn % 4) * 4; }
 
+// K-major SWIZZLE_128B tile [rows][32 k] (one 128-byte row per matrix row, 16-byte chunks XOR-ed with row%8)
+static int off_kmajor_sw128(int r, int k) { return (r / 8) * 1024 + (r % 8) * 128 + (((k / 4) ^ (r % 8)) * 16) + (k % 4) * 4; }
+
 static const uint32_t IDESC_BASE = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
 struct Hyp {
@@ -135,6 +149,7 @@ struct Hyp {
   int swap_desc;             // put LBO value in the SBO field and vice versa
   int mask_form;
   int version;
+  int sw128;                 // both operands K-major SWIZZLE_128B
 };
 
 int main() {
@@ -160,27 +175,23 @@ int main() {
   CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024));
 
   Hyp hyps[] = {
-      // name                       a_mn b_mn  a_lbo a_sbo b_lbo b_sbo swap mask ver
-      {"A:K B:MN as-coded",            0, 1,   128, 1024, 4096, 128,  0, 0, 1},
-      {"A:K B:MN mask-form",           0, 1,   128, 1024, 4096, 128,  0, 1, 1},
-      {"A:K B:MN version0",            0, 1,   128, 1024, 4096, 128,  0, 0, 0},
-      {"A:K B:MN swapped fields",      0, 1,   128, 1024, 4096, 128,  1, 0, 1},
-      {"A:K B:K  (B transposed img)",  0, 0,   128, 1024, 128, 1024,  0, 0, 1},
-      {"A:K B:K  swapped fields",      0, 0,   128, 1024, 128, 1024,  1, 0, 1},
-      {"A:MN B:MN",                    1, 1,  4096,  128, 4096, 128,  0, 0, 1},
-      {"A:MN B:MN swapped fields",     1, 1,  4096,  128, 4096, 128,  1, 0, 1},
-      {"A:K(alt: k-major groups) B:MN",0, 1,  2048,  128, 4096, 128,  0, 0, 1},
+      // name                       a_mn b_mn  a_lbo a_sbo b_lbo b_sbo swap mask ver sw128
+      {"A:K B:K no-swizzle",           0, 0,   128, 1024, 128, 1024,  0, 0, 1, 0},
+      {"A:K B:K SW128 lbo=16",         0, 0,    16, 1024,  16, 1024,  0, 0, 1, 1},
+      {"A:K B:K SW128 lbo=0",          0, 0,     0, 1024,   0, 1024,  0, 0, 1, 1},
   };
   for (const Hyp& h : hyps) {
     std::vector<uint8_t> ia(65536, 0), ib(65536, 0);
     for (int m = 0; m < 128; ++m)
       for (int k = 0; k < K; ++k) {
-        const int off = h.a_mn ? off_mnmajor(k, m, h.a_lbo, h.a_sbo) : off_kmajor(m, k, h.a_lbo, h.a_sbo);
+        const int off = h.sw128 ? off_kmajor_sw128(m, k)
+                                : (h.a_mn ? off_mnmajor(k, m, h.a_lbo, h.a_sbo) : off_kmajor(m, k, h.a_lbo, h.a_sbo));
         memcpy(&ia[off], &A[m * K + k], 4);
       }
     for (int n = 0; n < 128; ++n)
       for (int k = 0; k < K; ++k) {
-        const int off = h.b_mn ? off_mnmajor(k, n, h.b_lbo, h.b_sbo) : off_kmajor(n, k, h.b_lbo, h.b_sbo);
+        const int off = h.sw128 ? off_kmajor_sw128(n, k)
+                                : (h.b_mn ? off_mnmajor(k, n, h.b_lbo, h.b_sbo) : off_kmajor(n, k, h.b_lbo, h.b_sbo));
         memcpy(&ib[off], &Bm[k * 128 + n], 4);
       }
     CK(cudaMemcpy(da, ia.data(), 65536, cudaMemcpyHostToDevice));
@@ -193,11 +204,13 @@ int main() {
     P.b_lbo = h.swap_desc ? h.b_sbo : h.b_lbo;
     P.b_sbo = h.swap_desc ? h.b_lbo : h.b_sbo;
     // per k-step (8 k) advance: K-major -> 2 k-quads = 2*lbo ; MN-major -> one 8-k group = lbo
-    P.a_step = h.a_mn ? h.a_lbo : 2 * h.a_lbo;
-    P.b_step = h.b_mn ? h.b_lbo : 2 * h.b_lbo;
+    P.a_step = h.sw128 ? 32 : (h.a_mn ? h.a_lbo : 2 * h.a_lbo);
+    P.b_step = h.sw128 ? 32 : (h.b_mn ? h.b_lbo : 2 * h.b_lbo);
     P.ksteps = K / 8;
     P.use_mask_form = h.mask_form;
     P.version = h.version;
+    P.layout_type = h.sw128 ? 2 : 0;
+    P.repeat = 1;
     probe_kernel<<<1, 128, 140 * 1024>>>(da, db, 65536, 65536, P, dout, dinfo);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
@@ -218,6 +231,18 @@ int main() {
     }
     printf("%-34s : tmem=0x%08x waited=%u mismatches=%5d zeros=%5d maxerr=%.3f  D[0][0..3]=%.3f %.3f %.3f %.3f (ref %.3f %.3f %.3f %.3f)\n",
            h.name, info[0], info[1], bad, zeros, maxerr, out[0], out[1], out[2], out[3], ref[0], ref[1], ref[2], ref[3]);
+    // timing: many MMAs back to back on the same tiles (1 CTA, then all SMs busy)
+    for (int grid : {1, 148}) {
+      for (int rep : {16, 64}) {
+        P.repeat = rep;
+        probe_kernel<<<grid, 128, 140 * 1024>>>(da, db, 65536, 65536, P, dout, dinfo);
+        CK(cudaDeviceSynchronize());
+        uint32_t inf[3];
+        CK(cudaMemcpy(inf, dinfo, 12, cudaMemcpyDeviceToHost));
+        printf("    timing grid=%3d: %4d MMAs (128x128x8 tf32) in %8u cycles -> %.1f cycles/MMA\n", grid, rep * P.ksteps,
+               inf[2], (double)inf[2] / (rep * P.ksteps));
+      }
+    }
   }
   return 0;
 }
