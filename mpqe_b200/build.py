@@ -17,6 +17,7 @@ NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '--use_fast_math=false',
          '-Xcompiler', '-fPIC', '-Xcompiler', '-O2', '-Xcompiler', '-fvisibility=hidden', '--expt-relaxed-constexpr']
 FLAGS.remove('--use_fast_math=false')  # precise math only: fp32 parity with the reference is a requirement
+FLAGS += os.environ.get('MPQE_NVCC_FLAGS', '').split()  # e.g. -DMPQE_TC_STATS for the debug cycle accounting
 
 
 def sources():

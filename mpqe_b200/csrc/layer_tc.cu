@@ -15,6 +15,8 @@
 //                           epilogue of unit u overlaps the main loop of unit u+1)
 // The operands are staged by threads rather than by TMA because every element has to pass through registers once
 // anyway to be split into its hi/lo TF32 parts (and half of them need a transpose on the way).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mpqe {
@@ -33,6 +35,41 @@ constexpr int TILE_BYTES = BM * KC * 4;          // 16 KB: one operand tile (hi 
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;      // A_hi, A_lo, B_hi, B_lo
 constexpr int TMEM_COLS = 256;                   // two 128-column fp32 accumulators
 constexpr size_t TC_SMEM = size_t(STAGES) * STAGE_BYTES + 1024;  // + alignment slack
+
+// ---- optional event trace of CTA 0 (debug tool: mpqe_debug_set_trace) ----------------------------------------
+// Compiled in only with -DMPQE_TC_TRACE: every event costs a global atomic (~800 cycles).
+__device__ long long* g_trace = nullptr;  // [0] = event count, then (tag, value, clock64) triples
+__device__ __forceinline__ void trace(int tag, int value) {
+#ifdef MPQE_TC_TRACE
+  if (g_trace != nullptr && blockIdx.x == 0) {
+    const unsigned long long i = atomicAdd(reinterpret_cast<unsigned long long*>(g_trace), 1ull);
+    if (i < 8000) {
+      g_trace[1 + 3 * i] = tag;
+      g_trace[2 + 3 * i] = value;
+      g_trace[3 + 3 * i] = clock64();
+    }
+  }
+#else
+  (void)tag;
+  (void)value;
+#endif
+}
+
+// ---- optional per-role cycle accounting (debug tool, -DMPQE_TC_STATS + mpqe_debug_set_stats) ------------------
+__device__ long long* g_stats = nullptr;  // [CTA][16] cycle totals
+#ifdef MPQE_TC_STATS
+#define STAT_DECL long long st_t0 = 0, st_acc[6] = {0, 0, 0, 0, 0, 0}
+#define STAT_BEGIN() st_t0 = clock64()
+#define STAT_END(i) st_acc[i] += clock64() - st_t0
+#define STAT_FLUSH(base)                                                             \
+  if (g_stats != nullptr)                                                            \
+    for (int i_ = 0; i_ < 6; ++i_) g_stats[(long long)blockIdx.x * 16 + (base) + i_] = st_acc[i_]
+#else
+#define STAT_DECL
+#define STAT_BEGIN()
+#define STAT_END(i)
+#define STAT_FLUSH(base)
+#endif
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -128,8 +165,9 @@ __device__ __forceinline__ void split_tf32(const float4& x, float4& hi, float4& 
 // (Probed on B200 with tests/tc_probe.cu: K-major tf32 operands are exact with and without the 128-byte swizzle and
 // run at the same ~160 cycles per 128x128x8 MMA; MN-major no-swizzle tf32 operands yield zeros.)
 // Sources whose contiguous dimension is the tile's ROW dimension (weight matrices [k][n], and both operands of the
-// weight gradient) are transposed on the way into shared memory with 4-byte stores whose component order is rotated
-// per lane so that each warp instruction hits 32 distinct banks.
+// weight gradient) are read column-wise (lane <-> row of the tile, 4 scalar loads per 16-byte store), so that every
+// shared-memory store is a conflict-free 16-byte st.shared.v4 (a first version transposed with 4-byte stores and
+// spent 3x longer in the store pipe than in the tensor pipe).
 
 struct Frag {  // one pipeline stage worth of one operand, per producer thread
   float4 v[4];
@@ -159,42 +197,38 @@ __device__ __forceinline__ void store_kmajor(const Frag& f, uint8_t* hi_tile, ui
     *reinterpret_cast<float4*>(lo_tile + off) = lo;
   }
 }
-// Transposing stage: source is row-major [32 k][128 mn] (pitch floats between k rows); the tile wants mn as rows.
-//   instr t = pw*4+i: k half = t&1, mn4 pair = t>>1;  lane: k = 16*(t&1) + 4*r + (lane&3), r = (lane>>2)&3,
-//   mn4 = 2*(t>>1) + (lane>>4).  Loads: 32 contiguous bytes per k row (full sectors).
-__device__ __forceinline__ void load_transposed(Frag& f, const float* src, int64_t pitch, int k_valid, int pw,
-                                                int lane) {
+// Column-gather stage: the source is row-major [32 k][128 mn] (pitch floats between k rows) but the tile wants mn as
+// its rows.  Lane <-> mn (a warp instruction reads 128 contiguous bytes of one k row), each thread gathers 4
+// consecutive k of its column into a float4, which is exactly one 16-byte row of a core matrix -> one st.shared.v4.
+//   producer warp pw: mn = 32*(pw&3) + lane, k-quads kq = 4*(pw>>2) + i, i = 0..3
+__device__ __forceinline__ void load_columns(Frag& f, const float* src, int64_t pitch, int k_valid, int pw, int lane) {
+  const float* col = src + 32 * (pw & 3) + lane;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int t = pw * 4 + i;
-    const int k = 16 * (t & 1) + 4 * ((lane >> 2) & 3) + (lane & 3);
-    const int mn4 = 2 * (t >> 1) + (lane >> 4);
-    f.v[i] = k < k_valid ? *reinterpret_cast<const float4*>(src + k * pitch + mn4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int k0 = 16 * (pw >> 2) + 4 * i;
+    f.v[i].x = k0 + 0 < k_valid ? col[(k0 + 0) * pitch] : 0.f;
+    f.v[i].y = k0 + 1 < k_valid ? col[(k0 + 1) * pitch] : 0.f;
+    f.v[i].z = k0 + 2 < k_valid ? col[(k0 + 2) * pitch] : 0.f;
+    f.v[i].w = k0 + 3 < k_valid ? col[(k0 + 3) * pitch] : 0.f;
   }
 }
-__device__ __forceinline__ void store_transposed(const Frag& f, uint8_t* hi_tile, uint8_t* lo_tile, int pw, int lane) {
-  const int r = (lane >> 2) & 3;
+__device__ __forceinline__ void store_columns(const Frag& f, uint8_t* hi_tile, uint8_t* lo_tile, int pw, int lane) {
+  const int mn = 32 * (pw & 3) + lane;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int t = pw * 4 + i;
-    const int k = 16 * (t & 1) + 4 * r + (lane & 3);
-    const int mn4 = 2 * (t >> 1) + (lane >> 4);
+    const int kq = 4 * (pw >> 2) + i;
+    const int off = (mn >> 3) * 1024 + kq * 128 + (mn & 7) * 16;
     float4 hi, lo;
     split_tf32(f.v[i], hi, lo);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = (j + r) & 3;  // rotated component order: bank = ((mn%8)*4 + k%4) is distinct across the warp
-      const int mn = mn4 * 4 + c;
-      const int off = (mn >> 3) * 1024 + (k >> 2) * 128 + (mn & 7) * 16 + (k & 3) * 4;
-      const float h = c == 0 ? hi.x : c == 1 ? hi.y : c == 2 ? hi.z : hi.w;
-      const float l = c == 0 ? lo.x : c == 1 ? lo.y : c == 2 ? lo.z : lo.w;
-      *reinterpret_cast<float*>(hi_tile + off) = h;
-      *reinterpret_cast<float*>(lo_tile + off) = l;
-    }
+    *reinterpret_cast<float4*>(hi_tile + off) = hi;
+    *reinterpret_cast<float4*>(lo_tile + off) = lo;
   }
 }
 
+constexpr int EPI_PITCH = 36;  // floats per staged row: 16-byte aligned, rows 4 banks apart
+
 struct TcShared {
+  float epi[EPI_WARPS][32][EPI_PITCH];  // per epilogue warp: one 32x32 accumulator block being transposed
   uint64_t full[STAGES];
   uint64_t empty[STAGES];
   uint64_t acc_full[2];
@@ -240,16 +274,37 @@ __device__ __forceinline__ void issue_stage(uint32_t tmem_d, uint32_t stage_addr
 
 // MMA-issuer role, shared by both kernels: consumes `nsteps` stages for the unit with per-CTA index `uc`
 __device__ __forceinline__ void mma_unit(TcShared& sh, uint32_t smem_base, uint32_t tmem, int uc, int nsteps,
-                                         uint32_t& it) {
+                                         uint32_t& it, bool skip_mma = false, long long* stat = nullptr) {
   const int ab = uc & 1, use = uc >> 1;
+  long long t0 = 0;
+  (void)t0;
+#ifdef MPQE_TC_STATS
+  t0 = clock64();
+#endif
   if (use > 0) mbar_wait(smem_u32(&sh.acc_empty[ab]), (use - 1) & 1);   // epilogue drained this accumulator
+#ifdef MPQE_TC_STATS
+  if (stat) stat[0] += clock64() - t0;
+#endif
   tc_fence_after();
   for (int step = 0; step < nsteps; ++step, ++it) {
     const int s = it % STAGES;
+    trace(20, it);
+#ifdef MPQE_TC_STATS
+    t0 = clock64();
+#endif
     mbar_wait(smem_u32(&sh.full[s]), (it / STAGES) & 1);
+#ifdef MPQE_TC_STATS
+    if (stat) stat[1] += clock64() - t0;
+    t0 = clock64();
+#endif
+    trace(21, it);
     tc_fence_after();
-    issue_stage(tmem + ab * 128, smem_base + s * STAGE_BYTES, step == 0);
-    umma_commit(smem_u32(&sh.empty[s]));                                // frees the stage when the MMAs have read it
+    if (!skip_mma) issue_stage(tmem + ab * 128, smem_base + s * STAGE_BYTES, step == 0);
+    umma_commit(smem_u32(&sh.empty[s]));
+#ifdef MPQE_TC_STATS
+    if (stat) stat[2] += clock64() - t0;
+#endif
+    trace(22, it);                                // frees the stage when the MMAs have read it
   }
   umma_commit(smem_u32(&sh.acc_full[ab]));                              // accumulator complete
 }
@@ -279,10 +334,13 @@ __device__ __forceinline__ UnitInfo decode_unit(const LayerLaunch& L, int unit) 
     if (unit < units) break;
     unit -= units;
   }
+  // slot-major numbering inside a group: a persistent CTA's units (blockIdx, +grid, +2*grid, ...) then cycle through
+  // slots of different cost instead of always landing on the same (possibly heaviest) slot
+  const int tiles = int((L.g[gi].num_queries + BM - 1) / BM);
   UnitInfo u;
   u.gi = gi;
-  u.slot = unit % L.g[gi].num_out_slots;
-  u.q0 = int64_t(unit / L.g[gi].num_out_slots) * BM;
+  u.slot = unit / tiles;
+  u.q0 = int64_t(unit % tiles) * BM;
   return u;
 }
 
@@ -293,121 +351,200 @@ __device__ __forceinline__ uint32_t term_mask(const mpqe_layer_group_t& G, int s
   return m;
 }
 
-__global__ void __launch_bounds__(THREADS, 1) layer_tc_kernel(const __grid_constant__ LayerLaunch L, int total_units) {
+__global__ void __launch_bounds__(THREADS, 1) layer_tc_kernel(const __grid_constant__ LayerLaunch L, int total_units,
+                                                              int dbg) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ TcShared sh;
   uint8_t* smem = align_1024(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef MPQE_TC_STATS
+  const long long kernel_t0 = clock64();
+#endif
   setup(sh, warp, tid);
   const uint32_t tmem = sh.tmem_base;
+#ifdef MPQE_TC_STATS
+  if (tid == 0 && g_stats != nullptr) g_stats[(long long)blockIdx.x * 16 + 13] = clock64() - kernel_t0;  // setup
+#endif
 
   if (warp >= EPI_WARPS && warp < MMA_WARP) {
     // ===== producers =====
+    // Two register sets: the global loads of stage k+2 are issued right after stage k has been stored, so a full
+    // stage of store / fence / handshake work hides their latency.
     const int pw = warp - EPI_WARPS;
     uint32_t it = 0;
-    Frag fa, fb;
     // iterator over (unit, term, k chunk)
     int unit = blockIdx.x;
     UnitInfo U = decode_unit(L, unit < total_units ? unit : 0);
     uint32_t mask = unit < total_units ? term_mask(L.g[U.gi], U.slot) : 0u;
-    int kc = 0;
-    auto advance = [&]() {  // moves to the next (term, k chunk), crossing units; returns false when all work is done
+    int kc = -KC;
+    bool alive = unit < total_units;
+    // loads the next (term, k chunk) stage into (fa, fb); false when all of this CTA's work has been issued
+    auto load_next = [&](Frag& fa, Frag& fb) -> bool {
+      if (!alive) return false;
       kc += KC;
-      if (kc < D) return true;
-      kc = 0;
-      mask &= mask - 1;
-      while (mask == 0) {
+      if (kc >= D) {
+        kc = 0;
+        mask &= mask - 1;
+      }
+      while (mask == 0) {   // next unit (a unit without terms contributes no stages)
         unit += gridDim.x;
-        if (unit >= total_units) return false;
+        if (unit >= total_units) {
+          alive = false;
+          return false;
+        }
         U = decode_unit(L, unit);
         mask = term_mask(L.g[U.gi], U.slot);
+        kc = 0;
+      }
+      const mpqe_layer_group_t& G = L.g[U.gi];
+      const mpqe_term_t& T = G.terms[__ffs(mask) - 1];
+      if (!((dbg & 2) && it > 1)) {   // (dbg bit 1: timing experiment without global loads after the first stages)
+        load_kmajor(fa, T, U.q0, G.num_queries, kc, pw, lane);
+        load_columns(fb, T.m + (int64_t)kc * D, D, KC, pw, lane);
       }
       return true;
     };
-    auto load = [&]() {
-      const mpqe_layer_group_t& G = L.g[U.gi];
-      const mpqe_term_t& T = G.terms[__ffs(mask) - 1];
-      load_kmajor(fa, T, U.q0, G.num_queries, kc, pw, lane);
-      load_transposed(fb, T.m + (int64_t)kc * D, D, KC, pw, lane);
-    };
-    bool have = unit < total_units;
-    while (have && mask == 0) {  // (a unit without terms contributes no stages)
-      unit += gridDim.x;
-      have = unit < total_units;
-      if (have) {
-        U = decode_unit(L, unit);
-        mask = term_mask(L.g[U.gi], U.slot);
-      }
-    }
-    if (have) load();
-    while (have) {
+    STAT_DECL;
+    auto put = [&](const Frag& fa, const Frag& fb) {
+      STAT_BEGIN();
       uint8_t* st = acquire_stage(sh, smem, it);
-      store_kmajor(fa, st, st + TILE_BYTES, pw, lane);
-      store_transposed(fb, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, pw, lane);
-      have = advance();
-      if (have) load();          // the next stage's global loads fly while this stage is published and multiplied
+      STAT_END(0);   // waiting for a free stage
+      STAT_BEGIN();
+      if (!(dbg & 1)) {              // (dbg bit 0: timing experiment without the shared-memory stores)
+        store_kmajor(fa, st, st + TILE_BYTES, pw, lane);
+        store_columns(fb, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, pw, lane);
+      }
+      STAT_END(1);   // waiting for the loaded data + split + stores
+    };
+    Frag a0, b0, a1, b1;
+    bool h0 = load_next(a0, b0);
+    bool h1 = h0 && load_next(a1, b1);
+    while (h0) {
+      put(a0, b0);
+      STAT_BEGIN();
+      const bool n0 = h1 && load_next(a0, b0);
+      STAT_END(2);   // issuing loads
+      STAT_BEGIN();
       publish_stage(sh, it);
+      STAT_END(3);   // fence + arrive
       ++it;
+      if (!h1) break;
+      put(a1, b1);
+      STAT_BEGIN();
+      const bool n1 = n0 && load_next(a1, b1);
+      STAT_END(2);
+      STAT_BEGIN();
+      publish_stage(sh, it);
+      STAT_END(3);
+      ++it;
+      h0 = n0;
+      h1 = n1;
     }
+    if (pw == 0 && lane == 0) { STAT_FLUSH(0); }
   } else if (warp == MMA_WARP) {
     // ===== MMA issuer (one thread) =====
     if (lane == 0) {
       uint32_t it = 0;
       int uc = 0;
+      long long mstat[3] = {0, 0, 0};
       for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++uc) {
         const UnitInfo U = decode_unit(L, unit);
         const int nsteps = __popc(term_mask(L.g[U.gi], U.slot)) * (D / KC);
-        mma_unit(sh, smem_u32(smem), tmem, uc, nsteps, it);
+        mma_unit(sh, smem_u32(smem), tmem, uc, nsteps, it, (dbg & 4) != 0, mstat);
       }
+#ifdef MPQE_TC_STATS
+      if (g_stats != nullptr) {
+        for (int i = 0; i < 3; ++i) g_stats[(long long)blockIdx.x * 16 + 6 + i] = mstat[i];
+        g_stats[(long long)blockIdx.x * 16 + 9] = it;
+        g_stats[(long long)blockIdx.x * 16 + 10] = uc;
+      }
+#endif
     }
   } else {
     // ===== epilogue: one accumulator row per thread =====
     int uc = 0;
+    long long estat[2] = {0, 0}, et0 = 0;
+    (void)estat;
+    (void)et0;
     for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++uc) {
       const UnitInfo U = decode_unit(L, unit);
       const mpqe_layer_group_t& G = L.g[U.gi];
       const int nsteps = __popc(term_mask(G, U.slot)) * (D / KC);
       const int ab = uc & 1;
+      if (tid == 0) trace(30, uc);
+#ifdef MPQE_TC_STATS
+      et0 = clock64();
+#endif
       mbar_wait(smem_u32(&sh.acc_full[ab]), (uc >> 1) & 1);
+#ifdef MPQE_TC_STATS
+      estat[0] += clock64() - et0;
+      et0 = clock64();
+#endif
+      if (tid == 0) trace(31, uc);
       tc_fence_after();
-      const int64_t q = U.q0 + warp * 32 + lane;
+      // TMEM gives each thread one accumulator ROW; a 32x32 block per warp is transposed through shared memory so
+      // that every global store instruction writes 4 full 128-byte row segments (instead of 32 scattered 16-byte
+      // pieces, which kept the load/store pipe busier than the tensor pipe).
       const int oslot = G.out_slot_map[U.slot];
       const float bscale = G.bias != nullptr ? G.bias_scale[U.slot] : 0.f;
+      float* stage = &sh.epi[warp][0][0];
+      const int cq = (lane & 7) * 4;          // this lane's 4 columns inside the 32-column block
 #pragma unroll 1
       for (int c0 = 0; c0 < D; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + ab * 128 + c0, v);
-        if (q < G.num_queries) {
-          float* orow = G.out + (q * G.out_slots + oslot) * (int64_t)D + c0;
-          const float* mrow =
-              G.epilogue == MPQE_EPI_MASK ? G.mask + (q * G.mask_slots + oslot) * (int64_t)D + c0 : nullptr;
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            float4 o = nsteps > 0 ? make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]),
-                                                __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]))
-                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (G.bias != nullptr) {
-              const float4 b = *reinterpret_cast<const float4*>(G.bias + c0 + i);
-              o.x += bscale * b.x; o.y += bscale * b.y; o.z += bscale * b.z; o.w += bscale * b.w;
-            }
+        for (int i = 0; i < 32; i += 4)
+          *reinterpret_cast<float4*>(stage + lane * EPI_PITCH + i) =
+              make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
+                          __uint_as_float(v[i + 3]));
+        __syncwarp();
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (G.bias != nullptr) {
+          const float4 b = *reinterpret_cast<const float4*>(G.bias + c0 + cq);
+          bv = make_float4(bscale * b.x, bscale * b.y, bscale * b.z, bscale * b.w);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = 4 * i + (lane >> 3);
+          const int64_t q = U.q0 + warp * 32 + rr;
+          float4 o = *reinterpret_cast<const float4*>(stage + rr * EPI_PITCH + cq);
+          if (nsteps == 0) o = make_float4(0.f, 0.f, 0.f, 0.f);
+          o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+          if (q < G.num_queries && !(dbg & 8)) {
             if (G.epilogue == MPQE_EPI_RELU) {
               o = make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
             } else if (G.epilogue == MPQE_EPI_MASK) {
-              const float4 m = *reinterpret_cast<const float4*>(mrow + i);
+              const float4 m =
+                  *reinterpret_cast<const float4*>(G.mask + (q * G.mask_slots + oslot) * (int64_t)D + c0 + cq);
               o = make_float4(m.x > 0.f ? o.x : 0.f, m.y > 0.f ? o.y : 0.f, m.z > 0.f ? o.z : 0.f,
                               m.w > 0.f ? o.w : 0.f);
             }
-            *reinterpret_cast<float4*>(orow + i) = o;
+            *reinterpret_cast<float4*>(G.out + (q * G.out_slots + oslot) * (int64_t)D + c0 + cq) = o;
           }
         }
+        __syncwarp();
       }
       tc_fence_before();
       mbar_arrive(smem_u32(&sh.acc_empty[ab]));
+#ifdef MPQE_TC_STATS
+      estat[1] += clock64() - et0;
+#endif
+      if (tid == 0) trace(32, uc);
     }
+#ifdef MPQE_TC_STATS
+    if (tid == 0 && g_stats != nullptr) {
+      g_stats[(long long)blockIdx.x * 16 + 11] = estat[0];
+      g_stats[(long long)blockIdx.x * 16 + 12] = estat[1];
+    }
+#endif
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+#ifdef MPQE_TC_STATS
+  if (tid == 0 && g_stats != nullptr) g_stats[(long long)blockIdx.x * 16 + 14] = clock64() - kernel_t0;  // whole CTA
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -472,37 +609,56 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
   if (warp >= EPI_WARPS && warp < MMA_WARP) {
     const int pw = warp - EPI_WARPS;
     uint32_t it = 0;
-    Frag fa, fb;
-    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-      int j, c;
-      decode_wgrad_unit(L, unit, j, c);
-      WgradIter wi{0, 0, 0, 0};
-      bool more = wgrad_seek(L, L.d[j].m_fwd, L.chunks[j], c, wi);
-      auto load_next = [&]() {  // loads the tile the iterator points at, then advances it
-        const mpqe_layer_group_t& G = L.g[wi.g];
-        const mpqe_term_t& T = G.terms[wi.t];
-        const mpqe_wgrad_operand_t& O = L.go[wi.g];
-        const int valid = (int)(wi.qe - wi.q < KC ? wi.qe - wi.q : KC);
-        load_transposed(fa, T.a + (wi.q * T.a_slots + T.a_slot) * (int64_t)D, (int64_t)T.a_slots * D, valid, pw, lane);
-        const int gs = O.slot_map[T.out_slot];
-        load_transposed(fb, O.g + (wi.q * O.g_slots + gs) * (int64_t)D, (int64_t)O.g_slots * D, valid, pw, lane);
-        wi.q += KC;
-        if (wi.q >= wi.qe) {
-          ++wi.t;
-          more = wgrad_seek(L, L.d[j].m_fwd, L.chunks[j], c, wi);
+    // iterator over (unit, matching (group, term), 32-query tile), crossing units; two register sets as above
+    int unit = blockIdx.x - gridDim.x, j = 0, c = 0;
+    WgradIter wi{0, 0, 0, 0};
+    bool in_unit = false, alive = true;
+    auto load_next = [&](Frag& fa, Frag& fb) -> bool {
+      if (!alive) return false;
+      while (!in_unit) {
+        unit += gridDim.x;
+        if (unit >= total_units) {
+          alive = false;
+          return false;
         }
-      };
-      bool have = more;
-      if (have) load_next();
-      while (have) {
-        uint8_t* st = acquire_stage(sh, smem, it);
-        store_transposed(fa, st, st + TILE_BYTES, pw, lane);
-        store_transposed(fb, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, pw, lane);
-        have = more;
-        if (have) load_next();
-        publish_stage(sh, it);
-        ++it;
+        decode_wgrad_unit(L, unit, j, c);
+        wi = WgradIter{0, 0, 0, 0};
+        in_unit = wgrad_seek(L, L.d[j].m_fwd, L.chunks[j], c, wi);
       }
+      const mpqe_layer_group_t& G = L.g[wi.g];
+      const mpqe_term_t& T = G.terms[wi.t];
+      const mpqe_wgrad_operand_t& O = L.go[wi.g];
+      const int valid = (int)(wi.qe - wi.q < KC ? wi.qe - wi.q : KC);
+      load_columns(fa, T.a + (wi.q * T.a_slots + T.a_slot) * (int64_t)D, (int64_t)T.a_slots * D, valid, pw, lane);
+      const int gs = O.slot_map[T.out_slot];
+      load_columns(fb, O.g + (wi.q * O.g_slots + gs) * (int64_t)D, (int64_t)O.g_slots * D, valid, pw, lane);
+      wi.q += KC;
+      if (wi.q >= wi.qe) {
+        ++wi.t;
+        in_unit = wgrad_seek(L, L.d[j].m_fwd, L.chunks[j], c, wi);
+      }
+      return true;
+    };
+    auto put = [&](const Frag& fa, const Frag& fb) {
+      uint8_t* st = acquire_stage(sh, smem, it);
+      store_columns(fa, st, st + TILE_BYTES, pw, lane);
+      store_columns(fb, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, pw, lane);
+    };
+    Frag a0, b0, a1, b1;
+    bool h0 = load_next(a0, b0);
+    bool h1 = h0 && load_next(a1, b1);
+    while (h0) {
+      put(a0, b0);
+      const bool n0 = h1 && load_next(a0, b0);
+      publish_stage(sh, it);
+      ++it;
+      if (!h1) break;
+      put(a1, b1);
+      const bool n1 = n0 && load_next(a1, b1);
+      publish_stage(sh, it);
+      ++it;
+      h0 = n0;
+      h1 = n1;
     }
   } else if (warp == MMA_WARP) {
     if (lane == 0) {
@@ -524,17 +680,26 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
       mbar_wait(smem_u32(&sh.acc_full[ab]), (uc >> 1) & 1);
       tc_fence_after();
       float* P = L.partials + (int64_t)unit * D * D;   // units are numbered destination-major, chunk-minor
-      const int row = warp * 32 + lane;
+      float* stage = &sh.epi[warp][0][0];
+      const int cq = (lane & 7) * 4;
 #pragma unroll 1
       for (int c0 = 0; c0 < D; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + ab * 128 + c0, v);
 #pragma unroll
         for (int i = 0; i < 32; i += 4)
-          *reinterpret_cast<float4*>(P + row * D + c0 + i) =
-              nsteps > 0 ? make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
-                                       __uint_as_float(v[i + 3]))
-                         : make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(stage + lane * EPI_PITCH + i) =
+              make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
+                          __uint_as_float(v[i + 3]));
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = 4 * i + (lane >> 3);
+          float4 o = *reinterpret_cast<const float4*>(stage + rr * EPI_PITCH + cq);
+          if (nsteps == 0) o = make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(P + (warp * 32 + rr) * D + c0 + cq) = o;
+        }
+        __syncwarp();
       }
       tc_fence_before();
       mbar_arrive(smem_u32(&sh.acc_empty[ab]));
@@ -574,7 +739,12 @@ int layer_forward_tc(const mpqe_layer_group_t* groups, int num_groups, cudaStrea
   }
   MPQE_CHECK_ARG(units < (1ll << 31), "mpqe_layer_forward: too many tiles");
   const int grid = units < num_sms() ? (int)units : num_sms();
-  layer_tc_kernel<<<grid, THREADS, TC_SMEM, stream>>>(L, (int)units);
+  static int dbg = -1;  // MPQE_TC_DEBUG: timing experiments only (bit0 no smem stores, bit1 no global loads,
+  if (dbg < 0) {        //                 bit2 no MMAs, bit3 no epilogue stores); results are wrong when non-zero
+    const char* e = getenv("MPQE_TC_DEBUG");
+    dbg = e ? atoi(e) : 0;
+  }
+  layer_tc_kernel<<<grid, THREADS, TC_SMEM, stream>>>(L, (int)units, dbg);
   MPQE_CHECK_LAUNCH("layer_tc_kernel");
   return 0;
 }
@@ -595,3 +765,12 @@ int layer_wgrad_tc_launch(const WgradLaunch& launch, int total_chunks, cudaStrea
 }  // namespace mpqe
 
 extern "C" int mpqe_b200_has_tcgen05(void) { return 1; }
+
+extern "C" __attribute__((visibility("default"))) int mpqe_debug_set_stats(void* buf) {
+  return (int)cudaMemcpyToSymbol(mpqe::g_stats, &buf, sizeof(buf));
+}
+
+// debug only (not part of the public header): device buffer of >= 1 + 3*8000 int64 receiving CTA 0's event trace
+extern "C" __attribute__((visibility("default"))) int mpqe_debug_set_trace(void* buf) {
+  return (int)cudaMemcpyToSymbol(mpqe::g_trace, &buf, sizeof(buf));
+}
