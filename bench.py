@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument('--cpu-batch', type=int, default=256, help='queries per type in the CPU-baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--tensor-cores', type=int, default=-1, help='-1: library default, 0: fp32 FFMA, 1: tcgen05')
+    ap.add_argument('--no-graph', action='store_true', help='launch every kernel from Python instead of one CUDA graph')
     return ap.parse_args()
 
 
@@ -64,7 +65,8 @@ def workload_config(args, kg):
                             args.batch),
             'queries_per_step_per_gpu': 7 * args.batch, 'batch_per_type': args.batch, 'embed_dim': D,
             'num_layers': 2, 'readout': args.readout, 'parallelism': 'dp%d' % args.gpus,
-            'l2': 'flushed between timed steps (256 MiB memset outside the per-step events)'}
+            'l2': 'flushed between timed steps (256 MiB memset outside the per-step events)',
+            'launch': 'eager' if args.no_graph else 'one CUDA graph per step (+ eager NCCL exchange when N > 1)'}
 
 
 def make_formulas(kg, seed=0):
@@ -224,33 +226,53 @@ def main():
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up -------------------------------------------------------------------------------------------
+    # ---- warm-up (and CUDA-graph capture of the local step: forward, backward, row-gradient combine) ---------------
     for _ in range(max(args.warmup, 3)):
         ts.forward_backward(resident)
+    launches_per_step = None
+    if not args.no_graph:
+        l0 = ops.launch_count
+        ts.capture(host)
+        launches_per_step = (ops.launch_count - l0) // 3      # capture() runs the step 2x eagerly + 1x captured
+        for _ in range(3):
+            ts.replay()
     barrier()
+
+    def one_step():
+        return ts.replay() if not args.no_graph else ts.forward_backward(resident)
 
     # ---- timed region: K steps, device time per step, L2 flushed between steps --------------------------------
     sampler = ClockSampler(local_rank)
-    ops.profile = []
     launches0 = ops.launch_count
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     for s, e in ev:
         flush.zero_()
         s.record()
-        res = ts.forward_backward(resident)
+        res = one_step()
         e.record()
     barrier()
     clocks = sampler.stop()
     launches = ops.launch_count - launches0
-    prof = ops.profile
-    ops.profile = None
+    if launches_per_step is not None:
+        launches += launches_per_step * args.steps            # kernels inside the replayed graphs
     dev_ms = sum(s.elapsed_time(e) for s, e in ev)
     t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     ms_per_step = float(t.item()) / args.steps
     value = units * world / (ms_per_step * 1e-3)
+
+    # ---- per-kernel timing for the roofline: the same step launched eagerly with CUDA events around the layer and
+    # weight-gradient launches (events cannot be recorded inside a replayed graph) ---------------------------------
+    ops.profile = []
+    barrier()
+    for _ in range(args.steps):
+        flush.zero_()
+        ts.forward_backward(resident)
+    barrier()
+    prof = ops.profile
+    ops.profile = None
 
     # ---- end to end: pinned host ids -> H2D -> step -> D2H losses, wall clock --------------------------------
     for _ in range(3):

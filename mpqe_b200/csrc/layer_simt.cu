@@ -298,17 +298,33 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const __grid_constant
   for (int jj = 0; jj < j; ++jj) pbase += L.chunks[jj];
   const int e4 = blockIdx.x * 256 + threadIdx.x;  // float4 index into the [D,D] matrix
   if (e4 >= D * D / 4) return;
-  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int c = 0; c < L.chunks[j]; ++c) {
-    const float4 v = *reinterpret_cast<const float4*>(L.partials + (int64_t)(pbase + c) * D * D + e4 * 4);
-    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  const int n = L.chunks[j];
+  const float* base = L.partials + (int64_t)pbase * D * D + e4 * 4;
+  // four independent accumulation chains (chunks c = k mod 4), combined in a fixed order: bit-reproducible, and four
+  // loads in flight per thread instead of one dependent chain
+  float4 s[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) s[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  int c = 0;
+  for (; c + 4 <= n; c += 4) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 v = *reinterpret_cast<const float4*>(base + (int64_t)(c + k) * D * D);
+      s[k].x += v.x; s[k].y += v.y; s[k].z += v.z; s[k].w += v.w;
+    }
   }
+  for (int k = 0; c < n; ++c, ++k) {
+    const float4 v = *reinterpret_cast<const float4*>(base + (int64_t)c * D * D);
+    s[k].x += v.x; s[k].y += v.y; s[k].z += v.z; s[k].w += v.w;
+  }
+  float4 r = make_float4((s[0].x + s[1].x) + (s[2].x + s[3].x), (s[0].y + s[1].y) + (s[2].y + s[3].y),
+                         (s[0].z + s[1].z) + (s[2].z + s[3].z), (s[0].w + s[1].w) + (s[2].w + s[3].w));
   float4* dst = reinterpret_cast<float4*>(L.d[j].dm) + e4;
   if (L.d[j].accumulate) {
     const float4 o = *dst;
-    s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+    r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
   }
-  *dst = s;
+  *dst = r;
 }
 
 // ------------------------------------------------------------------------------------------------------------

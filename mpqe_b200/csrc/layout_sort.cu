@@ -208,31 +208,93 @@ int bits_for(int64_t max_key_exclusive) {
 }
 
 // ---- row-sparse combine -----------------------------------------------------------------------------------
-// single-CTA exclusive scan (int32) of n entries; total written to *total
-__global__ void __launch_bounds__(1024) exclusive_scan_kernel(int32_t* __restrict__ data, int64_t n,
-                                                              int64_t* __restrict__ total) {
-  __shared__ int64_t part[1024];
-  const int t = threadIdx.x;
-  const int64_t per = (n + 1023) / 1024;
-  const int64_t i0 = per * t;
-  const int64_t i1 = i0 + per < n ? i0 + per : n;
-  int64_t s = 0;
-  for (int64_t i = i0; i < i1; ++i) s += data[i];
-  part[t] = s;
+// Three-kernel exclusive scan (int32) of n entries in blocks of SCAN_BLOCK; total written to *total.
+constexpr int SCAN_BLOCK = 2048;   // 256 threads x 8 entries
+constexpr int SCAN_MAX_BLOCKS = 1024;
+
+__device__ __forceinline__ int block_exclusive_scan_256(int v, int* total) {
+  __shared__ int warp_sum[8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warp_sum[w] = incl;
   __syncthreads();
-  for (int o = 1; o < 1024; o <<= 1) {
-    const int64_t v = t >= o ? part[t - o] : 0;
+  int base = 0, all = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int s = warp_sum[k];
+    if (k < w) base += s;
+    all += s;
+  }
+  __syncthreads();
+  *total = all;
+  return base + incl - v;
+}
+
+__global__ void __launch_bounds__(256) scan_block_sums_kernel(const int32_t* __restrict__ data, int64_t n,
+                                                              int32_t* __restrict__ block_sum) {
+  const int64_t i0 = (int64_t)blockIdx.x * SCAN_BLOCK + threadIdx.x * 8;
+  int s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (i0 + k < n) s += data[i0 + k];
+  int total;
+  block_exclusive_scan_256(s, &total);
+  if (threadIdx.x == 0) block_sum[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_MAX_BLOCKS) scan_sums_kernel(int32_t* __restrict__ block_sum, int nblk,
+                                                                   int64_t* __restrict__ total) {
+  __shared__ int s[SCAN_MAX_BLOCKS];
+  const int t = threadIdx.x;
+  const int v = t < nblk ? block_sum[t] : 0;
+  s[t] = v;
+  __syncthreads();
+  for (int o = 1; o < SCAN_MAX_BLOCKS; o <<= 1) {
+    const int a = t >= o ? s[t - o] : 0;
     __syncthreads();
-    part[t] += v;
+    s[t] += a;
     __syncthreads();
   }
-  int64_t run = t == 0 ? 0 : part[t - 1];
-  for (int64_t i = i0; i < i1; ++i) {
-    const int32_t v = data[i];
-    data[i] = (int32_t)run;
-    run += v;
+  if (t < nblk) block_sum[t] = s[t] - v;
+  if (total != nullptr && t == SCAN_MAX_BLOCKS - 1) *total = s[t];
+}
+
+__global__ void __launch_bounds__(256) scan_apply_kernel(int32_t* __restrict__ data, int64_t n,
+                                                         const int32_t* __restrict__ block_off) {
+  const int64_t i0 = (int64_t)blockIdx.x * SCAN_BLOCK + threadIdx.x * 8;
+  int v[8];
+  int s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    v[k] = i0 + k < n ? data[i0 + k] : 0;
+    s += v[k];
   }
-  if (total != nullptr && t == 1023) *total = part[1023];
+  int total;
+  int run = block_off[blockIdx.x] + block_exclusive_scan_256(s, &total);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (i0 + k < n) data[i0 + k] = run;
+    run += v[k];
+  }
+}
+
+// exclusive scan of data[0..n) in place; block_sum is scratch for ceil(n / SCAN_BLOCK) ints
+int exclusive_scan(int32_t* data, int64_t n, int32_t* block_sum, int64_t* total, cudaStream_t st) {
+  const int64_t nblk = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+  MPQE_CHECK_ARG(nblk <= SCAN_MAX_BLOCKS, "scan of %lld entries exceeds the supported %d", (long long)n,
+                 SCAN_BLOCK * SCAN_MAX_BLOCKS);
+  scan_block_sums_kernel<<<(unsigned)nblk, 256, 0, st>>>(data, n, block_sum);
+  MPQE_CHECK_LAUNCH("scan_block_sums_kernel");
+  scan_sums_kernel<<<1, SCAN_MAX_BLOCKS, 0, st>>>(block_sum, (int)nblk, total);
+  MPQE_CHECK_LAUNCH("scan_sums_kernel");
+  scan_apply_kernel<<<(unsigned)nblk, 256, 0, st>>>(data, n, block_sum);
+  MPQE_CHECK_LAUNCH("scan_apply_kernel");
+  return 0;
 }
 
 __global__ void head_flags_kernel(const uint32_t* __restrict__ sorted, int64_t n, int32_t* __restrict__ flags) {
@@ -347,7 +409,7 @@ extern "C" int mpqe_relation_sort(const int64_t* edge_type, int64_t num_edges, i
 
 extern "C" size_t mpqe_sparse_rows_workspace_bytes(int64_t count) {
   const size_t n = (size_t)(count > 0 ? count : 1);
-  return carve_sort(nullptr, count).bytes + 2 * align_up(n * sizeof(int32_t), 256);
+  return carve_sort(nullptr, count).bytes + 2 * align_up(n * sizeof(int32_t), 256) + SCAN_MAX_BLOCKS * sizeof(int32_t);
 }
 
 extern "C" int mpqe_sparse_rows_combine(const int64_t* rows_id, const float* rows, int64_t count, int64_t table_rows,
@@ -362,14 +424,14 @@ extern "C" int mpqe_sparse_rows_combine(const int64_t* rows_id, const float* row
   SortBuffers s = carve_sort(workspace, count);
   int32_t* uid = (int32_t*)((char*)workspace + s.bytes);
   int32_t* seg_start = (int32_t*)((char*)uid + align_up((size_t)count * sizeof(int32_t), 256));
+  int32_t* block_sum = (int32_t*)((char*)seg_start + align_up((size_t)count * sizeof(int32_t), 256));
   narrow_keys_kernel<<<blocks_for(count, 256), 256, 0, st>>>(rows_id, count, s.k0);
   MPQE_CHECK_LAUNCH("narrow_keys_kernel");
   uint32_t *rk, *rv;
   if (radix_sort(s, count, bits_for(table_rows), st, &rk, &rv)) return 2;
   head_flags_kernel<<<blocks_for(count, 256), 256, 0, st>>>(rk, count, uid);
   MPQE_CHECK_LAUNCH("head_flags_kernel");
-  exclusive_scan_kernel<<<1, 1024, 0, st>>>(uid, count, num_unique);
-  MPQE_CHECK_LAUNCH("exclusive_scan_kernel");
+  if (exclusive_scan(uid, count, block_sum, num_unique, st)) return 2;
   segment_starts_kernel<<<blocks_for(count, 256), 256, 0, st>>>(rk, uid, count, seg_start);
   MPQE_CHECK_LAUNCH("segment_starts_kernel");
   segment_sum_kernel<<<blocks_for(count, 8), 256, 0, st>>>(rk, rv, seg_start, num_unique, count, rows, unique_ids,

@@ -96,24 +96,12 @@ class TrainStep(object):
         """Returns StepResult: per-batch losses, weighted total (device scalars), the flat dense gradient bucket
         (`.dense.flat`, views per parameter in `.dense`) and the row-sparse entity gradient
         `.sparse = (unique global row ids, summed rows, num_unique)` with global row = table_offsets[mode] + row."""
-        m = self.model
-        dev = m.mode_embeddings.weight.device
+        dev = self.model.mode_embeddings.weight.device
         with ops.device_guard(dev):
-            jobs = [self.refresh(b).job for b in batches]
-            tg = [b.targets for b in batches]
-            ng = [b.negatives for b in batches]
-            losses, W = loss_forward(m, jobs, tg, ng, self.margin, True)
-            key = tuple(b.weight for b in batches)
-            wts = getattr(self, '_wts', None)
-            if wts is None or wts[0] != key:
-                wts = self._wts = (key, torch.tensor(key, dtype=torch.float32, device=dev))
-            G = loss_backward(m, jobs, W, tg, ng, self.margin, wts[1], self.table_offsets)
-            rows, ids, used = G.rows.shared
-            sparse = ops.sparse_rows_combine(ids[:used], rows[:used], self.total_rows)
+            res = self._local_step(batches)
             if self.world > 1:
-                sparse = self.sync(G, sparse)
-            total = (losses * wts[1]).sum()
-        return StepResult(losses, total, G, sparse)
+                res = StepResult(res.losses, res.total, res.dense, self.sync(res.dense, res.sparse))
+        return res
 
     def sync(self, G, sparse):
         """Data-parallel exchange: all-reduce(dense bucket), all-gather(row ids, rows) + identical re-combine."""
@@ -133,11 +121,71 @@ class TrainStep(object):
         # padding entries are (row 0, zero row): harmless for the sum; rank order + stable sort => same bits everywhere
         return ops.sparse_rows_combine(all_ids, all_rows, self.total_rows)
 
+    def _local_step(self, batches):
+        """forward + backward + local row-gradient combine (no cross-rank exchange): the part that is graph-captured."""
+        m = self.model
+        dev = m.mode_embeddings.weight.device
+        jobs = [self.refresh(b).job for b in batches]
+        tg = [b.targets for b in batches]
+        ng = [b.negatives for b in batches]
+        losses, W = loss_forward(m, jobs, tg, ng, self.margin, True)
+        key = tuple(b.weight for b in batches)
+        wts = getattr(self, '_wts', None)
+        if wts is None or wts[0] != key:
+            wts = self._wts = (key, torch.tensor(key, dtype=torch.float32, device=dev))
+        G = loss_backward(m, jobs, W, tg, ng, self.margin, wts[1], self.table_offsets)
+        rows, ids, used = G.rows.shared
+        sparse = ops.sparse_rows_combine(ids[:used], rows[:used], self.total_rows)
+        total = (losses * wts[1]).sum()
+        return StepResult(losses, total, G, sparse)
+
+    # ---- CUDA-graph mode: the whole local step becomes one graph launch --------------------------------------
+    @torch.no_grad()
+    def capture(self, host_batches):
+        """Stages `host_batches` into static device buffers, warms up and captures the local step into a CUDA graph.
+        Later steps with batches of the same formulas and sizes call `replay(host_batches)`."""
+        m = self.model
+        dev = m.mode_embeddings.weight.device
+        with ops.device_guard(dev):
+            self._static = [self.to_device(hb) for hb in host_batches]
+            self._wts = None
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self._local_step(self._static)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize(dev)
+            profile, ops.profile = ops.profile, None      # CUDA events cannot be recorded during capture
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._graph_res = self._local_step(self._static)
+            ops.profile = profile
+        return self._graph_res
+
+    @torch.no_grad()
+    def replay(self, host_batches=None):
+        """One step through the captured graph; with `host_batches` their ids are first copied (async, pinned) into
+        the static buffers.  Returns the same StepResult object every time (its tensors are overwritten)."""
+        if host_batches is not None:
+            for b, hb in zip(self._static, host_batches):
+                b.job.anchor_ids.copy_(hb.anchor_ids, non_blocking=True)
+                b.targets.copy_(hb.targets, non_blocking=True)
+                b.negatives.copy_(hb.negatives, non_blocking=True)
+        self._graph.replay()
+        res = self._graph_res
+        if self.world > 1:
+            with ops.device_guard(res.dense.flat.device):
+                res = StepResult(res.losses, res.total, res.dense, self.sync(res.dense, res.sparse))
+        return res
+
     @torch.no_grad()
     def run_host(self, host_batches):
         """End-to-end step from pinned host ids: H2D copies, forward+backward(+sync), D2H of the losses."""
-        batches = [self.to_device(hb) for hb in host_batches]
-        res = self.forward_backward(batches)
+        if getattr(self, '_graph', None) is not None:
+            res = self.replay(host_batches)
+        else:
+            res = self.forward_backward([self.to_device(hb) for hb in host_batches])
         return res, res.losses.cpu()
 
     # ---- optional fused optimiser over the dense bucket (torch.optim.Adam defaults, train.py:86-88) -----
