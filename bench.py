@@ -140,7 +140,7 @@ class ClockSampler(object):
         self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
         try:
             self.p = subprocess.Popen(['nvidia-smi', '-i', str(gpu_index), '--query-gpu=' + self.FIELDS,
-                                       '--format=csv,noheader,nounits', '-lms', '100'], stdout=self.f,
+                                       '--format=csv,noheader,nounits', '-lms', '20'], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -226,6 +226,7 @@ def main():
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)   # samples clocks / throttle reasons from warm-up to the end of the e2e loop
     # ---- warm-up (and CUDA-graph capture of the local step: forward, backward, row-gradient combine) ---------------
     for _ in range(max(args.warmup, 3)):
         ts.forward_backward(resident)
@@ -242,7 +243,6 @@ def main():
         return ts.replay() if not args.no_graph else ts.forward_backward(resident)
 
     # ---- timed region: K steps, device time per step, L2 flushed between steps --------------------------------
-    sampler = ClockSampler(local_rank)
     launches0 = ops.launch_count
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
@@ -252,7 +252,6 @@ def main():
         res = one_step()
         e.record()
     barrier()
-    clocks = sampler.stop()
     launches = ops.launch_count - launches0
     if launches_per_step is not None:
         launches += launches_per_step * args.steps            # kernels inside the replayed graphs
@@ -287,6 +286,7 @@ def main():
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     e2e_value = units * world * args.steps / float(t.item())
+    clocks = sampler.stop()
     h2d = sum(hb.nbytes() for hb in host)
 
     # ---- roofline of the dominant kernel (the fused layer kernel: forward and input-gradient launches) ----------

@@ -1,0 +1,93 @@
+"""Evaluation metrics of the R-GCN path with the reference's definitions (mpqe/utils.py:25-95).
+
+`eval_auc_queries` / `eval_perc_queries` keep the reference's signatures and batching (128 queries, negatives drawn
+with `random.choice` under `random.seed(seed)`), but the ragged negative scoring and the percentile counts run in
+the CUDA kernels: scores never go through `.tolist()` + scipy per query.  AUC is the rank statistic of
+`sklearn.metrics.roc_auc_score` (average ranks for ties), computed on the host from the device scores.
+"""
+import random
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+def auc_from_scores(labels, scores):
+    """roc_auc_score(labels, nan_to_num(scores)) via the Mann-Whitney identity (average ranks for ties)."""
+    labels = np.asarray(labels).astype(bool)
+    scores = np.nan_to_num(np.asarray(scores, dtype=np.float64))
+    order = np.argsort(scores, kind='mergesort')
+    s = scores[order]
+    boundaries = np.flatnonzero(np.concatenate(([True], s[1:] != s[:-1], [True])))
+    ranks = np.empty(len(s), dtype=np.float64)
+    for lo, hi in zip(boundaries[:-1], boundaries[1:]):
+        ranks[lo:hi] = 0.5 * (lo + hi - 1) + 1.0
+    r = np.empty_like(ranks)
+    r[order] = ranks
+    npos = int(labels.sum())
+    nneg = len(labels) - npos
+    return (r[labels].sum() - npos * (npos + 1) / 2.0) / (npos * nneg)
+
+
+def percentile_from_counts(left, right, lengths):
+    """scipy.stats.percentileofscore(kind='rank'): (left + right + (left < right)) * 50 / n."""
+    left = np.asarray(left, dtype=np.int64)
+    right = np.asarray(right, dtype=np.int64)
+    return (left + right + (left < right)) * (50.0 / np.asarray(lengths, dtype=np.float64))
+
+
+def _get_perc_scores(scores, lengths):
+    """Reference signature (utils.py:25-32): scores = [pos..., ragged neg...] -> percentile rank per query."""
+    scores = torch.as_tensor(scores, dtype=torch.float32)
+    B = len(lengths)
+    lengths_t = torch.as_tensor(lengths, dtype=torch.int64)
+    offsets = torch.zeros(B + 1, dtype=torch.int64)
+    offsets[1:] = torch.cumsum(lengths_t, 0)
+    if scores.is_cuda:
+        with ops.device_guard(scores.device):
+            left, right = ops.rank_counts_ragged(scores[:B].contiguous(), scores[B:].contiguous(),
+                                                 offsets.to(scores.device))
+        left, right = left.cpu().numpy(), right.cpu().numpy()
+    else:
+        raise RuntimeError('percentile counts run on the device: pass CUDA scores (there is no CPU fallback)')
+    return percentile_from_counts(left, right, lengths).tolist()
+
+
+def _batches(formula_queries, batch_size):
+    for offset in range(0, len(formula_queries), batch_size):
+        yield formula_queries[offset:offset + batch_size]
+
+
+@torch.no_grad()
+def eval_auc_queries(test_queries, enc_dec, batch_size=128, hard_negatives=False, seed=0):
+    predictions, labels, formula_aucs = [], [], {}
+    random.seed(seed)
+    for formula, formula_queries in test_queries.items():
+        f_labels, f_scores = [], []
+        for batch in _batches(formula_queries, batch_size):
+            pool = (lambda q: q.hard_neg_samples) if hard_negatives else (lambda q: q.neg_samples)
+            negatives = [random.choice(pool(q)) for q in batch]
+            scores = enc_dec.forward(formula, batch, [q.target_node for q in batch], neg_nodes=negatives,
+                                     neg_lengths=[1] * len(batch))
+            f_labels.extend([1] * len(batch) + [0] * len(negatives))
+            f_scores.append(scores)
+        f_scores = torch.cat(f_scores).cpu().numpy()
+        formula_aucs[formula] = auc_from_scores(f_labels, f_scores)
+        labels.extend(f_labels)
+        predictions.append(f_scores)
+    return auc_from_scores(labels, np.concatenate(predictions)), formula_aucs
+
+
+@torch.no_grad()
+def eval_perc_queries(test_queries, enc_dec, batch_size=128, hard_negatives=False):
+    perc = []
+    for formula, formula_queries in test_queries.items():
+        for batch in _batches(formula_queries, batch_size):
+            pool = (lambda q: q.hard_neg_samples) if hard_negatives else (lambda q: q.neg_samples)
+            lengths = [len(pool(q)) for q in batch]
+            negatives = [n for q in batch for n in pool(q)]
+            scores = enc_dec.forward(formula, batch, [q.target_node for q in batch], neg_nodes=negatives,
+                                     neg_lengths=lengths)
+            perc.extend(_get_perc_scores(scores, lengths))
+    return float(np.mean(perc))

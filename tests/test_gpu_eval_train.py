@@ -1,0 +1,112 @@
+"""Callers of the hot path (SURVEY section 8 row f): eval metrics and the training loop, on the GPU, against the oracle."""
+import logging
+
+import numpy as np
+import pytest
+import torch
+
+from mpqe_b200 import data_utils, eval as mp_eval, synthetic, train_helpers, utils
+from mpqe_b200.graph import Query
+from oracle import mpqe_oracle as O
+from tests.helpers import assert_close
+from tests.model_utils import build_model
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def setup(readout='sum', seed=5, per_formula=40):
+    kg = synthetic.make_kg('tiny', seed=seed)
+    rels, _, node_maps = kg.raw()
+    cfg = O.Config(readout=readout, num_layers=2)
+    params = O.init_params(rels, node_maps, cfg, d=128, seed=1)
+    model = build_model(kg.raw(), cfg, params, DEV)
+    qsets = synthetic.make_query_sets(kg, queries_per_formula=per_formula, formulas_per_type=1, seed=2, num_neg=6)
+    return kg, cfg, params, model, qsets
+
+
+def test_auc_and_percentile_match_oracle_scores():
+    kg, cfg, params, model, qsets = setup()
+    rels, _, node_maps = kg.raw()
+    mode_ids, rel_ids = O.schema_ids(rels)
+    id2row = O.id_to_row(node_maps)
+    frm_rels, raw = qsets['3-inter_chain'][0]
+    queries = [Query.deserialize(r) for r in raw]
+    formula = queries[0].formula
+    test_queries = {formula: queries}
+    perc = utils.eval_perc_queries(test_queries, model, batch_size=16)
+    # oracle: same scores on CPU, same percentile definition
+    spec = O.formula_spec('3-inter_chain', frm_rels)
+    want = []
+    for off in range(0, len(queries), 16):
+        batch = queries[off:off + 16]
+        anchors = [q.anchor_nodes for q in batch]
+        a_ids, var_ids, ei, et, b = O.query_graph(spec, anchors, rel_ids, mode_ids)
+        lengths = [len(q.neg_samples) for q in batch]
+        negs = [n for q in batch for n in q.neg_samples]
+        with torch.no_grad():
+            s = O.forward_scores(params, cfg, spec, a_ids, var_ids, ei, et, b, id2row,
+                                 torch.tensor([q.target_node for q in batch]), torch.tensor(negs), lengths).numpy()
+        l, r = O.rank_counts(s[:len(batch)], s[len(batch):], lengths)
+        want.extend(O.percentile_from_counts(l, r, lengths))
+    assert abs(perc - float(np.mean(want))) < 1.0   # percentiles move in steps of 100/len; scores agree to 1e-5
+    auc, per_formula = utils.eval_auc_queries(test_queries, model, batch_size=16)
+    assert 0.0 <= auc <= 1.0 and formula in per_formula
+    assert utils.auc_from_scores([1, 1, 0, 0], [0.9, 0.4, 0.5, 0.1]) == O.auc([1, 1, 0, 0], [0.9, 0.4, 0.5, 0.1]) == 0.75
+
+
+def test_full_rank_eval_counts_and_metrics():
+    kg, cfg, params, model, qsets = setup(per_formula=33)
+    rels, _, node_maps = kg.raw()
+    mode_ids, rel_ids = O.schema_ids(rels)
+    id2row = O.id_to_row(node_maps)
+    frm_rels, raw = qsets['2-inter'][0]
+    queries = [Query.deserialize(r) for r in raw]
+    formula = queries[0].formula
+    left, right, pos, n = mp_eval.full_rank_counts(model, formula, queries, [q.target_node for q in queries])
+    spec = O.formula_spec('2-inter', frm_rels)
+    a_ids, var_ids, ei, et, b = O.query_graph(spec, [q.anchor_nodes for q in queries], rel_ids, mode_ids)
+    with torch.no_grad():
+        q = O.encode_queries(params, cfg, spec, a_ids, var_ids, ei, et, b, id2row).double()
+    table = params['enc.feat-%s.weight' % spec['target_mode']][:-1].double()
+    s = (q / q.norm(dim=1, keepdim=True)) @ (table / table.norm(dim=1, keepdim=True)).t()
+    p = pos.cpu().double().unsqueeze(1)
+    tol = 3e-6
+    l, r = left.cpu(), right.cpu()
+    assert n == table.shape[0]
+    assert bool(((l >= (s < p - tol).sum(1)) & (l <= (s < p + tol).sum(1))).all())
+    assert bool(((r >= (s <= p - tol).sum(1)) & (r <= (s <= p + tol).sum(1))).all())
+    m = mp_eval.ranking_metrics(left, right, n)
+    assert 0 < m['MRR'] <= 1 and 0 <= m['APR'] <= 100 and m['queries'] == 33
+    # two "shards" chained on one device give the same integers as one
+    from mpqe_b200 import ops
+    l2 = torch.zeros_like(left)
+    r2 = torch.zeros_like(right)
+    job = model.make_job(formula, queries)
+    from mpqe_b200.model import Weights
+    with torch.cuda.device(0):
+        model._engine.encode([job], Weights(model, False))
+        tab = model.enc.table(formula.target_mode)
+        for rank in range(3):
+            b0, b1 = mp_eval.shard_rows(n, rank, 3)
+            ops.rank_counts_table(job.q, pos, tab, b0, b1, l2, r2)
+    assert torch.equal(l2, left) and torch.equal(r2, right)
+
+
+def test_training_loop_runs_and_loss_decreases():
+    kg, cfg, params, model, qsets = setup(per_formula=64)
+    train = {qt: {Query.deserialize(raw[0]).formula: [Query.deserialize(r) for r in raw]}
+             for qt, groups in qsets.items() for (_, raw) in groups}
+    evalq = {'one_neg': {qt: {f: qs[:8] for f, qs in d.items()} for qt, d in train.items()},
+             'full_neg': {qt: {f: qs[:8] for f, qs in d.items()} for qt, d in train.items()}}
+    opt = torch.optim.Adam(model.parameters(), lr=0.01)
+    log = logging.getLogger('mpqe_test')
+    frm = next(iter(train['1-chain']))
+    qs = train['1-chain'][frm]
+    with torch.no_grad():
+        before = float(model.margin_loss_ids(frm, qs, [q.target_node for q in qs], [q.neg_samples[0] for q in qs]))
+    train_helpers.run_train(model, opt, train, evalq, evalq, log, max_burn_in=3, batch_size=32, log_every=1000,
+                            val_every=1000, max_iter=12)
+    with torch.no_grad():
+        after = float(model.margin_loss_ids(frm, qs, [q.target_node for q in qs], [q.neg_samples[0] for q in qs]))
+    assert np.isfinite(after) and after < before
