@@ -257,10 +257,11 @@ MPQE_API int mpqe_rank_counts_table(const float* q, int64_t B, const float* pos,
 /* ---- a16: row-sparse embedding gradients ----------------------------------------------------------------
  * Combine `count` (row id, gradient row) pairs: unique_ids ascending, rows summed in ascending pair order
  * (bit-reproducible).  num_unique is a device int64 scalar; outputs are sized for `count` rows and entries past
- * num_unique are zero rows with id 0. */
+ * num_unique are zero rows with id `pad_id`.  Input ids >= table_rows are padding of an earlier combine (use
+ * pad_id = table_rows when results are combined again, e.g. after an all-gather) and are dropped. */
 MPQE_API size_t mpqe_sparse_rows_workspace_bytes(int64_t count);
 MPQE_API int mpqe_sparse_rows_combine(const int64_t* rows_id, const float* rows, int64_t count, int64_t table_rows,
-                             int64_t* unique_ids, float* unique_rows, int64_t* num_unique,
+                             int64_t pad_id, int64_t* unique_ids, float* unique_rows, int64_t* num_unique,
                              void* workspace, size_t workspace_bytes, void* stream);
 /* dense[ids[i], :] (+)= rows[i, :] for i < *num (ids unique) */
 MPQE_API int mpqe_scatter_rows(const int64_t* ids, const float* rows, const int64_t* num, int64_t max_count,

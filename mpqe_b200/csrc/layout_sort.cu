@@ -128,9 +128,17 @@ __global__ void __launch_bounds__(SORT_WARPS * 32) radix_scatter_kernel(
   }
 }
 
-__global__ void narrow_keys_kernel(const int64_t* __restrict__ in, int64_t n, uint32_t* __restrict__ out) {
+// keys >= limit (padding entries of an earlier combine) are clamped to the sentinel `limit`
+__global__ void narrow_keys_kernel(const int64_t* __restrict__ in, int64_t n, uint32_t* __restrict__ out,
+                                   int64_t limit) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = (uint32_t)in[i];
+  if (i < n) out[i] = (uint32_t)(in[i] < limit ? in[i] : limit);
+}
+
+// the sentinel keys sort last and form one segment that must not count as a unique row
+__global__ void drop_sentinel_kernel(const uint32_t* __restrict__ sorted, int64_t n, uint32_t sentinel,
+                                     int64_t* __restrict__ num_unique) {
+  if (sorted[n - 1] >= sentinel) *num_unique -= 1;
 }
 
 __global__ void widen_vals_kernel(const uint32_t* __restrict__ in, int64_t n, int64_t* __restrict__ out) {
@@ -316,14 +324,14 @@ __global__ void __launch_bounds__(256) segment_sum_kernel(const uint32_t* __rest
                                                           const int64_t* __restrict__ num_unique, int64_t n,
                                                           const float* __restrict__ rows,
                                                           int64_t* __restrict__ unique_ids,
-                                                          float* __restrict__ unique_rows) {
+                                                          float* __restrict__ unique_rows, int64_t pad_id) {
   const int lane = threadIdx.x & 31;
   const int64_t u = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int64_t nu = *num_unique;
-  if (u >= nu) {  // padding entries: a zero row at index 0, so fixed-size consumers need no host sync
+  if (u >= nu) {  // padding entries: a zero row with id `pad_id`, so fixed-size consumers need no host sync
     if (u < n) {
       *reinterpret_cast<float4*>(unique_rows + u * D + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (lane == 0) unique_ids[u] = 0;
+      if (lane == 0) unique_ids[u] = pad_id;
     }
     return;
   }
@@ -396,7 +404,7 @@ extern "C" int mpqe_relation_sort(const int64_t* edge_type, int64_t num_edges, i
   SortBuffers s = carve_sort(workspace, num_edges);
   MPQE_CHECK_ARG(workspace && workspace_bytes >= s.bytes, "mpqe_relation_sort: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
-  narrow_keys_kernel<<<blocks_for(num_edges, 256), 256, 0, st>>>(edge_type, num_edges, s.k0);
+  narrow_keys_kernel<<<blocks_for(num_edges, 256), 256, 0, st>>>(edge_type, num_edges, s.k0, (int64_t)1 << 31);
   MPQE_CHECK_LAUNCH("narrow_keys_kernel");
   uint32_t *rk, *rv;
   if (radix_sort(s, num_edges, bits_for(num_relations), st, &rk, &rv)) return 2;
@@ -413,8 +421,8 @@ extern "C" size_t mpqe_sparse_rows_workspace_bytes(int64_t count) {
 }
 
 extern "C" int mpqe_sparse_rows_combine(const int64_t* rows_id, const float* rows, int64_t count, int64_t table_rows,
-                                        int64_t* unique_ids, float* unique_rows, int64_t* num_unique, void* workspace,
-                                        size_t workspace_bytes, void* stream) {
+                                        int64_t pad_id, int64_t* unique_ids, float* unique_rows, int64_t* num_unique,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
   MPQE_CHECK_ARG(rows_id && rows && unique_ids && unique_rows && num_unique && count >= 1 && count < (1ll << 31) &&
                      table_rows >= 1 && table_rows < (1ll << 32),
                  "mpqe_sparse_rows_combine: bad argument");
@@ -425,17 +433,19 @@ extern "C" int mpqe_sparse_rows_combine(const int64_t* rows_id, const float* row
   int32_t* uid = (int32_t*)((char*)workspace + s.bytes);
   int32_t* seg_start = (int32_t*)((char*)uid + align_up((size_t)count * sizeof(int32_t), 256));
   int32_t* block_sum = (int32_t*)((char*)seg_start + align_up((size_t)count * sizeof(int32_t), 256));
-  narrow_keys_kernel<<<blocks_for(count, 256), 256, 0, st>>>(rows_id, count, s.k0);
+  narrow_keys_kernel<<<blocks_for(count, 256), 256, 0, st>>>(rows_id, count, s.k0, table_rows);
   MPQE_CHECK_LAUNCH("narrow_keys_kernel");
   uint32_t *rk, *rv;
-  if (radix_sort(s, count, bits_for(table_rows), st, &rk, &rv)) return 2;
+  if (radix_sort(s, count, bits_for(table_rows + 1), st, &rk, &rv)) return 2;
   head_flags_kernel<<<blocks_for(count, 256), 256, 0, st>>>(rk, count, uid);
   MPQE_CHECK_LAUNCH("head_flags_kernel");
   if (exclusive_scan(uid, count, block_sum, num_unique, st)) return 2;
+  drop_sentinel_kernel<<<1, 1, 0, st>>>(rk, count, (uint32_t)table_rows, num_unique);
+  MPQE_CHECK_LAUNCH("drop_sentinel_kernel");
   segment_starts_kernel<<<blocks_for(count, 256), 256, 0, st>>>(rk, uid, count, seg_start);
   MPQE_CHECK_LAUNCH("segment_starts_kernel");
   segment_sum_kernel<<<blocks_for(count, 8), 256, 0, st>>>(rk, rv, seg_start, num_unique, count, rows, unique_ids,
-                                                         unique_rows);
+                                                         unique_rows, pad_id);
   MPQE_CHECK_LAUNCH("segment_sum_kernel");
   return 0;
 }

@@ -392,8 +392,10 @@ def relation_sort(edge_type, num_relations):
     return perm, offsets
 
 
-def sparse_rows_combine(rows_id, rows, table_rows):
-    """(unique_ids[count], unique_rows[count, D], num_unique[1]); entries past num_unique are unspecified."""
+def sparse_rows_combine(rows_id, rows, table_rows, pad_id=0):
+    """(unique_ids[count], unique_rows[count, D], num_unique[1]); entries past num_unique are (pad_id, zero row).
+    Input ids >= table_rows are treated as padding and dropped (pass pad_id=table_rows when the result is combined
+    again after an all-gather)."""
     lib = _lib.load()
     count = rows_id.numel()
     dev = rows.device
@@ -402,7 +404,7 @@ def sparse_rows_combine(rows_id, rows, table_rows):
     num = torch.empty(1, dtype=torch.int64, device=dev)
     ws = workspace(lib.mpqe_sparse_rows_workspace_bytes(count), dev, 'sparse')
     _lib.check(lib.mpqe_sparse_rows_combine(_ptr(_chk(rows_id, torch.int64, 'rows_id')),
-                                            _ptr(_chk(rows, torch.float32, 'rows')), count, table_rows, _ptr(uid),
+                                            _ptr(_chk(rows, torch.float32, 'rows')), count, table_rows, pad_id, _ptr(uid),
                                             _ptr(urows), _ptr(num), _ptr(ws), ws.numel(), _stream()),
                'mpqe_sparse_rows_combine')
     _count(10)

@@ -118,8 +118,9 @@ class TrainStep(object):
         dist.all_gather_into_tensor(all_rows, urows, group=self.pg)
         if scale != 1.0:
             all_rows.mul_(scale)
-        # padding entries are (row 0, zero row): harmless for the sum; rank order + stable sort => same bits everywhere
-        return ops.sparse_rows_combine(all_ids, all_rows, self.total_rows)
+        # padding entries carry the sentinel id `total_rows` and are dropped; rank order + stable sort => same bits
+        # on every rank
+        return ops.sparse_rows_combine(all_ids, all_rows, self.total_rows, pad_id=self.total_rows)
 
     def _local_step(self, batches):
         """forward + backward + local row-gradient combine (no cross-rank exchange): the part that is graph-captured."""
@@ -135,7 +136,7 @@ class TrainStep(object):
             wts = self._wts = (key, torch.tensor(key, dtype=torch.float32, device=dev))
         G = loss_backward(m, jobs, W, tg, ng, self.margin, wts[1], self.table_offsets)
         rows, ids, used = G.rows.shared
-        sparse = ops.sparse_rows_combine(ids[:used], rows[:used], self.total_rows)
+        sparse = ops.sparse_rows_combine(ids[:used], rows[:used], self.total_rows, pad_id=self.total_rows)
         total = (losses * wts[1]).sum()
         return StepResult(losses, total, G, sparse)
 

@@ -236,13 +236,14 @@ def relation_sort(edge_type, num_relations):
     return perm, off
 
 
-def sparse_rows_combine(rows_id, rows, table_rows):
+def sparse_rows_combine(rows_id, rows, table_rows, pad_id=0):
     count = rows_id.numel()
-    uniq, inv = torch.unique(rows_id, sorted=True, return_inverse=True)
-    uid = torch.zeros(count, dtype=torch.int64)
+    keep = rows_id < table_rows
+    uniq, inv = torch.unique(rows_id[keep], sorted=True, return_inverse=True)
+    uid = torch.full((count,), pad_id, dtype=torch.int64)
     urows = torch.zeros(count, D)
     uid[:uniq.numel()] = uniq
-    urows.index_add_(0, inv, rows)
+    urows.index_add_(0, inv, rows[keep])
     return uid, urows, torch.tensor([uniq.numel()], dtype=torch.int64)
 
 

@@ -78,7 +78,7 @@ def test_two_rank_gradients_equal_single_rank(tmp_path, monkeypatch):
     for m, (u, r, k) in {'all': res.sparse}.items():
         k = int(k)
         ids_dp, rows_dp = r0['sparse'][m]
-        nz = rows_dp.abs().sum(1) > 0          # the DP union may carry the padding id 0 with a zero row
+        nz = rows_dp.abs().sum(1) > 0
         want_nz = r[:k].abs().sum(1) > 0
         assert torch.equal(ids_dp[nz], u[:k][want_nz]), 'touched-row id set must be bit-exact'
         np.testing.assert_allclose(rows_dp[nz].numpy(), r[:k][want_nz].numpy(), rtol=1e-4, atol=1e-7)

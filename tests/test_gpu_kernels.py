@@ -311,3 +311,25 @@ def test_adam_matches_torch():
         opt.step()
         ops.adam_dense(pd, g.to(DEV), m, v, 0.01, 0.9, 0.999, 1e-8, step)
     assert_close(pd.cpu().numpy(), ref.detach().numpy(), 1e-5, 1e-6, 'adam')
+
+
+def test_sparse_rows_recombine_after_gather():
+    """Two ranks' padded combines, concatenated and combined again (what the data-parallel exchange does), equal the
+    combine of all pairs; the sentinel padding (id = table_rows) is dropped and does not form a long segment."""
+    table_rows = 1000
+    parts = []
+    all_ids, all_rows = [], []
+    for r in range(2):
+        ids = torch.randint(0, table_rows, (5000,), generator=torch.Generator().manual_seed(r))
+        rows = rnd(5000, D, seed=20 + r)
+        all_ids.append(ids)
+        all_rows.append(rows)
+        u, ur, k = ops.sparse_rows_combine(ids.to(DEV), rows.to(DEV), table_rows, pad_id=table_rows)
+        assert bool((u[int(k):] == table_rows).all()) and bool((ur[int(k):] == 0).all())
+        parts.append((u, ur))
+    u2, ur2, k2 = ops.sparse_rows_combine(torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts]), table_rows,
+                                          pad_id=table_rows)
+    want_u, want_r, want_k = E.sparse_rows_combine(torch.cat(all_ids), torch.cat(all_rows), table_rows)
+    k2 = int(k2)
+    assert k2 == int(want_k) and torch.equal(u2[:k2].cpu(), want_u[:k2])
+    assert_close(ur2[:k2].cpu().numpy(), want_r[:k2].numpy(), 1e-5, 1e-4, 'recombined rows')
