@@ -324,7 +324,8 @@ __global__ void __launch_bounds__(256) segment_sum_kernel(const uint32_t* __rest
                                                           const int64_t* __restrict__ num_unique, int64_t n,
                                                           const float* __restrict__ rows,
                                                           int64_t* __restrict__ unique_ids,
-                                                          float* __restrict__ unique_rows, int64_t pad_id) {
+                                                          float* __restrict__ unique_rows, int64_t pad_id,
+                                                          uint32_t sentinel) {
   const int lane = threadIdx.x & 31;
   const int64_t u = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int64_t nu = *num_unique;
@@ -335,8 +336,10 @@ __global__ void __launch_bounds__(256) segment_sum_kernel(const uint32_t* __rest
     }
     return;
   }
+  // the sentinel (padding) keys sort last as one more segment: the last real row must stop where it starts
+  const int64_t nu_all = nu + (sorted_key[n - 1] >= sentinel ? 1 : 0);
   const int64_t i0 = seg_start[u];
-  const int64_t i1 = (u + 1 < nu) ? seg_start[u + 1] : n;
+  const int64_t i1 = (u + 1 < nu_all) ? seg_start[u + 1] : n;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int64_t i = i0; i < i1; ++i) {  // ascending pair index (the sort is stable): fixed summation order
     const float4 v = *reinterpret_cast<const float4*>(rows + (int64_t)sorted_val[i] * D + lane * 4);
@@ -445,7 +448,7 @@ extern "C" int mpqe_sparse_rows_combine(const int64_t* rows_id, const float* row
   segment_starts_kernel<<<blocks_for(count, 256), 256, 0, st>>>(rk, uid, count, seg_start);
   MPQE_CHECK_LAUNCH("segment_starts_kernel");
   segment_sum_kernel<<<blocks_for(count, 8), 256, 0, st>>>(rk, rv, seg_start, num_unique, count, rows, unique_ids,
-                                                         unique_rows, pad_id);
+                                                         unique_rows, pad_id, (uint32_t)table_rows);
   MPQE_CHECK_LAUNCH("segment_sum_kernel");
   return 0;
 }
