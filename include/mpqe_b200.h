@@ -54,6 +54,7 @@ extern "C" {
 typedef struct {
   const float* a;
   const float* m;
+  const float* m_packed; /* optional: mpqe_pack_weights image of m (tcgen05 path stages it with one bulk copy) */
   int32_t a_slots;
   int16_t a_slot;
   int16_t out_slot;
@@ -133,6 +134,12 @@ MPQE_API int mpqe_broadcast_rows(const float* src, const int64_t* src_rows, int3
  * With transposed matrices and swapped slots the same entry point computes the input gradient. */
 MPQE_API int mpqe_layer_forward(const mpqe_layer_group_t* groups_host, int32_t num_groups, int32_t use_tensor_cores,
                        void* stream);
+
+/* Pre-split ("packed") weights for the tensor-core layer kernel: for each [d,d] matrix, MPQE_PACKED_FLOATS floats
+ * holding the tf32 hi / lo parts laid out as the kernel's shared-memory operand tiles.  mats_host is a HOST array of
+ * `count` device pointers; packed receives count * MPQE_PACKED_FLOATS floats.  Repack whenever the weights change. */
+#define MPQE_PACKED_FLOATS (2 * MPQE_D * MPQE_D)
+MPQE_API int mpqe_pack_weights(const float* const* mats_host, int32_t count, float* packed, void* stream);
 
 /* Weight gradients of the same term lists (deterministic: fixed split over queries, ordered reduction). */
 MPQE_API size_t mpqe_layer_wgrad_workspace_bytes(int32_t num_dests, int32_t num_ctas_hint);

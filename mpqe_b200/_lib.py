@@ -10,7 +10,7 @@ EPI_NONE, EPI_RELU, EPI_MASK = 0, 1, 2
 
 
 class Term(C.Structure):
-    _fields_ = [('a', C.c_void_p), ('m', C.c_void_p), ('a_slots', C.c_int32), ('a_slot', C.c_int16),
+    _fields_ = [('a', C.c_void_p), ('m', C.c_void_p), ('m_packed', C.c_void_p), ('a_slots', C.c_int32), ('a_slot', C.c_int16),
                 ('out_slot', C.c_int16)]
 
 
@@ -86,6 +86,7 @@ SIGNATURES = {
     'mpqe_sparse_rows_combine': (I32, [P, P, I64, I64, I64, P, P, P, P, SZ, P]),
     'mpqe_scatter_rows': (I32, [P, P, P, I64, P, I32, P]),
     'mpqe_adam_dense': (I32, [P, P, P, P, I64, F32, F32, F32, F32, I32, P]),
+    'mpqe_pack_weights': (I32, [P, I32, P, P]),
     'mpqe_gather_multi': (I32, [P, I32, I32, P]),
     'mpqe_cosine_margin_multi': (I32, [P, I32, F32, I32, P]),
     'mpqe_colsum_multi_workspace_bytes': (SZ, [P, I32]),

@@ -80,6 +80,15 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// 1-D bulk copy global -> shared through the async proxy (TMA engine, no tensor map); completes on `bar`
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -240,10 +249,10 @@ __device__ __forceinline__ uint8_t* align_1024(uint8_t* p) {
   return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023));
 }
 
-__device__ __forceinline__ void setup(TcShared& sh, int warp, int tid) {
+__device__ __forceinline__ void setup(TcShared& sh, int warp, int tid, int full_count) {
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(smem_u32(&sh.full[s]), PROD_THREADS);
+      mbar_init(smem_u32(&sh.full[s]), full_count);
       mbar_init(smem_u32(&sh.empty[s]), 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -360,7 +369,7 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc_kernel(const __grid_const
 #ifdef MPQE_TC_STATS
   const long long kernel_t0 = clock64();
 #endif
-  setup(sh, warp, tid);
+  setup(sh, warp, tid, PROD_THREADS + 1);   // + the thread that arms / stands in for the bulk copy of the B tiles
   const uint32_t tmem = sh.tmem_base;
 #ifdef MPQE_TC_STATS
   if (tid == 0 && g_stats != nullptr) g_stats[(long long)blockIdx.x * 16 + 13] = clock64() - kernel_t0;  // setup
@@ -379,7 +388,7 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc_kernel(const __grid_const
     int kc = -KC;
     bool alive = unit < total_units;
     // loads the next (term, k chunk) stage into (fa, fb); false when all of this CTA's work has been issued
-    auto load_next = [&](Frag& fa, Frag& fb) -> bool {
+    auto load_next = [&](Frag& fa, Frag& fb, const float*& packed) -> bool {
       if (!alive) return false;
       kc += KC;
       if (kc >= D) {
@@ -398,40 +407,52 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc_kernel(const __grid_const
       }
       const mpqe_layer_group_t& G = L.g[U.gi];
       const mpqe_term_t& T = G.terms[__ffs(mask) - 1];
+      // pre-split weight tiles (mpqe_pack_weights): [k chunk][hi 16 KB | lo 16 KB], already in the smem tile layout
+      packed = T.m_packed != nullptr ? T.m_packed + (kc / KC) * (2 * TILE_BYTES / 4) : nullptr;
       if (!((dbg & 2) && it > 1)) {   // (dbg bit 1: timing experiment without global loads after the first stages)
         load_kmajor(fa, T, U.q0, G.num_queries, kc, pw, lane);
-        load_columns(fb, T.m + (int64_t)kc * D, D, KC, pw, lane);
+        if (packed == nullptr) load_columns(fb, T.m + (int64_t)kc * D, D, KC, pw, lane);
       }
       return true;
     };
     STAT_DECL;
-    auto put = [&](const Frag& fa, const Frag& fb) {
+    auto put = [&](const Frag& fa, const Frag& fb, const float* packed) {
       STAT_BEGIN();
       uint8_t* st = acquire_stage(sh, smem, it);
       STAT_END(0);   // waiting for a free stage
       STAT_BEGIN();
+      if (pw == 0 && lane == 0) {    // the B tiles: one 32 KB bulk copy, or (unpacked weights) a plain arrival
+        const uint32_t bar = smem_u32(&sh.full[it % STAGES]);
+        if (packed != nullptr) {
+          mbar_arrive_expect_tx(bar, 2 * TILE_BYTES);
+          bulk_copy_g2s(smem_u32(st + 2 * TILE_BYTES), packed, 2 * TILE_BYTES, bar);
+        } else {
+          mbar_arrive(bar);
+        }
+      }
       if (!(dbg & 1)) {              // (dbg bit 0: timing experiment without the shared-memory stores)
         store_kmajor(fa, st, st + TILE_BYTES, pw, lane);
-        store_columns(fb, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, pw, lane);
+        if (packed == nullptr) store_columns(fb, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, pw, lane);
       }
       STAT_END(1);   // waiting for the loaded data + split + stores
     };
     Frag a0, b0, a1, b1;
-    bool h0 = load_next(a0, b0);
-    bool h1 = h0 && load_next(a1, b1);
+    const float *p0 = nullptr, *p1 = nullptr;
+    bool h0 = load_next(a0, b0, p0);
+    bool h1 = h0 && load_next(a1, b1, p1);
     while (h0) {
-      put(a0, b0);
+      put(a0, b0, p0);
       STAT_BEGIN();
-      const bool n0 = h1 && load_next(a0, b0);
+      const bool n0 = h1 && load_next(a0, b0, p0);
       STAT_END(2);   // issuing loads
       STAT_BEGIN();
       publish_stage(sh, it);
       STAT_END(3);   // fence + arrive
       ++it;
       if (!h1) break;
-      put(a1, b1);
+      put(a1, b1, p1);
       STAT_BEGIN();
-      const bool n1 = n0 && load_next(a1, b1);
+      const bool n1 = n0 && load_next(a1, b1, p1);
       STAT_END(2);
       STAT_BEGIN();
       publish_stage(sh, it);
@@ -603,7 +624,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
   __shared__ TcShared sh;
   uint8_t* smem = align_1024(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  setup(sh, warp, tid);
+  setup(sh, warp, tid, PROD_THREADS);
   const uint32_t tmem = sh.tmem_base;
 
   if (warp >= EPI_WARPS && warp < MMA_WARP) {
@@ -710,6 +731,32 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 }
 
+// Pre-split weights for the layer kernel: out[m][k chunk] = [hi tile 16 KB | lo tile 16 KB] of B[n][k] = M[k][n],
+// i.e. byte-exact images of the shared-memory operand tiles, so that staging them is one bulk copy.
+struct PackLaunch {
+  const float* m[64];
+};
+
+__global__ void __launch_bounds__(256) pack_weights_kernel(const __grid_constant__ PackLaunch P, float* __restrict__ out) {
+  const float* M = P.m[blockIdx.y];
+  const int kcb = blockIdx.x;                       // k chunk (32 k)
+  float* hi_tile = out + ((int64_t)blockIdx.y * (D / KC) + kcb) * (2 * TILE_BYTES / 4);
+  float* lo_tile = hi_tile + TILE_BYTES / 4;
+  for (int e = threadIdx.x; e < 128 * 8; e += 256) {  // e -> (n, k quad): lanes run over n (coalesced reads of M rows)
+    const int n = e & 127, kq = e >> 7;
+    float4 x;
+    x.x = M[(int64_t)(kcb * KC + kq * 4 + 0) * D + n];
+    x.y = M[(int64_t)(kcb * KC + kq * 4 + 1) * D + n];
+    x.z = M[(int64_t)(kcb * KC + kq * 4 + 2) * D + n];
+    x.w = M[(int64_t)(kcb * KC + kq * 4 + 3) * D + n];
+    float4 hi, lo;
+    split_tf32(x, hi, lo);
+    const int off = ((n >> 3) * 1024 + kq * 128 + (n & 7) * 16) / 4;
+    *reinterpret_cast<float4*>(hi_tile + off) = hi;
+    *reinterpret_cast<float4*>(lo_tile + off) = lo;
+  }
+}
+
 int num_sms() {
   static int sms = 0;
   if (sms == 0) {
@@ -765,6 +812,24 @@ int layer_wgrad_tc_launch(const WgradLaunch& launch, int total_chunks, cudaStrea
 }  // namespace mpqe
 
 extern "C" int mpqe_b200_has_tcgen05(void) { return 1; }
+
+using namespace mpqe;
+
+extern "C" int mpqe_pack_weights(const float* const* mats_host, int32_t count, float* packed, void* stream) {
+  MPQE_CHECK_ARG(mats_host != nullptr && packed != nullptr && count >= 1, "mpqe_pack_weights: bad argument");
+  for (int base = 0; base < count; base += 64) {
+    PackLaunch P;
+    const int n = count - base < 64 ? count - base : 64;
+    for (int i = 0; i < n; ++i) {
+      MPQE_CHECK_ARG(mats_host[base + i] != nullptr, "mpqe_pack_weights: matrix %d is null", base + i);
+      P.m[i] = mats_host[base + i];
+    }
+    pack_weights_kernel<<<dim3(MPQE_D / 32, n), 256, 0, (cudaStream_t)stream>>>(
+        P, packed + (int64_t)base * MPQE_PACKED_FLOATS);
+    MPQE_CHECK_LAUNCH("pack_weights_kernel");
+  }
+  return 0;
+}
 
 extern "C" __attribute__((visibility("default"))) int mpqe_debug_set_stats(void* buf) {
   return (int)cudaMemcpyToSymbol(mpqe::g_stats, &buf, sizeof(buf));

@@ -197,6 +197,14 @@ class Weights(object):
         if need_grad:
             self.wt = [ops.transpose(w) for w in self.w]
             self.roott = [ops.transpose(r) for r in self.root]
+        # tcgen05 path: tf32 hi/lo tile images of every matrix, staged by the kernel with one bulk copy per tile
+        self.wp = self.rootp = self.wtp = self.roottp = None
+        if ops.tensor_cores_default():
+            self.wp = [ops.pack_weights(w) for w in self.w]
+            self.rootp = [ops.pack_weights([r])[0] for r in self.root]
+            if need_grad:
+                self.wtp = [ops.pack_weights(w) for w in self.wt]
+                self.roottp = [ops.pack_weights([r])[0] for r in self.roott]
             if ro is not None:
                 self.w1b = ops.transpose(self.w1t.view(self.blocks, D, D))     # [blocks, D(u), D(h)] contiguous
 
@@ -247,9 +255,11 @@ class Engine(object):
         li = self.layer_index(p, job.P)
         x = job.acts[p]
         pos = {s: k for k, s in enumerate(outs)}
-        terms = [Term(x, n, t.src[e], W.w[li][job.rels[e]], pos[t.dst[e]])
+        wp = W.wp[li] if W.wp is not None else None
+        rp = W.rootp[li] if W.rootp is not None else None
+        terms = [Term(x, n, t.src[e], W.w[li][job.rels[e]], pos[t.dst[e]], wp[job.rels[e]] if wp is not None else None)
                  for e in range(t.num_edges) if t.dst[e] in pos]
-        terms += [Term(x, n, s, W.root[li], pos[s]) for s in outs]
+        terms += [Term(x, n, s, W.root[li], pos[s], rp) for s in outs]
         return terms, li
 
     def encode(self, jobs, W):
@@ -372,9 +382,12 @@ class Engine(object):
                     {t.src[e] for e in range(t.num_edges) if t.dst[e] in outs} | set(outs))
                 pos = {s: k for k, s in enumerate(ins)}
                 okey = {s: k for k, s in enumerate(outs)}
-                terms = [Term(g, g_slots, smap[okey[t.dst[e]]], W.wt[li][job.rels[e]], pos[t.src[e]])
+                wtp = W.wtp[li] if W.wtp is not None else None
+                rtp = W.roottp[li] if W.roottp is not None else None
+                terms = [Term(g, g_slots, smap[okey[t.dst[e]]], W.wt[li][job.rels[e]], pos[t.src[e]],
+                              wtp[job.rels[e]] if wtp is not None else None)
                          for e in range(t.num_edges) if t.dst[e] in okey and t.src[e] in pos]
-                terms += [Term(g, g_slots, smap[okey[s]], W.roott[li], pos[s]) for s in outs if s in pos]
+                terms += [Term(g, g_slots, smap[okey[s]], W.roott[li], pos[s], rtp) for s in outs if s in pos]
                 if readout == 'concat' and p > 0:
                     # h_p also feeds block p-1 of the concat MLP
                     terms += [Term(job.du, n, j, W.w1b[p - 1], pos[j]) for j in range(n)]

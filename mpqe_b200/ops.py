@@ -82,10 +82,11 @@ def workspace(nbytes, device, tag='ws'):
 class Term(object):
     """out[q, out_slot] += A[q, a_slot] @ M.  `a` is a [B, a_slots, D] tensor (a_slots = 0: one broadcast row set
     [rows, D], a_slot selects the row), `m` a contiguous [D, D] tensor (view)."""
-    __slots__ = ('a', 'a_slots', 'a_slot', 'm', 'out_slot')
+    __slots__ = ('a', 'a_slots', 'a_slot', 'm', 'out_slot', 'mp')
 
-    def __init__(self, a, a_slots, a_slot, m, out_slot):
+    def __init__(self, a, a_slots, a_slot, m, out_slot, mp=None):
         self.a, self.a_slots, self.a_slot, self.m, self.out_slot = a, int(a_slots), int(a_slot), m, int(out_slot)
+        self.mp = mp   # optional pack_weights() image of m
 
 
 class Group(object):
@@ -111,6 +112,7 @@ class Group(object):
             if t.m.numel() != D * D:
                 raise _lib.MpqeError('term matrix must be [%d,%d]' % (D, D))
             g.terms[i].a, g.terms[i].m = t.a.data_ptr(), t.m.data_ptr()
+            g.terms[i].m_packed = t.mp.data_ptr() if t.mp is not None else 0
             g.terms[i].a_slots, g.terms[i].a_slot, g.terms[i].out_slot = t.a_slots, t.a_slot, t.out_slot
         g.out = _chk(self.out, torch.float32, 'out').data_ptr() if self.out is not None else 0
         g.out_slots, g.epilogue = self.out_slots, self.epilogue
@@ -194,6 +196,23 @@ def layer_wgrad(groups, grad_operands, dests, ctas_hint=296, use_tensor_cores=No
         _lib.check(lib.mpqe_layer_wgrad(garr, oarr, len(groups), darr, len(dests), int(tc), _ptr(ws), ws.numel(),
                                         _stream()), 'mpqe_layer_wgrad')
     _count(2)
+
+
+PACKED_FLOATS = 2 * D * D
+
+
+def pack_weights(mats):
+    """mats: [count, D, D] tensor (or list of [D, D] views) -> [count, PACKED_FLOATS] tf32 hi/lo tile images for the
+    tensor-core layer kernel (see mpqe_pack_weights)."""
+    lib = _lib.load()
+    views = [mats[i] for i in range(mats.shape[0])] if torch.is_tensor(mats) else list(mats)
+    for v in views:
+        _chk(v, torch.float32, 'matrix')
+    out = torch.empty(len(views), PACKED_FLOATS, dtype=torch.float32, device=views[0].device)
+    ptrs = (C.c_void_p * len(views))(*[v.data_ptr() for v in views])
+    _lib.check(lib.mpqe_pack_weights(ptrs, len(views), _ptr(out), _stream()), 'mpqe_pack_weights')
+    _count((len(views) + 63) // 64)
+    return out
 
 
 def colsum(src, rows, stride, out, scale=1.0, accumulate=False):

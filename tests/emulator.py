@@ -263,6 +263,7 @@ def install(monkeypatch):
                  'cosine_margin_multi', 'colsum_multi'):
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(ops, 'device_guard', lambda device: contextlib.nullcontext())
+    monkeypatch.setattr(ops, 'tensor_cores_default', lambda: False)
 
 
 def gather_multi(items, backward=False):

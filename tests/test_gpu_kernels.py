@@ -333,3 +333,30 @@ def test_sparse_rows_recombine_after_gather():
     k2 = int(k2)
     assert k2 == int(want_k) and torch.equal(u2[:k2].cpu(), want_u[:k2])
     assert_close(ur2[:k2].cpu().numpy(), want_r[:k2].numpy(), 1e-5, 1e-4, 'recombined rows')
+
+
+@pytest.mark.parametrize('B', [100, 4096])
+def test_layer_forward_packed_weights(B):
+    """tcgen05 path with pre-split weight tiles (bulk-copy staging) == column-gather staging == CPU."""
+    need_tc(True)
+    n = 3
+    x = rnd(B, n, D, seed=1)
+    w = rnd(4, D, D, seed=2, scale=0.05)
+    bias = rnd(D, seed=3)
+    out = torch.zeros(B, n, D)
+    terms = [ops.Term(x, n, 0, w[0], 2), ops.Term(x, n, 1, w[1], 2), ops.Term(x, n, 2, w[3], 2),
+             ops.Term(x, n, 0, w[3], 0), ops.Term(x, n, 1, w[2], 1)]
+    E.layer_forward([ops.Group(B, terms, n, out, n, epilogue=ops.EPI_RELU, bias=bias)])
+    xd, wd, bd = x.to(DEV), w.to(DEV), bias.to(DEV)
+    wp = ops.pack_weights(wd)
+    outs = []
+    for packed in (False, True):
+        od = torch.zeros(B, n, D, device=DEV)
+        # mixed: some terms packed, some not, in the same launch
+        td = [ops.Term(xd, n, 0, wd[0], 2, wp[0] if packed else None), ops.Term(xd, n, 1, wd[1], 2),
+              ops.Term(xd, n, 2, wd[3], 2, wp[3] if packed else None), ops.Term(xd, n, 0, wd[3], 0, wp[3] if packed else None),
+              ops.Term(xd, n, 1, wd[2], 1, wp[2] if packed else None)]
+        ops.layer_forward([ops.Group(B, td, n, od, n, epilogue=ops.EPI_RELU, bias=bd)], use_tensor_cores=True)
+        outs.append(od.cpu())
+        assert_close(outs[-1].numpy(), out.numpy(), 1e-5, 2e-5, 'packed=%s' % packed)
+    assert torch.equal(outs[0], outs[1]), 'packed and unpacked staging must give identical bits'
