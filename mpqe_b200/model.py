@@ -197,6 +197,8 @@ class Weights(object):
         if need_grad:
             self.wt = [ops.transpose(w) for w in self.w]
             self.roott = [ops.transpose(r) for r in self.root]
+            if ro is not None:
+                self.w1b = ops.transpose(self.w1t.view(self.blocks, D, D))     # [blocks, D(u), D(h)] contiguous
         # tcgen05 path: tf32 hi/lo tile images of every matrix, staged by the kernel with one bulk copy per tile
         self.wp = self.rootp = self.wtp = self.roottp = None
         if ops.tensor_cores_default():
@@ -205,8 +207,6 @@ class Weights(object):
             if need_grad:
                 self.wtp = [ops.pack_weights(w) for w in self.wt]
                 self.roottp = [ops.pack_weights([r])[0] for r in self.roott]
-            if ro is not None:
-                self.w1b = ops.transpose(self.w1t.view(self.blocks, D, D))     # [blocks, D(u), D(h)] contiguous
 
 
 def _needed_slots(job, readout):
