@@ -368,6 +368,8 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc_kernel(const __grid_const
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 #ifdef MPQE_TC_STATS
   const long long kernel_t0 = clock64();
+  unsigned long long gt0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0));
 #endif
   setup(sh, warp, tid, PROD_THREADS + 1);   // + the thread that arms / stands in for the bulk copy of the B tiles
   const uint32_t tmem = sh.tmem_base;
@@ -564,7 +566,13 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc_kernel(const __grid_const
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 #ifdef MPQE_TC_STATS
-  if (tid == 0 && g_stats != nullptr) g_stats[(long long)blockIdx.x * 16 + 14] = clock64() - kernel_t0;  // whole CTA
+  if (tid == 0 && g_stats != nullptr) {
+    g_stats[(long long)blockIdx.x * 16 + 14] = clock64() - kernel_t0;  // whole CTA
+    unsigned long long gt1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
+    g_stats[(long long)blockIdx.x * 16 + 15] = (long long)gt0;          // absolute start (ns)
+    g_stats[(long long)blockIdx.x * 16 + 4] = (long long)(gt1 - gt0);   // CTA lifetime (ns)
+  }
 #endif
 }
 

@@ -153,6 +153,9 @@ class _Profiled(object):
 
     def __enter__(self):
         if self.on:
+            # keep the GPU busy (~150 us spin) while the host prepares and enqueues [start, kernel, end]; otherwise
+            # an idle GPU stamps `start` long before the launch arrives and the interval includes host latency
+            torch.cuda._sleep(300000)
             self.s.record()
 
     def __exit__(self, *exc):
