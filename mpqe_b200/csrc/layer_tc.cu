@@ -741,8 +741,9 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
 
 // Pre-split weights for the layer kernel: out[m][k chunk] = [hi tile 16 KB | lo tile 16 KB] of B[n][k] = M[k][n],
 // i.e. byte-exact images of the shared-memory operand tiles, so that staging them is one bulk copy.
+constexpr int PACK_MAX = 256;
 struct PackLaunch {
-  const float* m[64];
+  const float* m[PACK_MAX];
 };
 
 __global__ void __launch_bounds__(256) pack_weights_kernel(const __grid_constant__ PackLaunch P, float* __restrict__ out) {
@@ -825,9 +826,9 @@ using namespace mpqe;
 
 extern "C" int mpqe_pack_weights(const float* const* mats_host, int32_t count, float* packed, void* stream) {
   MPQE_CHECK_ARG(mats_host != nullptr && packed != nullptr && count >= 1, "mpqe_pack_weights: bad argument");
-  for (int base = 0; base < count; base += 64) {
-    PackLaunch P;
-    const int n = count - base < 64 ? count - base : 64;
+  for (int base = 0; base < count; base += PACK_MAX) {
+    static thread_local PackLaunch P;
+    const int n = count - base < PACK_MAX ? count - base : PACK_MAX;
     for (int i = 0; i < n; ++i) {
       MPQE_CHECK_ARG(mats_host[base + i] != nullptr, "mpqe_pack_weights: matrix %d is null", base + i);
       P.m[i] = mats_host[base + i];

@@ -199,14 +199,29 @@ class Weights(object):
             self.roott = [ops.transpose(r) for r in self.root]
             if ro is not None:
                 self.w1b = ops.transpose(self.w1t.view(self.blocks, D, D))     # [blocks, D(u), D(h)] contiguous
-        # tcgen05 path: tf32 hi/lo tile images of every matrix, staged by the kernel with one bulk copy per tile
+        # tcgen05 path: tf32 hi/lo tile images of every matrix, staged by the kernel with one bulk copy per tile;
+        # all matrices of the step are packed by ONE launch
         self.wp = self.rootp = self.wtp = self.roottp = None
         if ops.tensor_cores_default():
-            self.wp = [ops.pack_weights(w) for w in self.w]
-            self.rootp = [ops.pack_weights([r])[0] for r in self.root]
-            if need_grad:
-                self.wtp = [ops.pack_weights(w) for w in self.wt]
-                self.roottp = [ops.pack_weights([r])[0] for r in self.roott]
+            mats = []
+            for li in range(len(self.w)):
+                mats += [self.w[li][r] for r in range(self.w[li].shape[0])] + [self.root[li]]
+                if need_grad:
+                    mats += [self.wt[li][r] for r in range(self.wt[li].shape[0])] + [self.roott[li]]
+            packed = ops.pack_weights(mats)
+            self.wp, self.rootp, self.wtp, self.roottp = [], [], [], []
+            off = 0
+            for li in range(len(self.w)):
+                R = self.w[li].shape[0]
+                self.wp.append(packed[off:off + R])
+                self.rootp.append(packed[off + R])
+                off += R + 1
+                if need_grad:
+                    self.wtp.append(packed[off:off + R])
+                    self.roottp.append(packed[off + R])
+                    off += R + 1
+            if not need_grad:
+                self.wtp = self.roottp = None
 
 
 def _needed_slots(job, readout):

@@ -192,10 +192,12 @@ def layer_wgrad(groups, grad_operands, dests, ctas_hint=296, use_tensor_cores=No
     for j, (m_fwd, dm, acc) in enumerate(dests):
         darr[j].m_fwd, darr[j].dm, darr[j].accumulate = m_fwd.data_ptr(), _chk(dm, torch.float32, 'dm').data_ptr(), int(acc)
     dev = groups[0].terms[0].a.device
+    tc = tensor_cores_default() if use_tensor_cores is None else bool(use_tensor_cores)
+    if tc:
+        ctas_hint = min(ctas_hint, 148)   # the tcgen05 kernel is persistent: one unit per SM is enough parallelism
     nbytes = lib.mpqe_layer_wgrad_workspace_bytes(len(dests), ctas_hint)
     ws = workspace(nbytes, dev, 'wgrad')
     with _Profiled('wgrad', groups, grad_operands):
-        tc = tensor_cores_default() if use_tensor_cores is None else bool(use_tensor_cores)
         _lib.check(lib.mpqe_layer_wgrad(garr, oarr, len(groups), darr, len(dests), int(tc), _ptr(ws), ws.numel(),
                                         _stream()), 'mpqe_layer_wgrad')
     _count(2)
@@ -214,7 +216,7 @@ def pack_weights(mats):
     out = torch.empty(len(views), PACKED_FLOATS, dtype=torch.float32, device=views[0].device)
     ptrs = (C.c_void_p * len(views))(*[v.data_ptr() for v in views])
     _lib.check(lib.mpqe_pack_weights(ptrs, len(views), _ptr(out), _stream()), 'mpqe_pack_weights')
-    _count((len(views) + 63) // 64)
+    _count((len(views) + 255) // 256)
     return out
 
 

@@ -110,3 +110,37 @@ def test_training_loop_runs_and_loss_decreases():
     with torch.no_grad():
         after = float(model.margin_loss_ids(frm, qs, [q.target_node for q in qs], [q.neg_samples[0] for q in qs]))
     assert np.isfinite(after) and after < before
+
+
+def test_train_step_graph_replay_equals_eager():
+    """The CUDA-graph step (row (f)1) gives the same bits as the eager step, and follows new ids copied into the
+    static buffers."""
+    from mpqe_b200.graph import Formula
+    from mpqe_b200.train_step import HostBatch, TrainStep
+    kg = synthetic.make_kg('aifb', seed=3)
+    rels, _, node_maps = kg.raw()
+    cfg = O.Config(readout='sum', num_layers=2)
+    params = O.init_params(rels, node_maps, cfg, d=128, seed=1)
+    model = build_model(kg.raw(), cfg, params, DEV, sparse_grad=True)
+    frng = np.random.RandomState(0)
+    formulas = [Formula(qt, kg.sample_formula(qt, frng)) for qt in synthetic.QUERY_TYPES]
+
+    def host(seed):
+        rng = np.random.RandomState(seed)
+        return [HostBatch(f, *[torch.from_numpy(x) for x in synthetic.sample_id_batch(kg, f, 500, rng)]) for f in formulas]
+
+    ts = TrainStep(model)
+    h1, h2 = host(1), host(2)
+    eager1 = ts.forward_backward([ts.to_device(hb) for hb in h1])
+    e1 = (eager1.losses.clone(), eager1.dense.flat.clone(), [x.clone() for x in eager1.sparse])
+    eager2 = ts.forward_backward([ts.to_device(hb) for hb in h2])
+    e2 = (eager2.losses.clone(), eager2.dense.flat.clone(), [x.clone() for x in eager2.sparse])
+    ts.capture(h1)
+    for hb, want in ((h1, e1), (h2, e2), (h1, e1)):
+        res, losses_host = ts.run_host(hb)
+        torch.cuda.synchronize()
+        assert torch.equal(res.losses, want[0]) and torch.equal(losses_host, want[0].cpu())
+        assert torch.equal(res.dense.flat, want[1]), 'dense gradients differ between graph replay and eager step'
+        k = int(want[2][2])
+        assert int(res.sparse[2]) == k and torch.equal(res.sparse[0][:k], want[2][0][:k])
+        assert torch.equal(res.sparse[1][:k], want[2][1][:k])
