@@ -308,6 +308,43 @@ def main():
                         'avg_launch_us': lk['avg_us'], 'achieved_TFLOPs': lk['TFLOPs'],
                         'share_of_step': lk['ms_per_step'] / ms_per_step}
 
+    # ---- second headline: full-entity ranking eval (queries/s), entity table sharded over the ranks ----------------
+    from mpqe_b200 import eval as mp_eval
+    from mpqe_b200.graph import Query
+    eval_info = None
+    try:
+        ef = formulas[4]                                       # 3-inter
+        erng = np.random.RandomState(7)
+        ea, et_, _ = synthetic.sample_id_batch(kg, ef, args.batch, erng)   # same queries on every rank (replicated)
+        ea_d = torch.from_numpy(ea)
+        et_d = torch.from_numpy(et_).to(dev)
+        eq = [None] * args.batch
+        t, var_ids, rels_e = data_utils.RGCNQueryDataset.formula_layout(ef, model.rel_ids, model.mode_ids)
+        qg = data_utils.QueryGraphBatch(t, rels_e, args.batch)
+        var_t = torch.tensor(var_ids, dtype=torch.int64)
+
+        def eval_step():
+            return mp_eval.full_rank_counts(model, ef, eq, et_d, anchor_ids=ea_d, var_ids=var_t, q_graphs=qg)
+
+        for _ in range(3):
+            l_, r_, _, n_ent = eval_step()
+        barrier()
+        es, ee = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        es.record()
+        for _ in range(5):
+            l_, r_, _, n_ent = eval_step()
+        ee.record()
+        barrier()
+        ems = torch.tensor([es.elapsed_time(ee) / 5], dtype=torch.float64, device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(ems, op=torch.distributed.ReduceOp.MAX)
+        m = mp_eval.ranking_metrics(l_, r_, n_ent)
+        eval_info = {'metric': 'full-rank eval queries/s', 'value': args.batch / (float(ems.item()) * 1e-3),
+                     'unit': 'queries/s', 'ms_per_batch': float(ems.item()), 'queries': args.batch,
+                     'candidates_per_query': int(n_ent), 'table_sharded_over': world, 'MRR': m['MRR'], 'APR': m['APR']}
+    except Exception as exc:  # the train metric is the contract line; never lose it to the extra one
+        eval_info = {'error': repr(exc)}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         params = {k: v.detach().cpu() for k, v in model.state_dict().items()}
@@ -322,7 +359,8 @@ def main():
                 'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
                         'd2h_bytes_per_step': 4 * len(host)},
                 'gpu_launches': launches, 'clocks': clocks, 'kernels': kernels,
-                'tensor_cores': bool(ops.tensor_cores_default()), 'loss': [float(x) for x in losses_host]}
+                'tensor_cores': bool(ops.tensor_cores_default()), 'loss': [float(x) for x in losses_host],
+                'eval': eval_info}
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()

@@ -766,6 +766,179 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const __grid_constant
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Full-entity rank counts on tensor cores (mpqe_rank_counts_table, use_tensor_cores = 1).
+// D[candidate, query] = table_row . q  for a 128-candidate x 128-query tile, K = 128; both operands are K-major as
+// stored.  A CTA owns one (query tile, slice of the candidate range): the query tile is split into tf32 hi/lo ONCE
+// and stays resident in shared memory (128 KB), candidate tiles stream through 2 x 32 KB stages.  The epilogue scales
+// by 1/||row|| and 1/max(||q||,eps), compares with the positive score and counts with warp ballots; only integer
+// atomics touch global memory.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int RANK_STAGES = 2;
+constexpr int RANK_A_STAGE = 2 * TILE_BYTES;                       // A_hi | A_lo
+constexpr size_t RANK_SMEM = size_t(D / KC) * 2 * TILE_BYTES + size_t(RANK_STAGES) * RANK_A_STAGE + 1024;
+
+struct RankLaunch {
+  const float* table;      // rows [row_begin, row_begin + rows)
+  int64_t row_begin, rows;
+  const float* inv_norm;   // [rows]
+  const float* q;          // [B, D]
+  const float* qinv;       // [B]
+  const float* pos;        // [B]
+  int64_t B;
+  unsigned long long* left;
+  unsigned long long* right;
+  int splits;              // candidate-range slices per query tile
+};
+
+__device__ __forceinline__ void load_rows_kmajor(Frag& f, const float* base, int64_t first_row, int64_t num_rows,
+                                                 int kc, int pw, int lane) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int idx = pw * 4 + i;
+    int64_t r = first_row + (idx >> 1) * 8 + (lane & 7);
+    if (r >= num_rows) r = num_rows - 1;
+    const int kq = (idx & 1) * 4 + (lane >> 3);
+    f.v[i] = *reinterpret_cast<const float4*>(base + r * D + kc + kq * 4);
+  }
+}
+
+__global__ void __launch_bounds__(THREADS, 1) rank_tc_kernel(const __grid_constant__ RankLaunch R) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ TcShared sh;
+  __shared__ uint64_t bres_full;
+  __shared__ float s_qinv[BM], s_pos[BM];
+  uint8_t* smem = align_1024(smem_raw);
+  uint8_t* bres = smem;                                             // [k chunk][hi | lo]
+  uint8_t* astage = smem + (D / KC) * 2 * TILE_BYTES;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) mbar_init(smem_u32(&bres_full), PROD_THREADS);
+  setup(sh, warp, tid, PROD_THREADS);
+  const uint32_t tmem = sh.tmem_base;
+
+  const int qt = blockIdx.x / R.splits, split = blockIdx.x % R.splits;
+  const int64_t b0 = (int64_t)qt * BM;
+  const int64_t tiles = (R.rows + BM - 1) / BM;
+  const int64_t per = (tiles + R.splits - 1) / R.splits;
+  const int64_t t0 = per * split, t1 = t0 + per < tiles ? t0 + per : tiles;   // candidate tiles of this CTA
+  const int num_units = t1 > t0 ? (int)(t1 - t0) : 0;
+
+  if (warp >= EPI_WARPS && warp < MMA_WARP) {
+    const int pw = warp - EPI_WARPS;
+    Frag f;
+    for (int kcb = 0; kcb < D / KC; ++kcb) {                        // resident query tile
+      load_rows_kmajor(f, R.q, b0, R.B, kcb * KC, pw, lane);
+      store_kmajor(f, bres + kcb * 2 * TILE_BYTES, bres + kcb * 2 * TILE_BYTES + TILE_BYTES, pw, lane);
+    }
+    fence_proxy_async();
+    mbar_arrive(smem_u32(&bres_full));
+    uint32_t it = 0;
+    Frag f0, f1;
+    const int total = num_units * (D / KC);
+    auto ld = [&](Frag& fr, int step) {
+      load_rows_kmajor(fr, R.table + R.row_begin * D, (t0 + step / (D / KC)) * BM, R.rows, (step % (D / KC)) * KC, pw,
+                       lane);
+    };
+    auto put = [&](const Frag& fr) {
+      const int s = it % RANK_STAGES;
+      const uint32_t use = it / RANK_STAGES;
+      if (use > 0) mbar_wait(smem_u32(&sh.empty[s]), (use - 1) & 1);
+      uint8_t* st = astage + s * RANK_A_STAGE;
+      store_kmajor(fr, st, st + TILE_BYTES, pw, lane);
+    };
+    if (total > 0) ld(f0, 0);
+    if (total > 1) ld(f1, 1);
+    for (int step = 0; step < total; step += 2) {
+      put(f0);
+      if (step + 2 < total) ld(f0, step + 2);
+      fence_proxy_async();
+      mbar_arrive(smem_u32(&sh.full[it % RANK_STAGES]));
+      ++it;
+      if (step + 1 >= total) break;
+      put(f1);
+      if (step + 3 < total) ld(f1, step + 3);
+      fence_proxy_async();
+      mbar_arrive(smem_u32(&sh.full[it % RANK_STAGES]));
+      ++it;
+    }
+  } else if (warp == MMA_WARP) {
+    if (lane == 0) {
+      mbar_wait(smem_u32(&bres_full), 0);
+      tc_fence_after();
+      uint32_t it = 0;
+      const uint32_t bres_a = smem_u32(bres), ast_a = smem_u32(astage);
+      for (int uc = 0; uc < num_units; ++uc) {
+        const int ab = uc & 1, use = uc >> 1;
+        if (use > 0) mbar_wait(smem_u32(&sh.acc_empty[ab]), (use - 1) & 1);
+        tc_fence_after();
+        for (int kcb = 0; kcb < D / KC; ++kcb, ++it) {
+          const int s = it % RANK_STAGES;
+          mbar_wait(smem_u32(&sh.full[s]), (it / RANK_STAGES) & 1);
+          tc_fence_after();
+          const uint32_t a_hi = ast_a + s * RANK_A_STAGE, a_lo = a_hi + TILE_BYTES;
+          const uint32_t b_hi = bres_a + kcb * 2 * TILE_BYTES, b_lo = b_hi + TILE_BYTES;
+#pragma unroll
+          for (int j = 0; j < KC / 8; ++j) {
+            const uint64_t dah = make_desc(a_hi + j * 256, 128, 1024), dal = make_desc(a_lo + j * 256, 128, 1024);
+            const uint64_t dbh = make_desc(b_hi + j * 256, 128, 1024), dbl = make_desc(b_lo + j * 256, 128, 1024);
+            umma_tf32(tmem + ab * 128, dal, dbh, IDESC_TF32, (kcb == 0 && j == 0) ? 0u : 1u);
+            umma_tf32(tmem + ab * 128, dah, dbl, IDESC_TF32, 1u);
+            umma_tf32(tmem + ab * 128, dah, dbh, IDESC_TF32, 1u);
+          }
+          umma_commit(smem_u32(&sh.empty[s]));
+        }
+        umma_commit(smem_u32(&sh.acc_full[ab]));
+      }
+    }
+  } else {
+    // epilogue: thread = candidate row, columns = the 128 queries of the tile
+    for (int c = tid; c < BM; c += EPI_WARPS * 32) {
+      const int64_t b = b0 + c;
+      s_qinv[c] = b < R.B ? R.qinv[b] : 0.f;
+      s_pos[c] = b < R.B ? R.pos[b] : 0.f;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32));          // only the epilogue warps
+    unsigned lt[4] = {0, 0, 0, 0}, le[4] = {0, 0, 0, 0};             // lane c holds the counts of columns c0 + c
+    for (int uc = 0; uc < num_units; ++uc) {
+      const int ab = uc & 1;
+      mbar_wait(smem_u32(&sh.acc_full[ab]), (uc >> 1) & 1);
+      tc_fence_after();
+      const int64_t row = (t0 + uc) * BM + warp * 32 + lane;
+      const bool valid = row < R.rows;
+      const float inr = valid ? R.inv_norm[row] : 0.f;
+#pragma unroll
+      for (int cb = 0; cb < 4; ++cb) {
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + ab * 128 + cb * 32, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float sc = __uint_as_float(v[i]) * inr * s_qinv[cb * 32 + i];
+          const float p = s_pos[cb * 32 + i];
+          const unsigned m_lt = __ballot_sync(0xffffffffu, valid && sc < p);
+          const unsigned m_le = __ballot_sync(0xffffffffu, valid && sc <= p);
+          if (lane == i) {
+            lt[cb] += __popc(m_lt);
+            le[cb] += __popc(m_le);
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(&sh.acc_empty[ab]));
+    }
+#pragma unroll
+    for (int cb = 0; cb < 4; ++cb) {
+      const int64_t b = b0 + cb * 32 + lane;
+      if (b < R.B) {
+        if (lt[cb]) atomicAdd(R.left + b, (unsigned long long)lt[cb]);
+        if (le[cb]) atomicAdd(R.right + b, (unsigned long long)le[cb]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+}
+
 int num_sms() {
   static int sms = 0;
   if (sms == 0) {
@@ -815,6 +988,29 @@ int layer_wgrad_tc_launch(const WgradLaunch& launch, int total_chunks, cudaStrea
   const int grid = total_chunks < num_sms() ? total_chunks : num_sms();
   wgrad_tc_kernel<<<grid, THREADS, TC_SMEM, stream>>>(launch, total_chunks);
   MPQE_CHECK_LAUNCH("wgrad_tc_kernel");
+  return 0;
+}
+
+int rank_counts_table_tc(const float* table, int64_t row_begin, int64_t rows, const float* inv_norm, const float* q,
+                         const float* qinv, const float* pos, int64_t B, unsigned long long* left,
+                         unsigned long long* right, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    MPQE_CUDA(cudaFuncSetAttribute(rank_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RANK_SMEM));
+    configured = true;
+  }
+  RankLaunch R;
+  R.table = table; R.row_begin = row_begin; R.rows = rows; R.inv_norm = inv_norm; R.q = q; R.qinv = qinv; R.pos = pos;
+  R.B = B; R.left = left; R.right = right;
+  const int64_t qtiles = (B + BM - 1) / BM;
+  const int64_t ctiles = (rows + BM - 1) / BM;
+  int64_t splits = (num_sms() + qtiles - 1) / qtiles;
+  if (splits > ctiles) splits = ctiles;
+  if (splits < 1) splits = 1;
+  R.splits = (int)splits;
+  MPQE_CHECK_ARG(qtiles * splits < (1ll << 31), "mpqe_rank_counts_table: too many tiles");
+  rank_tc_kernel<<<(unsigned)(qtiles * splits), THREADS, RANK_SMEM, stream>>>(R);
+  MPQE_CHECK_LAUNCH("rank_tc_kernel");
   return 0;
 }
 

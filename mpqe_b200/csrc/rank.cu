@@ -203,7 +203,6 @@ extern "C" int mpqe_rank_counts_table(const float* q, int64_t B, const float* po
                                       void* stream) {
   MPQE_CHECK_ARG(q && pos && table && left && right && B >= 1 && row_begin >= 0 && row_end >= row_begin,
                  "mpqe_rank_counts_table: bad argument");
-  MPQE_CHECK_ARG(use_tensor_cores == 0, "mpqe_rank_counts_table: tcgen05 path not built into this library");
   const int64_t rows = row_end - row_begin;
   if (rows == 0) return 0;
   RankWs w = carve_rank(workspace, B, rows);
@@ -219,6 +218,9 @@ extern "C" int mpqe_rank_counts_table(const float* q, int64_t B, const float* po
   MPQE_CHECK_LAUNCH("prep_queries_kernel");
   row_inv_norm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(table, row_begin, rows, w.inv_norm);
   MPQE_CHECK_LAUNCH("row_inv_norm_kernel");
+  if (use_tensor_cores)
+    return rank_counts_table_tc(table, row_begin, rows, w.inv_norm, q, w.qinv, pos, B, (unsigned long long*)left,
+                                (unsigned long long*)right, st);
   dim3 grid((unsigned)((rows + BM - 1) / BM), (unsigned)(w.Bp / BN));
   MPQE_CHECK_ARG(grid.y <= 65535, "mpqe_rank_counts_table: too many queries (%lld)", (long long)B);
   rank_counts_table_kernel<<<grid, THREADS, RANK_SMEM, st>>>(table, row_begin, rows, w.inv_norm, w.qt, w.Bp, w.qinv,

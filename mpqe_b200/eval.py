@@ -24,7 +24,7 @@ def shard_rows(num_rows, rank, world):
 
 @torch.no_grad()
 def full_rank_counts(model, formula, queries, target_nodes, anchor_ids=None, var_ids=None, q_graphs=None,
-                     process_group=None, use_tensor_cores=False):
+                     process_group=None, use_tensor_cores=None):
     """(count_lt, count_le, positive scores, N): counts of entities of the target mode scoring below / not above each
     query's positive.  The spare last table row (data_utils.py:31) is not a candidate."""
     dist = torch.distributed
@@ -42,7 +42,8 @@ def full_rank_counts(model, formula, queries, target_nodes, anchor_ids=None, var
         left = torch.zeros(job.B, dtype=torch.int64, device=device)
         right = torch.zeros(job.B, dtype=torch.int64, device=device)
         begin, end = shard_rows(num_entities, rank, world)
-        ops.rank_counts_table(job.q, pos, table, begin, end, left, right, use_tensor_cores=use_tensor_cores)
+        tc = ops.tensor_cores_default() if use_tensor_cores is None else bool(use_tensor_cores)
+        ops.rank_counts_table(job.q, pos, table, begin, end, left, right, use_tensor_cores=tc)
         if world > 1:
             both = torch.stack((left, right))
             dist.all_reduce(both, group=process_group)     # integer sum: exact, order independent
@@ -60,7 +61,7 @@ def ranking_metrics(left, right, num_entities):
 
 
 @torch.no_grad()
-def eval_full_rank(model, test_queries, batch_size=4096, process_group=None, use_tensor_cores=False):
+def eval_full_rank(model, test_queries, batch_size=4096, process_group=None, use_tensor_cores=None):
     """{formula: [queries]} -> overall APR / MRR against all entities of each target mode."""
     lefts, rights, ns = [], [], []
     for formula, formula_queries in test_queries.items():

@@ -275,8 +275,10 @@ def test_sparse_rows_combine(count, table_rows):
     assert_close(dense.cpu().numpy(), ref.numpy(), 1e-5, 1e-4 * max(1.0, count / table_rows / 10), 'dense scatter')
 
 
-@pytest.mark.parametrize('B,N', [(5, 100), (130, 1000), (64, 20000)])
-def test_rank_counts_table_sandwich(B, N):
+@pytest.mark.parametrize('tc', [False, True])
+@pytest.mark.parametrize('B,N', [(5, 100), (130, 1000), (64, 20000), (300, 777)])
+def test_rank_counts_table_sandwich(B, N, tc):
+    need_tc(tc)
     table = rnd(N, D, seed=1, scale=1.0 / D)
     q = rnd(B, D, seed=2)
     tgt = torch.randint(0, N, (B,), generator=torch.Generator().manual_seed(3))
@@ -285,13 +287,13 @@ def test_rank_counts_table_sandwich(B, N):
     left = torch.zeros(B, dtype=torch.int64, device=DEV)
     right = torch.zeros(B, dtype=torch.int64, device=DEV)
     half = N // 3
-    ops.rank_counts_table(qd, pos, td, 0, half, left, right)      # two shards chained = one table
-    ops.rank_counts_table(qd, pos, td, half, N, left, right)
+    ops.rank_counts_table(qd, pos, td, 0, half, left, right, use_tensor_cores=tc)      # two shards chained = one table
+    ops.rank_counts_table(qd, pos, td, half, N, left, right, use_tensor_cores=tc)
     # float64 scores on the CPU bracket the fp32 ones: counts must lie between the counts at pos -/+ tol
     y = table.double() / table.double().norm(dim=1, keepdim=True)
     s = (q.double() / q.double().norm(dim=1, keepdim=True)) @ y.t()
     p = pos.cpu().double().unsqueeze(1)
-    tol = 2e-6
+    tol = 4e-6 if tc else 2e-6
     lo_lt, hi_lt = (s < p - tol).sum(1), (s < p + tol).sum(1)
     lo_le, hi_le = (s <= p - tol).sum(1), (s <= p + tol).sum(1)
     l, r = left.cpu(), right.cpu()
