@@ -55,7 +55,11 @@ def test_auc_and_percentile_match_oracle_scores():
     assert utils.auc_from_scores([1, 1, 0, 0], [0.9, 0.4, 0.5, 0.1]) == O.auc([1, 1, 0, 0], [0.9, 0.4, 0.5, 0.1]) == 0.75
 
 
-def test_full_rank_eval_counts_and_metrics():
+@pytest.mark.parametrize('tc', [False, True])
+def test_full_rank_eval_counts_and_metrics(tc):
+    from mpqe_b200 import _lib
+    if tc and not _lib.load().mpqe_b200_has_tcgen05():
+        pytest.skip('library built without tcgen05 kernels')
     kg, cfg, params, model, qsets = setup(per_formula=33)
     rels, _, node_maps = kg.raw()
     mode_ids, rel_ids = O.schema_ids(rels)
@@ -63,7 +67,8 @@ def test_full_rank_eval_counts_and_metrics():
     frm_rels, raw = qsets['2-inter'][0]
     queries = [Query.deserialize(r) for r in raw]
     formula = queries[0].formula
-    left, right, pos, n = mp_eval.full_rank_counts(model, formula, queries, [q.target_node for q in queries])
+    left, right, pos, n = mp_eval.full_rank_counts(model, formula, queries, [q.target_node for q in queries],
+                                                   use_tensor_cores=tc)
     spec = O.formula_spec('2-inter', frm_rels)
     a_ids, var_ids, ei, et, b = O.query_graph(spec, [q.anchor_nodes for q in queries], rel_ids, mode_ids)
     with torch.no_grad():
@@ -71,7 +76,7 @@ def test_full_rank_eval_counts_and_metrics():
     table = params['enc.feat-%s.weight' % spec['target_mode']][:-1].double()
     s = (q / q.norm(dim=1, keepdim=True)) @ (table / table.norm(dim=1, keepdim=True)).t()
     p = pos.cpu().double().unsqueeze(1)
-    tol = 3e-6
+    tol = 6e-6 if tc else 3e-6
     l, r = left.cpu(), right.cpu()
     assert n == table.shape[0]
     assert bool(((l >= (s < p - tol).sum(1)) & (l <= (s < p + tol).sum(1))).all())
@@ -89,7 +94,7 @@ def test_full_rank_eval_counts_and_metrics():
         tab = model.enc.table(formula.target_mode)
         for rank in range(3):
             b0, b1 = mp_eval.shard_rows(n, rank, 3)
-            ops.rank_counts_table(job.q, pos, tab, b0, b1, l2, r2)
+            ops.rank_counts_table(job.q, pos, tab, b0, b1, l2, r2, use_tensor_cores=tc)
     assert torch.equal(l2, left) and torch.equal(r2, right)
 
 
