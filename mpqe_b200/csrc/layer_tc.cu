@@ -330,6 +330,24 @@ __device__ __forceinline__ void publish_stage(TcShared& sh, uint32_t it) {
   mbar_arrive(smem_u32(&sh.full[it % STAGES]));
 }
 
+// Static unit -> CTA assignment computed on the host (longest-processing-time first): with a few units per CTA
+// (B = 4096: 224..768 units on 148 CTAs) round-robin leaves some CTAs with twice the work of others.
+constexpr int SCHED_MAX_UNITS = 2048;
+constexpr int SCHED_MAX_CTAS = 160;
+struct Schedule {
+  int count;                                 // 0: round-robin (unit = blockIdx + k * gridDim)
+  uint16_t start[SCHED_MAX_CTAS + 1];
+  uint16_t unit[SCHED_MAX_UNITS];
+};
+__device__ __forceinline__ int sched_unit(const Schedule& S, int k, int total_units) {
+  if (S.count == 0) {
+    const int u = blockIdx.x + k * gridDim.x;
+    return u < total_units ? u : -1;
+  }
+  const int i = S.start[blockIdx.x] + k;
+  return i < S.start[blockIdx.x + 1] ? (int)S.unit[i] : -1;
+}
+
 struct UnitInfo {
   int gi, slot;
   int64_t q0;
@@ -360,7 +378,8 @@ __device__ __forceinline__ uint32_t term_mask(const mpqe_layer_group_t& G, int s
   return m;
 }
 
-__global__ void __launch_bounds__(THREADS, 1) layer_tc_kernel(const __grid_constant__ LayerLaunch L, int total_units,
+__global__ void __launch_bounds__(THREADS, 1) layer_tc_kernel(const __grid_constant__ LayerLaunch L,
+                                                              const __grid_constant__ Schedule S, int total_units,
                                                               int dbg) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ TcShared sh;
@@ -384,11 +403,12 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc_kernel(const __grid_const
     const int pw = warp - EPI_WARPS;
     uint32_t it = 0;
     // iterator over (unit, term, k chunk)
-    int unit = blockIdx.x;
-    UnitInfo U = decode_unit(L, unit < total_units ? unit : 0);
-    uint32_t mask = unit < total_units ? term_mask(L.g[U.gi], U.slot) : 0u;
+    int uk = 0;
+    int unit = sched_unit(S, 0, total_units);
+    UnitInfo U = decode_unit(L, unit >= 0 ? unit : 0);
+    uint32_t mask = unit >= 0 ? term_mask(L.g[U.gi], U.slot) : 0u;
     int kc = -KC;
-    bool alive = unit < total_units;
+    bool alive = unit >= 0;
     // loads the next (term, k chunk) stage into (fa, fb); false when all of this CTA's work has been issued
     auto load_next = [&](Frag& fa, Frag& fb, const float*& packed) -> bool {
       if (!alive) return false;
@@ -398,8 +418,8 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc_kernel(const __grid_const
         mask &= mask - 1;
       }
       while (mask == 0) {   // next unit (a unit without terms contributes no stages)
-        unit += gridDim.x;
-        if (unit >= total_units) {
+        unit = sched_unit(S, ++uk, total_units);
+        if (unit < 0) {
           alive = false;
           return false;
         }
@@ -470,7 +490,7 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc_kernel(const __grid_const
       uint32_t it = 0;
       int uc = 0;
       long long mstat[3] = {0, 0, 0};
-      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++uc) {
+      for (int unit; (unit = sched_unit(S, uc, total_units)) >= 0; ++uc) {
         const UnitInfo U = decode_unit(L, unit);
         const int nsteps = __popc(term_mask(L.g[U.gi], U.slot)) * (D / KC);
         mma_unit(sh, smem_u32(smem), tmem, uc, nsteps, it, (dbg & 4) != 0, mstat);
@@ -489,7 +509,7 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc_kernel(const __grid_const
     long long estat[2] = {0, 0}, et0 = 0;
     (void)estat;
     (void)et0;
-    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++uc) {
+    for (int unit; (unit = sched_unit(S, uc, total_units)) >= 0; ++uc) {
       const UnitInfo U = decode_unit(L, unit);
       const mpqe_layer_group_t& G = L.g[U.gi];
       const int nsteps = __popc(term_mask(G, U.slot)) * (D / KC);
@@ -968,12 +988,44 @@ int layer_forward_tc(const mpqe_layer_group_t* groups, int num_groups, cudaStrea
   }
   MPQE_CHECK_ARG(units < (1ll << 31), "mpqe_layer_forward: too many tiles");
   const int grid = units < num_sms() ? (int)units : num_sms();
-  static int dbg = -1;  // MPQE_TC_DEBUG: timing experiments only (bit0 no smem stores, bit1 no global loads,
-  if (dbg < 0) {        //                 bit2 no MMAs, bit3 no epilogue stores); results are wrong when non-zero
-    const char* e = getenv("MPQE_TC_DEBUG");
-    dbg = e ? atoi(e) : 0;
+  // longest-processing-time-first assignment of units to the persistent CTAs (cost = terms of the unit's slot)
+  static thread_local Schedule S;
+  S.count = 0;
+  if (units > grid && units <= SCHED_MAX_UNITS && grid <= SCHED_MAX_CTAS) {
+    static thread_local int cost[SCHED_MAX_UNITS], order[SCHED_MAX_UNITS], owner[SCHED_MAX_UNITS];
+    int u = 0;
+    for (int i = 0; i < num_groups; ++i) {
+      const int tiles = (int)((groups[i].num_queries + BM - 1) / BM);
+      for (int slot = 0; slot < groups[i].num_out_slots; ++slot) {
+        int nt = 0;
+        for (int t = 0; t < groups[i].num_terms; ++t) nt += groups[i].terms[t].out_slot == slot;
+        for (int k = 0; k < tiles; ++k) cost[u++] = nt;     // slot-major numbering, as decode_unit
+      }
+    }
+    // counting sort by cost, descending (costs are <= MPQE_MAX_TERMS)
+    int pos = 0;
+    for (int c = MPQE_MAX_TERMS; c >= 0; --c)
+      for (int i = 0; i < (int)units; ++i)
+        if (cost[i] == c) order[pos++] = i;
+    long long load[SCHED_MAX_CTAS];
+    int cnt[SCHED_MAX_CTAS];
+    for (int c = 0; c < grid; ++c) load[c] = 0, cnt[c] = 0;
+    for (int i = 0; i < (int)units; ++i) {
+      int best = 0;
+      for (int c = 1; c < grid; ++c)
+        if (load[c] < load[best]) best = c;
+      owner[order[i]] = best;
+      load[best] += cost[order[i]] + 1;                        // +1: per-unit epilogue / pipeline refill
+      ++cnt[best];
+    }
+    S.start[0] = 0;
+    for (int c = 0; c < grid; ++c) S.start[c + 1] = (uint16_t)(S.start[c] + cnt[c]);
+    int fill[SCHED_MAX_CTAS];
+    for (int c = 0; c < grid; ++c) fill[c] = S.start[c];
+    for (int i = 0; i < (int)units; ++i) S.unit[fill[owner[order[i]]]++] = (uint16_t)order[i];   // heavy units first
+    S.count = (int)units;
   }
-  layer_tc_kernel<<<grid, THREADS, TC_SMEM, stream>>>(L, (int)units, dbg);
+  layer_tc_kernel<<<grid, THREADS, TC_SMEM, stream>>>(L, S, (int)units, dbg);
   MPQE_CHECK_LAUNCH("layer_tc_kernel");
   return 0;
 }
