@@ -1025,6 +1025,11 @@ int layer_forward_tc(const mpqe_layer_group_t* groups, int num_groups, cudaStrea
     for (int i = 0; i < (int)units; ++i) S.unit[fill[owner[order[i]]]++] = (uint16_t)order[i];   // heavy units first
     S.count = (int)units;
   }
+  static int dbg = -1;  // MPQE_TC_DEBUG: timing experiments only (bit0 no smem stores, bit1 no global loads,
+  if (dbg < 0) {        //                 bit2 no MMAs, bit3 no epilogue stores); results are wrong when non-zero
+    const char* e = getenv("MPQE_TC_DEBUG");
+    dbg = e ? atoi(e) : 0;
+  }
   layer_tc_kernel<<<grid, THREADS, TC_SMEM, stream>>>(L, S, (int)units, dbg);
   MPQE_CHECK_LAUNCH("layer_tc_kernel");
   return 0;
