@@ -69,12 +69,14 @@ typedef struct {
   float* out;                            /* [num_queries, out_slots, d] */
   int32_t out_slots;                     /* slots per query in `out` (row stride / d) */
   int32_t epilogue;                      /* MPQE_EPI_* */
-  const float* bias;                     /* [d] or NULL (model.py:303-304) */
+  const float* bias;                     /* [d] or NULL (model.py:303-304); out slot j adds bias_scale[j] *
+                                            bias[j*bias_slot_stride .. +d] */
   float bias_scale[MPQE_MAX_SLOTS];      /* bias multiplier per out slot (n for a fused sum readout) */
   int16_t out_slot_map[MPQE_MAX_SLOTS];  /* out slot j is stored at out[q, out_slot_map[j], :] */
   const float* mask;                     /* EPI_MASK: [num_queries, mask_slots, d], slot = out_slot_map[j] */
   int32_t mask_slots;
-  int32_t reserved;
+  int32_t bias_slot_stride;              /* 0: one bias vector for all slots; d: a vector per out slot (used for the
+                                            contribution of batch-constant input rows, computed once per group) */
 } mpqe_layer_group_t;
 
 /* One weight-gradient destination: dM = sum over every term (of every group) whose `m` equals `m_fwd` of

@@ -19,7 +19,7 @@ class LayerGroup(C.Structure):
                 ('terms', Term * MAX_TERMS), ('out', C.c_void_p), ('out_slots', C.c_int32),
                 ('epilogue', C.c_int32), ('bias', C.c_void_p), ('bias_scale', C.c_float * MAX_SLOTS),
                 ('out_slot_map', C.c_int16 * MAX_SLOTS), ('mask', C.c_void_p), ('mask_slots', C.c_int32),
-                ('reserved', C.c_int32)]
+                ('bias_slot_stride', C.c_int32)]
 
 
 class WgradDest(C.Structure):

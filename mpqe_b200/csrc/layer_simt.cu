@@ -132,8 +132,9 @@ __global__ void __launch_bounds__(THREADS, 2) layer_simt_kernel(const __grid_con
   float4 bv0 = make_float4(0.f, 0.f, 0.f, 0.f), bv1 = bv0;
   if (G.bias != nullptr) {
     const float s = G.bias_scale[slot];
-    const float4 t0 = *reinterpret_cast<const float4*>(G.bias + c0);
-    const float4 t1 = *reinterpret_cast<const float4*>(G.bias + c1);
+    const float* bj = G.bias + (int64_t)slot * G.bias_slot_stride;
+    const float4 t0 = *reinterpret_cast<const float4*>(bj + c0);
+    const float4 t1 = *reinterpret_cast<const float4*>(bj + c1);
     bv0 = make_float4(s * t0.x, s * t0.y, s * t0.z, s * t0.w);
     bv1 = make_float4(s * t1.x, s * t1.y, s * t1.z, s * t1.w);
   }

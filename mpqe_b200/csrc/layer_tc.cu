@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc_kernel(const __grid_const
         __syncwarp();
         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (G.bias != nullptr) {
-          const float4 b = *reinterpret_cast<const float4*>(G.bias + c0 + cq);
+          const float4 b = *reinterpret_cast<const float4*>(G.bias + (int64_t)U.slot * G.bias_slot_stride + c0 + cq);
           bv = make_float4(bscale * b.x, bscale * b.y, bscale * b.z, bscale * b.w);
         }
 #pragma unroll

@@ -243,8 +243,10 @@ class Engine(object):
 
     # ---- forward ------------------------------------------------------------------------------------------
     def build_inputs(self, jobs, W):
-        """x[b, i<a] = normalised anchor rows, x[b, i>=a] = variable-type embedding rows (reference model.py:418-421):
-        one multi-item launch for every (job, node slot)."""
+        """x[b, i<a] = normalised anchor rows (reference model.py:418-420), one multi-item launch for every (job, anchor
+        slot).  The variable slots x[b, i>=a] = mode_embeddings[var_ids] (model.py:421) are the same row for every query
+        of the batch, so they are never materialised: their contribution to the first pass is a per-slot constant
+        (see `pass_terms`)."""
         enc = self.m.enc
         items = []
         for job in jobs:
@@ -253,9 +255,6 @@ class Engine(object):
             for i, mode in enumerate(job.anchor_modes):
                 items.append(ops.GatherItem(enc.table(mode), enc.node_maps, job.anchor_ids, B, ids_offset=i,
                                             ids_stride=t.num_anchors, out=x, out_offset=i * D, out_stride=n * D))
-            for k in range(t.num_vars):
-                items.append(ops.GatherItem(W.mode_emb, None, job.var_rows, B, ids_offset=k, ids_stride=0, out=x,
-                                            out_offset=(t.num_anchors + k) * D, out_stride=n * D, normalize=False))
             job.acts = [x]
         ops.gather_multi(items)
 
@@ -265,17 +264,31 @@ class Engine(object):
         return p if p < P - 1 else self.m.num_layers - 1
 
     def pass_terms(self, job, p, W, outs):
-        """Forward terms of pass p restricted to the output slots `outs` (term.out_slot = index into outs)."""
-        t, n = job.t, job.t.num_nodes
+        """Forward terms of pass p restricted to the output slots `outs` (term.out_slot = index into outs), split into
+        (per-query terms, batch-constant terms, layer index).  In pass 0 every term whose source is a variable slot
+        multiplies the same variable-type embedding row for all queries: it is evaluated once per group (a 1-row
+        launch) and enters the big launch as a per-slot bias; its weight gradient is a rank-1 update and its input
+        gradient a column sum (see `backward`)."""
+        t, n, a = job.t, job.t.num_nodes, job.t.num_anchors
         li = self.layer_index(p, job.P)
         x = job.acts[p]
         pos = {s: k for k, s in enumerate(outs)}
         wp = W.wp[li] if W.wp is not None else None
         rp = W.rootp[li] if W.rootp is not None else None
-        terms = [Term(x, n, t.src[e], W.w[li][job.rels[e]], pos[t.dst[e]], wp[job.rels[e]] if wp is not None else None)
-                 for e in range(t.num_edges) if t.dst[e] in pos]
-        terms += [Term(x, n, s, W.root[li], pos[s], rp) for s in outs]
-        return terms, li
+        main, const = [], []
+
+        def add(src, m, mp, out):
+            if p == 0 and src >= a:
+                const.append(Term(W.mode_emb, 0, job.var_rows_host[src - a], m, out))
+            else:
+                main.append(Term(x, n, src, m, out, mp))
+
+        for e in range(t.num_edges):
+            if t.dst[e] in pos:
+                add(t.src[e], W.w[li][job.rels[e]], wp[job.rels[e]] if wp is not None else None, pos[t.dst[e]])
+        for s in outs:
+            add(s, W.root[li], rp, pos[s])
+        return main, const, li
 
     def encode(self, jobs, W):
         """Runs every pass of every job; leaves job.q [B, D] (query embeddings)."""
@@ -286,29 +299,44 @@ class Engine(object):
             job.fwd_groups = [None] * job.P
         max_p = max(job.P for job in jobs)
         for p in range(max_p):
-            groups = []
+            groups, const_groups = [], []
             for job in jobs:
                 if p >= job.P:
                     continue
                 B, n = job.B, job.t.num_nodes
                 outs = job.outs[p]
-                terms, li = self.pass_terms(job, p, W, outs)
+                terms, const, li = self.pass_terms(job, p, W, outs)
                 dev = job.anchor_ids.device
+                fused = p == job.P - 1 and readout in ('sum', 'mp')
+                nb = 1 if fused else len(outs)
+                if fused:      # readout folded into the last pass: every term accumulates into the single output row
+                    for term in terms + const:
+                        term.out_slot = 0
+                bias, bias_scale, stride = W.bias[li], ([float(len(outs))] if fused else [1.0] * nb), 0
+                job.fused_bias_count = float(len(outs)) if fused else 1.0
+                if p == 0:
+                    job.const_fwd = None
+                if const:      # batch-constant part (+ bias), evaluated on one row and added as a per-slot bias
+                    cb = torch.empty(1, nb, D, dtype=torch.float32, device=dev)
+                    job.const_fwd = Group(1, const, nb, cb, nb, bias=bias, bias_scale=bias_scale)
+                    const_groups.append(job.const_fwd)
+                    bias, bias_scale, stride = cb, [1.0] * nb, D
                 if p < job.P - 1:
                     h = torch.empty(B, n, D, dtype=torch.float32, device=dev)
-                    g = Group(B, terms, len(outs), h, n, out_slot_map=outs, epilogue=EPI_RELU, bias=W.bias[li])
+                    g = Group(B, terms, nb, h, n, out_slot_map=outs, epilogue=EPI_RELU, bias=bias, bias_scale=bias_scale,
+                              bias_slot_stride=stride)
                     job.acts.append(h)
-                elif readout in ('sum', 'mp'):
-                    # readout folded into the last pass: every term accumulates into the single output row
-                    for term in terms:
-                        term.out_slot = 0
+                elif fused:
                     job.q = torch.empty(B, D, dtype=torch.float32, device=dev)
-                    g = Group(B, terms, 1, job.q, 1, out_slot_map=[0], bias=W.bias[li], bias_scale=[float(len(outs))])
+                    g = Group(B, terms, 1, job.q, 1, out_slot_map=[0], bias=bias, bias_scale=bias_scale)
                 else:
                     job.z = torch.empty(B, n, D, dtype=torch.float32, device=dev)
-                    g = Group(B, terms, len(outs), job.z, n, out_slot_map=outs, bias=W.bias[li])
+                    g = Group(B, terms, nb, job.z, n, out_slot_map=outs, bias=bias, bias_scale=bias_scale,
+                              bias_slot_stride=stride)
                 job.fwd_groups[p] = g
                 groups.append(g)
+            if const_groups:
+                ops.layer_forward(const_groups, use_tensor_cores=False)   # 1-row groups: the FFMA kernel
             ops.layer_forward(groups)
         if readout == 'max':
             for job in jobs:
@@ -379,13 +407,28 @@ class Engine(object):
                     g, g_slots, smap = cur[job]
                     if g_slots == 1:
                         # sum readout: the bias was added once per node; target-message: once
-                        scale = float(job.fwd_groups[p].bias_scale[0])
-                        G.colsum(g, job.B, D, G.dbias[li], scale)
+                        G.colsum(g, job.B, D, G.dbias[li], job.fused_bias_count)
                     elif len(smap) == g_slots:
                         G.colsum(g, job.B * g_slots, D, G.dbias[li])
                     else:
                         for s in smap:
                             G.colsum(g[:, s], job.B, g_slots * D, G.dbias[li])
+            # ---- batch-constant terms of pass 0: per-slot column sums of the output gradient, consumed after flush
+            if p == 0:
+                for job in active:
+                    if job.const_fwd is None:
+                        continue
+                    g, g_slots, smap = cur[job]
+                    n = job.t.num_nodes
+                    if g_slots == 1:
+                        job.cs = torch.zeros(1, 1, D, dtype=torch.float32, device=g.device)
+                        G.colsum(g, job.B, D, job.cs[0, 0])
+                        job.cs_operand = (job.cs, 1, [0] * len(smap))
+                    else:
+                        job.cs = torch.zeros(1, n, D, dtype=torch.float32, device=g.device)
+                        for s_ in smap:
+                            G.colsum(g[:, s_], job.B, g_slots * D, job.cs[0, s_])
+                        job.cs_operand = (job.cs, n, list(smap))
             # ---- input gradients of pass p
             groups, nxt = [], {}
             for job in active:
@@ -393,8 +436,13 @@ class Engine(object):
                 g, g_slots, smap = cur[job]
                 li = self.layer_index(p, job.P)
                 outs = job.outs[p]
-                ins = job.outs[p - 1] if p > 0 else sorted(
-                    {t.src[e] for e in range(t.num_edges) if t.dst[e] in outs} | set(outs))
+                if p > 0:
+                    ins = job.outs[p - 1]
+                else:   # only the anchors receive a per-query gradient; variable slots get a column sum (below)
+                    ins = sorted(s_ for s_ in ({t.src[e] for e in range(t.num_edges) if t.dst[e] in outs} | set(outs))
+                                 if s_ < t.num_anchors)
+                if not ins:
+                    continue
                 pos = {s: k for k, s in enumerate(ins)}
                 okey = {s: k for k, s in enumerate(outs)}
                 wtp = W.wtp[li] if W.wtp is not None else None
@@ -413,17 +461,65 @@ class Engine(object):
                 else:
                     groups.append(Group(job.B, terms, len(ins), dx, n, out_slot_map=ins))
                 nxt[job] = (dx, n, ins)
-            ops.layer_forward(groups)
+            if groups:
+                ops.layer_forward(groups)
             for job in active:
+                if job not in nxt:
+                    continue
                 dx, n, ins = nxt[job]
                 if p > 0:
                     cur[job] = (dx, n, ins)
                 else:
                     self.input_backward(job, dx, ins, G)
         G.flush()
+        self.constant_backward(jobs, W, G)
+
+    def constant_backward(self, jobs, W, G):
+        """Gradients of the batch-constant pass-0 terms from the per-slot column sums cs[s] = sum_q dZ0[q, s]:
+        dW += v^T cs[dst] (a 1-row weight-gradient launch) and d mode_embedding[v] += cs[dst] @ W^T (a 1-row layer
+        launch followed by 1-row column sums)."""
+        cjobs = [job for job in jobs if getattr(job, 'const_fwd', None) is not None]
+        if not cjobs:
+            return
+        by_layer = {}
+        for job in cjobs:
+            by_layer.setdefault(self.layer_index(0, job.P), []).append(job)
+        dgroups = []
+        for li, ljobs in by_layer.items():
+            for i in range(0, len(ljobs), ops.MAX_GROUPS):
+                chunk = ljobs[i:i + ops.MAX_GROUPS]
+                mats = {}
+                for job in chunk:
+                    for term in job.const_fwd.terms:
+                        mats[term.m.data_ptr()] = term.m
+                dests = []
+                for r in range(W.w[li].shape[0]):
+                    if W.w[li][r].data_ptr() in mats:
+                        dests.append((W.w[li][r], G.dw[li][r], 1))
+                if W.root[li].data_ptr() in mats:
+                    dests.append((W.root[li], G.droot[li], 1))
+                ops.layer_wgrad([job.const_fwd for job in chunk], [job.cs_operand for job in chunk], dests,
+                                use_tensor_cores=False)
+            for job in ljobs:
+                t, n, a = job.t, job.t.num_nodes, job.t.num_anchors
+                cs, cs_slots, smap = job.cs_operand
+                outs = job.outs[0]
+                okey = {s: k for k, s in enumerate(outs)}
+                var_slots = sorted({t.src[e] for e in range(t.num_edges) if t.dst[e] in okey and t.src[e] >= a} |
+                                   {s for s in outs if s >= a})
+                pos = {s: k for k, s in enumerate(var_slots)}
+                terms = [Term(cs, cs_slots, smap[okey[t.dst[e]]], W.wt[li][job.rels[e]], pos[t.src[e]])
+                         for e in range(t.num_edges) if t.dst[e] in okey and t.src[e] in pos]
+                terms += [Term(cs, cs_slots, smap[okey[s]], W.roott[li], pos[s]) for s in outs if s in pos]
+                job.dconst = torch.empty(1, n, D, dtype=torch.float32, device=cs.device)
+                dgroups.append(Group(1, terms, len(var_slots), job.dconst, n, out_slot_map=var_slots))
+                for s in var_slots:
+                    G.colsum(job.dconst[:, s], 1, n * D, G.dmode[job.var_rows_host[s - a]])
+        ops.layer_forward(dgroups, use_tensor_cores=False)
+        G.flush()
 
     def input_backward(self, job, dx, ins, G):
-        """d loss / d x -> anchor table rows (through the normalisation) and variable-type embedding rows."""
+        """d loss / d x (anchor slots) -> entity-table rows through the normalisation."""
         t, n, B = job.t, job.t.num_nodes, job.B
         enc = self.m.enc
         for i, mode in enumerate(job.anchor_modes):
@@ -433,10 +529,6 @@ class Engine(object):
             G.gathers.append(ops.GatherItem(enc.table(mode), enc.node_maps, job.anchor_ids, B, ids_offset=i,
                                             ids_stride=t.num_anchors, grad=dx, grad_offset=i * D, grad_stride=n * D,
                                             rows_out=rows, rows_id=rows_id, rows_offset=off, id_offset=id_off))
-        for k, row in enumerate(job.var_rows_host):
-            s = t.num_anchors + k
-            if s in ins:
-                G.colsum(dx[:, s], B, n * D, G.dmode[row])
 
     def mlp_backward(self, jobs, W, dqs, G, last):
         """Backward of the MLP readouts; fills last[job] (gradient wrt the last R-GCN pass output) and job.du."""

@@ -93,13 +93,14 @@ class Group(object):
     """One formula group of a layer launch (see mpqe_layer_group_t)."""
 
     def __init__(self, num_queries, terms, num_out_slots, out, out_slots, out_slot_map=None, epilogue=EPI_NONE,
-                 bias=None, bias_scale=None, mask=None, mask_slots=0):
+                 bias=None, bias_scale=None, mask=None, mask_slots=0, bias_slot_stride=0):
         self.num_queries, self.terms, self.num_out_slots = int(num_queries), list(terms), int(num_out_slots)
         self.out, self.out_slots = out, int(out_slots)
         self.out_slot_map = list(out_slot_map) if out_slot_map is not None else list(range(num_out_slots))
         self.epilogue, self.bias = epilogue, bias
         self.bias_scale = list(bias_scale) if bias_scale is not None else [1.0] * num_out_slots
         self.mask, self.mask_slots = mask, int(mask_slots)
+        self.bias_slot_stride = int(bias_slot_stride)   # 0: one bias vector; D: bias is [num_out_slots, D]
 
     def to_c(self):
         if len(self.terms) > MAX_TERMS or self.num_out_slots > MAX_SLOTS:
@@ -122,6 +123,7 @@ class Group(object):
             g.out_slot_map[j] = int(self.out_slot_map[j])
         g.mask = _chk(self.mask, torch.float32, 'mask').data_ptr() if self.mask is not None else 0
         g.mask_slots = self.mask_slots
+        g.bias_slot_stride = self.bias_slot_stride
         return g
 
 

@@ -33,7 +33,8 @@ def layer_forward(groups, use_tensor_cores=None):
         for j in range(g.num_out_slots):
             v = acc[j]
             if g.bias is not None:
-                v = v + g.bias_scale[j] * g.bias
+                stride = getattr(g, 'bias_slot_stride', 0)
+                v = v + g.bias_scale[j] * g.bias.reshape(-1)[j * stride:j * stride + D]
             s = g.out_slot_map[j]
             if g.epilogue == ops.EPI_RELU:
                 v = torch.relu(v)
