@@ -200,7 +200,9 @@ def layer_wgrad(groups, grad_operands, dests, ctas_hint=296, use_tensor_cores=No
     nbytes = lib.mpqe_layer_wgrad_workspace_bytes(len(dests), ctas_hint)
     ws = workspace(nbytes, dev, 'wgrad')
     with _Profiled('wgrad', groups, grad_operands):
-        _lib.check(lib.mpqe_layer_wgrad(garr, oarr, len(groups), darr, len(dests), int(tc), _ptr(ws), ws.numel(),
+        # the chunking (hence the summation order) follows the workspace size: pass the requested size, not the
+        # size of the cached buffer, so that results do not depend on what ran before
+        _lib.check(lib.mpqe_layer_wgrad(garr, oarr, len(groups), darr, len(dests), int(tc), _ptr(ws), nbytes,
                                         _stream()), 'mpqe_layer_wgrad')
     _count(2)
 
