@@ -164,6 +164,68 @@ __global__ void __launch_bounds__(THREADS, 2) layer_simt_kernel(const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// One-row groups (the batch-constant terms of pass 0: the variable-type embedding row is the same for every query
+// of a batch, reference model.py:421).  out[slot] = bias + sum_t a_t @ M_t is a [1,128]x[128,128] product per term:
+// one CTA per (group, out slot), its 8 warps each take 16 k's of every term, partial sums combined in a fixed order.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) layer_row_kernel(const __grid_constant__ LayerLaunch L) {
+  __shared__ float4 part[8][32];
+  int unit = blockIdx.x;
+  int gi = 0;
+  for (; gi < L.num_groups - 1; ++gi) {
+    if (unit < L.g[gi].num_out_slots) break;
+    unit -= L.g[gi].num_out_slots;
+  }
+  const mpqe_layer_group_t& G = L.g[gi];
+  const int slot = unit;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = 0; t < G.num_terms; ++t) {
+    const mpqe_term_t& T = G.terms[t];
+    if (T.out_slot != slot) continue;
+    const float* a = T.a + (int64_t)T.a_slot * D + w * 16;
+    const float* m = T.m + (int64_t)(w * 16) * D + lane * 4;
+    float av[16];
+    float4 bv[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      av[k] = __ldg(a + k);
+      bv[k] = __ldg(reinterpret_cast<const float4*>(m + (int64_t)k * D));
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      acc.x = fmaf(av[k], bv[k].x, acc.x);
+      acc.y = fmaf(av[k], bv[k].y, acc.y);
+      acc.z = fmaf(av[k], bv[k].z, acc.z);
+      acc.w = fmaf(av[k], bv[k].w, acc.w);
+    }
+  }
+  part[w][lane] = acc;
+  __syncthreads();
+  if (w != 0) return;
+  float4 p[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) p[i] = part[i][lane];
+  float4 v = make_float4(((p[0].x + p[1].x) + (p[2].x + p[3].x)) + ((p[4].x + p[5].x) + (p[6].x + p[7].x)),
+                         ((p[0].y + p[1].y) + (p[2].y + p[3].y)) + ((p[4].y + p[5].y) + (p[6].y + p[7].y)),
+                         ((p[0].z + p[1].z) + (p[2].z + p[3].z)) + ((p[4].z + p[5].z) + (p[6].z + p[7].z)),
+                         ((p[0].w + p[1].w) + (p[2].w + p[3].w)) + ((p[4].w + p[5].w) + (p[6].w + p[7].w)));
+  if (G.bias != nullptr) {
+    const float s = G.bias_scale[slot];
+    const float4 b = *reinterpret_cast<const float4*>(G.bias + (int64_t)slot * G.bias_slot_stride + lane * 4);
+    v = make_float4(fmaf(s, b.x, v.x), fmaf(s, b.y, v.y), fmaf(s, b.z, v.z), fmaf(s, b.w, v.w));
+  }
+  const int oslot = G.out_slot_map[slot];
+  if (G.epilogue == MPQE_EPI_RELU) {
+    v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+  } else if (G.epilogue == MPQE_EPI_MASK) {
+    const float4 m = *reinterpret_cast<const float4*>(G.mask + (int64_t)oslot * D + lane * 4);
+    v = make_float4(m.x > 0.f ? v.x : 0.f, m.y > 0.f ? v.y : 0.f, m.z > 0.f ? v.z : 0.f, m.w > 0.f ? v.w : 0.f);
+  }
+  *reinterpret_cast<float4*>(G.out + (int64_t)oslot * D + lane * 4) = v;
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Weight gradient: dM_j = sum over matching terms, over queries, of A[q]^T G[q]  (a [128,B]x[B,128] reduction).
 // Each CTA owns (destination j, chunk c) and a fixed query range per group; partials are reduced in order.
 // ------------------------------------------------------------------------------------------------------------
@@ -328,6 +390,37 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const __grid_constant
   *dst = r;
 }
 
+// One-row groups: dM_j (+)= sum over matching terms of a_t^T g[slot] -- rank-1 updates, summed in term order by the
+// thread that owns the element; no partials, no second stage.
+__global__ void __launch_bounds__(256) wgrad_row_kernel(const __grid_constant__ WgradLaunch L) {
+  const int j = blockIdx.y;
+  const int e4 = blockIdx.x * 256 + threadIdx.x;  // float4 index into the [D,D] matrix
+  if (e4 >= D * D / 4) return;
+  const int row = e4 / (D / 4), c4 = e4 % (D / 4);
+  const float* m_fwd = L.d[j].m_fwd;
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int g = 0; g < L.num_groups; ++g) {
+    const mpqe_layer_group_t& G = L.g[g];
+    const mpqe_wgrad_operand_t& O = L.go[g];
+    for (int t = 0; t < G.num_terms; ++t) {
+      const mpqe_term_t& T = G.terms[t];
+      if (T.m != m_fwd) continue;
+      const float a = __ldg(T.a + (int64_t)T.a_slot * D + row);
+      const float4 gv = __ldg(reinterpret_cast<const float4*>(O.g + (int64_t)O.slot_map[T.out_slot] * D) + c4);
+      r.x = fmaf(a, gv.x, r.x);
+      r.y = fmaf(a, gv.y, r.y);
+      r.z = fmaf(a, gv.z, r.z);
+      r.w = fmaf(a, gv.w, r.w);
+    }
+  }
+  float4* dst = reinterpret_cast<float4*>(L.d[j].dm) + e4;
+  if (L.d[j].accumulate) {
+    const float4 o = *dst;
+    r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w;
+  }
+  *dst = r;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Column sums (bias and mode-embedding gradients), two deterministic stages.
 // ------------------------------------------------------------------------------------------------------------
@@ -411,6 +504,21 @@ int layer_forward_simt(const mpqe_layer_group_t* groups, int num_groups, cudaStr
   return 0;
 }
 
+// every group has one row: one CTA per (group, out slot)
+static int layer_forward_rows(const mpqe_layer_group_t* groups, int num_groups, cudaStream_t stream) {
+  LayerLaunch L;
+  memset(&L, 0, sizeof(L));
+  L.num_groups = num_groups;
+  int units = 0;
+  for (int i = 0; i < num_groups; ++i) {
+    L.g[i] = groups[i];
+    units += groups[i].num_out_slots;
+  }
+  layer_row_kernel<<<units, 256, 0, stream>>>(L);
+  MPQE_CHECK_LAUNCH("layer_row_kernel");
+  return 0;
+}
+
 }  // namespace mpqe
 
 using namespace mpqe;
@@ -423,6 +531,9 @@ extern "C" int mpqe_layer_forward(const mpqe_layer_group_t* groups_host, int32_t
     MPQE_CHECK_ARG(groups_host[i].epilogue != MPQE_EPI_MASK || groups_host[i].mask != nullptr,
                    "mpqe_layer_forward: group %d: EPI_MASK without mask", i);
   }
+  bool rows_only = true;
+  for (int i = 0; i < num_groups; ++i) rows_only = rows_only && groups_host[i].num_queries == 1;
+  if (rows_only) return layer_forward_rows(groups_host, num_groups, (cudaStream_t)stream);
   if (use_tensor_cores) return layer_forward_tc(groups_host, num_groups, (cudaStream_t)stream);
   return layer_forward_simt(groups_host, num_groups, (cudaStream_t)stream);
 }
@@ -454,6 +565,17 @@ extern "C" int mpqe_layer_wgrad(const mpqe_layer_group_t* groups_host, const mpq
     L.g[i] = groups_host[i];
     L.go[i] = grads_host[i];
     MPQE_CHECK_ARG(grads_host[i].g != nullptr, "mpqe_layer_wgrad: group %d: null gradient operand", i);
+  }
+  bool rows_only = true;
+  for (int i = 0; i < num_groups; ++i) rows_only = rows_only && groups_host[i].num_queries == 1;
+  if (rows_only) {   // rank-1 updates: no partials
+    for (int j = 0; j < num_dests; ++j) {
+      L.d[j] = dests_host[j];
+      MPQE_CHECK_ARG(dests_host[j].dm != nullptr, "mpqe_layer_wgrad: dest %d: null dm", j);
+    }
+    wgrad_row_kernel<<<dim3(D * D / 4 / 256, num_dests), 256, 0, (cudaStream_t)stream>>>(L);
+    MPQE_CHECK_LAUNCH("wgrad_row_kernel");
+    return 0;
   }
   // chunks per destination proportional to its query-rows of work; total bounded by the workspace
   const int64_t max_parts = (int64_t)(workspace_bytes / (D * D * sizeof(float)));

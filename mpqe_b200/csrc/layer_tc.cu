@@ -515,6 +515,27 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc_kernel(const __grid_const
       const int nsteps = __popc(term_mask(G, U.slot)) * (D / KC);
       const int ab = uc & 1;
       if (tid == 0) trace(30, uc);
+      // The ReLU mask (and the bias) of a 32-column block are fetched one block ahead, all eight rows at once and
+      // through the read-only path: loaded inside the store loop they cannot be hoisted above the stores (possible
+      // aliasing) and every row pays a full memory round trip -- 32 serialised round trips per unit.
+      const int oslot = G.out_slot_map[U.slot];
+      const int cq = (lane & 7) * 4;          // this lane's 4 columns inside the 32-column block
+      const bool masked = G.epilogue == MPQE_EPI_MASK;
+      float4 mk[8], bnext = make_float4(0.f, 0.f, 0.f, 0.f);
+      auto fetch = [&](int c0) {
+        if (masked) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int64_t q = U.q0 + warp * 32 + 4 * i + (lane >> 3);
+            mk[i] = q < G.num_queries
+                        ? __ldg(reinterpret_cast<const float4*>(G.mask + (q * G.mask_slots + oslot) * (int64_t)D + c0 + cq))
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        if (G.bias != nullptr)
+          bnext = __ldg(reinterpret_cast<const float4*>(G.bias + (int64_t)U.slot * G.bias_slot_stride + c0 + cq));
+      };
+      fetch(0);
 #ifdef MPQE_TC_STATS
       et0 = clock64();
 #endif
@@ -528,10 +549,8 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc_kernel(const __grid_const
       // TMEM gives each thread one accumulator ROW; a 32x32 block per warp is transposed through shared memory so
       // that every global store instruction writes 4 full 128-byte row segments (instead of 32 scattered 16-byte
       // pieces, which kept the load/store pipe busier than the tensor pipe).
-      const int oslot = G.out_slot_map[U.slot];
       const float bscale = G.bias != nullptr ? G.bias_scale[U.slot] : 0.f;
       float* stage = &sh.epi[warp][0][0];
-      const int cq = (lane & 7) * 4;          // this lane's 4 columns inside the 32-column block
 #pragma unroll 1
       for (int c0 = 0; c0 < D; c0 += 32) {
         uint32_t v[32];
@@ -542,11 +561,11 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc_kernel(const __grid_const
               make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
                           __uint_as_float(v[i + 3]));
         __syncwarp();
-        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (G.bias != nullptr) {
-          const float4 b = *reinterpret_cast<const float4*>(G.bias + (int64_t)U.slot * G.bias_slot_stride + c0 + cq);
-          bv = make_float4(bscale * b.x, bscale * b.y, bscale * b.z, bscale * b.w);
-        }
+        const float4 bv = make_float4(bscale * bnext.x, bscale * bnext.y, bscale * bnext.z, bscale * bnext.w);
+        float4 mc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mc[i] = mk[i];
+        if (c0 + 32 < D) fetch(c0 + 32);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rr = 4 * i + (lane >> 3);
@@ -557,11 +576,9 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc_kernel(const __grid_const
           if (q < G.num_queries && !(dbg & 8)) {
             if (G.epilogue == MPQE_EPI_RELU) {
               o = make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
-            } else if (G.epilogue == MPQE_EPI_MASK) {
-              const float4 m =
-                  *reinterpret_cast<const float4*>(G.mask + (q * G.mask_slots + oslot) * (int64_t)D + c0 + cq);
-              o = make_float4(m.x > 0.f ? o.x : 0.f, m.y > 0.f ? o.y : 0.f, m.z > 0.f ? o.z : 0.f,
-                              m.w > 0.f ? o.w : 0.f);
+            } else if (masked) {
+              o = make_float4(mc[i].x > 0.f ? o.x : 0.f, mc[i].y > 0.f ? o.y : 0.f, mc[i].z > 0.f ? o.z : 0.f,
+                              mc[i].w > 0.f ? o.w : 0.f);
             }
             *reinterpret_cast<float4*>(G.out + (q * G.out_slots + oslot) * (int64_t)D + c0 + cq) = o;
           }

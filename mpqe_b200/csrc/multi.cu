@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(ROW_THREADS) margin_bwd_multi_kernel(const __g
   }
 }
 
-// ---- column sums of many sources in three launches ------------------------------------------------------------
+// ---- column sums of many sources in two launches ------------------------------------------------------------
 constexpr int CS_ROWS = 128;  // rows per CTA (8 warps x 16 rows)
 
 __device__ __forceinline__ int64_t cs_blocks(int64_t rows) { return (rows + CS_ROWS - 1) / CS_ROWS; }
@@ -186,19 +186,32 @@ __global__ void __launch_bounds__(256) colsum_partial_multi_kernel(const __grid_
   }
 }
 
-__global__ void __launch_bounds__(128) colsum_item_multi_kernel(const __grid_constant__ ColsumLaunch L) {
+// Second stage: one CTA per item; the first item of each destination ("leader") folds the block partials of every item
+// that shares its destination, in item order, and writes the destination once: dst = ((dst + t_i) + t_k) + ...
+__global__ void __launch_bounds__(128) colsum_finish_multi_kernel(const __grid_constant__ ColsumLaunch L) {
   const int item = blockIdx.x;
+  float* dst = L.it[item].dst;
+  for (int i = 0; i < item; ++i)
+    if (L.it[i].dst == dst) return;
   int64_t base = 0;
   for (int i = 0; i < item; ++i) base += cs_blocks(L.it[i].rows);
-  const int64_t nb = cs_blocks(L.it[item].rows);
-  float s = 0.f;
-  for (int64_t b = 0; b < nb; ++b) s += L.partials[(base + b) * D + threadIdx.x];
-  L.totals[(int64_t)item * D + threadIdx.x] = s * L.it[item].scale;
-}
-
-__global__ void __launch_bounds__(128) colsum_apply_multi_kernel(const __grid_constant__ ColsumLaunch L) {
-  for (int i = 0; i < L.n; ++i)  // item order: several items may accumulate into the same destination
-    L.it[i].dst[threadIdx.x] += L.totals[(int64_t)i * D + threadIdx.x];
+  float acc = dst[threadIdx.x];
+  for (int k = item; k < L.n; ++k) {
+    const int64_t nb = cs_blocks(L.it[k].rows);
+    if (L.it[k].dst == dst) {
+      const float* p = L.partials + base * D + threadIdx.x;
+      float s = 0.f;
+      int64_t b = 0;
+      for (; b + 4 <= nb; b += 4) {   // four loads in flight, summed in block order
+        const float v0 = p[(b + 0) * D], v1 = p[(b + 1) * D], v2 = p[(b + 2) * D], v3 = p[(b + 3) * D];
+        s += v0; s += v1; s += v2; s += v3;
+      }
+      for (; b < nb; ++b) s += p[b * D];
+      acc += s * L.it[k].scale;
+    }
+    base += nb;
+  }
+  dst[threadIdx.x] = acc;
 }
 
 }  // namespace
@@ -287,9 +300,7 @@ extern "C" int mpqe_colsum_multi(const mpqe_colsum_item_t* items_host, int32_t n
   L.totals = L.partials + blocks * D;
   colsum_partial_multi_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(L);
   MPQE_CHECK_LAUNCH("colsum_partial_multi_kernel");
-  colsum_item_multi_kernel<<<n, 128, 0, (cudaStream_t)stream>>>(L);
-  MPQE_CHECK_LAUNCH("colsum_item_multi_kernel");
-  colsum_apply_multi_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(L);
-  MPQE_CHECK_LAUNCH("colsum_apply_multi_kernel");
+  colsum_finish_multi_kernel<<<n, 128, 0, (cudaStream_t)stream>>>(L);
+  MPQE_CHECK_LAUNCH("colsum_finish_multi_kernel");
   return 0;
 }

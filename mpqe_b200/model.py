@@ -415,20 +415,22 @@ class Engine(object):
                             G.colsum(g[:, s], job.B, g_slots * D, G.dbias[li])
             # ---- batch-constant terms of pass 0: per-slot column sums of the output gradient, consumed after flush
             if p == 0:
-                for job in active:
-                    if job.const_fwd is None:
-                        continue
+                cjobs = [job for job in active if job.const_fwd is not None]
+                if cjobs:      # one zero-filled buffer for every job's sums (one memset, not one per job)
+                    widths = [1 if cur[job][1] == 1 else job.t.num_nodes for job in cjobs]
+                    cs_all = torch.zeros(sum(widths), D, dtype=torch.float32, device=cur[cjobs[0]][0].device)
+                    off = 0
+                for job, width in zip(cjobs, widths if cjobs else []):
                     g, g_slots, smap = cur[job]
-                    n = job.t.num_nodes
+                    job.cs = cs_all[off:off + width].view(1, width, D)
+                    off += width
                     if g_slots == 1:
-                        job.cs = torch.zeros(1, 1, D, dtype=torch.float32, device=g.device)
                         G.colsum(g, job.B, D, job.cs[0, 0])
                         job.cs_operand = (job.cs, 1, [0] * len(smap))
                     else:
-                        job.cs = torch.zeros(1, n, D, dtype=torch.float32, device=g.device)
                         for s_ in smap:
                             G.colsum(g[:, s_], job.B, g_slots * D, job.cs[0, s_])
-                        job.cs_operand = (job.cs, n, list(smap))
+                        job.cs_operand = (job.cs, width, list(smap))
             # ---- input gradients of pass p
             groups, nxt = [], {}
             for job in active:

@@ -173,7 +173,8 @@ def layer_forward(groups, use_tensor_cores=None):
     for i in range(0, len(groups), MAX_GROUPS):
         chunk = groups[i:i + MAX_GROUPS]
         arr = (_lib.LayerGroup * len(chunk))(*[g.to_c() for g in chunk])
-        with _Profiled('layer', chunk):
+        rows_only = all(g.num_queries == 1 for g in chunk)     # batch-constant rows: the one-row kernel
+        with _Profiled('layer_rows' if rows_only else 'layer', chunk):
             _lib.check(lib.mpqe_layer_forward(arr, len(chunk), int(tc), _stream()), 'mpqe_layer_forward')
         _count()
 
@@ -199,12 +200,13 @@ def layer_wgrad(groups, grad_operands, dests, ctas_hint=296, use_tensor_cores=No
         ctas_hint = min(ctas_hint, 148)   # the tcgen05 kernel is persistent: one unit per SM is enough parallelism
     nbytes = lib.mpqe_layer_wgrad_workspace_bytes(len(dests), ctas_hint)
     ws = workspace(nbytes, dev, 'wgrad')
-    with _Profiled('wgrad', groups, grad_operands):
+    rows_only = all(g.num_queries == 1 for g in groups)
+    with _Profiled('wgrad_rows' if rows_only else 'wgrad', groups, grad_operands):
         # the chunking (hence the summation order) follows the workspace size: pass the requested size, not the
         # size of the cached buffer, so that results do not depend on what ran before
         _lib.check(lib.mpqe_layer_wgrad(garr, oarr, len(groups), darr, len(dests), int(tc), _ptr(ws), nbytes,
                                         _stream()), 'mpqe_layer_wgrad')
-    _count(2)
+    _count(1 if rows_only else 2)
 
 
 PACKED_FLOATS = 2 * D * D
@@ -536,11 +538,11 @@ class ColsumItem(object):
 
 
 def colsum_multi(items, device):
-    """Applies every item in order (3 launches per <=64 items)."""
+    """Applies every item in order (2 launches per <=64 items)."""
     lib = _lib.load()
     for i in range(0, len(items), _lib.MAX_COLSUM_ITEMS):
         chunk = items[i:i + _lib.MAX_COLSUM_ITEMS]
         arr = (_lib.ColsumItem * len(chunk))(*[it.to_c() for it in chunk])
         ws = workspace(lib.mpqe_colsum_multi_workspace_bytes(arr, len(chunk)), device, 'colsum')
         _lib.check(lib.mpqe_colsum_multi(arr, len(chunk), _ptr(ws), ws.numel(), _stream()), 'mpqe_colsum_multi')
-        _count(3)
+        _count(2)
