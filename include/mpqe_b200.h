@@ -196,7 +196,8 @@ MPQE_API int mpqe_cosine_scores_bwd(const float* q, int64_t B, const int64_t* of
 /* One (group, node slot) of the input build (model.py:418-421) or of its backward.
  * forward : out[i*out_stride .. +d] = normalize ? table[row]/||table[row]|| : table[row],
  *           row = id2row ? id2row[ids[i*ids_stride]] : ids[i*ids_stride]   (ids_stride 0 broadcasts one row)
- * backward: rows_out[i] = normalise-backward of grad[i*grad_stride .. +d], rows_id[i] = row + id_offset */
+ * backward: rows_out[i] = normalise-backward of grad[i*grad_stride .. +d], rows_id[i] = row + id_offset
+ * backward == 2 ("ids"): only rows_id[i] = row + id_offset (input of mpqe_sparse_rows_plan) */
 typedef struct {
   const float* table;
   int64_t table_rows;
@@ -272,6 +273,14 @@ MPQE_API size_t mpqe_sparse_rows_workspace_bytes(int64_t count);
 MPQE_API int mpqe_sparse_rows_combine(const int64_t* rows_id, const float* rows, int64_t count, int64_t table_rows,
                              int64_t pad_id, int64_t* unique_ids, float* unique_rows, int64_t* num_unique,
                              void* workspace, size_t workspace_bytes, void* stream);
+/* The same combine in two phases sharing one workspace.  `plan` needs only the row ids (stable sort, segment heads,
+ * num_unique) -- the ids of a training step are known before its backward has produced any gradient row, so the
+ * plan can run on another stream meanwhile; `apply` then sums the rows (one kernel).  plan + apply == combine. */
+MPQE_API int mpqe_sparse_rows_plan(const int64_t* rows_id, int64_t count, int64_t table_rows, int64_t* num_unique,
+                          void* workspace, size_t workspace_bytes, void* stream);
+MPQE_API int mpqe_sparse_rows_apply(const float* rows, int64_t count, int64_t table_rows, int64_t pad_id,
+                           int64_t* unique_ids, float* unique_rows, const int64_t* num_unique,
+                           void* workspace, size_t workspace_bytes, void* stream);
 /* dense[ids[i], :] (+)= rows[i, :] for i < *num (ids unique) */
 MPQE_API int mpqe_scatter_rows(const int64_t* ids, const float* rows, const int64_t* num, int64_t max_count,
                       float* dense, int32_t accumulate, void* stream);

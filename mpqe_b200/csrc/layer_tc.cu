@@ -172,7 +172,9 @@ __device__ __forceinline__ void split_tf32(const float4& x, float4& hi, float4& 
 // Every operand tile is K-major [128 rows][32 k]: element (row, k) at (row/8)*1024 + (k/4)*128 + (row%8)*16 + (k%4)*4
 // bytes; descriptor for k-step j (k = 8j..8j+7): start + j*256, LBO = 128 (next 4 k), SBO = 1024 (next 8 rows).
 // (Probed on B200 with tests/tc_probe.cu: K-major tf32 operands are exact with and without the 128-byte swizzle and
-// run at the same ~160 cycles per 128x128x8 MMA; MN-major no-swizzle tf32 operands yield zeros.)
+// run at the same ~160 cycles per 128x128x8 MMA; with either MN-major bit of the instruction descriptor set, every
+// canonical MN-major layout tried -- no swizzle and 128-byte swizzle, LBO/SBO in both orders -- accumulates exact
+// zeros, even on an all-ones operand: kind::tf32 takes K-major operands only here.)
 // Sources whose contiguous dimension is the tile's ROW dimension (weight matrices [k][n], and both operands of the
 // weight gradient) are read column-wise (lane <-> row of the tile, 4 scalar loads per 16-byte store), so that every
 // shared-memory store is a conflict-free 16-byte st.shared.v4 (a first version transposed with 4-byte stores and
@@ -210,8 +212,8 @@ __device__ __forceinline__ void store_kmajor(const Frag& f, uint8_t* hi_tile, ui
 // its rows.  Lane <-> mn (a warp instruction reads 128 contiguous bytes of one k row), each thread gathers 4
 // consecutive k of its column into a float4, which is exactly one 16-byte row of a core matrix -> one st.shared.v4.
 //   producer warp pw: mn = 32*(pw&3) + lane, k-quads kq = 4*(pw>>2) + i, i = 0..3
-__device__ __forceinline__ void load_columns(Frag& f, const float* src, int64_t pitch, int k_valid, int pw, int lane) {
-  const float* col = src + 32 * (pw & 3) + lane;
+// `col` = address of this thread's column in k row 0 (src + 32*(pw&3) + lane)
+__device__ __forceinline__ void load_columns_at(Frag& f, const float* col, int64_t pitch, int k_valid, int pw) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int k0 = 16 * (pw >> 2) + 4 * i;
@@ -220,6 +222,9 @@ __device__ __forceinline__ void load_columns(Frag& f, const float* src, int64_t 
     f.v[i].z = k0 + 2 < k_valid ? col[(k0 + 2) * pitch] : 0.f;
     f.v[i].w = k0 + 3 < k_valid ? col[(k0 + 3) * pitch] : 0.f;
   }
+}
+__device__ __forceinline__ void load_columns(Frag& f, const float* src, int64_t pitch, int k_valid, int pw, int lane) {
+  load_columns_at(f, src + 32 * (pw & 3) + lane, pitch, k_valid, pw);
 }
 __device__ __forceinline__ void store_columns(const Frag& f, uint8_t* hi_tile, uint8_t* lo_tile, int pw, int lane) {
   const int mn = 32 * (pw & 3) + lane;
@@ -402,38 +407,53 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc_kernel(const __grid_const
     // stage of store / fence / handshake work hides their latency.
     const int pw = warp - EPI_WARPS;
     uint32_t it = 0;
-    // iterator over (unit, term, k chunk)
+    // iterator over (unit, term, k chunk).  Everything a stage needs from the launch descriptor is fetched ONCE per
+    // term into registers (four row pointers, the weight pointers): the descriptor lives in the kernel-parameter
+    // constant bank and is indexed dynamically, and such loads (LDC with a register index) cost a dependent
+    // constant-cache round trip each -- per stage they added up to a third of the stage time.
     int uk = 0;
-    int unit = sched_unit(S, 0, total_units);
-    UnitInfo U = decode_unit(L, unit >= 0 ? unit : 0);
-    uint32_t mask = unit >= 0 ? term_mask(L.g[U.gi], U.slot) : 0u;
-    int kc = -KC;
-    bool alive = unit >= 0;
+    uint32_t mask = 0u;
+    int kc = D - KC;          // "previous term finished": the first call moves to the first term of the first unit
+    bool alive = true;
+    UnitInfo U{0, 0, 0};
+    const float* rowp[4] = {nullptr, nullptr, nullptr, nullptr};   // this thread's four source rows, k = 0
+    const float* packed_base = nullptr;
+    const float* plain_base = nullptr;
     // loads the next (term, k chunk) stage into (fa, fb); false when all of this CTA's work has been issued
     auto load_next = [&](Frag& fa, Frag& fb, const float*& packed) -> bool {
       if (!alive) return false;
       kc += KC;
-      if (kc >= D) {
+      if (kc >= D) {          // next term
         kc = 0;
         mask &= mask - 1;
-      }
-      while (mask == 0) {   // next unit (a unit without terms contributes no stages)
-        unit = sched_unit(S, ++uk, total_units);
-        if (unit < 0) {
-          alive = false;
-          return false;
+        while (mask == 0) {   // next unit (a unit without terms contributes no stages)
+          const int unit = sched_unit(S, uk++, total_units);
+          if (unit < 0) {
+            alive = false;
+            return false;
+          }
+          U = decode_unit(L, unit);
+          mask = term_mask(L.g[U.gi], U.slot);
         }
-        U = decode_unit(L, unit);
-        mask = term_mask(L.g[U.gi], U.slot);
-        kc = 0;
+        const mpqe_layer_group_t& G = L.g[U.gi];
+        const mpqe_term_t& T = G.terms[__ffs(mask) - 1];
+        const float* a = T.a;
+        const int64_t a_slots = T.a_slots, a_slot = T.a_slot, nq = G.num_queries;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {   // same row / k-quad assignment as store_kmajor
+          const int idx = pw * 4 + i;
+          int64_t q = U.q0 + (idx >> 1) * 8 + (lane & 7);
+          if (q >= nq) q = nq - 1;
+          rowp[i] = a + (q * a_slots + a_slot) * (int64_t)D + ((idx & 1) * 4 + (lane >> 3)) * 4;
+        }
+        packed_base = T.m_packed;   // pre-split weight tiles (mpqe_pack_weights): [k chunk][hi 16 KB | lo 16 KB]
+        plain_base = T.m;
       }
-      const mpqe_layer_group_t& G = L.g[U.gi];
-      const mpqe_term_t& T = G.terms[__ffs(mask) - 1];
-      // pre-split weight tiles (mpqe_pack_weights): [k chunk][hi 16 KB | lo 16 KB], already in the smem tile layout
-      packed = T.m_packed != nullptr ? T.m_packed + (kc / KC) * (2 * TILE_BYTES / 4) : nullptr;
+      packed = packed_base != nullptr ? packed_base + (kc / KC) * (2 * TILE_BYTES / 4) : nullptr;
       if (!((dbg & 2) && it > 1)) {   // (dbg bit 1: timing experiment without global loads after the first stages)
-        load_kmajor(fa, T, U.q0, G.num_queries, kc, pw, lane);
-        if (packed == nullptr) load_columns(fb, T.m + (int64_t)kc * D, D, KC, pw, lane);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) fa.v[i] = *reinterpret_cast<const float4*>(rowp[i] + kc);
+        if (packed == nullptr) load_columns(fb, plain_base + (int64_t)kc * D, D, KC, pw, lane);
       }
       return true;
     };
@@ -506,7 +526,7 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc_kernel(const __grid_const
   } else {
     // ===== epilogue: one accumulator row per thread =====
     int uc = 0;
-    long long estat[2] = {0, 0}, et0 = 0;
+    long long estat[4] = {0, 0, 0, 0}, et0 = 0;
     (void)estat;
     (void)et0;
     for (int unit; (unit = sched_unit(S, uc, total_units)) >= 0; ++uc) {
@@ -515,25 +535,33 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc_kernel(const __grid_const
       const int nsteps = __popc(term_mask(G, U.slot)) * (D / KC);
       const int ab = uc & 1;
       if (tid == 0) trace(30, uc);
-      // The ReLU mask (and the bias) of a 32-column block are fetched one block ahead, all eight rows at once and
-      // through the read-only path: loaded inside the store loop they cannot be hoisted above the stores (possible
-      // aliasing) and every row pays a full memory round trip -- 32 serialised round trips per unit.
+      // Everything the store loop needs is pulled out of the launch descriptor into registers here, once per unit
+      // (dynamically indexed kernel-parameter loads inside the loop cost a dependent constant-cache round trip per
+      // store).  The ReLU mask and the bias of a 32-column block are fetched one block ahead through the read-only
+      // path, all eight rows at once: loaded inside the store loop they cannot be hoisted above the stores
+      // (possible aliasing) and every row pays a full memory round trip.
       const int oslot = G.out_slot_map[U.slot];
       const int cq = (lane & 7) * 4;          // this lane's 4 columns inside the 32-column block
-      const bool masked = G.epilogue == MPQE_EPI_MASK;
+      const int epi = G.epilogue;
+      const bool masked = epi == MPQE_EPI_MASK;
+      const int row0 = warp * 32 + (lane >> 3);                  // this lane's rows: row0 + 4 i
+      const int64_t rows_left = G.num_queries - U.q0 - row0;     // row 4 i exists iff 4 i < rows_left
+      float* outp = G.out + ((U.q0 + row0) * (int64_t)G.out_slots + oslot) * (int64_t)D + cq;
+      const int64_t out_step = 4 * (int64_t)G.out_slots * D;
+      const float* maskp = masked ? G.mask + ((U.q0 + row0) * (int64_t)G.mask_slots + oslot) * (int64_t)D + cq : nullptr;
+      const int64_t mask_step = 4 * (int64_t)G.mask_slots * D;
+      const float* biasp = G.bias != nullptr ? G.bias + (int64_t)U.slot * G.bias_slot_stride + cq : nullptr;
+      const float bscale = biasp != nullptr ? G.bias_scale[U.slot] : 0.f;
+      const bool store = !(dbg & 8);
       float4 mk[8], bnext = make_float4(0.f, 0.f, 0.f, 0.f);
       auto fetch = [&](int c0) {
         if (masked) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int64_t q = U.q0 + warp * 32 + 4 * i + (lane >> 3);
-            mk[i] = q < G.num_queries
-                        ? __ldg(reinterpret_cast<const float4*>(G.mask + (q * G.mask_slots + oslot) * (int64_t)D + c0 + cq))
-                        : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+          for (int i = 0; i < 8; ++i)
+            mk[i] = 4 * i < rows_left ? __ldg(reinterpret_cast<const float4*>(maskp + i * mask_step + c0))
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        if (G.bias != nullptr)
-          bnext = __ldg(reinterpret_cast<const float4*>(G.bias + (int64_t)U.slot * G.bias_slot_stride + c0 + cq));
+        if (biasp != nullptr) bnext = __ldg(reinterpret_cast<const float4*>(biasp + c0));
       };
       fetch(0);
 #ifdef MPQE_TC_STATS
@@ -549,11 +577,23 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc_kernel(const __grid_const
       // TMEM gives each thread one accumulator ROW; a 32x32 block per warp is transposed through shared memory so
       // that every global store instruction writes 4 full 128-byte row segments (instead of 32 scattered 16-byte
       // pieces, which kept the load/store pipe busier than the tensor pipe).
-      const float bscale = G.bias != nullptr ? G.bias_scale[U.slot] : 0.f;
       float* stage = &sh.epi[warp][0][0];
 #pragma unroll 1
       for (int c0 = 0; c0 < D; c0 += 32) {
+        // the fetched block: bias scaled, mask compressed to one bit per element; then the next block's loads go out
+        const float4 bv = make_float4(bscale * bnext.x, bscale * bnext.y, bscale * bnext.z, bscale * bnext.w);
+        uint32_t mbits = 0;
+        if (masked) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            mbits |= ((mk[i].x > 0.f ? 1u : 0u) | (mk[i].y > 0.f ? 2u : 0u) | (mk[i].z > 0.f ? 4u : 0u) |
+                      (mk[i].w > 0.f ? 8u : 0u)) << (4 * i);
+        }
+        if (c0 + 32 < D) fetch(c0 + 32);
         uint32_t v[32];
+#ifdef MPQE_TC_STATS
+        const long long tl0 = clock64();
+#endif
         tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + ab * 128 + c0, v);
 #pragma unroll
         for (int i = 0; i < 32; i += 4)
@@ -561,29 +601,27 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc_kernel(const __grid_const
               make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
                           __uint_as_float(v[i + 3]));
         __syncwarp();
-        const float4 bv = make_float4(bscale * bnext.x, bscale * bnext.y, bscale * bnext.z, bscale * bnext.w);
-        float4 mc[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) mc[i] = mk[i];
-        if (c0 + 32 < D) fetch(c0 + 32);
+#ifdef MPQE_TC_STATS
+        estat[2] += clock64() - tl0;
+        const long long tl1 = clock64();
+#endif
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int rr = 4 * i + (lane >> 3);
-          const int64_t q = U.q0 + warp * 32 + rr;
-          float4 o = *reinterpret_cast<const float4*>(stage + rr * EPI_PITCH + cq);
+          float4 o = *reinterpret_cast<const float4*>(stage + (4 * i + (lane >> 3)) * EPI_PITCH + cq);
           if (nsteps == 0) o = make_float4(0.f, 0.f, 0.f, 0.f);
           o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
-          if (q < G.num_queries && !(dbg & 8)) {
-            if (G.epilogue == MPQE_EPI_RELU) {
-              o = make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
-            } else if (masked) {
-              o = make_float4(mc[i].x > 0.f ? o.x : 0.f, mc[i].y > 0.f ? o.y : 0.f, mc[i].z > 0.f ? o.z : 0.f,
-                              mc[i].w > 0.f ? o.w : 0.f);
-            }
-            *reinterpret_cast<float4*>(G.out + (q * G.out_slots + oslot) * (int64_t)D + c0 + cq) = o;
+          if (epi == MPQE_EPI_RELU) {
+            o = make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
+          } else if (masked) {
+            const uint32_t mb = mbits >> (4 * i);
+            o = make_float4((mb & 1u) ? o.x : 0.f, (mb & 2u) ? o.y : 0.f, (mb & 4u) ? o.z : 0.f, (mb & 8u) ? o.w : 0.f);
           }
+          if (4 * i < rows_left && store) *reinterpret_cast<float4*>(outp + i * out_step + c0) = o;
         }
         __syncwarp();
+#ifdef MPQE_TC_STATS
+        estat[3] += clock64() - tl1;
+#endif
       }
       tc_fence_before();
       mbar_arrive(smem_u32(&sh.acc_empty[ab]));
@@ -596,6 +634,8 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc_kernel(const __grid_const
     if (tid == 0 && g_stats != nullptr) {
       g_stats[(long long)blockIdx.x * 16 + 11] = estat[0];
       g_stats[(long long)blockIdx.x * 16 + 12] = estat[1];
+      g_stats[(long long)blockIdx.x * 16 + 5] = estat[2];
+      g_stats[(long long)blockIdx.x * 16 + 13] = estat[3];
     }
 #endif
   }
@@ -679,6 +719,19 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
     int unit = blockIdx.x - gridDim.x, j = 0, c = 0;
     WgradIter wi{0, 0, 0, 0};
     bool in_unit = false, alive = true;
+    // per-term state in registers (see layer_tc_kernel: no descriptor loads on the per-stage path)
+    const float *a_col = nullptr, *g_col = nullptr;
+    int64_t a_pitch = 0, g_pitch = 0;
+    auto enter_term = [&]() {
+      const mpqe_layer_group_t& G = L.g[wi.g];
+      const mpqe_term_t& T = G.terms[wi.t];
+      const mpqe_wgrad_operand_t& O = L.go[wi.g];
+      const int col = 32 * (pw & 3) + lane;
+      a_pitch = (int64_t)T.a_slots * D;
+      a_col = T.a + (int64_t)T.a_slot * D + col;
+      g_pitch = (int64_t)O.g_slots * D;
+      g_col = O.g + (int64_t)O.slot_map[T.out_slot] * D + col;
+    };
     auto load_next = [&](Frag& fa, Frag& fb) -> bool {
       if (!alive) return false;
       while (!in_unit) {
@@ -690,18 +743,16 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
         decode_wgrad_unit(L, unit, j, c);
         wi = WgradIter{0, 0, 0, 0};
         in_unit = wgrad_seek(L, L.d[j].m_fwd, L.chunks[j], c, wi);
+        if (in_unit) enter_term();
       }
-      const mpqe_layer_group_t& G = L.g[wi.g];
-      const mpqe_term_t& T = G.terms[wi.t];
-      const mpqe_wgrad_operand_t& O = L.go[wi.g];
       const int valid = (int)(wi.qe - wi.q < KC ? wi.qe - wi.q : KC);
-      load_columns(fa, T.a + (wi.q * T.a_slots + T.a_slot) * (int64_t)D, (int64_t)T.a_slots * D, valid, pw, lane);
-      const int gs = O.slot_map[T.out_slot];
-      load_columns(fb, O.g + (wi.q * O.g_slots + gs) * (int64_t)D, (int64_t)O.g_slots * D, valid, pw, lane);
+      load_columns_at(fa, a_col + wi.q * a_pitch, a_pitch, valid, pw);
+      load_columns_at(fb, g_col + wi.q * g_pitch, g_pitch, valid, pw);
       wi.q += KC;
       if (wi.q >= wi.qe) {
         ++wi.t;
         in_unit = wgrad_seek(L, L.d[j].m_fwd, L.chunks[j], c, wi);
+        if (in_unit) enter_term();
       }
       return true;
     };

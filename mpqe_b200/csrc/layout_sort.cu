@@ -423,34 +423,72 @@ extern "C" size_t mpqe_sparse_rows_workspace_bytes(int64_t count) {
   return carve_sort(nullptr, count).bytes + 2 * align_up(n * sizeof(int32_t), 256) + SCAN_MAX_BLOCKS * sizeof(int32_t);
 }
 
+namespace {
+struct CombineBuffers {
+  SortBuffers s;
+  int32_t *uid, *seg_start, *block_sum;
+  uint32_t *rk, *rv;   // where the sorted keys / source positions end up (depends on the pass count only)
+};
+CombineBuffers carve_combine(void* workspace, int64_t count, int64_t table_rows) {
+  CombineBuffers c;
+  c.s = carve_sort(workspace, count);
+  c.uid = (int32_t*)((char*)workspace + c.s.bytes);
+  c.seg_start = (int32_t*)((char*)c.uid + align_up((size_t)count * sizeof(int32_t), 256));
+  c.block_sum = (int32_t*)((char*)c.seg_start + align_up((size_t)count * sizeof(int32_t), 256));
+  const int passes = (bits_for(table_rows + 1) + 9) / 10;
+  c.rk = (passes & 1) ? c.s.k1 : c.s.k0;
+  c.rv = (passes & 1) ? c.s.v1 : c.s.v0;
+  return c;
+}
+}  // namespace
+
+// The part of the combine that needs only the row ids: stable sort, segment heads, number of distinct rows.  It can
+// run (on another stream) while the gradient rows are still being computed; mpqe_sparse_rows_apply then sums them.
+extern "C" int mpqe_sparse_rows_plan(const int64_t* rows_id, int64_t count, int64_t table_rows, int64_t* num_unique,
+                                     void* workspace, size_t workspace_bytes, void* stream) {
+  MPQE_CHECK_ARG(rows_id && num_unique && count >= 1 && count < (1ll << 31) && table_rows >= 1 &&
+                     table_rows < (1ll << 32),
+                 "mpqe_sparse_rows_plan: bad argument");
+  MPQE_CHECK_ARG(workspace && workspace_bytes >= mpqe_sparse_rows_workspace_bytes(count),
+                 "mpqe_sparse_rows_plan: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  CombineBuffers c = carve_combine(workspace, count, table_rows);
+  narrow_keys_kernel<<<blocks_for(count, 256), 256, 0, st>>>(rows_id, count, c.s.k0, table_rows);
+  MPQE_CHECK_LAUNCH("narrow_keys_kernel");
+  uint32_t *rk, *rv;
+  if (radix_sort(c.s, count, bits_for(table_rows + 1), st, &rk, &rv)) return 2;
+  MPQE_CHECK_ARG(rk == c.rk && rv == c.rv, "mpqe_sparse_rows_plan: internal buffer parity mismatch");
+  head_flags_kernel<<<blocks_for(count, 256), 256, 0, st>>>(rk, count, c.uid);
+  MPQE_CHECK_LAUNCH("head_flags_kernel");
+  if (exclusive_scan(c.uid, count, c.block_sum, num_unique, st)) return 2;
+  drop_sentinel_kernel<<<1, 1, 0, st>>>(rk, count, (uint32_t)table_rows, num_unique);
+  MPQE_CHECK_LAUNCH("drop_sentinel_kernel");
+  segment_starts_kernel<<<blocks_for(count, 256), 256, 0, st>>>(rk, c.uid, count, c.seg_start);
+  MPQE_CHECK_LAUNCH("segment_starts_kernel");
+  return 0;
+}
+
+extern "C" int mpqe_sparse_rows_apply(const float* rows, int64_t count, int64_t table_rows, int64_t pad_id,
+                                      int64_t* unique_ids, float* unique_rows, const int64_t* num_unique,
+                                      void* workspace, size_t workspace_bytes, void* stream) {
+  MPQE_CHECK_ARG(rows && unique_ids && unique_rows && num_unique && count >= 1 && count < (1ll << 31) &&
+                     table_rows >= 1 && table_rows < (1ll << 32),
+                 "mpqe_sparse_rows_apply: bad argument");
+  MPQE_CHECK_ARG(workspace && workspace_bytes >= mpqe_sparse_rows_workspace_bytes(count),
+                 "mpqe_sparse_rows_apply: workspace too small");
+  CombineBuffers c = carve_combine(workspace, count, table_rows);
+  segment_sum_kernel<<<blocks_for(count, 8), 256, 0, (cudaStream_t)stream>>>(
+      c.rk, c.rv, c.seg_start, num_unique, count, rows, unique_ids, unique_rows, pad_id, (uint32_t)table_rows);
+  MPQE_CHECK_LAUNCH("segment_sum_kernel");
+  return 0;
+}
+
 extern "C" int mpqe_sparse_rows_combine(const int64_t* rows_id, const float* rows, int64_t count, int64_t table_rows,
                                         int64_t pad_id, int64_t* unique_ids, float* unique_rows, int64_t* num_unique,
                                         void* workspace, size_t workspace_bytes, void* stream) {
-  MPQE_CHECK_ARG(rows_id && rows && unique_ids && unique_rows && num_unique && count >= 1 && count < (1ll << 31) &&
-                     table_rows >= 1 && table_rows < (1ll << 32),
-                 "mpqe_sparse_rows_combine: bad argument");
-  MPQE_CHECK_ARG(workspace && workspace_bytes >= mpqe_sparse_rows_workspace_bytes(count),
-                 "mpqe_sparse_rows_combine: workspace too small");
-  cudaStream_t st = (cudaStream_t)stream;
-  SortBuffers s = carve_sort(workspace, count);
-  int32_t* uid = (int32_t*)((char*)workspace + s.bytes);
-  int32_t* seg_start = (int32_t*)((char*)uid + align_up((size_t)count * sizeof(int32_t), 256));
-  int32_t* block_sum = (int32_t*)((char*)seg_start + align_up((size_t)count * sizeof(int32_t), 256));
-  narrow_keys_kernel<<<blocks_for(count, 256), 256, 0, st>>>(rows_id, count, s.k0, table_rows);
-  MPQE_CHECK_LAUNCH("narrow_keys_kernel");
-  uint32_t *rk, *rv;
-  if (radix_sort(s, count, bits_for(table_rows + 1), st, &rk, &rv)) return 2;
-  head_flags_kernel<<<blocks_for(count, 256), 256, 0, st>>>(rk, count, uid);
-  MPQE_CHECK_LAUNCH("head_flags_kernel");
-  if (exclusive_scan(uid, count, block_sum, num_unique, st)) return 2;
-  drop_sentinel_kernel<<<1, 1, 0, st>>>(rk, count, (uint32_t)table_rows, num_unique);
-  MPQE_CHECK_LAUNCH("drop_sentinel_kernel");
-  segment_starts_kernel<<<blocks_for(count, 256), 256, 0, st>>>(rk, uid, count, seg_start);
-  MPQE_CHECK_LAUNCH("segment_starts_kernel");
-  segment_sum_kernel<<<blocks_for(count, 8), 256, 0, st>>>(rk, rv, seg_start, num_unique, count, rows, unique_ids,
-                                                         unique_rows, pad_id, (uint32_t)table_rows);
-  MPQE_CHECK_LAUNCH("segment_sum_kernel");
-  return 0;
+  if (mpqe_sparse_rows_plan(rows_id, count, table_rows, num_unique, workspace, workspace_bytes, stream)) return 1;
+  return mpqe_sparse_rows_apply(rows, count, table_rows, pad_id, unique_ids, unique_rows, num_unique, workspace,
+                                workspace_bytes, stream);
 }
 
 extern "C" int mpqe_scatter_rows(const int64_t* ids, const float* rows, const int64_t* num, int64_t max_count,

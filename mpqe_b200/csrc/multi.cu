@@ -72,6 +72,16 @@ __global__ void __launch_bounds__(ROW_THREADS) gather_bwd_multi_kernel(const __g
   if (lane == 0) T.rows_id[i] = row + T.id_offset;
 }
 
+// ids only (one thread per entry): rows_id[i] = row + id_offset, exactly what the backward kernels emit -- lets the
+// row-gradient sort (mpqe_sparse_rows_plan) start before any gradient exists
+__global__ void __launch_bounds__(256) gather_ids_multi_kernel(const __grid_constant__ GatherLaunch L) {
+  int item;
+  int64_t i;
+  if (!find_item(L, (int64_t)blockIdx.x * 256 + threadIdx.x, item, i)) return;
+  const mpqe_gather_item_t& T = L.it[item];
+  T.rows_id[i] = resolve_row(T.id2row, T.ids, T.ids_stride, i) + T.id_offset;
+}
+
 template <class Launch>
 __device__ __forceinline__ bool find_query(const Launch& L, int64_t w, int& item, int64_t& local) {
   for (int i = 0; i < L.n; ++i) {
@@ -228,7 +238,9 @@ extern "C" int mpqe_gather_multi(const mpqe_gather_item_t* items_host, int32_t n
   for (int i = 0; i < n; ++i) {
     const mpqe_gather_item_t& T = items_host[i];
     MPQE_CHECK_ARG(T.table && T.ids && T.count >= 0 && T.ids_stride >= 0, "mpqe_gather_multi: item %d: bad argument", i);
-    if (backward)
+    if (backward == 2)
+      MPQE_CHECK_ARG(T.rows_id != nullptr, "mpqe_gather_multi: item %d: ids mode without rows_id", i);
+    else if (backward)
       MPQE_CHECK_ARG(T.grad && T.rows_out && T.rows_id && T.grad_stride >= D, "mpqe_gather_multi: item %d: bad bwd argument", i);
     else
       MPQE_CHECK_ARG(T.out && T.out_stride >= D, "mpqe_gather_multi: item %d: bad fwd argument", i);
@@ -236,7 +248,9 @@ extern "C" int mpqe_gather_multi(const mpqe_gather_item_t* items_host, int32_t n
     total += T.count;
   }
   if (total == 0) return 0;
-  if (backward)
+  if (backward == 2)
+    gather_ids_multi_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(L);
+  else if (backward)
     gather_bwd_multi_kernel<<<row_blocks(total), ROW_THREADS, 0, (cudaStream_t)stream>>>(L);
   else
     gather_fwd_multi_kernel<<<row_blocks(total), ROW_THREADS, 0, (cudaStream_t)stream>>>(L);

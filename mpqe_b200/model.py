@@ -441,8 +441,7 @@ class Engine(object):
                 if p > 0:
                     ins = job.outs[p - 1]
                 else:   # only the anchors receive a per-query gradient; variable slots get a column sum (below)
-                    ins = sorted(s_ for s_ in ({t.src[e] for e in range(t.num_edges) if t.dst[e] in outs} | set(outs))
-                                 if s_ < t.num_anchors)
+                    ins = self.grad_anchor_slots(job)
                 if not ins:
                     continue
                 pos = {s: k for k, s in enumerate(ins)}
@@ -520,14 +519,22 @@ class Engine(object):
         ops.layer_forward(dgroups, use_tensor_cores=False)
         G.flush()
 
+    def grad_anchor_slots(self, job):
+        """Anchor slots that receive a gradient: the sources (and self-loops) of the first pass's output slots."""
+        t = job.t
+        outs = _needed_slots(job, self.m.readout_str)[0]
+        return sorted(s for s in ({t.src[e] for e in range(t.num_edges) if t.dst[e] in outs} | set(outs))
+                      if s < t.num_anchors)
+
     def input_backward(self, job, dx, ins, G):
         """d loss / d x (anchor slots) -> entity-table rows through the normalisation."""
         t, n, B = job.t, job.t.num_nodes, job.B
         enc = self.m.enc
+        planned = getattr(job, 'anchor_res', None) if G.rows.planned else None
         for i, mode in enumerate(job.anchor_modes):
             if i not in ins:
                 continue
-            rows, rows_id, off, id_off = G.rows.reserve(mode, B)
+            rows, rows_id, off, id_off = planned[i] if planned is not None else G.rows.reserve(mode, B)
             G.gathers.append(ops.GatherItem(enc.table(mode), enc.node_maps, job.anchor_ids, B, ids_offset=i,
                                             ids_stride=t.num_anchors, grad=dx, grad_offset=i * D, grad_stride=n * D,
                                             rows_out=rows, rows_id=rows_id, rows_offset=off, id_offset=id_off))
@@ -575,6 +582,7 @@ class RowGrads(object):
     def __init__(self, capacities, device, table_offsets=None):
         self.buf = {}
         self.table_offsets = table_offsets
+        self.planned = False     # True: every slot was reserved (and its row ids emitted) before the backward
         if table_offsets is not None:
             cap = sum(capacities.values())
             self.shared = [torch.empty(cap, D, dtype=torch.float32, device=device),
@@ -597,7 +605,7 @@ class RowGrads(object):
 class Grads(object):
     """Dense gradient buffers (zero-initialised, kernels accumulate) + the row-gradient collector."""
 
-    def __init__(self, model, W, row_capacities, device, table_offsets=None):
+    def __init__(self, model, W, row_capacities, device, table_offsets=None, rows=None):
         self.device = device
         self.colsums, self.gathers, self.keep = [], [], []
         # one flat zeroed bucket: a single memset here, a single NCCL all-reduce in data-parallel training
@@ -616,7 +624,7 @@ class Grads(object):
         self.dmode = views[3 * L]
         if W.ro is not None:
             self.dw1t, self.dw2t, self.db1, self.db2 = views[3 * L + 1:3 * L + 5]
-        self.rows = RowGrads(row_capacities, device, table_offsets)
+        self.rows = rows if rows is not None else RowGrads(row_capacities, device, table_offsets)
 
     def colsum(self, src, rows, stride, dst, scale=1.0):
         """Deferred dst += scale * column-sum(src): all of a backward's reductions run in one multi-item launch."""
@@ -827,18 +835,46 @@ def loss_forward(model, jobs, targets, negatives, margin, need_grad):
     return losses, W
 
 
-def loss_backward(model, jobs, W, targets, negatives, margin, grad_losses, table_offsets=None):
-    """Backward of `loss_forward` for d(total)/d(loss_i) = grad_losses[i] (device tensor [len(jobs)]).
-    Returns the filled `Grads` (dense bucket + (row id, gradient row) pairs, not yet combined)."""
+def plan_rows(model, jobs, targets, negatives, table_offsets):
+    """Reserves every row-gradient slot of a step in the shared (row id, row) buffer BEFORE the forward and emits the
+    row ids with one launch, so that the id-only half of the combine (`ops.SparseRowsPlan`) can overlap the step.
+    The reservations are left on the jobs (`margin_res`, `anchor_res`) for `loss_backward(..., rows=...)`."""
     device = jobs[0].anchor_ids.device
+    enc = model.enc
     cap = model._row_capacities(jobs, [(job.target_mode, 2 * job.B) for job in jobs])
-    G = Grads(model, W, cap, device, table_offsets)
+    R = RowGrads(cap, device, table_offsets)
+    items = []
+    for job, tgt, neg in zip(jobs, targets, negatives):
+        res = job.margin_res = R.reserve(job.target_mode, 2 * job.B)
+        table = enc.table(job.target_mode)
+        items.append(ops.GatherItem(table, enc.node_maps, tgt, job.B, rows_id=res[1], rows_offset=res[2], id_offset=res[3]))
+        items.append(ops.GatherItem(table, enc.node_maps, neg, job.B, rows_id=res[1], rows_offset=res[2] + job.B,
+                                    id_offset=res[3]))
+    for job in jobs:
+        job.anchor_res = {}
+        for i in model._engine.grad_anchor_slots(job):
+            mode = job.anchor_modes[i]
+            res = job.anchor_res[i] = R.reserve(mode, job.B)
+            items.append(ops.GatherItem(enc.table(mode), enc.node_maps, job.anchor_ids, job.B, ids_offset=i,
+                                        ids_stride=job.t.num_anchors, rows_id=res[1], rows_offset=res[2], id_offset=res[3]))
+    ops.gather_multi(items, backward='ids')
+    R.planned = True
+    return R
+
+
+def loss_backward(model, jobs, W, targets, negatives, margin, grad_losses, table_offsets=None, rows=None):
+    """Backward of `loss_forward` for d(total)/d(loss_i) = grad_losses[i] (device tensor [len(jobs)]).
+    Returns the filled `Grads` (dense bucket + (row id, gradient row) pairs, not yet combined).  `rows`: a RowGrads
+    from `plan_rows` (slots reserved and ids already emitted)."""
+    device = jobs[0].anchor_ids.device
+    cap = model._row_capacities(jobs, [(job.target_mode, 2 * job.B) for job in jobs]) if rows is None else None
+    G = Grads(model, W, cap, device, table_offsets, rows)
     dqs, items = [], []
     for i, (job, tgt, neg) in enumerate(zip(jobs, targets, negatives)):
-        rows, ids, off, id_off = G.rows.reserve(job.target_mode, 2 * job.B)
+        rbuf, ids, off, id_off = job.margin_res if G.rows.planned else G.rows.reserve(job.target_mode, 2 * job.B)
         dq = torch.empty(job.B, D, dtype=torch.float32, device=device)
         items.append(ops.MarginItem(job.q, model.enc.table(job.target_mode), model.enc.node_maps, tgt, neg,
-                                    grad_loss=grad_losses[i:i + 1], dq=dq, rows_out=rows, rows_id=ids, rows_offset=off,
+                                    grad_loss=grad_losses[i:i + 1], dq=dq, rows_out=rbuf, rows_id=ids, rows_offset=off,
                                     id_offset=id_off))
         dqs.append(dq)
     ops.cosine_margin_multi(items, margin, backward=True)

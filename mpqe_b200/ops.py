@@ -441,6 +441,33 @@ def sparse_rows_combine(rows_id, rows, table_rows, pad_id=0):
     return uid, urows, num
 
 
+class SparseRowsPlan(object):
+    """The id-only half of `sparse_rows_combine` (mpqe_sparse_rows_plan): sort + segmentation of `rows_id`, held in a
+    private workspace until `apply(rows)` sums the gradient rows.  The plan may be built on another stream."""
+
+    def __init__(self, rows_id, table_rows):
+        lib = _lib.load()
+        self.count, self.table_rows = rows_id.numel(), int(table_rows)
+        dev = rows_id.device
+        self.num = torch.empty(1, dtype=torch.int64, device=dev)
+        nbytes = lib.mpqe_sparse_rows_workspace_bytes(self.count)
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)   # private: lives across streams
+        self.nbytes = nbytes
+        _lib.check(lib.mpqe_sparse_rows_plan(_ptr(_chk(rows_id, torch.int64, 'rows_id')), self.count, self.table_rows,
+                                             _ptr(self.num), _ptr(self.ws), nbytes, _stream()), 'mpqe_sparse_rows_plan')
+        _count(9)
+
+    def apply(self, rows, pad_id=0):
+        lib = _lib.load()
+        uid = torch.empty(self.count, dtype=torch.int64, device=rows.device)
+        urows = torch.empty(self.count, D, dtype=torch.float32, device=rows.device)
+        _lib.check(lib.mpqe_sparse_rows_apply(_ptr(_chk(rows, torch.float32, 'rows')), self.count, self.table_rows,
+                                              pad_id, _ptr(uid), _ptr(urows), _ptr(self.num), _ptr(self.ws), self.nbytes,
+                                              _stream()), 'mpqe_sparse_rows_apply')
+        _count()
+        return uid, urows, self.num
+
+
 def scatter_rows(ids, rows, num, dense, accumulate=False):
     lib = _lib.load()
     _lib.check(lib.mpqe_scatter_rows(_ptr(ids), _ptr(rows), _ptr(num), ids.numel(), _ptr(_chk(dense, torch.float32, 'dense')),
@@ -487,7 +514,9 @@ class GatherItem(object):
 
 
 def gather_multi(items, backward=False):
+    """backward: False = forward gather, True = backward (rows + ids), 'ids' = only the row ids of the backward."""
     lib = _lib.load()
+    backward = 2 if backward == 'ids' else int(bool(backward))
     for i in range(0, len(items), _lib.MAX_GATHER_ITEMS):
         chunk = items[i:i + _lib.MAX_GATHER_ITEMS]
         arr = (_lib.GatherItem * len(chunk))(*[it.to_c() for it in chunk])

@@ -42,8 +42,8 @@ e2.record()
 torch.cuda.synchronize()
 print('kernel us without stats buffer %.1f' % (1e3 * s2.elapsed_time(e2)))
 st = stats.cpu().view(148, 16).numpy().astype(np.float64)
-names = ['P wait empty', 'P data+stores', 'P issue loads', 'P fence+arrive', '-', '-', 'M wait acc_empty', 'M wait full',
-         'M issue+commit', 'stages', 'units', 'E wait acc_full', 'E work', 'setup', 'CTA total', '-']
+names = ['P wait empty', 'P data+stores', 'P issue loads', 'P fence+arrive', '-', 'E tmem ld+sts', 'M wait acc_empty', 'M wait full',
+         'M issue+commit', 'stages', 'units', 'E wait acc_full', 'E work', 'E fetch+stores', 'CTA total', '-']
 for i, nm in enumerate(names):
     if nm != '-':
         print('%-18s mean %9.0f  min %9.0f  max %9.0f' % (nm, st[:, i].mean(), st[:, i].min(), st[:, i].max()))

@@ -248,6 +248,16 @@ def sparse_rows_combine(rows_id, rows, table_rows, pad_id=0):
     return uid, urows, torch.tensor([uniq.numel()], dtype=torch.int64)
 
 
+class SparseRowsPlan(object):
+    """plan(ids) + apply(rows) == sparse_rows_combine(ids, rows)."""
+
+    def __init__(self, rows_id, table_rows):
+        self.rows_id, self.table_rows = rows_id.clone(), table_rows
+
+    def apply(self, rows, pad_id=0):
+        return sparse_rows_combine(self.rows_id, rows, self.table_rows, pad_id)
+
+
 def scatter_rows(ids, rows, num, dense, accumulate=False):
     k = int(num.item()) if num is not None else ids.numel()
     if accumulate:
@@ -260,7 +270,8 @@ def install(monkeypatch):
     for name in ('layer_forward', 'layer_wgrad', 'colsum', 'transpose', 'gather_normalize', 'gather_normalize_bwd',
                  'broadcast_rows', 'max_readout', 'max_readout_bwd', 'cosine_margin', 'cosine_margin_bwd',
                  'cosine_scores', 'cosine_scores_bwd', 'rank_counts_ragged', 'rank_counts_table',
-                 'build_query_graph', 'relation_sort', 'sparse_rows_combine', 'scatter_rows', 'gather_multi',
+                 'build_query_graph', 'relation_sort', 'sparse_rows_combine', 'SparseRowsPlan', 'scatter_rows',
+                 'gather_multi',
                  'cosine_margin_multi', 'colsum_multi'):
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(ops, 'device_guard', lambda device: contextlib.nullcontext())
@@ -269,7 +280,10 @@ def install(monkeypatch):
 
 def gather_multi(items, backward=False):
     for it in items:
-        if backward:
+        if backward == 'ids':
+            idx = it.ids.reshape(-1)[it.ids_offset::max(it.ids_stride, 1)][:it.count]
+            it.rows_id[it.rows_offset:it.rows_offset + it.count] = _resolve(it.id2row, idx) + it.id_offset
+        elif backward:
             gather_normalize_bwd(it.table, it.id2row, it.ids, it.grad, it.rows_out, it.rows_id, it.grad_offset,
                                  it.grad_stride, it.ids_offset, max(it.ids_stride, 1), it.count, it.rows_offset)
             it.rows_id[it.rows_offset:it.rows_offset + it.count] += it.id_offset

@@ -40,7 +40,8 @@ struct Params {
   int ksteps;
   int use_mask_form;        // CUTLASS 4-register disable_output_lane form
   int version;
-  int layout_type;          // 0 none, 2 = SWIZZLE_128B
+  int layout_type;          // 0 none, 2 = SWIZZLE_128B (operand A)
+  int b_layout_type;        // same for operand B
   int repeat;               // timing: issue the k-step sequence this many times
 };
 
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(128) probe_kernel(const uint8_t* a_img, const 
     for (int rep = 0; rep < P.repeat; ++rep)
     for (int j = 0; j < P.ksteps; ++j) {
       const uint64_t da = make_desc(smem_u32(sa) + j * P.a_step, P.a_lbo, P.a_sbo, P.version, P.layout_type);
-      const uint64_t db = make_desc(smem_u32(sb) + j * P.b_step, P.b_lbo, P.b_sbo, P.version, P.layout_type);
+      const uint64_t db = make_desc(smem_u32(sb) + j * P.b_step, P.b_lbo, P.b_sbo, P.version, P.b_layout_type);
       const uint32_t acc = (j > 0 || rep > 0) ? 1u : 0u;
       if (P.use_mask_form) {
         asm volatile(
@@ -139,18 +140,32 @@ static int off_mnmajor(int k, int mn, int lbo, int sbo) { return (mn / 4) * sbo 
 
 // K-major SWIZZLE_128B tile [rows][32 k] (one 128-byte row per matrix row, 16-byte chunks XOR-ed with row%8)
 static int off_kmajor_sw128(int r, int k) { return (r / 8) * 1024 + (r % 8) * 128 + (((k / 4) ^ (r % 8)) * 16) + (k % 4) * 4; }
+// MN-major SWIZZLE_128B (CUTLASS canonical ((T,8,m),(8,k)):((1,T,LBO),(8T,SBO)) with Swizzle<3,4,3>): a 1024-byte atom
+// is 8 k-rows of 128 bytes (32 mn), chunks XOR-ed with k%8; mn blocks of 32 are LBO apart, k blocks of 8 SBO apart
+static int off_mnmajor_sw128(int k, int mn, int lbo, int sbo) {
+  return (mn / 32) * lbo + (k / 8) * sbo + (k % 8) * 128 + ((((mn % 32) / 4) ^ (k % 8)) * 16) + (mn % 4) * 4;
+}
 
 static const uint32_t IDESC_BASE = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
+struct Operand {
+  int mn;        // 1: MN-major
+  int sw128;     // 1: SWIZZLE_128B
+  int lbo, sbo;  // descriptor fields (bytes); for the image: K-major (lbo = k-quad stride, sbo = 8-row stride),
+                 // MN-major no swizzle (lbo = k-block stride, sbo = mn-block(4) stride), MN-major SW128 (lbo = mn-block(32)
+                 // stride, sbo = k-block stride)
+  int swap;      // write lbo into the SBO field and vice versa
+  int step;      // descriptor start advance per k-step (bytes)
+};
 struct Hyp {
   const char* name;
-  int a_mn, b_mn;            // operand majors
-  int a_lbo, a_sbo, b_lbo, b_sbo;
-  int swap_desc;             // put LBO value in the SBO field and vice versa
-  int mask_form;
-  int version;
-  int sw128;                 // both operands K-major SWIZZLE_128B
+  Operand a, b;
 };
+
+static int off_of(const Operand& o, int mn, int k) {
+  if (!o.mn) return o.sw128 ? off_kmajor_sw128(mn, k) : off_kmajor(mn, k, o.lbo, o.sbo);
+  return o.sw128 ? off_mnmajor_sw128(k, mn, o.lbo, o.sbo) : off_mnmajor(k, mn, o.lbo, o.sbo);
+}
 
 int main() {
   const int K = 32;  // 4 k-steps
@@ -174,47 +189,55 @@ int main() {
   CK(cudaMalloc(&dinfo, 64));
   CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024));
 
+  const Operand KM = {0, 0, 128, 1024, 0, 256};            // K-major, no swizzle (known good)
+  const Operand KSW = {0, 1, 16, 1024, 0, 32};             // K-major SW128 (known good)
   Hyp hyps[] = {
-      // name                       a_mn b_mn  a_lbo a_sbo b_lbo b_sbo swap mask ver sw128
-      {"A:K B:K no-swizzle",           0, 0,   128, 1024, 128, 1024,  0, 0, 1, 0},
-      {"A:K B:K SW128 lbo=16",         0, 0,    16, 1024,  16, 1024,  0, 0, 1, 1},
-      {"A:K B:K SW128 lbo=0",          0, 0,     0, 1024,   0, 1024,  0, 0, 1, 1},
+      {"A:K  B:K  no-swizzle (control)", KM, KM},
+      {"A:MN nosw lbo=128 sbo=512", {1, 0, 128, 512, 0, 128}, KM},
+      {"A:MN nosw lbo=128 sbo=512 swapped", {1, 0, 128, 512, 1, 128}, KM},
+      {"A:MN nosw lbo=4096 sbo=128", {1, 0, 4096, 128, 0, 4096}, KM},
+      {"A:MN nosw lbo=4096 sbo=128 swapped", {1, 0, 4096, 128, 1, 4096}, KM},
+      {"A:MN nosw lbo=128 sbo=528 (padded)", {1, 0, 128, 528, 0, 128}, KM},
+      {"B:MN nosw lbo=128 sbo=512", KM, {1, 0, 128, 512, 0, 128}},
+      {"A:MN B:MN nosw lbo=128 sbo=512", {1, 0, 128, 512, 0, 128}, {1, 0, 128, 512, 0, 128}},
+      {"A:MN SW128 lbo=4096 sbo=1024", {1, 1, 4096, 1024, 0, 1024}, KM},
+      {"A:MN SW128 lbo=4096 sbo=1024 swapped", {1, 1, 4096, 1024, 1, 1024}, KM},
+      {"A:MN SW128 lbo=1024 sbo=4096", {1, 1, 1024, 4096, 0, 4096}, KM},
+      {"A:MN SW128 lbo=1024 sbo=4096 swapped", {1, 1, 1024, 4096, 1, 4096}, KM},
+      {"A:MN B:MN SW128 lbo=4096 sbo=1024", {1, 1, 4096, 1024, 0, 1024}, {1, 1, 4096, 1024, 0, 1024}},
+      {"A:MN SW128, B:K SW128", {1, 1, 4096, 1024, 0, 1024}, KSW},
   };
   for (const Hyp& h : hyps) {
     std::vector<uint8_t> ia(65536, 0), ib(65536, 0);
+    if (getenv("PROBE_FILL")) {   // diagnostic: operand A reads 1.0 wherever the hardware looks
+      const float one = 1.0f;
+      for (int i = 0; i < 65536; i += 4) memcpy(&ia[i], &one, 4);
+    } else
     for (int m = 0; m < 128; ++m)
-      for (int k = 0; k < K; ++k) {
-        const int off = h.sw128 ? off_kmajor_sw128(m, k)
-                                : (h.a_mn ? off_mnmajor(k, m, h.a_lbo, h.a_sbo) : off_kmajor(m, k, h.a_lbo, h.a_sbo));
-        memcpy(&ia[off], &A[m * K + k], 4);
-      }
+      for (int k = 0; k < K; ++k) memcpy(&ia[off_of(h.a, m, k)], &A[m * K + k], 4);
     for (int n = 0; n < 128; ++n)
-      for (int k = 0; k < K; ++k) {
-        const int off = h.sw128 ? off_kmajor_sw128(n, k)
-                                : (h.b_mn ? off_mnmajor(k, n, h.b_lbo, h.b_sbo) : off_kmajor(n, k, h.b_lbo, h.b_sbo));
-        memcpy(&ib[off], &Bm[k * 128 + n], 4);
-      }
+      for (int k = 0; k < K; ++k) memcpy(&ib[off_of(h.b, n, k)], &Bm[k * 128 + n], 4);
     CK(cudaMemcpy(da, ia.data(), 65536, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(db, ib.data(), 65536, cudaMemcpyHostToDevice));
     CK(cudaMemset(dout, 0xff, 128 * 128 * 4));
     Params P;
-    P.idesc = IDESC_BASE | (h.a_mn ? (1u << 15) : 0) | (h.b_mn ? (1u << 16) : 0);
-    P.a_lbo = h.swap_desc ? h.a_sbo : h.a_lbo;
-    P.a_sbo = h.swap_desc ? h.a_lbo : h.a_sbo;
-    P.b_lbo = h.swap_desc ? h.b_sbo : h.b_lbo;
-    P.b_sbo = h.swap_desc ? h.b_lbo : h.b_sbo;
-    // per k-step (8 k) advance: K-major -> 2 k-quads = 2*lbo ; MN-major -> one 8-k group = lbo
-    P.a_step = h.sw128 ? 32 : (h.a_mn ? h.a_lbo : 2 * h.a_lbo);
-    P.b_step = h.sw128 ? 32 : (h.b_mn ? h.b_lbo : 2 * h.b_lbo);
+    P.idesc = IDESC_BASE | (h.a.mn ? (1u << 15) : 0) | (h.b.mn ? (1u << 16) : 0);
+    P.a_lbo = h.a.swap ? h.a.sbo : h.a.lbo;
+    P.a_sbo = h.a.swap ? h.a.lbo : h.a.sbo;
+    P.b_lbo = h.b.swap ? h.b.sbo : h.b.lbo;
+    P.b_sbo = h.b.swap ? h.b.lbo : h.b.sbo;
+    P.a_step = h.a.step;
+    P.b_step = h.b.step;
     P.ksteps = K / 8;
-    P.use_mask_form = h.mask_form;
-    P.version = h.version;
-    P.layout_type = h.sw128 ? 2 : 0;
+    P.use_mask_form = 0;
+    P.version = 1;
+    P.layout_type = h.a.sw128 ? 2 : 0;
+    P.b_layout_type = h.b.sw128 ? 2 : 0;
     P.repeat = 1;
     probe_kernel<<<1, 128, 140 * 1024>>>(da, db, 65536, 65536, P, dout, dinfo);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
-      printf("%-34s : launch error %s\n", h.name, cudaGetErrorString(e));
+      printf("%-40s : launch error %s\n", h.name, cudaGetErrorString(e));
       return 1;
     }
     std::vector<float> out(128 * 128);
@@ -229,19 +252,16 @@ int main() {
       if (out[i] == 0.f) ++zeros;
       if (err > maxerr) maxerr = err;
     }
-    printf("%-34s : tmem=0x%08x waited=%u mismatches=%5d zeros=%5d maxerr=%.3f  D[0][0..3]=%.3f %.3f %.3f %.3f (ref %.3f %.3f %.3f %.3f)\n",
-           h.name, info[0], info[1], bad, zeros, maxerr, out[0], out[1], out[2], out[3], ref[0], ref[1], ref[2], ref[3]);
-    // timing: many MMAs back to back on the same tiles (1 CTA, then all SMs busy)
-    for (int grid : {1, 148}) {
-      for (int rep : {16, 64}) {
-        P.repeat = rep;
-        probe_kernel<<<grid, 128, 140 * 1024>>>(da, db, 65536, 65536, P, dout, dinfo);
-        CK(cudaDeviceSynchronize());
-        uint32_t inf[3];
-        CK(cudaMemcpy(inf, dinfo, 12, cudaMemcpyDeviceToHost));
-        printf("    timing grid=%3d: %4d MMAs (128x128x8 tf32) in %8u cycles -> %.1f cycles/MMA\n", grid, rep * P.ksteps,
-               inf[2], (double)inf[2] / (rep * P.ksteps));
-      }
+    printf("%-40s : waited=%u mismatches=%5d zeros=%5d maxerr=%.3f  D[0][0..3]=%.3f %.3f %.3f %.3f (ref %.3f %.3f %.3f %.3f)\n",
+           h.name, info[1], bad, zeros, maxerr, out[0], out[1], out[2], out[3], ref[0], ref[1], ref[2], ref[3]);
+    if (bad == 0) {   // timing: many MMAs back to back on the same tiles, all SMs busy
+      P.repeat = 64;
+      probe_kernel<<<148, 128, 140 * 1024>>>(da, db, 65536, 65536, P, dout, dinfo);
+      CK(cudaDeviceSynchronize());
+      uint32_t inf[3];
+      CK(cudaMemcpy(inf, dinfo, 12, cudaMemcpyDeviceToHost));
+      printf("    timing grid=148: %4d MMAs (128x128x8 tf32) in %8u cycles -> %.1f cycles/MMA\n", 64 * P.ksteps, inf[2],
+             (double)inf[2] / (64 * P.ksteps));
     }
   }
   return 0;

@@ -337,6 +337,31 @@ def test_sparse_rows_recombine_after_gather():
     assert_close(ur2[:k2].cpu().numpy(), want_r[:k2].numpy(), 1e-5, 1e-4, 'recombined rows')
 
 
+@pytest.mark.parametrize('count,table_rows', [(7, 10), (3000, 400), (100000, 372584)])
+def test_sparse_rows_plan_apply_equals_combine(count, table_rows):
+    """The two-phase combine (id-only plan on a second stream, then the row summation) is bit-identical to the
+    one-call combine; the ids come from the ids-only mode of the multi-item gather."""
+    ids = torch.randint(0, table_rows, (count,), generator=torch.Generator().manual_seed(count))
+    rows = rnd(count, D, seed=4).to(DEV)
+    table = torch.zeros(table_rows, D, device=DEV)
+    ids_d = ids.to(DEV)
+    rid = torch.empty(count, dtype=torch.int64, device=DEV)
+    half = count // 2
+    ops.gather_multi([ops.GatherItem(table, None, ids_d, half, rows_id=rid, id_offset=0),
+                      ops.GatherItem(table, None, ids_d, count - half, ids_offset=half, rows_id=rid, rows_offset=half)],
+                     backward='ids')
+    assert torch.equal(rid.cpu(), ids), 'ids-only gather must reproduce the row ids'
+    side = torch.cuda.Stream(device=DEV)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        plan = ops.SparseRowsPlan(rid, table_rows)
+    torch.cuda.current_stream().wait_stream(side)
+    u1, r1, k1 = plan.apply(rows, pad_id=table_rows)
+    u2, r2, k2 = ops.sparse_rows_combine(ids_d, rows, table_rows, pad_id=table_rows)
+    assert int(k1) == int(k2)
+    assert torch.equal(u1, u2) and torch.equal(r1, r2)
+
+
 @pytest.mark.parametrize('B', [100, 4096])
 def test_layer_forward_packed_weights(B):
     """tcgen05 path with pre-split weight tiles (bulk-copy staging) == column-gather staging == CPU."""
