@@ -41,20 +41,21 @@ __device__ __forceinline__ unsigned digit_of(uint32_t key, int shift, unsigned m
 __global__ void __launch_bounds__(SORT_WARPS * 32) radix_hist_kernel(const uint32_t* __restrict__ keys, int64_t n,
                                                                      int shift, int bins, int nchunks,
                                                                      int32_t* __restrict__ hist) {
-  __shared__ int cnt[SORT_WARPS][MAX_BINS];
+  extern __shared__ int sort_smem[];   // [SORT_WARPS][bins]
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int* cnt = sort_smem + w * bins;
   const int chunk = blockIdx.x * SORT_WARPS + w;
-  for (int b = lane; b < bins; b += 32) cnt[w][b] = 0;
+  for (int b = lane; b < bins; b += 32) cnt[b] = 0;
   __syncwarp();
   if (chunk < nchunks) {
     const int64_t i0 = (int64_t)chunk * SORT_CHUNK;
 #pragma unroll
     for (int r = 0; r < SORT_CHUNK; r += 32) {
       const int64_t i = i0 + r + lane;
-      if (i < n) atomicAdd(&cnt[w][digit_of(keys[i], shift, bins - 1)], 1);
+      if (i < n) atomicAdd(&cnt[digit_of(keys[i], shift, bins - 1)], 1);
     }
     __syncwarp();
-    for (int b = lane; b < bins; b += 32) hist[(int64_t)b * nchunks + chunk] = cnt[w][b];
+    for (int b = lane; b < bins; b += 32) hist[(int64_t)b * nchunks + chunk] = cnt[b];
   }
 }
 
@@ -101,11 +102,12 @@ __global__ void __launch_bounds__(SORT_WARPS * 32) radix_scatter_kernel(
     const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, int64_t n, int shift, int bins,
     int nchunks, const int32_t* __restrict__ hist, const int32_t* __restrict__ bin_base,
     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
-  __shared__ int run[SORT_WARPS][MAX_BINS];
+  extern __shared__ int sort_smem[];   // [SORT_WARPS][bins]
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int* run = sort_smem + w * bins;
   const int chunk = blockIdx.x * SORT_WARPS + w;
   if (chunk >= nchunks) return;
-  for (int b = lane; b < bins; b += 32) run[w][b] = bin_base[b] + hist[(int64_t)b * nchunks + chunk];
+  for (int b = lane; b < bins; b += 32) run[b] = bin_base[b] + hist[(int64_t)b * nchunks + chunk];
   __syncwarp();
   const int64_t i0 = (int64_t)chunk * SORT_CHUNK;
 #pragma unroll 1
@@ -117,9 +119,9 @@ __global__ void __launch_bounds__(SORT_WARPS * 32) radix_scatter_kernel(
     const unsigned peers = __match_any_sync(0xffffffffu, dg);
     const int rank = __popc(peers & ((1u << lane) - 1u));
     int pos = 0;
-    if (ok) pos = run[w][dg] + rank;
+    if (ok) pos = run[dg] + rank;
     __syncwarp();
-    if (ok && rank == 0) run[w][dg] += __popc(peers);
+    if (ok && rank == 0) run[dg] += __popc(peers);
     __syncwarp();
     if (ok) {
       keys_out[pos] = key;
@@ -183,22 +185,32 @@ SortBuffers carve_sort(void* ws, int64_t n) {
   return s;
 }
 
-// sorts k0 by the low `key_bits` bits; result ends in (*rk, *rv)
-int radix_sort(SortBuffers& s, int64_t n, int key_bits, cudaStream_t st, uint32_t** rk, uint32_t** rv) {
+// number of passes for keys of `key_bits` bits with digits of at most `max_digit_bits` bits
+int sort_passes(int key_bits, int max_digit_bits) {
   if (key_bits < 1) key_bits = 1;
-  const int passes = (key_bits + 9) / 10;
+  return (key_bits + max_digit_bits - 1) / max_digit_bits;
+}
+
+// sorts k0 by the low `key_bits` bits; result ends in (*rk, *rv).  max_digit_bits = 10 minimises the passes;
+// 7 keeps the per-CTA shared memory at 4 KB so that the sort can share an SM with a resident tcgen05 CTA when it
+// runs on a second stream (mpqe_sparse_rows_plan).
+int radix_sort(SortBuffers& s, int64_t n, int key_bits, cudaStream_t st, uint32_t** rk, uint32_t** rv,
+               int max_digit_bits = 10) {
+  if (key_bits < 1) key_bits = 1;
+  const int passes = sort_passes(key_bits, max_digit_bits);
+  const size_t smem = (size_t)SORT_WARPS * (1u << ((key_bits + passes - 1) / passes)) * sizeof(int);
   const int digit_bits = (key_bits + passes - 1) / passes;
   const int bins = 1 << digit_bits;
   uint32_t *ki = s.k0, *vi = nullptr, *ko = s.k1, *vo = s.v1;
   const int blocks = (s.nchunks + SORT_WARPS - 1) / SORT_WARPS;
   for (int p = 0; p < passes; ++p) {
-    radix_hist_kernel<<<blocks, SORT_WARPS * 32, 0, st>>>(ki, n, digit_bits * p, bins, s.nchunks, s.hist);
+    radix_hist_kernel<<<blocks, SORT_WARPS * 32, smem, st>>>(ki, n, digit_bits * p, bins, s.nchunks, s.hist);
     MPQE_CHECK_LAUNCH("radix_hist_kernel");
     radix_row_scan_kernel<<<(bins + 7) / 8, 256, 0, st>>>(s.hist, bins, s.nchunks, s.bin_total);
     MPQE_CHECK_LAUNCH("radix_row_scan_kernel");
     radix_bin_scan_kernel<<<1, MAX_BINS, 0, st>>>(s.bin_total, bins);
     MPQE_CHECK_LAUNCH("radix_bin_scan_kernel");
-    radix_scatter_kernel<<<blocks, SORT_WARPS * 32, 0, st>>>(ki, vi, n, digit_bits * p, bins, s.nchunks, s.hist,
+    radix_scatter_kernel<<<blocks, SORT_WARPS * 32, smem, st>>>(ki, vi, n, digit_bits * p, bins, s.nchunks, s.hist,
                                                             s.bin_total, ko, vo);
     MPQE_CHECK_LAUNCH("radix_scatter_kernel");
     uint32_t* tk = ki; ki = ko; ko = tk;
@@ -424,18 +436,19 @@ extern "C" size_t mpqe_sparse_rows_workspace_bytes(int64_t count) {
 }
 
 namespace {
+constexpr int PLAN_DIGIT_BITS = 7;
 struct CombineBuffers {
   SortBuffers s;
   int32_t *uid, *seg_start, *block_sum;
   uint32_t *rk, *rv;   // where the sorted keys / source positions end up (depends on the pass count only)
 };
-CombineBuffers carve_combine(void* workspace, int64_t count, int64_t table_rows) {
+CombineBuffers carve_combine(void* workspace, int64_t count, int64_t table_rows, int digit_bits) {
   CombineBuffers c;
   c.s = carve_sort(workspace, count);
   c.uid = (int32_t*)((char*)workspace + c.s.bytes);
   c.seg_start = (int32_t*)((char*)c.uid + align_up((size_t)count * sizeof(int32_t), 256));
   c.block_sum = (int32_t*)((char*)c.seg_start + align_up((size_t)count * sizeof(int32_t), 256));
-  const int passes = (bits_for(table_rows + 1) + 9) / 10;
+  const int passes = sort_passes(bits_for(table_rows + 1), digit_bits);
   c.rk = (passes & 1) ? c.s.k1 : c.s.k0;
   c.rv = (passes & 1) ? c.s.v1 : c.s.v0;
   return c;
@@ -444,19 +457,19 @@ CombineBuffers carve_combine(void* workspace, int64_t count, int64_t table_rows)
 
 // The part of the combine that needs only the row ids: stable sort, segment heads, number of distinct rows.  It can
 // run (on another stream) while the gradient rows are still being computed; mpqe_sparse_rows_apply then sums them.
-extern "C" int mpqe_sparse_rows_plan(const int64_t* rows_id, int64_t count, int64_t table_rows, int64_t* num_unique,
-                                     void* workspace, size_t workspace_bytes, void* stream) {
+static int sparse_rows_plan(const int64_t* rows_id, int64_t count, int64_t table_rows, int64_t* num_unique,
+                            void* workspace, size_t workspace_bytes, void* stream, int digit_bits) {
   MPQE_CHECK_ARG(rows_id && num_unique && count >= 1 && count < (1ll << 31) && table_rows >= 1 &&
                      table_rows < (1ll << 32),
                  "mpqe_sparse_rows_plan: bad argument");
   MPQE_CHECK_ARG(workspace && workspace_bytes >= mpqe_sparse_rows_workspace_bytes(count),
                  "mpqe_sparse_rows_plan: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
-  CombineBuffers c = carve_combine(workspace, count, table_rows);
+  CombineBuffers c = carve_combine(workspace, count, table_rows, digit_bits);
   narrow_keys_kernel<<<blocks_for(count, 256), 256, 0, st>>>(rows_id, count, c.s.k0, table_rows);
   MPQE_CHECK_LAUNCH("narrow_keys_kernel");
   uint32_t *rk, *rv;
-  if (radix_sort(c.s, count, bits_for(table_rows + 1), st, &rk, &rv)) return 2;
+  if (radix_sort(c.s, count, bits_for(table_rows + 1), st, &rk, &rv, digit_bits)) return 2;
   MPQE_CHECK_ARG(rk == c.rk && rv == c.rv, "mpqe_sparse_rows_plan: internal buffer parity mismatch");
   head_flags_kernel<<<blocks_for(count, 256), 256, 0, st>>>(rk, count, c.uid);
   MPQE_CHECK_LAUNCH("head_flags_kernel");
@@ -468,27 +481,41 @@ extern "C" int mpqe_sparse_rows_plan(const int64_t* rows_id, int64_t count, int6
   return 0;
 }
 
-extern "C" int mpqe_sparse_rows_apply(const float* rows, int64_t count, int64_t table_rows, int64_t pad_id,
-                                      int64_t* unique_ids, float* unique_rows, const int64_t* num_unique,
-                                      void* workspace, size_t workspace_bytes, void* stream) {
+static int sparse_rows_apply(const float* rows, int64_t count, int64_t table_rows, int64_t pad_id, int64_t* unique_ids,
+                             float* unique_rows, const int64_t* num_unique, void* workspace, size_t workspace_bytes,
+                             void* stream, int digit_bits) {
   MPQE_CHECK_ARG(rows && unique_ids && unique_rows && num_unique && count >= 1 && count < (1ll << 31) &&
                      table_rows >= 1 && table_rows < (1ll << 32),
                  "mpqe_sparse_rows_apply: bad argument");
   MPQE_CHECK_ARG(workspace && workspace_bytes >= mpqe_sparse_rows_workspace_bytes(count),
                  "mpqe_sparse_rows_apply: workspace too small");
-  CombineBuffers c = carve_combine(workspace, count, table_rows);
+  CombineBuffers c = carve_combine(workspace, count, table_rows, digit_bits);
   segment_sum_kernel<<<blocks_for(count, 8), 256, 0, (cudaStream_t)stream>>>(
       c.rk, c.rv, c.seg_start, num_unique, count, rows, unique_ids, unique_rows, pad_id, (uint32_t)table_rows);
   MPQE_CHECK_LAUNCH("segment_sum_kernel");
   return 0;
 }
 
+// two-phase form: 7-bit digits (4 KB of shared memory per sort CTA) so that the plan can share SMs with the resident
+// tcgen05 CTAs of the stream it overlaps; the one-call form uses 10-bit digits (fewest passes)
+extern "C" int mpqe_sparse_rows_plan(const int64_t* rows_id, int64_t count, int64_t table_rows, int64_t* num_unique,
+                                     void* workspace, size_t workspace_bytes, void* stream) {
+  return sparse_rows_plan(rows_id, count, table_rows, num_unique, workspace, workspace_bytes, stream, PLAN_DIGIT_BITS);
+}
+
+extern "C" int mpqe_sparse_rows_apply(const float* rows, int64_t count, int64_t table_rows, int64_t pad_id,
+                                      int64_t* unique_ids, float* unique_rows, const int64_t* num_unique,
+                                      void* workspace, size_t workspace_bytes, void* stream) {
+  return sparse_rows_apply(rows, count, table_rows, pad_id, unique_ids, unique_rows, num_unique, workspace,
+                           workspace_bytes, stream, PLAN_DIGIT_BITS);
+}
+
 extern "C" int mpqe_sparse_rows_combine(const int64_t* rows_id, const float* rows, int64_t count, int64_t table_rows,
                                         int64_t pad_id, int64_t* unique_ids, float* unique_rows, int64_t* num_unique,
                                         void* workspace, size_t workspace_bytes, void* stream) {
-  if (mpqe_sparse_rows_plan(rows_id, count, table_rows, num_unique, workspace, workspace_bytes, stream)) return 1;
-  return mpqe_sparse_rows_apply(rows, count, table_rows, pad_id, unique_ids, unique_rows, num_unique, workspace,
-                                workspace_bytes, stream);
+  if (sparse_rows_plan(rows_id, count, table_rows, num_unique, workspace, workspace_bytes, stream, 10)) return 1;
+  return sparse_rows_apply(rows, count, table_rows, pad_id, unique_ids, unique_rows, num_unique, workspace,
+                           workspace_bytes, stream, 10);
 }
 
 extern "C" int mpqe_scatter_rows(const int64_t* ids, const float* rows, const int64_t* num, int64_t max_count,

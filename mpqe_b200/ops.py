@@ -455,7 +455,8 @@ class SparseRowsPlan(object):
         self.nbytes = nbytes
         _lib.check(lib.mpqe_sparse_rows_plan(_ptr(_chk(rows_id, torch.int64, 'rows_id')), self.count, self.table_rows,
                                              _ptr(self.num), _ptr(self.ws), nbytes, _stream()), 'mpqe_sparse_rows_plan')
-        _count(9)
+        passes = (max(1, self.table_rows.bit_length()) + 6) // 7      # 7-bit digits, see mpqe_sparse_rows_plan
+        _count(7 + 4 * passes)
 
     def apply(self, rows, pad_id=0):
         lib = _lib.load()
