@@ -23,6 +23,8 @@ struct ColsumLaunch {
   int n;
   float* partials;  // [total blocks][D]
   float* totals;    // [n][D]
+  int* counter;     // finished second-stage CTAs (zeroed by the first stage)
+  uint8_t leader[MPQE_MAX_COLSUM_ITEMS];   // first item with the same destination
   mpqe_colsum_item_t it[MPQE_MAX_COLSUM_ITEMS];
 };
 
@@ -164,6 +166,7 @@ __device__ __forceinline__ int64_t cs_blocks(int64_t rows) { return (rows + CS_R
 
 __global__ void __launch_bounds__(256) colsum_partial_multi_kernel(const __grid_constant__ ColsumLaunch L) {
   __shared__ float4 red[8][32];
+  if (blockIdx.x == 0 && threadIdx.x == 0) *L.counter = 0;   // for the second stage's "last CTA" election
   int64_t blk = blockIdx.x;
   int item = 0;
   for (; item < L.n - 1; ++item) {
@@ -196,32 +199,41 @@ __global__ void __launch_bounds__(256) colsum_partial_multi_kernel(const __grid_
   }
 }
 
-// Second stage: one CTA per item; the first item of each destination ("leader") folds the block partials of every item
-// that shares its destination, in item order, and writes the destination once: dst = ((dst + t_i) + t_k) + ...
+// Second stage: one CTA per item sums the item's block partials (in block order) into totals[item]; the CTA that
+// finishes last then folds the totals into the destinations, items in order: dst = ((dst + t_i) + t_k) + ...
+// (leader[i] = first item with the same destination, computed on the host) -- bit-reproducible, one launch.
 __global__ void __launch_bounds__(128) colsum_finish_multi_kernel(const __grid_constant__ ColsumLaunch L) {
-  const int item = blockIdx.x;
-  float* dst = L.it[item].dst;
-  for (int i = 0; i < item; ++i)
-    if (L.it[i].dst == dst) return;
+  __shared__ int s_last;
+  const int item = blockIdx.x, tid = threadIdx.x;
   int64_t base = 0;
   for (int i = 0; i < item; ++i) base += cs_blocks(L.it[i].rows);
-  float acc = dst[threadIdx.x];
-  for (int k = item; k < L.n; ++k) {
-    const int64_t nb = cs_blocks(L.it[k].rows);
-    if (L.it[k].dst == dst) {
-      const float* p = L.partials + base * D + threadIdx.x;
-      float s = 0.f;
-      int64_t b = 0;
-      for (; b + 4 <= nb; b += 4) {   // four loads in flight, summed in block order
-        const float v0 = p[(b + 0) * D], v1 = p[(b + 1) * D], v2 = p[(b + 2) * D], v3 = p[(b + 3) * D];
-        s += v0; s += v1; s += v2; s += v3;
-      }
-      for (; b < nb; ++b) s += p[b * D];
-      acc += s * L.it[k].scale;
-    }
-    base += nb;
+  const int64_t nb = cs_blocks(L.it[item].rows);
+  const float* p = L.partials + base * D + tid;
+  float s = 0.f;
+  int64_t b = 0;
+  for (; b + 8 <= nb; b += 8) {   // eight loads in flight, summed in block order
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = p[(b + k) * D];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += v[k];
   }
-  dst[threadIdx.x] = acc;
+  for (; b < nb; ++b) s += p[b * D];
+  L.totals[(int64_t)item * D + tid] = s * L.it[item].scale;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(L.counter, 1) == L.n - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int i = 0; i < L.n; ++i) {
+    if (L.leader[i] != i) continue;
+    float* dst = L.it[i].dst;
+    float acc = dst[tid];
+    for (int k = i; k < L.n; ++k)
+      if (L.leader[k] == i) acc += __ldcg(L.totals + (int64_t)k * D + tid);
+    dst[tid] = acc;
+  }
 }
 
 }  // namespace
@@ -312,6 +324,16 @@ extern "C" int mpqe_colsum_multi(const mpqe_colsum_item_t* items_host, int32_t n
   }
   L.partials = (float*)workspace;
   L.totals = L.partials + blocks * D;
+  L.counter = reinterpret_cast<int*>(L.totals + (int64_t)n * D);   // the spare row of the workspace
+  for (int i = 0; i < n; ++i) {
+    int lead = i;
+    for (int k = 0; k < i; ++k)
+      if (items_host[k].dst == items_host[i].dst) {
+        lead = k;
+        break;
+      }
+    L.leader[i] = (uint8_t)lead;
+  }
   colsum_partial_multi_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(L);
   MPQE_CHECK_LAUNCH("colsum_partial_multi_kernel");
   colsum_finish_multi_kernel<<<n, 128, 0, (cudaStream_t)stream>>>(L);

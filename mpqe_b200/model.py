@@ -404,6 +404,8 @@ class Engine(object):
                     dests = [(W.w[li][r], G.dw[li][r], 1) for r in rels] + [(W.root[li], G.droot[li], 1)]
                     ops.layer_wgrad([job.fwd_groups[p] for job in chunk], [cur[job] for job in chunk], dests)
                 for job in ljobs:
+                    if p == 0 and job.const_fwd is not None:
+                        continue   # bias gradient = sum of the per-slot sums taken below (see constant_backward)
                     g, g_slots, smap = cur[job]
                     if g_slots == 1:
                         # sum readout: the bias was added once per node; target-message: once
@@ -504,6 +506,8 @@ class Engine(object):
             for job in ljobs:
                 t, n, a = job.t, job.t.num_nodes, job.t.num_anchors
                 cs, cs_slots, smap = job.cs_operand
+                # d bias of pass 0 from the same sums: one row per slot (zero rows for slots outside `smap`)
+                G.colsum(cs.view(-1, D), cs_slots, D, G.dbias[li], job.fused_bias_count if cs_slots == 1 else 1.0)
                 outs = job.outs[0]
                 okey = {s: k for k, s in enumerate(outs)}
                 var_slots = sorted({t.src[e] for e in range(t.num_edges) if t.dst[e] in okey and t.src[e] >= a} |
