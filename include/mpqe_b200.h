@@ -275,10 +275,11 @@ MPQE_API int mpqe_sparse_rows_combine(const int64_t* rows_id, const float* rows,
                              void* workspace, size_t workspace_bytes, void* stream);
 /* The same combine in two phases sharing one workspace.  `plan` needs only the row ids (stable sort, segment heads,
  * num_unique) -- the ids of a training step are known before its backward has produced any gradient row, so the
- * plan can run on another stream meanwhile; `apply` then sums the rows (one kernel).  plan + apply == combine. */
+ * plan can run on another stream meanwhile; `apply` then sums the rows (one kernel) and multiplies every sum by
+ * `scale` (1/world_size of a data-parallel average).  plan + apply(scale = 1) == combine. */
 MPQE_API int mpqe_sparse_rows_plan(const int64_t* rows_id, int64_t count, int64_t table_rows, int64_t* num_unique,
                           void* workspace, size_t workspace_bytes, void* stream);
-MPQE_API int mpqe_sparse_rows_apply(const float* rows, int64_t count, int64_t table_rows, int64_t pad_id,
+MPQE_API int mpqe_sparse_rows_apply(const float* rows, int64_t count, int64_t table_rows, int64_t pad_id, float scale,
                            int64_t* unique_ids, float* unique_rows, const int64_t* num_unique,
                            void* workspace, size_t workspace_bytes, void* stream);
 /* dense[ids[i], :] (+)= rows[i, :] for i < *num (ids unique) */

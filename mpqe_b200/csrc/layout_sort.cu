@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(256) segment_sum_kernel(const uint32_t* __rest
                                                           const float* __restrict__ rows,
                                                           int64_t* __restrict__ unique_ids,
                                                           float* __restrict__ unique_rows, int64_t pad_id,
-                                                          uint32_t sentinel) {
+                                                          uint32_t sentinel, float scale) {
   const int lane = threadIdx.x & 31;
   const int64_t u = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int64_t nu = *num_unique;
@@ -357,7 +357,8 @@ __global__ void __launch_bounds__(256) segment_sum_kernel(const uint32_t* __rest
     const float4 v = *reinterpret_cast<const float4*>(rows + (int64_t)sorted_val[i] * D + lane * 4);
     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
   }
-  *reinterpret_cast<float4*>(unique_rows + u * D + lane * 4) = acc;
+  *reinterpret_cast<float4*>(unique_rows + u * D + lane * 4) =
+      make_float4(acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale);
   if (lane == 0) unique_ids[u] = (int64_t)sorted_key[i0];
 }
 
@@ -481,9 +482,9 @@ static int sparse_rows_plan(const int64_t* rows_id, int64_t count, int64_t table
   return 0;
 }
 
-static int sparse_rows_apply(const float* rows, int64_t count, int64_t table_rows, int64_t pad_id, int64_t* unique_ids,
-                             float* unique_rows, const int64_t* num_unique, void* workspace, size_t workspace_bytes,
-                             void* stream, int digit_bits) {
+static int sparse_rows_apply(const float* rows, int64_t count, int64_t table_rows, int64_t pad_id, float scale,
+                             int64_t* unique_ids, float* unique_rows, const int64_t* num_unique, void* workspace,
+                             size_t workspace_bytes, void* stream, int digit_bits) {
   MPQE_CHECK_ARG(rows && unique_ids && unique_rows && num_unique && count >= 1 && count < (1ll << 31) &&
                      table_rows >= 1 && table_rows < (1ll << 32),
                  "mpqe_sparse_rows_apply: bad argument");
@@ -491,7 +492,7 @@ static int sparse_rows_apply(const float* rows, int64_t count, int64_t table_row
                  "mpqe_sparse_rows_apply: workspace too small");
   CombineBuffers c = carve_combine(workspace, count, table_rows, digit_bits);
   segment_sum_kernel<<<blocks_for(count, 8), 256, 0, (cudaStream_t)stream>>>(
-      c.rk, c.rv, c.seg_start, num_unique, count, rows, unique_ids, unique_rows, pad_id, (uint32_t)table_rows);
+      c.rk, c.rv, c.seg_start, num_unique, count, rows, unique_ids, unique_rows, pad_id, (uint32_t)table_rows, scale);
   MPQE_CHECK_LAUNCH("segment_sum_kernel");
   return 0;
 }
@@ -503,10 +504,10 @@ extern "C" int mpqe_sparse_rows_plan(const int64_t* rows_id, int64_t count, int6
   return sparse_rows_plan(rows_id, count, table_rows, num_unique, workspace, workspace_bytes, stream, PLAN_DIGIT_BITS);
 }
 
-extern "C" int mpqe_sparse_rows_apply(const float* rows, int64_t count, int64_t table_rows, int64_t pad_id,
+extern "C" int mpqe_sparse_rows_apply(const float* rows, int64_t count, int64_t table_rows, int64_t pad_id, float scale,
                                       int64_t* unique_ids, float* unique_rows, const int64_t* num_unique,
                                       void* workspace, size_t workspace_bytes, void* stream) {
-  return sparse_rows_apply(rows, count, table_rows, pad_id, unique_ids, unique_rows, num_unique, workspace,
+  return sparse_rows_apply(rows, count, table_rows, pad_id, scale, unique_ids, unique_rows, num_unique, workspace,
                            workspace_bytes, stream, PLAN_DIGIT_BITS);
 }
 
@@ -514,7 +515,7 @@ extern "C" int mpqe_sparse_rows_combine(const int64_t* rows_id, const float* row
                                         int64_t pad_id, int64_t* unique_ids, float* unique_rows, int64_t* num_unique,
                                         void* workspace, size_t workspace_bytes, void* stream) {
   if (sparse_rows_plan(rows_id, count, table_rows, num_unique, workspace, workspace_bytes, stream, 10)) return 1;
-  return sparse_rows_apply(rows, count, table_rows, pad_id, unique_ids, unique_rows, num_unique, workspace,
+  return sparse_rows_apply(rows, count, table_rows, pad_id, 1.0f, unique_ids, unique_rows, num_unique, workspace,
                            workspace_bytes, stream, 10);
 }
 

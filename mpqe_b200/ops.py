@@ -458,13 +458,13 @@ class SparseRowsPlan(object):
         passes = (max(1, self.table_rows.bit_length()) + 6) // 7      # 7-bit digits, see mpqe_sparse_rows_plan
         _count(7 + 4 * passes)
 
-    def apply(self, rows, pad_id=0):
+    def apply(self, rows, pad_id=0, scale=1.0):
         lib = _lib.load()
         uid = torch.empty(self.count, dtype=torch.int64, device=rows.device)
         urows = torch.empty(self.count, D, dtype=torch.float32, device=rows.device)
         _lib.check(lib.mpqe_sparse_rows_apply(_ptr(_chk(rows, torch.float32, 'rows')), self.count, self.table_rows,
-                                              pad_id, _ptr(uid), _ptr(urows), _ptr(self.num), _ptr(self.ws), self.nbytes,
-                                              _stream()), 'mpqe_sparse_rows_apply')
+                                              pad_id, float(scale), _ptr(uid), _ptr(urows), _ptr(self.num), _ptr(self.ws),
+                                              self.nbytes, _stream()), 'mpqe_sparse_rows_apply')
         _count()
         return uid, urows, self.num
 

@@ -254,8 +254,9 @@ class SparseRowsPlan(object):
     def __init__(self, rows_id, table_rows):
         self.rows_id, self.table_rows = rows_id.clone(), table_rows
 
-    def apply(self, rows, pad_id=0):
-        return sparse_rows_combine(self.rows_id, rows, self.table_rows, pad_id)
+    def apply(self, rows, pad_id=0, scale=1.0):
+        uid, urows, num = sparse_rows_combine(self.rows_id, rows, self.table_rows, pad_id)
+        return uid, urows * scale, num
 
 
 def scatter_rows(ids, rows, num, dense, accumulate=False):
