@@ -302,9 +302,17 @@ def main():
                              'TFLOPs': sum(p[4] for p in sel) / ms / 1e9}
         lk = kernels.get('layer')
         if lk:
+            # DRAM bytes per launch of the same kernel on the same workload, from the committed `ncu --set full`
+            # capture (dram__bytes_read.sum + dram__bytes_write.sum, averaged over the step's launches)
+            traffic = None
+            tpath = os.path.join(ROOT, 'profiles', 'layer_kernel_traffic.json')
+            if os.path.isfile(tpath):
+                with open(tpath) as f:
+                    tinfo = json.load(f)
+                traffic = tinfo.get('layer_tc_kernel' if ops.tensor_cores_default() else 'layer_simt_kernel')
             roofline = {'kernel': 'layer_tc_kernel' if ops.tensor_cores_default() else 'layer_simt_kernel',
                         'bound': 'hbm', 'achieved': lk['algorithmic_GBps'], 'peak': peak, 'unit': 'GB/s',
-                        'frac': lk['algorithmic_GBps'] / peak, 'traffic': None, 'peak_source': peak_src,
+                        'frac': lk['algorithmic_GBps'] / peak, 'traffic': traffic, 'peak_source': peak_src,
                         'avg_launch_us': lk['avg_us'], 'achieved_TFLOPs': lk['TFLOPs'],
                         'share_of_step': lk['ms_per_step'] / ms_per_step}
 

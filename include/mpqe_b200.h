@@ -98,7 +98,7 @@ typedef struct {
 MPQE_API const char* mpqe_b200_last_error(void);
 MPQE_API int mpqe_b200_version(void);
 /* sizeof the ABI structs (0: term, 1: layer group, 2: wgrad dest, 3: wgrad operand, 4: gather item, 5: margin item,
- * 6: colsum item) so bindings can self-check */
+ * 6: colsum item, 7: matsum item) so bindings can self-check */
 MPQE_API int mpqe_b200_sizeof(int which);
 /* 1 if the library was built with the tcgen05 (sm_100a tensor core) layer kernels */
 MPQE_API int mpqe_b200_has_tcgen05(void);
@@ -156,6 +156,20 @@ MPQE_API int mpqe_colsum(const float* src, int64_t rows, int64_t stride, float s
 
 /* batched transpose of [count, d, d] (or one [rows, cols]) matrices */
 MPQE_API int mpqe_transpose(const float* src, float* dst, int64_t count, int32_t rows, int32_t cols, void* stream);
+
+/* Sums of [d, d] matrices: dst (+)= src[0] + src[1] + ... (in this order).  With a sum readout every term of the last
+ * pass leaves a node slot through the same output row, so the terms of one source slot collapse into ONE term with
+ * the matrix  root + sum_{edges e out of the slot} basis[rel[e]]  (model.py:292-304 are linear in the weights); the
+ * backward spreads the gradient of such a sum back over its summands with the same entry point. */
+#define MPQE_MAX_MATSUM_ITEMS 64
+#define MPQE_MAX_MATSUM_SRCS 32
+typedef struct {
+  float* dst;
+  const float* src[MPQE_MAX_MATSUM_SRCS];
+  int32_t num_src;
+  int32_t accumulate;   /* 0: overwrite dst, 1: add to it */
+} mpqe_matsum_item_t;
+MPQE_API int mpqe_matrix_sum_multi(const mpqe_matsum_item_t* items_host, int32_t n, void* stream);
 
 /* ---- a11: max readout (model.py:383-385; torch_scatter.scatter_max) -------------------------------------
  * q[b, c] = max_i z[b, i, c]; argmax[b, c] = smallest i attaining it (int64 node ROW b*n+i, like scatter_max). */

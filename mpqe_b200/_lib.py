@@ -50,7 +50,15 @@ class ColsumItem(C.Structure):
 
 
 MAX_GATHER_ITEMS, MAX_MARGIN_ITEMS, MAX_COLSUM_ITEMS = 32, 8, 64
-ABI_STRUCTS = (Term, LayerGroup, WgradDest, WgradOperand, GatherItem, MarginItem, ColsumItem)
+MAX_MATSUM_ITEMS, MAX_MATSUM_SRCS = 64, 32
+
+
+class MatsumItem(C.Structure):
+    _fields_ = [('dst', C.c_void_p), ('src', C.c_void_p * MAX_MATSUM_SRCS), ('num_src', C.c_int32),
+                ('accumulate', C.c_int32)]
+
+
+ABI_STRUCTS = (Term, LayerGroup, WgradDest, WgradOperand, GatherItem, MarginItem, ColsumItem, MatsumItem)
 
 P, I32, I64, F32, SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
 
@@ -72,6 +80,7 @@ SIGNATURES = {
     'mpqe_colsum_workspace_bytes': (SZ, [I64]),
     'mpqe_colsum': (I32, [P, I64, I64, F32, P, I32, P, SZ, P]),
     'mpqe_transpose': (I32, [P, P, I64, I32, I32, P]),
+    'mpqe_matrix_sum_multi': (I32, [P, I32, P]),
     'mpqe_max_readout_fwd': (I32, [P, I64, I32, P, P, P]),
     'mpqe_max_readout_bwd': (I32, [P, P, I64, I32, P, P]),
     'mpqe_margin_loss_workspace_bytes': (SZ, [I64]),

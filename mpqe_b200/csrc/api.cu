@@ -25,6 +25,7 @@ extern "C" int mpqe_b200_sizeof(int which) {
     case 4: return (int)sizeof(mpqe_gather_item_t);
     case 5: return (int)sizeof(mpqe_margin_item_t);
     case 6: return (int)sizeof(mpqe_colsum_item_t);
+    case 7: return (int)sizeof(mpqe_matsum_item_t);
     default: return -1;
   }
 }

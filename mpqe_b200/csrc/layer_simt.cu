@@ -631,6 +631,46 @@ extern "C" int mpqe_colsum(const float* src, int64_t rows, int64_t stride, float
   return 0;
 }
 
+namespace mpqe {
+namespace {
+struct MatsumLaunch {
+  mpqe_matsum_item_t it[MPQE_MAX_MATSUM_ITEMS];
+};
+// one float4 of one destination per thread; summands in item order (fixed: bit-reproducible)
+__global__ void __launch_bounds__(256) matrix_sum_multi_kernel(const __grid_constant__ MatsumLaunch L) {
+  const mpqe_matsum_item_t& T = L.it[blockIdx.y];
+  const int e4 = blockIdx.x * 256 + threadIdx.x;
+  if (e4 >= D * D / 4) return;
+  float4* dst = reinterpret_cast<float4*>(T.dst) + e4;
+  float4 s = T.accumulate ? *dst : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < T.num_src; ++k) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(T.src[k]) + e4);
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  *dst = s;
+}
+}  // namespace
+}  // namespace mpqe
+
+extern "C" int mpqe_matrix_sum_multi(const mpqe_matsum_item_t* items_host, int32_t n, void* stream) {
+  MPQE_CHECK_ARG(items_host != nullptr && n >= 1 && n <= MPQE_MAX_MATSUM_ITEMS,
+                 "mpqe_matrix_sum_multi: n must be in [1,%d]", MPQE_MAX_MATSUM_ITEMS);
+  static thread_local MatsumLaunch L;
+  for (int i = 0; i < n; ++i) {
+    const mpqe_matsum_item_t& T = items_host[i];
+    MPQE_CHECK_ARG(T.dst != nullptr && T.num_src >= 1 && T.num_src <= MPQE_MAX_MATSUM_SRCS,
+                   "mpqe_matrix_sum_multi: item %d: bad argument", i);
+    for (int k = 0; k < T.num_src; ++k)
+      MPQE_CHECK_ARG(T.src[k] != nullptr, "mpqe_matrix_sum_multi: item %d: null summand %d", i, k);
+    for (int j = 0; j < i; ++j)
+      MPQE_CHECK_ARG(items_host[j].dst != T.dst, "mpqe_matrix_sum_multi: items %d and %d share a destination", j, i);
+    L.it[i] = T;
+  }
+  matrix_sum_multi_kernel<<<dim3(D * D / 4 / 256, n), 256, 0, (cudaStream_t)stream>>>(L);
+  MPQE_CHECK_LAUNCH("matrix_sum_multi_kernel");
+  return 0;
+}
+
 extern "C" int mpqe_transpose(const float* src, float* dst, int64_t count, int32_t rows, int32_t cols, void* stream) {
   MPQE_CHECK_ARG(src != nullptr && dst != nullptr && count >= 1 && rows >= 1 && cols >= 1 && count < 65536,
                  "mpqe_transpose: bad argument");

@@ -239,6 +239,39 @@ __device__ __forceinline__ void store_columns(const Frag& f, uint8_t* hi_tile, u
   }
 }
 
+// Block-transposing stage (both weight-gradient operands): same source orientation as above, but read with 16-byte
+// loads.  Thread (producer warp pw, lane) owns the 4x4 block {k = 4 pw .. 4 pw + 3} x {mn = 4 lane .. 4 lane + 3}:
+// four ld.global.v4 (a warp instruction reads one whole 512-byte source row), transposed in registers into the four
+// 16-byte K-major rows mn = 4 lane + j.  Lane l stores row j = (i + l/2) mod 4 in its i-th store, so that every
+// quarter-warp writes eight different 16-byte bank groups (rows 4 lane + j of consecutive lanes would otherwise hit
+// only two): 4 wavefronts per 512-byte store instruction, the minimum.  4x fewer load instructions than the
+// scalar column gather.
+//   `base` = address of (k row 0, mn = 4 lane)
+__device__ __forceinline__ void load_block4(Frag& f, const float* base, int64_t pitch, int k_valid, int pw) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int k = 4 * pw + r;
+    f.v[r] = k < k_valid ? __ldg(reinterpret_cast<const float4*>(base + k * pitch)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+__device__ __forceinline__ float pick4(const float4& v, int j) {
+  const float lo = (j & 1) ? v.y : v.x, hi = (j & 1) ? v.w : v.z;
+  return (j & 2) ? hi : lo;
+}
+__device__ __forceinline__ void store_block4(const Frag& f, uint8_t* hi_tile, uint8_t* lo_tile, int pw, int lane) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int j = (i + (lane >> 1)) & 3;
+    const int mn = 4 * lane + j;
+    const int off = (mn >> 3) * 1024 + pw * 128 + (mn & 7) * 16;
+    const float4 x = make_float4(pick4(f.v[0], j), pick4(f.v[1], j), pick4(f.v[2], j), pick4(f.v[3], j));
+    float4 hi, lo;
+    split_tf32(x, hi, lo);
+    *reinterpret_cast<float4*>(hi_tile + off) = hi;
+    *reinterpret_cast<float4*>(lo_tile + off) = lo;
+  }
+}
+
 constexpr int EPI_PITCH = 36;  // floats per staged row: 16-byte aligned, rows 4 banks apart
 
 struct TcShared {
@@ -726,7 +759,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
       const mpqe_layer_group_t& G = L.g[wi.g];
       const mpqe_term_t& T = G.terms[wi.t];
       const mpqe_wgrad_operand_t& O = L.go[wi.g];
-      const int col = 32 * (pw & 3) + lane;
+      const int col = 4 * lane;          // this thread's 4x4 block: columns 4 lane .. 4 lane + 3 (load_block4)
       a_pitch = (int64_t)T.a_slots * D;
       a_col = T.a + (int64_t)T.a_slot * D + col;
       g_pitch = (int64_t)O.g_slots * D;
@@ -746,8 +779,8 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
         if (in_unit) enter_term();
       }
       const int valid = (int)(wi.qe - wi.q < KC ? wi.qe - wi.q : KC);
-      load_columns_at(fa, a_col + wi.q * a_pitch, a_pitch, valid, pw);
-      load_columns_at(fb, g_col + wi.q * g_pitch, g_pitch, valid, pw);
+      load_block4(fa, a_col + wi.q * a_pitch, a_pitch, valid, pw);
+      load_block4(fb, g_col + wi.q * g_pitch, g_pitch, valid, pw);
       wi.q += KC;
       if (wi.q >= wi.qe) {
         ++wi.t;
@@ -758,8 +791,8 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
     };
     auto put = [&](const Frag& fa, const Frag& fb) {
       uint8_t* st = acquire_stage(sh, smem, it);
-      store_columns(fa, st, st + TILE_BYTES, pw, lane);
-      store_columns(fb, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, pw, lane);
+      store_block4(fa, st, st + TILE_BYTES, pw, lane);
+      store_block4(fb, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, pw, lane);
     };
     Frag a0, b0, a1, b1;
     bool h0 = load_next(a0, b0);

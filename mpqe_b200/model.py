@@ -272,6 +272,9 @@ class Engine(object):
         t, n, a = job.t, job.t.num_nodes, job.t.num_anchors
         li = self.layer_index(p, job.P)
         x = job.acts[p]
+        if p > 0 and p == job.P - 1 and job.collapsed is not None:
+            # fused readout: one term per source slot with the summed matrix (see collapse_last_pass)
+            return [Term(x, n, c[0], self._cmat(W, c, 'm'), 0, self._cmat(W, c, 'mp')) for c in job.collapsed], [], li
         pos = {s: k for k, s in enumerate(outs)}
         wp = W.wp[li] if W.wp is not None else None
         rp = W.rootp[li] if W.rootp is not None else None
@@ -290,6 +293,99 @@ class Engine(object):
             add(s, W.root[li], rp, pos[s])
         return main, const, li
 
+    # ---- last pass under a sum / target-message readout: terms collapse per source slot --------------------
+    @staticmethod
+    def _pmat(W, li, key, kind):
+        """Parameter matrix `key` (('root',) or ('w', r)) of layer li as: 'm' forward, 'mp' its packed image,
+        't' transposed, 'tp' packed transposed."""
+        if key[0] == 'root':
+            src = {'m': W.root, 'mp': W.rootp, 't': W.roott, 'tp': W.roottp}[kind]
+            return src[li] if src is not None else None
+        src = {'m': W.w, 'mp': W.wp, 't': W.wt, 'tp': W.wtp}[kind]
+        return src[li][key[1]] if src is not None else None
+
+    def _cmat(self, W, c, kind):
+        """Matrix of a collapsed term c = (slot, li, keys, k): the summed matrix k, or the single parameter matrix."""
+        s, li, keys, k = c
+        if k is None:
+            return self._pmat(W, li, keys[0], kind)
+        src = {'m': W.msum, 'mp': W.msump, 't': W.msumt, 'tp': W.msumtp}[kind]
+        return src[k] if src is not None else None
+
+    def collapse_last_pass(self, jobs, W):
+        """With a sum (or target-message) readout the last pass writes ONE row per query: all terms that leave a source
+        slot read the same input row and add into the same output row, so they collapse into one term with the matrix
+        root + sum of basis[rel] over the slot's edges (the layer is linear in its weights, model.py:292-304) --
+        41 -> 24 term tiles per query on the bench workload, in the forward, the input gradient and the weight
+        gradient.  job.collapsed = [(slot, layer, keys of the summed parameter matrices, index k into the step's
+        summed-matrix buffers or None for a single matrix)]."""
+        for job in jobs:
+            job.collapsed = None
+        W.msum = W.msump = W.msumt = W.msumtp = W.dmsum = None
+        W.msum_keys = []
+        if self.m.readout_str not in ('sum', 'mp'):
+            return
+        for job in jobs:
+            if job.P < 2:
+                continue
+            t, li, outs = job.t, self.layer_index(job.P - 1, job.P), job.outs[job.P - 1]
+            by_src = {}
+            for s in outs:
+                by_src.setdefault(s, []).append(('root',))
+            for e in range(t.num_edges):
+                if t.dst[e] in outs:
+                    by_src.setdefault(t.src[e], []).append(('w', job.rels[e]))
+            job.collapsed = []
+            for s in sorted(by_src):
+                keys, k = by_src[s], None
+                if len(keys) > 1:
+                    k = len(W.msum_keys)
+                    W.msum_keys.append((li, keys))
+                job.collapsed.append((s, li, keys, k))
+        if not W.msum_keys:
+            return
+        dev = jobs[0].anchor_ids.device
+        W.msum = torch.empty(len(W.msum_keys), D, D, dtype=torch.float32, device=dev)
+        ops.matrix_sum_multi([(W.msum[k], [self._pmat(W, li, key, 'm') for key in keys], False)
+                              for k, (li, keys) in enumerate(W.msum_keys)])
+        tc = ops.tensor_cores_default()
+        if W.need_grad:
+            W.msumt = ops.transpose(W.msum)
+        if tc:
+            packed = ops.pack_weights([W.msum[k] for k in range(len(W.msum_keys))] +
+                                      ([W.msumt[k] for k in range(len(W.msum_keys))] if W.need_grad else []))
+            W.msump = packed[:len(W.msum_keys)]
+            W.msumtp = packed[len(W.msum_keys):] if W.need_grad else None
+
+    @staticmethod
+    def _pgrad(G, li, key):
+        return G.droot[li] if key[0] == 'root' else G.dw[li][key[1]]
+
+    def wgrad_dests(self, job, p, li, W, G, spread):
+        """{matrix address: (forward matrix, gradient destination, accumulate)} of job's pass p.  Summed matrices of a
+        collapsed last pass get their own (overwritten) gradient; `spread` collects where those go afterwards."""
+        dests = {}
+        if p > 0 and p == job.P - 1 and job.collapsed is not None:
+            for c in job.collapsed:
+                s, cli, keys, k = c
+                if k is None:
+                    m = self._pmat(W, cli, keys[0], 'm')
+                    dests[m.data_ptr()] = (m, self._pgrad(G, cli, keys[0]), 1)
+                else:
+                    if W.dmsum is None:
+                        W.dmsum = torch.empty_like(W.msum)
+                    dests[W.msum[k].data_ptr()] = (W.msum[k], W.dmsum[k], 0)
+                    for key in keys:
+                        spread.setdefault((cli, key), []).append(W.dmsum[k])
+            return dests
+        used = {term.m.data_ptr() for term in job.fwd_groups[p].terms}   # (pass 0: without the batch-constant terms)
+        for r in sorted(set(job.rels)):
+            if W.w[li][r].data_ptr() in used:
+                dests[W.w[li][r].data_ptr()] = (W.w[li][r], G.dw[li][r], 1)
+        if W.root[li].data_ptr() in used:
+            dests[W.root[li].data_ptr()] = (W.root[li], G.droot[li], 1)
+        return dests
+
     def encode(self, jobs, W):
         """Runs every pass of every job; leaves job.q [B, D] (query embeddings)."""
         readout = self.m.readout_str
@@ -297,6 +393,7 @@ class Engine(object):
         for job in jobs:
             job.outs = _needed_slots(job, readout)
             job.fwd_groups = [None] * job.P
+        self.collapse_last_pass(jobs, W)
         max_p = max(job.P for job in jobs)
         for p in range(max_p):
             groups, const_groups = [], []
@@ -397,12 +494,23 @@ class Engine(object):
             by_layer = {}
             for job in active:
                 by_layer.setdefault(self.layer_index(p, job.P), []).append(job)
+            spread = {}    # (layer, parameter key) -> gradients of the summed matrices it is a summand of
             for li, ljobs in by_layer.items():
-                for i in range(0, len(ljobs), ops.MAX_GROUPS):
-                    chunk = ljobs[i:i + ops.MAX_GROUPS]
-                    rels = sorted({r for job in chunk for r in job.rels})
-                    dests = [(W.w[li][r], G.dw[li][r], 1) for r in rels] + [(W.root[li], G.droot[li], 1)]
-                    ops.layer_wgrad([job.fwd_groups[p] for job in chunk], [cur[job] for job in chunk], dests)
+                chunk, dests = [], {}
+                for job in ljobs + [None]:
+                    jd = self.wgrad_dests(job, p, li, W, G, spread) if job is not None else {}
+                    if chunk and (job is None or len(chunk) == ops.MAX_GROUPS or
+                                  len(set(dests) | set(jd)) > ops.MAX_DESTS):
+                        if dests:
+                            ops.layer_wgrad([j.fwd_groups[p] for j in chunk], [cur[j] for j in chunk],
+                                            list(dests.values()))
+                        chunk, dests = [], {}
+                    if job is not None:
+                        chunk.append(job)
+                        dests.update(jd)
+            if spread:     # d(root + sum basis[rel]) goes to every summand, in a fixed order
+                ops.matrix_sum_multi([(self._pgrad(G, li, key), srcs, True) for (li, key), srcs in spread.items()])
+            for li, ljobs in by_layer.items():
                 for job in ljobs:
                     if p == 0 and job.const_fwd is not None:
                         continue   # bias gradient = sum of the per-slot sums taken below (see constant_backward)
@@ -450,10 +558,15 @@ class Engine(object):
                 okey = {s: k for k, s in enumerate(outs)}
                 wtp = W.wtp[li] if W.wtp is not None else None
                 rtp = W.roottp[li] if W.roottp is not None else None
-                terms = [Term(g, g_slots, smap[okey[t.dst[e]]], W.wt[li][job.rels[e]], pos[t.src[e]],
-                              wtp[job.rels[e]] if wtp is not None else None)
-                         for e in range(t.num_edges) if t.dst[e] in okey and t.src[e] in pos]
-                terms += [Term(g, g_slots, smap[okey[s]], W.roott[li], pos[s], rtp) for s in outs if s in pos]
+                if p > 0 and p == job.P - 1 and job.collapsed is not None:
+                    # collapsed last pass: d h[:, s] = dq @ (root + sum basis[rel])^T, one term per source slot
+                    terms = [Term(g, g_slots, 0, self._cmat(W, c, 't'), pos[c[0]], self._cmat(W, c, 'tp'))
+                             for c in job.collapsed if c[0] in pos]
+                else:
+                    terms = [Term(g, g_slots, smap[okey[t.dst[e]]], W.wt[li][job.rels[e]], pos[t.src[e]],
+                                  wtp[job.rels[e]] if wtp is not None else None)
+                             for e in range(t.num_edges) if t.dst[e] in okey and t.src[e] in pos]
+                    terms += [Term(g, g_slots, smap[okey[s]], W.roott[li], pos[s], rtp) for s in outs if s in pos]
                 if readout == 'concat' and p > 0:
                     # h_p also feeds block p-1 of the concat MLP
                     terms += [Term(job.du, n, j, W.w1b[p - 1], pos[j]) for j in range(n)]

@@ -209,6 +209,32 @@ def layer_wgrad(groups, grad_operands, dests, ctas_hint=296, use_tensor_cores=No
     _count(1 if rows_only else 2)
 
 
+def matrix_sum_multi(items):
+    """items: [(dst [D, D] view, [src [D, D] views], accumulate)]; dst (+)= sum(src) in order (mpqe_matrix_sum_multi).
+    Destinations must be distinct within one call; a summand list longer than MPQE_MAX_MATSUM_SRCS is continued by
+    accumulating follow-up launches."""
+    lib = _lib.load()
+    pending = [(dst, list(srcs), bool(acc)) for dst, srcs, acc in items]
+    while pending:
+        later = []
+        for i in range(0, len(pending), _lib.MAX_MATSUM_ITEMS):
+            chunk = pending[i:i + _lib.MAX_MATSUM_ITEMS]
+            arr = (_lib.MatsumItem * len(chunk))()
+            for j, (dst, srcs, acc) in enumerate(chunk):
+                head, tail = srcs[:_lib.MAX_MATSUM_SRCS], srcs[_lib.MAX_MATSUM_SRCS:]
+                arr[j].dst = _chk(dst, torch.float32, 'dst').data_ptr()
+                for k, m in enumerate(head):
+                    if m.numel() != D * D:
+                        raise _lib.MpqeError('matrix_sum_multi: summands must be [%d,%d]' % (D, D))
+                    arr[j].src[k] = _chk(m, torch.float32, 'summand').data_ptr()
+                arr[j].num_src, arr[j].accumulate = len(head), int(acc)
+                if tail:
+                    later.append((dst, tail, True))
+            _lib.check(lib.mpqe_matrix_sum_multi(arr, len(chunk), _stream()), 'mpqe_matrix_sum_multi')
+            _count()
+        pending = later
+
+
 PACKED_FLOATS = 2 * D * D
 
 

@@ -272,7 +272,7 @@ def install(monkeypatch):
                  'broadcast_rows', 'max_readout', 'max_readout_bwd', 'cosine_margin', 'cosine_margin_bwd',
                  'cosine_scores', 'cosine_scores_bwd', 'rank_counts_ragged', 'rank_counts_table',
                  'build_query_graph', 'relation_sort', 'sparse_rows_combine', 'SparseRowsPlan', 'scatter_rows',
-                 'gather_multi',
+                 'gather_multi', 'matrix_sum_multi',
                  'cosine_margin_multi', 'colsum_multi'):
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(ops, 'device_guard', lambda device: contextlib.nullcontext())
@@ -307,6 +307,14 @@ def cosine_margin_multi(items, margin, backward=False):
             it.rows_id[it.rows_offset:it.rows_offset + 2 * B] += it.id_offset
         else:
             cosine_margin(it.q, it.table, it.id2row, it.ids_pos, it.ids_neg, margin, loss_out=it.loss)
+
+
+def matrix_sum_multi(items):
+    for dst, srcs, acc in items:
+        total = dst.clone() if acc else torch.zeros_like(dst)
+        for m in srcs:
+            total = total + m.reshape(dst.shape)
+        dst.copy_(total)
 
 
 def colsum_multi(items, device):
