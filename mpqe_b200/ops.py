@@ -197,7 +197,8 @@ def layer_wgrad(groups, grad_operands, dests, ctas_hint=296, use_tensor_cores=No
     dev = groups[0].terms[0].a.device
     tc = tensor_cores_default() if use_tensor_cores is None else bool(use_tensor_cores)
     if tc:
-        ctas_hint = min(ctas_hint, 148)   # the tcgen05 kernel is persistent: one unit per SM is enough parallelism
+        import os
+        ctas_hint = int(os.environ.get('MPQE_WGRAD_UNITS', '148'))   # persistent tcgen05 kernel: units per launch
     nbytes = lib.mpqe_layer_wgrad_workspace_bytes(len(dests), ctas_hint)
     ws = workspace(nbytes, dev, 'wgrad')
     rows_only = all(g.num_queries == 1 for g in groups)
