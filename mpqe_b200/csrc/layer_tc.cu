@@ -17,6 +17,8 @@
 // anyway to be split into its hi/lo TF32 parts (and half of them need a transpose on the way).
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace mpqe {
@@ -737,7 +739,8 @@ __device__ __forceinline__ int wgrad_unit_steps(const WgradLaunch& L, int j, int
   return steps;
 }
 
-__global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_constant__ WgradLaunch L, int total_units) {
+__global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_constant__ WgradLaunch L,
+                                                              const __grid_constant__ Schedule S, int total_units) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ TcShared sh;
   uint8_t* smem = align_1024(smem_raw);
@@ -749,7 +752,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
     const int pw = warp - EPI_WARPS;
     uint32_t it = 0;
     // iterator over (unit, matching (group, term), 32-query tile), crossing units; two register sets as above
-    int unit = blockIdx.x - gridDim.x, j = 0, c = 0;
+    int uk = 0, j = 0, c = 0;
     WgradIter wi{0, 0, 0, 0};
     bool in_unit = false, alive = true;
     // per-term state in registers (see layer_tc_kernel: no descriptor loads on the per-stage path)
@@ -768,8 +771,8 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
     auto load_next = [&](Frag& fa, Frag& fb) -> bool {
       if (!alive) return false;
       while (!in_unit) {
-        unit += gridDim.x;
-        if (unit >= total_units) {
+        const int unit = sched_unit(S, uk++, total_units);
+        if (unit < 0) {
           alive = false;
           return false;
         }
@@ -814,7 +817,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
     if (lane == 0) {
       uint32_t it = 0;
       int uc = 0;
-      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++uc) {
+      for (int unit; (unit = sched_unit(S, uc, total_units)) >= 0; ++uc) {
         int j, c;
         decode_wgrad_unit(L, unit, j, c);
         mma_unit(sh, smem_u32(smem), tmem, uc, wgrad_unit_steps(L, j, c), it);
@@ -822,7 +825,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
     }
   } else {
     int uc = 0;
-    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++uc) {
+    for (int unit; (unit = sched_unit(S, uc, total_units)) >= 0; ++uc) {
       int j, c;
       decode_wgrad_unit(L, unit, j, c);
       const int nsteps = wgrad_unit_steps(L, j, c);
@@ -1073,6 +1076,31 @@ int num_sms() {
 
 }  // namespace
 
+// Longest-processing-time-first assignment of `units` work units (cost[u] stages each, + 1 for the per-unit epilogue /
+// pipeline refill) to `grid` persistent CTAs; every CTA runs its units heaviest first.
+static void build_lpt(Schedule& S, const int* cost, int units, int grid) {
+  static thread_local int order[SCHED_MAX_UNITS], owner[SCHED_MAX_UNITS];
+  for (int i = 0; i < units; ++i) order[i] = i;
+  std::stable_sort(order, order + units, [&](int a, int b) { return cost[a] > cost[b]; });
+  long long load[SCHED_MAX_CTAS];
+  int cnt[SCHED_MAX_CTAS];
+  for (int c = 0; c < grid; ++c) load[c] = 0, cnt[c] = 0;
+  for (int i = 0; i < units; ++i) {
+    int best = 0;
+    for (int c = 1; c < grid; ++c)
+      if (load[c] < load[best]) best = c;
+    owner[order[i]] = best;
+    load[best] += cost[order[i]] + 1;
+    ++cnt[best];
+  }
+  S.start[0] = 0;
+  for (int c = 0; c < grid; ++c) S.start[c + 1] = (uint16_t)(S.start[c] + cnt[c]);
+  int fill[SCHED_MAX_CTAS];
+  for (int c = 0; c < grid; ++c) fill[c] = S.start[c];
+  for (int i = 0; i < units; ++i) S.unit[fill[owner[order[i]]]++] = (uint16_t)order[i];
+  S.count = units;
+}
+
 int layer_forward_tc(const mpqe_layer_group_t* groups, int num_groups, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
@@ -1093,7 +1121,7 @@ int layer_forward_tc(const mpqe_layer_group_t* groups, int num_groups, cudaStrea
   static thread_local Schedule S;
   S.count = 0;
   if (units > grid && units <= SCHED_MAX_UNITS && grid <= SCHED_MAX_CTAS) {
-    static thread_local int cost[SCHED_MAX_UNITS], order[SCHED_MAX_UNITS], owner[SCHED_MAX_UNITS];
+    static thread_local int cost[SCHED_MAX_UNITS];
     int u = 0;
     for (int i = 0; i < num_groups; ++i) {
       const int tiles = (int)((groups[i].num_queries + BM - 1) / BM);
@@ -1103,28 +1131,7 @@ int layer_forward_tc(const mpqe_layer_group_t* groups, int num_groups, cudaStrea
         for (int k = 0; k < tiles; ++k) cost[u++] = nt;     // slot-major numbering, as decode_unit
       }
     }
-    // counting sort by cost, descending (costs are <= MPQE_MAX_TERMS)
-    int pos = 0;
-    for (int c = MPQE_MAX_TERMS; c >= 0; --c)
-      for (int i = 0; i < (int)units; ++i)
-        if (cost[i] == c) order[pos++] = i;
-    long long load[SCHED_MAX_CTAS];
-    int cnt[SCHED_MAX_CTAS];
-    for (int c = 0; c < grid; ++c) load[c] = 0, cnt[c] = 0;
-    for (int i = 0; i < (int)units; ++i) {
-      int best = 0;
-      for (int c = 1; c < grid; ++c)
-        if (load[c] < load[best]) best = c;
-      owner[order[i]] = best;
-      load[best] += cost[order[i]] + 1;                        // +1: per-unit epilogue / pipeline refill
-      ++cnt[best];
-    }
-    S.start[0] = 0;
-    for (int c = 0; c < grid; ++c) S.start[c + 1] = (uint16_t)(S.start[c] + cnt[c]);
-    int fill[SCHED_MAX_CTAS];
-    for (int c = 0; c < grid; ++c) fill[c] = S.start[c];
-    for (int i = 0; i < (int)units; ++i) S.unit[fill[owner[order[i]]]++] = (uint16_t)order[i];   // heavy units first
-    S.count = (int)units;
+    build_lpt(S, cost, (int)units, grid);
   }
   static int dbg = -1;  // MPQE_TC_DEBUG: timing experiments only (bit0 no smem stores, bit1 no global loads,
   if (dbg < 0) {        //                 bit2 no MMAs, bit3 no epilogue stores); results are wrong when non-zero
@@ -1144,7 +1151,31 @@ int layer_wgrad_tc_launch(const WgradLaunch& launch, int total_chunks, cudaStrea
     configured = true;
   }
   const int grid = total_chunks < num_sms() ? total_chunks : num_sms();
-  wgrad_tc_kernel<<<grid, THREADS, TC_SMEM, stream>>>(launch, total_chunks);
+  static thread_local Schedule S;
+  S.count = 0;
+  if (total_chunks > grid && total_chunks <= SCHED_MAX_UNITS && grid <= SCHED_MAX_CTAS) {
+    // stages of every (destination, chunk) unit, as wgrad_unit_steps computes them on the device
+    static thread_local int cost[SCHED_MAX_UNITS];
+    int u = 0;
+    for (int j = 0; j < launch.num_dests; ++j)
+      for (int c = 0; c < launch.chunks[j]; ++c) {
+        int steps = 0;
+        for (int g = 0; g < launch.num_groups; ++g) {
+          const int64_t B = launch.g[g].num_queries;
+          int64_t per = (B + launch.chunks[j] - 1) / launch.chunks[j];
+          per = (per + KC - 1) / KC * KC;
+          int64_t qb = per * c, qe = qb + per;
+          if (qb > B) qb = B;
+          if (qe > B) qe = B;
+          const int tiles = (int)((qe - qb + KC - 1) / KC);
+          for (int t = 0; t < launch.g[g].num_terms; ++t)
+            if (launch.g[g].terms[t].m == launch.d[j].m_fwd) steps += tiles;
+        }
+        cost[u++] = steps;
+      }
+    build_lpt(S, cost, total_chunks, grid);
+  }
+  wgrad_tc_kernel<<<grid, THREADS, TC_SMEM, stream>>>(launch, S, total_chunks);
   MPQE_CHECK_LAUNCH("wgrad_tc_kernel");
   return 0;
 }
