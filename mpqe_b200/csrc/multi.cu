@@ -156,6 +156,11 @@ __global__ void __launch_bounds__(ROW_THREADS) margin_bwd_multi_kernel(const __g
   if (lane == 0) {
     T.rows_id[b] = rp + T.id_offset;
     T.rows_id[B + b] = rn + T.id_offset;
+    if (T.hinge != nullptr) {   // fused forward + backward (mode 2): the forward outputs, same arithmetic
+      if (T.score_pos != nullptr) T.score_pos[b] = cp.score;
+      if (T.score_neg != nullptr) T.score_neg[b] = cn.score;
+      T.hinge[b] = fmaxf(L.margin - (cp.score - cn.score), 0.f);
+    }
   }
 }
 
@@ -283,7 +288,7 @@ extern "C" int mpqe_cosine_margin_multi(const mpqe_margin_item_t* items_host, in
     MPQE_CHECK_ARG(T.q && T.table && T.ids_pos && T.ids_neg && T.B >= 1, "mpqe_cosine_margin_multi: item %d: bad argument", i);
     if (backward)
       MPQE_CHECK_ARG(T.grad_loss && T.dq && T.rows_out && T.rows_id, "mpqe_cosine_margin_multi: item %d: bad bwd argument", i);
-    else
+    if (backward != 1)
       MPQE_CHECK_ARG(T.hinge && T.loss, "mpqe_cosine_margin_multi: item %d: bad fwd argument", i);
     L.it[i] = T;
     total += T.B;
@@ -291,6 +296,10 @@ extern "C" int mpqe_cosine_margin_multi(const mpqe_margin_item_t* items_host, in
   if (backward) {
     margin_bwd_multi_kernel<<<row_blocks(total), ROW_THREADS, 0, (cudaStream_t)stream>>>(L);
     MPQE_CHECK_LAUNCH("margin_bwd_multi_kernel");
+    if (backward == 2) {   // fused: the gradient of the total wrt each loss is known up front (grad_loss)
+      margin_mean_multi_kernel<<<n, 1024, 0, (cudaStream_t)stream>>>(L);
+      MPQE_CHECK_LAUNCH("margin_mean_multi_kernel");
+    }
   } else {
     margin_fwd_multi_kernel<<<row_blocks(total), ROW_THREADS, 0, (cudaStream_t)stream>>>(L);
     MPQE_CHECK_LAUNCH("margin_fwd_multi_kernel");

@@ -386,14 +386,24 @@ class Engine(object):
             dests[W.root[li].data_ptr()] = (W.root[li], G.droot[li], 1)
         return dests
 
-    def encode(self, jobs, W):
-        """Runs every pass of every job; leaves job.q [B, D] (query embeddings)."""
+    def prepare(self, jobs, W):
+        """Everything of a step that depends only on the weights and the formulas (needed slots, summed matrices of
+        a collapsed last pass).  May be called ahead of `encode`, e.g. on a second stream (see TrainStep)."""
         readout = self.m.readout_str
-        self.build_inputs(jobs, W)
         for job in jobs:
             job.outs = _needed_slots(job, readout)
             job.fwd_groups = [None] * job.P
         self.collapse_last_pass(jobs, W)
+        W.prepared = jobs
+
+    def encode(self, jobs, W):
+        """Runs every pass of every job; leaves job.q [B, D] (query embeddings)."""
+        readout = self.m.readout_str
+        self.build_inputs(jobs, W)
+        if getattr(W, 'prepared', None) is not jobs:
+            self.prepare(jobs, W)
+        if getattr(W, 'ready_event', None) is not None:    # weights prepared on another stream
+            torch.cuda.current_stream().wait_event(W.ready_event)
         max_p = max(job.P for job in jobs)
         for p in range(max_p):
             groups, const_groups = [], []
@@ -935,20 +945,30 @@ class RGCNEncoderDecoder(nn.Module):
         return tuple(by_param.get(id(p)) for p in self.parameters())
 
 
-def loss_forward(model, jobs, targets, negatives, margin, need_grad):
+def loss_forward(model, jobs, targets, negatives, margin, need_grad, grad_losses=None, W=None):
     """Encodes every job once and scores it against its positives and negatives.
-    Returns (per-job losses [len(jobs)] on the device, Weights)."""
+    Returns (per-job losses [len(jobs)] on the device, Weights).  With `grad_losses` (d total / d loss_i, known up
+    front in a training step) and row slots reserved by `plan_rows`, the margin backward (job.dq and the target /
+    negative row gradients) is produced by the same pass over q and the table rows; `loss_backward` then skips it."""
     device = jobs[0].anchor_ids.device
-    W = Weights(model, need_grad)
+    if W is None:
+        W = Weights(model, need_grad)
     model._engine.encode(jobs, W)
     losses = torch.empty(len(jobs), dtype=torch.float32, device=device)
     hinge = torch.empty(sum(job.B for job in jobs), dtype=torch.float32, device=device)
     items, off = [], 0
     for i, (job, tgt, neg) in enumerate(zip(jobs, targets, negatives)):
-        items.append(ops.MarginItem(job.q, model.enc.table(job.target_mode), model.enc.node_maps, tgt, neg,
-                                    hinge=hinge[off:off + job.B], loss=losses[i:i + 1]))
+        it = ops.MarginItem(job.q, model.enc.table(job.target_mode), model.enc.node_maps, tgt, neg,
+                            hinge=hinge[off:off + job.B], loss=losses[i:i + 1])
+        job.dq = None
+        if grad_losses is not None:
+            rbuf, ids, roff, id_off = job.margin_res
+            job.dq = torch.empty(job.B, D, dtype=torch.float32, device=device)
+            it.grad_loss, it.dq = grad_losses[i:i + 1], job.dq
+            it.rows_out, it.rows_id, it.rows_offset, it.id_offset = rbuf, ids, roff, id_off
+        items.append(it)
         off += job.B
-    ops.cosine_margin_multi(items, margin)
+    ops.cosine_margin_multi(items, margin, backward='both' if grad_losses is not None else False)
     return losses, W
 
 
@@ -988,13 +1008,17 @@ def loss_backward(model, jobs, W, targets, negatives, margin, grad_losses, table
     G = Grads(model, W, cap, device, table_offsets, rows)
     dqs, items = [], []
     for i, (job, tgt, neg) in enumerate(zip(jobs, targets, negatives)):
+        if G.rows.planned and getattr(job, 'dq', None) is not None:
+            dqs.append(job.dq)      # margin backward already done by loss_forward(grad_losses=...)
+            continue
         rbuf, ids, off, id_off = job.margin_res if G.rows.planned else G.rows.reserve(job.target_mode, 2 * job.B)
         dq = torch.empty(job.B, D, dtype=torch.float32, device=device)
         items.append(ops.MarginItem(job.q, model.enc.table(job.target_mode), model.enc.node_maps, tgt, neg,
                                     grad_loss=grad_losses[i:i + 1], dq=dq, rows_out=rbuf, rows_id=ids, rows_offset=off,
                                     id_offset=id_off))
         dqs.append(dq)
-    ops.cosine_margin_multi(items, margin, backward=True)
+    if items:
+        ops.cosine_margin_multi(items, margin, backward=True)
     model._engine.backward(jobs, W, dqs, G)
     return G
 

@@ -573,13 +573,16 @@ class MarginItem(object):
 
 
 def cosine_margin_multi(items, margin, backward=False):
+    """backward: False = forward (losses), True = backward (dq, table rows), 'both' = one pass doing both (needs
+    grad_loss before the forward: a training step knows d total / d loss_i up front)."""
     lib = _lib.load()
+    mode = 2 if backward == 'both' else int(bool(backward))
     for i in range(0, len(items), _lib.MAX_MARGIN_ITEMS):
         chunk = items[i:i + _lib.MAX_MARGIN_ITEMS]
         arr = (_lib.MarginItem * len(chunk))(*[it.to_c() for it in chunk])
-        _lib.check(lib.mpqe_cosine_margin_multi(arr, len(chunk), margin, int(backward), _stream()),
+        _lib.check(lib.mpqe_cosine_margin_multi(arr, len(chunk), margin, mode, _stream()),
                    'mpqe_cosine_margin_multi')
-        _count(1 if backward else 2)
+        _count(1 if mode == 1 else 2)
 
 
 class ColsumItem(object):

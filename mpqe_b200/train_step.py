@@ -12,7 +12,7 @@ pairs, followed by the same deterministic combine on every rank, so that all ran
 import torch
 
 from . import ops
-from .model import Job, loss_backward, loss_forward, plan_rows
+from .model import Job, Weights, loss_backward, loss_forward, plan_rows
 from .ops import D
 
 
@@ -118,6 +118,22 @@ class TrainStep(object):
         plan.num.record_stream(cur)
         return plan
 
+    def _weights_on_side_stream(self, jobs, dev):
+        """`Weights` + `Engine.prepare` on the second stream; `W.ready_event` orders the first layer launch after it.
+        (None on the CPU emulator: `loss_forward` then builds the weights itself.)"""
+        if dev.type != 'cuda':
+            return None
+        cur = torch.cuda.current_stream(dev)
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=dev)
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            W = Weights(self.model, True)
+            self.model._engine.prepare(jobs, W)
+            W.ready_event = torch.cuda.Event()
+            W.ready_event.record(self._side)
+        return W
+
     def _join_side(self, dev):
         if dev.type == 'cuda':
             torch.cuda.current_stream(dev).wait_stream(self._side)
@@ -154,14 +170,18 @@ class TrainStep(object):
         # half of the combine (stable sort + segmentation, ~10 small latency-bound launches) on a second stream, under
         # the forward and backward; only the final row summation waits for the gradient rows.
         # With several ranks the pairs are exchanged raw and combined once, after the all-gather (see `sync`).
+        # The per-step weight preparation (transposes, tf32 tile images, summed matrices) goes to that stream too, ahead
+        # of the sort: it overlaps the input gather; the first layer launch waits for its event.
         R = plan_rows(m, jobs, tg, ng, self.table_offsets)
         rows, ids, used = R.shared
+        W = self._weights_on_side_stream(jobs, dev)
         plan = self._plan_on_side_stream(ids[:used], dev) if self.world == 1 else None
-        losses, W = loss_forward(m, jobs, tg, ng, self.margin, True)
         key = tuple(b.weight for b in batches)
         wts = getattr(self, '_wts', None)
         if wts is None or wts[0] != key:
             wts = self._wts = (key, torch.tensor(key, dtype=torch.float32, device=dev))
+        # d total / d loss_i = the batch weights, known now: the margin backward rides on the margin forward
+        losses, W = loss_forward(m, jobs, tg, ng, self.margin, True, grad_losses=wts[1], W=W)
         G = loss_backward(m, jobs, W, tg, ng, self.margin, wts[1], self.table_offsets, rows=R)
         if plan is not None:
             self._join_side(dev)

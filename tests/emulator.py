@@ -299,6 +299,8 @@ def gather_multi(items, backward=False):
 
 def cosine_margin_multi(items, margin, backward=False):
     for it in items:
+        if backward == 'both':
+            cosine_margin(it.q, it.table, it.id2row, it.ids_pos, it.ids_neg, margin, loss_out=it.loss)
         if backward:
             dq = cosine_margin_bwd(it.q, it.table, it.id2row, it.ids_pos, it.ids_neg, margin, it.grad_loss, it.rows_out,
                                    it.rows_id, it.rows_offset)
