@@ -234,6 +234,7 @@ def main():
     if not args.no_graph:
         l0 = ops.launch_count
         ts.capture(host)
+        host = ts.staging()      # the step's ids in ONE pinned buffer (what a loader fills in place): one H2D copy
         launches_per_step = (ops.launch_count - l0) // 3      # capture() runs the step 2x eagerly + 1x captured
         for _ in range(3):
             ts.replay()

@@ -26,11 +26,12 @@ class Batch(object):
 class HostBatch(object):
     """Pinned host ids of one formula batch (what a data loader hands over)."""
 
-    def __init__(self, formula, anchor_ids, targets, negatives, weight=1.0):
+    def __init__(self, formula, anchor_ids, targets, negatives, weight=1.0, pin=True):
         self.formula = formula
-        self.anchor_ids = anchor_ids.contiguous().pin_memory() if torch.cuda.is_available() else anchor_ids
-        self.targets = targets.contiguous().pin_memory() if torch.cuda.is_available() else targets
-        self.negatives = negatives.contiguous().pin_memory() if torch.cuda.is_available() else negatives
+        pin = pin and torch.cuda.is_available()      # pin=False: the tensors already are views of pinned memory
+        self.anchor_ids = anchor_ids.contiguous().pin_memory() if pin else anchor_ids
+        self.targets = targets.contiguous().pin_memory() if pin else targets
+        self.negatives = negatives.contiguous().pin_memory() if pin else negatives
         self.weight = float(weight)
 
     def nbytes(self):
@@ -76,14 +77,16 @@ class TrainStep(object):
                                         torch.tensor(var_ids, dtype=torch.int64, device=dev), m.num_passes(formula))
         return lay
 
-    def to_device(self, hb):
-        """H2D copy of one host batch (async from pinned memory) -> Batch."""
+    def to_device(self, hb, device_ids=None):
+        """H2D copy of one host batch (async from pinned memory) -> Batch.  `device_ids` = (anchor ids, targets,
+        negatives) already on the device (views of the step's id buffer in graph mode)."""
         dev = self.model.mode_embeddings.weight.device
         t, rels, var_host, var_dev, passes = self.layout(hb.formula)
-        a = hb.anchor_ids.to(dev, non_blocking=True)
-        job = Job(t, rels, var_dev, hb.formula.anchor_modes, hb.formula.target_mode, a, passes)
+        if device_ids is None:
+            device_ids = tuple(x.to(dev, non_blocking=True) for x in (hb.anchor_ids, hb.targets, hb.negatives))
+        job = Job(t, rels, var_dev, hb.formula.anchor_modes, hb.formula.target_mode, device_ids[0], passes)
         job.var_rows_host = var_host
-        return Batch(job, hb.targets.to(dev, non_blocking=True), hb.negatives.to(dev, non_blocking=True), hb.weight)
+        return Batch(job, device_ids[1], device_ids[2], hb.weight)
 
     def refresh(self, batch):
         """A Batch can be re-run: drop the activations of the previous step."""
@@ -199,7 +202,23 @@ class TrainStep(object):
         m = self.model
         dev = m.mode_embeddings.weight.device
         with ops.device_guard(dev):
-            self._static = [self.to_device(hb) for hb in host_batches]
+            # all ids of a step live in ONE device buffer mirrored by ONE pinned host buffer: a step's input is a
+            # single H2D copy instead of three small copies per formula batch
+            total = sum(hb.anchor_ids.numel() + hb.targets.numel() + hb.negatives.numel() for hb in host_batches)
+            self._host_ids = torch.empty(total, dtype=torch.int64).pin_memory()
+            self._dev_ids = torch.empty(total, dtype=torch.int64, device=dev)
+            self._static, self._staging, off = [], [], 0
+            for hb in host_batches:
+                views = []
+                for src in (hb.anchor_ids, hb.targets, hb.negatives):
+                    n = src.numel()
+                    hv = self._host_ids[off:off + n].view(src.shape)
+                    hv.copy_(src)
+                    views.append((hv, self._dev_ids[off:off + n].view(src.shape)))
+                    off += n
+                self._staging.append(HostBatch(hb.formula, views[0][0], views[1][0], views[2][0], hb.weight, pin=False))
+                self._static.append(self.to_device(hb, tuple(v[1] for v in views)))
+            self._dev_ids.copy_(self._host_ids, non_blocking=True)
             self._wts = None
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream())
@@ -220,16 +239,24 @@ class TrainStep(object):
         """One step through the captured graph; with `host_batches` their ids are first copied (async, pinned) into
         the static buffers.  Returns the same StepResult object every time (its tensors are overwritten)."""
         if host_batches is not None:
-            for b, hb in zip(self._static, host_batches):
-                b.job.anchor_ids.copy_(hb.anchor_ids, non_blocking=True)
-                b.targets.copy_(hb.targets, non_blocking=True)
-                b.negatives.copy_(hb.negatives, non_blocking=True)
+            if host_batches is not self._staging:    # not written in place (see `staging`): pack on the host first
+                for st, hb in zip(self._staging, host_batches):
+                    st.anchor_ids.copy_(hb.anchor_ids)
+                    st.targets.copy_(hb.targets)
+                    st.negatives.copy_(hb.negatives)
+            self._dev_ids.copy_(self._host_ids, non_blocking=True)
         self._graph.replay()
         res = self._graph_res
         if self.world > 1:
             with ops.device_guard(res.dense.flat.device):
                 res = StepResult(res.losses, res.total, res.dense, self.sync(res.dense, res.sparse))
         return res
+
+    def staging(self):
+        """Graph mode: HostBatch objects whose id tensors are views of the step's single pinned host buffer.  A data
+        loader that writes the next batch into them in place and passes this very list to `replay` / `run_host` gets
+        the whole step's input across in one H2D copy, with no packing on the host."""
+        return self._staging
 
     @torch.no_grad()
     def run_host(self, host_batches):
