@@ -472,13 +472,23 @@ class Engine(object):
             terms = [Term(a, s, j, W.w1t[b * D:(b + 1) * D], k) for k, srcs in enumerate(units) for (a, s, j, b) in srcs]
             job.u = torch.empty(job.B, nu, D, dtype=torch.float32, device=dev)
             job.mlp1 = Group(job.B, terms, nu, job.u, nu, epilogue=EPI_RELU, bias=W.b1)
-            job.q = torch.empty(job.B, D, dtype=torch.float32, device=dev)
-            job.mlp2 = Group(job.B, [Term(job.u, nu, k, W.w2t, 0) for k in range(nu)], 1, job.q, 1, out_slot_map=[0],
-                             bias=W.b2, bias_scale=[float(nu)])
+            if self.m.scatter_op == 'max':     # per-unit outputs, then the per-feature max over the query's units
+                job.z2 = torch.empty(job.B, nu, D, dtype=torch.float32, device=dev)
+                job.mlp2 = Group(job.B, [Term(job.u, nu, k, W.w2t, k) for k in range(nu)], nu, job.z2, nu, bias=W.b2)
+            else:                              # add / mean: the second linear layer sums over the units directly
+                job.q = torch.empty(job.B, D, dtype=torch.float32, device=dev)
+                job.mlp2 = Group(job.B, [Term(job.u, nu, k, W.w2t, 0) for k in range(nu)], 1, job.q, 1,
+                                 out_slot_map=[0], bias=W.b2, bias_scale=[float(nu)])
             g1.append(job.mlp1)
             g2.append(job.mlp2)
         ops.layer_forward(g1)
         ops.layer_forward(g2)
+        for job in jobs:
+            nu = job.u.shape[1]
+            if self.m.scatter_op == 'max':
+                job.q, job.argmax2 = ops.max_readout(job.z2, job.B, nu)
+            elif self.m.scatter_op == 'mean':  # scatter_mean = scatter_add / units per query (exact for 2 and 4 units)
+                job.q.mul_(1.0 / nu)
 
     # ---- backward -----------------------------------------------------------------------------------------
     def backward(self, jobs, W, dqs, G):
@@ -668,28 +678,38 @@ class Engine(object):
 
     def mlp_backward(self, jobs, W, dqs, G, last):
         """Backward of the MLP readouts; fills last[job] (gradient wrt the last R-GCN pass output) and job.du."""
-        ro = self.m.readout_str
-        g_du = []
+        ro, op = self.m.readout_str, self.m.scatter_op
+        g_du, g2 = [], []      # g2[i] = gradient operand of the second linear layer: (tensor, slots, slot map)
         for job, dq in zip(jobs, dqs):
             nu = job.u.shape[1]
             job.du = torch.empty_like(job.u)
-            # dU[:, k] = (dq @ W2) * (u > 0)       (W2 is stored [out, in] = the matrix this product needs)
-            g_du.append(Group(job.B, [Term(dq, 1, 0, W.w2, k) for k in range(nu)], nu, job.du, nu, epilogue=EPI_MASK,
-                              mask=job.u, mask_slots=nu))
+            if op == 'max':    # the gradient reaches only the unit that attained the maximum, feature by feature
+                dz2 = ops.max_readout_bwd(dq, job.argmax2, job.B, nu)
+                g2.append((dz2, nu, list(range(nu))))
+            else:
+                if op == 'mean':
+                    dq = dq * (1.0 / nu)
+                g2.append((dq, 1, [0] * nu))
+            g, gs, smap = g2[-1]
+            # dU[:, k] = (dZ2[:, k] @ W2) * (u > 0)       (W2 is stored [out, in] = the matrix this product needs)
+            g_du.append(Group(job.B, [Term(g, gs, smap[k], W.w2, k) for k in range(nu)], nu, job.du, nu,
+                              epilogue=EPI_MASK, mask=job.u, mask_slots=nu))
         ops.layer_forward(g_du)
         for i in range(0, len(jobs), ops.MAX_GROUPS):
             chunk = jobs[i:i + ops.MAX_GROUPS]
-            cdq = dqs[i:i + ops.MAX_GROUPS]
-            ops.layer_wgrad([job.mlp2 for job in chunk], [(dq, 1, [0]) for dq in cdq], [(W.w2t, G.dw2t, 1)])
+            ops.layer_wgrad([job.mlp2 for job in chunk], g2[i:i + ops.MAX_GROUPS], [(W.w2t, G.dw2t, 1)])
             dests = [(W.w1t[b * D:(b + 1) * D], G.dw1t[b * D:(b + 1) * D], 1) for b in range(W.blocks)]
             ops.layer_wgrad([job.mlp1 for job in chunk],
                             [(job.du, job.u.shape[1], list(range(job.u.shape[1]))) for job in chunk], dests)
         g_last = []
-        for job, dq in zip(jobs, dqs):
+        for job, (g, gs, smap) in zip(jobs, g2):
             nu, n, t = job.u.shape[1], job.t.num_nodes, job.t
-            G.colsum(dq, job.B, D, G.db2, float(nu))
+            if gs == 1:
+                G.colsum(g, job.B, D, G.db2, float(nu))
+            else:
+                G.colsum(g, job.B * nu, D, G.db2)
             G.colsum(job.du, job.B * nu, D, G.db1)
-            gz = torch.empty(job.B, n, D, dtype=torch.float32, device=dq.device)
+            gz = torch.empty(job.B, n, D, dtype=torch.float32, device=g.device)
             if ro == 'targetmlp':
                 others = [j for j in range(n) if j != t.target_slot]
                 terms = [Term(job.du, nu, k, W.w1b[0], t.target_slot) for k in range(nu)]
@@ -808,8 +828,6 @@ class RGCNEncoderDecoder(nn.Module):
             self.readout = self.target_message_readout
         else:
             raise ValueError(f'Unknown readout function {readout}')
-        if readout in MLP_READOUTS and scatter_op != 'add':
-            raise NotImplementedError('MLP readouts are fused with scatter_op="add" only (the reference default)')
 
         self.dropout = nn.Dropout(dropout)  # constructed but never applied, as in the reference (model.py:377)
         self.weight_decay = weight_decay

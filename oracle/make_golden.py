@@ -44,6 +44,11 @@ CASES = [
     ('tm_shared_3interchain', '3-inter_chain', 'mp', 3, True, True, 0.0, False),
     ('mlp_2inter', '2-inter', 'mlp', 2, False, False, 1e-3, False),
     ('targetmlp_3inter', '3-inter', 'targetmlp', 2, False, False, 1e-3, False),
+    # scatter_op variants of the MLP readouts (model.py:350-355, 507-513): 9th field
+    ('concat_max_3inter', '3-inter', 'concat', 2, False, False, 1e-3, True, 'max'),
+    ('mlp_mean_3chain', '3-chain', 'mlp', 2, False, False, 1e-3, True, 'mean'),
+    ('targetmlp_max_3interchain', '3-inter_chain', 'targetmlp', 2, False, False, 1e-3, False, 'max'),
+    ('concat_mean_2inter', '2-inter', 'concat', 2, False, False, 1e-3, False, 'mean'),
 ]
 D = 128
 B = 6
@@ -63,13 +68,15 @@ def load_params_into(model, params, cfg):
 
 
 def run_case(case, kg, qsets):
-    name, qt, ro, nl, adaptive, shared, wd, store_grads = case
+    name, qt, ro, nl, adaptive, shared, wd, store_grads = case[:8]
+    scatter_op = case[8] if len(case) > 8 else 'add'
     ref = ref_loader.load()
-    cfg = O.Config(readout=ro, num_layers=nl, adaptive=adaptive, shared_layers=shared, weight_decay=wd)
+    cfg = O.Config(readout=ro, num_layers=nl, adaptive=adaptive, shared_layers=shared, weight_decay=wd,
+                   scatter_op=scatter_op)
     rels, raw_queries = qsets[qt][0]
     raw_queries = raw_queries[:B]
     model, graph, id2row = ref_loader.build_reference_model(
-        kg.raw(), D, ro, nl, adaptive, shared_layers=shared, weight_decay=wd)
+        kg.raw(), D, ro, nl, adaptive, shared_layers=shared, weight_decay=wd, scatter_op=scatter_op)
     params = O.init_params(kg.raw()[0], kg.raw()[2], cfg, d=D, seed=11)
     load_params_into(model, params, cfg)
     queries = ref_loader.deserialize_queries(raw_queries)
@@ -78,7 +85,7 @@ def run_case(case, kg, qsets):
     anchor_ids, var_ids, qg = ref['data_utils'].RGCNQueryDataset.get_query_graph(
         formula, queries, model.rel_ids, model.mode_ids)
     out = dict(query_type=qt, rels_json=json.dumps(rels), readout=ro, num_layers=nl, adaptive=adaptive,
-               shared_layers=shared, weight_decay=wd, kg_seed=KG_SEED, param_seed=11, d=D,
+               shared_layers=shared, weight_decay=wd, scatter_op=scatter_op, kg_seed=KG_SEED, param_seed=11, d=D,
                anchor_ids=anchor_ids.numpy(), var_ids=var_ids.numpy(), edge_index=qg.edge_index.numpy(),
                edge_type=qg.edge_type.numpy(), batch=qg.batch.numpy(),
                targets=np.array([q.target_node for q in queries], dtype=np.int64))
@@ -129,7 +136,10 @@ def main():
     kg = synthetic.make_kg('tiny', seed=KG_SEED)
     qsets = synthetic.make_query_sets(kg, queries_per_formula=B, formulas_per_type=1, seed=KG_SEED,
                                       num_neg=5, num_hard_neg=2)
+    only = set(sys.argv[1].split(',')) if len(sys.argv) > 1 else None    # regenerate just these cases
     for case in CASES:
+        if only is not None and case[0] not in only:
+            continue
         name, out = run_case(case, kg, qsets)
         path = os.path.join(GOLDEN_DIR, name + '.npz')
         np.savez_compressed(path, **out)

@@ -29,7 +29,8 @@ class GoldenCase(object):
         self.rels = _tuplify(json.loads(str(z['rels_json'])))
         self.cfg = O.Config(readout=str(z['readout']), num_layers=int(z['num_layers']),
                             adaptive=bool(z['adaptive']), shared_layers=bool(z['shared_layers']),
-                            weight_decay=float(z['weight_decay']))
+                            weight_decay=float(z['weight_decay']),
+                            scatter_op=str(z['scatter_op']) if 'scatter_op' in z.files else 'add')
         self.d = int(z['d'])
         self.kg = synthetic.make_kg('tiny', seed=int(z['kg_seed']))
         rels, _, node_maps = self.kg.raw()

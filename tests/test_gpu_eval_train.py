@@ -149,3 +149,12 @@ def test_train_step_graph_replay_equals_eager():
         k = int(want[2][2])
         assert int(res.sparse[2]) == k and torch.equal(res.sparse[0][:k], want[2][0][:k])
         assert torch.equal(res.sparse[1][:k], want[2][1][:k])
+    # a loader writing the next batch in place into the step's single pinned buffer: one H2D copy, same result
+    staging = ts.staging()
+    for st, hb in zip(staging, h2):
+        st.anchor_ids.copy_(hb.anchor_ids)
+        st.targets.copy_(hb.targets)
+        st.negatives.copy_(hb.negatives)
+    res, losses_host = ts.run_host(staging)
+    torch.cuda.synchronize()
+    assert torch.equal(losses_host, e2[0].cpu()) and torch.equal(res.dense.flat, e2[1])
