@@ -23,8 +23,9 @@ struct ColsumLaunch {
   int n;
   float* partials;  // [total blocks][D]
   float* totals;    // [n][D]
-  int* counter;     // finished second-stage CTAs (zeroed by the first stage)
+  int* counter;     // [n] finished second-stage CTAs per destination (zeroed by the first stage)
   uint8_t leader[MPQE_MAX_COLSUM_ITEMS];   // first item with the same destination
+  uint8_t group[MPQE_MAX_COLSUM_ITEMS];    // for a leader: number of items of its destination
   mpqe_colsum_item_t it[MPQE_MAX_COLSUM_ITEMS];
 };
 
@@ -171,7 +172,7 @@ __device__ __forceinline__ int64_t cs_blocks(int64_t rows) { return (rows + CS_R
 
 __global__ void __launch_bounds__(256) colsum_partial_multi_kernel(const __grid_constant__ ColsumLaunch L) {
   __shared__ float4 red[8][32];
-  if (blockIdx.x == 0 && threadIdx.x == 0) *L.counter = 0;   // for the second stage's "last CTA" election
+  if (blockIdx.x == 0 && threadIdx.x < L.n) L.counter[threadIdx.x] = 0;   // second stage's "last CTA" elections
   int64_t blk = blockIdx.x;
   int item = 0;
   for (; item < L.n - 1; ++item) {
@@ -204,9 +205,10 @@ __global__ void __launch_bounds__(256) colsum_partial_multi_kernel(const __grid_
   }
 }
 
-// Second stage: one CTA per item sums the item's block partials (in block order) into totals[item]; the CTA that
-// finishes last then folds the totals into the destinations, items in order: dst = ((dst + t_i) + t_k) + ...
-// (leader[i] = first item with the same destination, computed on the host) -- bit-reproducible, one launch.
+// Second stage: one CTA per item sums the item's block partials (in block order) into totals[item]; per destination,
+// the CTA that finishes last folds the totals of that destination's items, in item order:
+// dst = ((dst + t_i) + t_k) + ...  (leader[i] = first item with the same destination, group[i] = number of items of
+// leader i's destination; both computed on the host) -- bit-reproducible, one launch, destinations fold in parallel.
 __global__ void __launch_bounds__(128) colsum_finish_multi_kernel(const __grid_constant__ ColsumLaunch L) {
   __shared__ int s_last;
   const int item = blockIdx.x, tid = threadIdx.x;
@@ -224,21 +226,26 @@ __global__ void __launch_bounds__(128) colsum_finish_multi_kernel(const __grid_c
     for (int k = 0; k < 8; ++k) s += v[k];
   }
   for (; b < nb; ++b) s += p[b * D];
+  const int lead = L.leader[item], group = L.group[lead];
+  float* dst = L.it[item].dst;
+  if (group == 1) {               // the only item of its destination: no hand-over needed
+    dst[tid] += s * L.it[item].scale;
+    return;
+  }
   L.totals[(int64_t)item * D + tid] = s * L.it[item].scale;
   __threadfence();
   __syncthreads();
-  if (tid == 0) s_last = atomicAdd(L.counter, 1) == L.n - 1;
+  if (tid == 0) s_last = atomicAdd(L.counter + lead, 1) == group - 1;
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  for (int i = 0; i < L.n; ++i) {
-    if (L.leader[i] != i) continue;
-    float* dst = L.it[i].dst;
-    float acc = dst[tid];
-    for (int k = i; k < L.n; ++k)
-      if (L.leader[k] == i) acc += __ldcg(L.totals + (int64_t)k * D + tid);
-    dst[tid] = acc;
-  }
+  float t[MPQE_MAX_COLSUM_ITEMS];
+  int m = 0;
+  for (int k = lead; k < L.n; ++k)
+    if (L.leader[k] == lead) t[m++] = __ldcg(L.totals + (int64_t)k * D + tid);   // independent loads first
+  float acc = dst[tid];
+  for (int k = 0; k < m; ++k) acc += t[k];
+  dst[tid] = acc;
 }
 
 }  // namespace
@@ -343,6 +350,8 @@ extern "C" int mpqe_colsum_multi(const mpqe_colsum_item_t* items_host, int32_t n
       }
     L.leader[i] = (uint8_t)lead;
   }
+  for (int i = 0; i < n; ++i) L.group[i] = 0;
+  for (int i = 0; i < n; ++i) ++L.group[L.leader[i]];
   colsum_partial_multi_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(L);
   MPQE_CHECK_LAUNCH("colsum_partial_multi_kernel");
   colsum_finish_multi_kernel<<<n, 128, 0, (cudaStream_t)stream>>>(L);
