@@ -491,7 +491,7 @@ class Engine(object):
                 job.q.mul_(1.0 / nu)
 
     # ---- backward -----------------------------------------------------------------------------------------
-    def backward(self, jobs, W, dqs, G):
+    def backward(self, jobs, W, dqs, G, defer_constant=False):
         """dqs[i] = d loss / d job.q.  Accumulates dense gradients into `G` (a Grads) and row gradients into G.rows."""
         readout = self.m.readout_str
         # gradient wrt the last pass output, as (tensor, slots, slot_map over outs[P-1])
@@ -608,7 +608,10 @@ class Engine(object):
                 else:
                     self.input_backward(job, dx, ins, G)
         G.flush()
-        self.constant_backward(jobs, W, G)
+        if defer_constant:      # the caller runs it (e.g. on another stream, under independent work)
+            G.finish = lambda: self.constant_backward(jobs, W, G)
+        else:
+            self.constant_backward(jobs, W, G)
 
     def constant_backward(self, jobs, W, G):
         """Gradients of the batch-constant pass-0 terms from the per-slot column sums cs[s] = sum_q dZ0[q, s]:
@@ -1017,10 +1020,12 @@ def plan_rows(model, jobs, targets, negatives, table_offsets):
     return R
 
 
-def loss_backward(model, jobs, W, targets, negatives, margin, grad_losses, table_offsets=None, rows=None):
+def loss_backward(model, jobs, W, targets, negatives, margin, grad_losses, table_offsets=None, rows=None,
+                  defer_constant=False):
     """Backward of `loss_forward` for d(total)/d(loss_i) = grad_losses[i] (device tensor [len(jobs)]).
     Returns the filled `Grads` (dense bucket + (row id, gradient row) pairs, not yet combined).  `rows`: a RowGrads
-    from `plan_rows` (slots reserved and ids already emitted)."""
+    from `plan_rows` (slots reserved and ids already emitted).  `defer_constant`: leave the batch-constant tail of the
+    backward to the caller as `G.finish()` (the dense gradients are complete only after it)."""
     device = jobs[0].anchor_ids.device
     cap = model._row_capacities(jobs, [(job.target_mode, 2 * job.B) for job in jobs]) if rows is None else None
     G = Grads(model, W, cap, device, table_offsets, rows)
@@ -1037,7 +1042,7 @@ def loss_backward(model, jobs, W, targets, negatives, margin, grad_losses, table
         dqs.append(dq)
     if items:
         ops.cosine_margin_multi(items, margin, backward=True)
-    model._engine.backward(jobs, W, dqs, G)
+    model._engine.backward(jobs, W, dqs, G, defer_constant=defer_constant)
     return G
 
 

@@ -39,8 +39,15 @@ class HostBatch(object):
 
 
 class StepResult(object):
-    def __init__(self, losses, total, dense, sparse):
-        self.losses, self.total, self.dense, self.sparse = losses, total, dense, sparse
+    """losses [batches] (device), dense = Grads (flat bucket + views), sparse = (unique ids, rows, count);
+    `total` = weighted sum of the losses, computed on demand (two small launches kept out of the step)."""
+
+    def __init__(self, losses, weights, dense, sparse):
+        self.losses, self.weights, self.dense, self.sparse = losses, weights, dense, sparse
+
+    @property
+    def total(self):
+        return (self.losses * self.weights).sum()
 
 
 class TrainStep(object):
@@ -104,7 +111,7 @@ class TrainStep(object):
         with ops.device_guard(dev):
             res = self._local_step(batches)
             if self.world > 1:
-                res = StepResult(res.losses, res.total, res.dense, self.sync(res.dense, res.sparse))
+                res = StepResult(res.losses, res.weights, res.dense, self.sync(res.dense, res.sparse))
         return res
 
     def _plan_on_side_stream(self, ids, dev):
@@ -185,14 +192,23 @@ class TrainStep(object):
             wts = self._wts = (key, torch.tensor(key, dtype=torch.float32, device=dev))
         # d total / d loss_i = the batch weights, known now: the margin backward rides on the margin forward
         losses, W = loss_forward(m, jobs, tg, ng, self.margin, True, grad_losses=wts[1], W=W)
-        G = loss_backward(m, jobs, W, tg, ng, self.margin, wts[1], self.table_offsets, rows=R)
+        overlap_tail = plan is not None and dev.type == 'cuda'
+        G = loss_backward(m, jobs, W, tg, ng, self.margin, wts[1], self.table_offsets, rows=R,
+                          defer_constant=overlap_tail)
         if plan is not None:
             self._join_side(dev)
+            if overlap_tail:
+                # the batch-constant tail of the backward (five small latency-bound launches) runs on the second
+                # stream under the row summation, which does not depend on it
+                self._side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(self._side):
+                    G.finish()
             sparse = plan.apply(rows[:used], pad_id=self.total_rows)
+            if overlap_tail:
+                self._join_side(dev)
         else:
             sparse = (ids[:used], rows[:used], None)
-        total = (losses * wts[1]).sum()
-        return StepResult(losses, total, G, sparse)
+        return StepResult(losses, wts[1], G, sparse)
 
     # ---- CUDA-graph mode: the whole local step becomes one graph launch --------------------------------------
     @torch.no_grad()
@@ -249,7 +265,7 @@ class TrainStep(object):
         res = self._graph_res
         if self.world > 1:
             with ops.device_guard(res.dense.flat.device):
-                res = StepResult(res.losses, res.total, res.dense, self.sync(res.dense, res.sparse))
+                res = StepResult(res.losses, res.weights, res.dense, self.sync(res.dense, res.sparse))
         return res
 
     def staging(self):
