@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(1024) margin_mean_multi_kernel(const __grid_co
   if (threadIdx.x == 0) T.loss[0] = s[0] / (float)T.B;
 }
 
-__global__ void __launch_bounds__(ROW_THREADS) margin_bwd_multi_kernel(const __grid_constant__ MarginLaunch L) {
+__global__ void __launch_bounds__(ROW_THREADS, 5) margin_bwd_multi_kernel(const __grid_constant__ MarginLaunch L) {
   const int lane = threadIdx.x & 31;
   int item;
   int64_t b;

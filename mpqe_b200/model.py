@@ -263,15 +263,15 @@ class Engine(object):
             return 0
         return p if p < P - 1 else self.m.num_layers - 1
 
-    def pass_terms(self, job, p, W, outs):
+    def pass_terms(self, job, p, W, outs, const_only=False):
         """Forward terms of pass p restricted to the output slots `outs` (term.out_slot = index into outs), split into
         (per-query terms, batch-constant terms, layer index).  In pass 0 every term whose source is a variable slot
         multiplies the same variable-type embedding row for all queries: it is evaluated once per group (a 1-row
         launch) and enters the big launch as a per-slot bias; its weight gradient is a rank-1 update and its input
-        gradient a column sum (see `backward`)."""
+        gradient a column sum (see `backward`).  `const_only`: just the batch-constant terms (no activations needed)."""
         t, n, a = job.t, job.t.num_nodes, job.t.num_anchors
         li = self.layer_index(p, job.P)
-        x = job.acts[p]
+        x = job.acts[p] if not const_only else None
         if p > 0 and p == job.P - 1 and job.collapsed is not None:
             # fused readout: one term per source slot with the summed matrix (see collapse_last_pass)
             return [Term(x, n, c[0], self._cmat(W, c, 'm'), 0, self._cmat(W, c, 'mp')) for c in job.collapsed], [], li
@@ -283,7 +283,7 @@ class Engine(object):
         def add(src, m, mp, out):
             if p == 0 and src >= a:
                 const.append(Term(W.mode_emb, 0, job.var_rows_host[src - a], m, out))
-            else:
+            elif not const_only:
                 main.append(Term(x, n, src, m, out, mp))
 
         for e in range(t.num_edges):
@@ -394,6 +394,26 @@ class Engine(object):
             job.outs = _needed_slots(job, readout)
             job.fwd_groups = [None] * job.P
         self.collapse_last_pass(jobs, W)
+        # batch-constant part of pass 0 (+ bias), evaluated on one row per group: job.const_fwd.out enters the big
+        # launch as a per-slot bias
+        const_groups = []
+        for job in jobs:
+            job.const_fwd = None
+            outs = job.outs[0]
+            _, const, li = self.pass_terms(job, 0, W, outs, const_only=True)
+            if not const:
+                continue
+            fused = job.P == 1 and readout in ('sum', 'mp')
+            nb = 1 if fused else len(outs)
+            if fused:
+                for term in const:
+                    term.out_slot = 0
+            cb = torch.empty(1, nb, D, dtype=torch.float32, device=job.anchor_ids.device)
+            job.const_fwd = Group(1, const, nb, cb, nb, bias=W.bias[li],
+                                  bias_scale=[float(len(outs))] if fused else [1.0] * nb)
+            const_groups.append(job.const_fwd)
+        if const_groups:
+            ops.layer_forward(const_groups, use_tensor_cores=False)   # 1-row groups: the one-row kernel
         W.prepared = jobs
 
     def encode(self, jobs, W):
@@ -406,28 +426,23 @@ class Engine(object):
             torch.cuda.current_stream().wait_event(W.ready_event)
         max_p = max(job.P for job in jobs)
         for p in range(max_p):
-            groups, const_groups = [], []
+            groups = []
             for job in jobs:
                 if p >= job.P:
                     continue
                 B, n = job.B, job.t.num_nodes
                 outs = job.outs[p]
-                terms, const, li = self.pass_terms(job, p, W, outs)
+                terms, _, li = self.pass_terms(job, p, W, outs)
                 dev = job.anchor_ids.device
                 fused = p == job.P - 1 and readout in ('sum', 'mp')
                 nb = 1 if fused else len(outs)
                 if fused:      # readout folded into the last pass: every term accumulates into the single output row
-                    for term in terms + const:
+                    for term in terms:
                         term.out_slot = 0
                 bias, bias_scale, stride = W.bias[li], ([float(len(outs))] if fused else [1.0] * nb), 0
                 job.fused_bias_count = float(len(outs)) if fused else 1.0
-                if p == 0:
-                    job.const_fwd = None
-                if const:      # batch-constant part (+ bias), evaluated on one row and added as a per-slot bias
-                    cb = torch.empty(1, nb, D, dtype=torch.float32, device=dev)
-                    job.const_fwd = Group(1, const, nb, cb, nb, bias=bias, bias_scale=bias_scale)
-                    const_groups.append(job.const_fwd)
-                    bias, bias_scale, stride = cb, [1.0] * nb, D
+                if p == 0 and job.const_fwd is not None:   # constant part + bias, computed by `prepare`
+                    bias, bias_scale, stride = job.const_fwd.out, [1.0] * nb, D
                 if p < job.P - 1:
                     h = torch.empty(B, n, D, dtype=torch.float32, device=dev)
                     g = Group(B, terms, nb, h, n, out_slot_map=outs, epilogue=EPI_RELU, bias=bias, bias_scale=bias_scale,
@@ -442,8 +457,6 @@ class Engine(object):
                               bias_slot_stride=stride)
                 job.fwd_groups[p] = g
                 groups.append(g)
-            if const_groups:
-                ops.layer_forward(const_groups, use_tensor_cores=False)   # 1-row groups: the FFMA kernel
             ops.layer_forward(groups)
         if readout == 'max':
             for job in jobs:
