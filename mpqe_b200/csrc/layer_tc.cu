@@ -378,6 +378,10 @@ struct Schedule {
   int count;                                 // 0: round-robin (unit = blockIdx + k * gridDim)
   uint16_t start[SCHED_MAX_CTAS + 1];
   uint16_t unit[SCHED_MAX_UNITS];
+  // layer kernel only: the decoded unit at the same position (so that a role needs two parameter loads per unit
+  // instead of a dependent chain of ~25): query tile, and group << 24 | out slot << 16 | term bit mask
+  uint16_t tile[SCHED_MAX_UNITS];
+  uint32_t gsm[SCHED_MAX_UNITS];
 };
 __device__ __forceinline__ int sched_unit(const Schedule& S, int k, int total_units) {
   if (S.count == 0) {
@@ -418,6 +422,26 @@ __device__ __forceinline__ uint32_t term_mask(const mpqe_layer_group_t& G, int s
   return m;
 }
 
+// k-th unit of this CTA: decoded from the schedule, or (round-robin mode) from the unit number
+__device__ __forceinline__ bool sched_next(const LayerLaunch& L, const Schedule& S, int k, int total_units, UnitInfo& U,
+                                           uint32_t& mask) {
+  if (S.count == 0) {
+    const int u = blockIdx.x + k * gridDim.x;
+    if (u >= total_units) return false;
+    U = decode_unit(L, u);
+    mask = term_mask(L.g[U.gi], U.slot);
+    return true;
+  }
+  const int i = S.start[blockIdx.x] + k;
+  if (i >= S.start[blockIdx.x + 1]) return false;
+  const uint32_t g = S.gsm[i];
+  U.gi = (int)(g >> 24);
+  U.slot = (int)((g >> 16) & 0xffu);
+  U.q0 = (int64_t)S.tile[i] * BM;
+  mask = g & 0xffffu;
+  return true;
+}
+
 __global__ void __launch_bounds__(THREADS, 1) layer_tc_kernel(const __grid_constant__ LayerLaunch L,
                                                               const __grid_constant__ Schedule S, int total_units,
                                                               int dbg) {
@@ -454,21 +478,20 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc_kernel(const __grid_const
     const float* rowp[4] = {nullptr, nullptr, nullptr, nullptr};   // this thread's four source rows, k = 0
     const float* packed_base = nullptr;
     const float* plain_base = nullptr;
-    // loads the next (term, k chunk) stage into (fa, fb); false when all of this CTA's work has been issued
-    auto load_next = [&](Frag& fa, Frag& fb, const float*& packed) -> bool {
+    // advance(): bookkeeping of the next (term, k chunk) stage -- no loads; false when all of this CTA's work has
+    // been issued.  It runs BEFORE the warp waits for the stage it is about to store, so that its descriptor
+    // look-ups overlap the latency of the loads already in flight; issue() then fires the stage's loads.
+    auto advance = [&](const float*& packed) -> bool {
       if (!alive) return false;
       kc += KC;
       if (kc >= D) {          // next term
         kc = 0;
         mask &= mask - 1;
         while (mask == 0) {   // next unit (a unit without terms contributes no stages)
-          const int unit = sched_unit(S, uk++, total_units);
-          if (unit < 0) {
+          if (!sched_next(L, S, uk++, total_units, U, mask)) {
             alive = false;
             return false;
           }
-          U = decode_unit(L, unit);
-          mask = term_mask(L.g[U.gi], U.slot);
         }
         const mpqe_layer_group_t& G = L.g[U.gi];
         const mpqe_term_t& T = G.terms[__ffs(mask) - 1];
@@ -485,12 +508,14 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc_kernel(const __grid_const
         plain_base = T.m;
       }
       packed = packed_base != nullptr ? packed_base + (kc / KC) * (2 * TILE_BYTES / 4) : nullptr;
+      return true;
+    };
+    auto issue = [&](Frag& fa, Frag& fb, const float* packed) {
       if (!((dbg & 2) && it > 1)) {   // (dbg bit 1: timing experiment without global loads after the first stages)
 #pragma unroll
         for (int i = 0; i < 4; ++i) fa.v[i] = *reinterpret_cast<const float4*>(rowp[i] + kc);
         if (packed == nullptr) load_columns(fb, plain_base + (int64_t)kc * D, D, KC, pw, lane);
       }
-      return true;
     };
     STAT_DECL;
     auto put = [&](const Frag& fa, const Frag& fb, const float* packed) {
@@ -514,23 +539,33 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc_kernel(const __grid_const
       STAT_END(1);   // waiting for the loaded data + split + stores
     };
     Frag a0, b0, a1, b1;
-    const float *p0 = nullptr, *p1 = nullptr;
-    bool h0 = load_next(a0, b0, p0);
-    bool h1 = h0 && load_next(a1, b1, p1);
+    const float *p0 = nullptr, *p1 = nullptr, *pn = nullptr;
+    bool h0 = advance(p0);
+    if (h0) issue(a0, b0, p0);
+    bool h1 = h0 && advance(p1);
+    if (h1) issue(a1, b1, p1);
     while (h0) {
-      put(a0, b0, p0);
       STAT_BEGIN();
-      const bool n0 = h1 && load_next(a0, b0, p0);
-      STAT_END(2);   // issuing loads
+      const bool n0 = h1 && advance(pn);
+      STAT_END(2);   // bookkeeping of the next stage
+      put(a0, b0, p0);
+      if (n0) {
+        p0 = pn;
+        issue(a0, b0, p0);
+      }
       STAT_BEGIN();
       publish_stage(sh, it);
       STAT_END(3);   // fence + arrive
       ++it;
       if (!h1) break;
-      put(a1, b1, p1);
       STAT_BEGIN();
-      const bool n1 = n0 && load_next(a1, b1, p1);
+      const bool n1 = n0 && advance(pn);
       STAT_END(2);
+      put(a1, b1, p1);
+      if (n1) {
+        p1 = pn;
+        issue(a1, b1, p1);
+      }
       STAT_BEGIN();
       publish_stage(sh, it);
       STAT_END(3);
@@ -545,9 +580,9 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc_kernel(const __grid_const
       uint32_t it = 0;
       int uc = 0;
       long long mstat[3] = {0, 0, 0};
-      for (int unit; (unit = sched_unit(S, uc, total_units)) >= 0; ++uc) {
-        const UnitInfo U = decode_unit(L, unit);
-        const int nsteps = __popc(term_mask(L.g[U.gi], U.slot)) * (D / KC);
+      UnitInfo U{0, 0, 0};
+      for (uint32_t umask; sched_next(L, S, uc, total_units, U, umask); ++uc) {
+        const int nsteps = __popc(umask) * (D / KC);
         mma_unit(sh, smem_u32(smem), tmem, uc, nsteps, it, (dbg & 4) != 0, mstat);
       }
 #ifdef MPQE_TC_STATS
@@ -564,10 +599,10 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc_kernel(const __grid_const
     long long estat[4] = {0, 0, 0, 0}, et0 = 0;
     (void)estat;
     (void)et0;
-    for (int unit; (unit = sched_unit(S, uc, total_units)) >= 0; ++uc) {
-      const UnitInfo U = decode_unit(L, unit);
+    UnitInfo U{0, 0, 0};
+    for (uint32_t umask; sched_next(L, S, uc, total_units, U, umask); ++uc) {
       const mpqe_layer_group_t& G = L.g[U.gi];
-      const int nsteps = __popc(term_mask(G, U.slot)) * (D / KC);
+      const int nsteps = __popc(umask) * (D / KC);
       const int ab = uc & 1;
       if (tid == 0) trace(30, uc);
       // Everything the store loop needs is pulled out of the launch descriptor into registers here, once per unit
@@ -1122,16 +1157,29 @@ int layer_forward_tc(const mpqe_layer_group_t* groups, int num_groups, cudaStrea
   S.count = 0;
   if (units > grid && units <= SCHED_MAX_UNITS && grid <= SCHED_MAX_CTAS) {
     static thread_local int cost[SCHED_MAX_UNITS];
+    static thread_local uint16_t tile_of[SCHED_MAX_UNITS];
+    static thread_local uint32_t gsm_of[SCHED_MAX_UNITS];
     int u = 0;
     for (int i = 0; i < num_groups; ++i) {
       const int tiles = (int)((groups[i].num_queries + BM - 1) / BM);
       for (int slot = 0; slot < groups[i].num_out_slots; ++slot) {
         int nt = 0;
-        for (int t = 0; t < groups[i].num_terms; ++t) nt += groups[i].terms[t].out_slot == slot;
-        for (int k = 0; k < tiles; ++k) cost[u++] = nt;     // slot-major numbering, as decode_unit
+        uint32_t mask = 0;
+        for (int t = 0; t < groups[i].num_terms; ++t)
+          if (groups[i].terms[t].out_slot == slot) ++nt, mask |= 1u << t;
+        for (int k = 0; k < tiles; ++k) {     // slot-major numbering, as decode_unit
+          cost[u] = nt;
+          tile_of[u] = (uint16_t)k;
+          gsm_of[u] = ((uint32_t)i << 24) | ((uint32_t)slot << 16) | mask;
+          ++u;
+        }
       }
     }
     build_lpt(S, cost, (int)units, grid);
+    for (int pos = 0; pos < (int)units; ++pos) {
+      S.tile[pos] = tile_of[S.unit[pos]];
+      S.gsm[pos] = gsm_of[S.unit[pos]];
+    }
   }
   static int dbg = -1;  // MPQE_TC_DEBUG: timing experiments only (bit0 no smem stores, bit1 no global loads,
   if (dbg < 0) {        //                 bit2 no MMAs, bit3 no epilogue stores); results are wrong when non-zero

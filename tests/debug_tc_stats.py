@@ -22,6 +22,8 @@ for gi, (n, edges) in enumerate(T):
     x = torch.randn(B, n, 128, device=dev)
     out = torch.empty(B, n, 128, device=dev)
     terms = [ops.Term(x, n, s, w[3 * gi + e], d, wp[3 * gi + e]) for e, (s, d) in enumerate(edges)] + [ops.Term(x, n, i, w[39], i, wp[39]) for i in range(n)]
+    if os.environ.get('STATS_SINGLE'):   # one term per output slot (the shape of the first forward pass / last input-gradient pass)
+        terms = [ops.Term(x, n, i, w[39], i, wp[39]) for i in range(n)]
     groups.append(ops.Group(B, terms, n, out, n, epilogue=ops.EPI_RELU, bias=bias))
 for _ in range(3):
     ops.layer_forward(groups, use_tensor_cores=True)
