@@ -387,3 +387,71 @@ def test_layer_forward_packed_weights(B):
         outs.append(od.cpu())
         assert_close(outs[-1].numpy(), out.numpy(), 1e-5, 2e-5, 'packed=%s' % packed)
     assert torch.equal(outs[0], outs[1]), 'packed and unpacked staging must give identical bits'
+
+
+def test_matrix_sum_multi():
+    """dst (+)= sum of [D, D] matrices in item order; long summand lists continue with accumulating launches."""
+    mats = rnd(40, D, D, seed=5)
+    md = mats.to(DEV)
+    dst = rnd(3, D, D, seed=6)
+    dd = dst.to(DEV)
+    items_cpu = [(dst[0], [mats[i] for i in (0, 3, 3, 7)], False), (dst[1], [mats[i] for i in range(40)], True),
+                 (dst[2], [mats[9]], True)]
+    items_gpu = [(dd[0], [md[i] for i in (0, 3, 3, 7)], False), (dd[1], [md[i] for i in range(40)], True),
+                 (dd[2], [md[9]], True)]
+    E.matrix_sum_multi(items_cpu)
+    ops.matrix_sum_multi(items_gpu)
+    assert_close(dd.cpu().numpy(), dst.numpy(), 1e-6, 1e-5, 'matrix sums')
+    with pytest.raises(Exception):
+        ops.matrix_sum_multi([(dd[0], [md[0]], False), (dd[0], [md[1]], False)])   # shared destination in one call
+
+
+def test_cosine_margin_multi_fused_equals_forward_then_backward():
+    """Mode 'both' (margin backward inside the forward pass) gives the same bits as the two separate launches."""
+    B, N = 333, 500
+    table = rnd(N, D, seed=1, scale=1.0 / D).to(DEV)
+    gl = torch.tensor([0.3, 1.7], device=DEV)
+    res = []
+    for mode in ('split', 'both'):
+        items, outs = [], []
+        for j in range(2):
+            q = rnd(B, D, seed=10 + j).to(DEV)
+            ip = torch.randint(0, N, (B,), generator=torch.Generator().manual_seed(20 + j)).to(DEV)
+            ineg = torch.randint(0, N, (B,), generator=torch.Generator().manual_seed(30 + j)).to(DEV)
+            hinge, loss = torch.empty(B, device=DEV), torch.empty(1, device=DEV)
+            dq = torch.empty(B, D, device=DEV)
+            rows, rid = torch.empty(2 * B, D, device=DEV), torch.empty(2 * B, dtype=torch.int64, device=DEV)
+            items.append(ops.MarginItem(q, table, None, ip, ineg, hinge=hinge, loss=loss, grad_loss=gl[j:j + 1], dq=dq,
+                                        rows_out=rows, rows_id=rid, id_offset=7 * j))
+            outs.append((loss, dq, rows, rid))
+        if mode == 'split':
+            ops.cosine_margin_multi(items, 1.0)
+            ops.cosine_margin_multi(items, 1.0, backward=True)
+        else:
+            ops.cosine_margin_multi(items, 1.0, backward='both')
+        res.append([[t.clone() for t in o] for o in outs])
+    for a, b in zip(res[0], res[1]):
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
+
+
+def test_colsum_multi_shared_destinations():
+    """Items sharing a destination are folded in item order (bit-reproducible); single-item destinations too."""
+    srcs = [rnd(r, D, seed=40 + i) for i, r in enumerate((1, 130, 4096, 7, 1000, 257))]
+    dst = rnd(3, D, seed=50)
+    dd = dst.to(DEV)
+    want = dst.clone()
+    plan = [(0, 0, 1.0), (1, 1, 2.0), (2, 0, 1.0), (3, 2, 0.5), (4, 0, 1.0), (5, 1, 1.0)]
+    items = []
+    for i, d, scale in plan:
+        want[d] += scale * srcs[i].sum(0)
+        sd = srcs[i].to(DEV)
+        items.append(ops.ColsumItem(sd, sd.shape[0], D, dd[d], scale))
+    outs = []
+    for _ in range(2):
+        cur = dst.to(DEV)
+        its = [ops.ColsumItem(it.src, it.rows, it.stride, cur[plan[k][1]], it.scale) for k, it in enumerate(items)]
+        ops.colsum_multi(its, torch.device(DEV))
+        outs.append(cur.cpu())
+    assert_close(outs[0].numpy(), want.numpy(), 1e-5, 1e-4, 'column sums')
+    assert torch.equal(outs[0], outs[1])
