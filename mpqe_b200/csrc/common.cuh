@@ -58,9 +58,10 @@ struct WgradLaunch {
 int layer_forward_simt(const mpqe_layer_group_t* groups, int num_groups, cudaStream_t stream);
 int layer_forward_tc(const mpqe_layer_group_t* groups, int num_groups, cudaStream_t stream);
 int layer_wgrad_tc_launch(const WgradLaunch& launch, int total_chunks, cudaStream_t stream);
+size_t rank_packed_bytes(int64_t rows);   // bytes of the pre-split candidate tile images (tcgen05 rank kernel)
 int rank_counts_table_tc(const float* table, int64_t row_begin, int64_t rows, const float* inv_norm, const float* q,
                          const float* qinv, const float* pos, int64_t B, unsigned long long* left,
-                         unsigned long long* right, cudaStream_t stream);
+                         unsigned long long* right, float* packed, cudaStream_t stream);
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -277,7 +277,6 @@ __device__ __forceinline__ void store_block4(const Frag& f, uint8_t* hi_tile, ui
 constexpr int EPI_PITCH = 36;  // floats per staged row: 16-byte aligned, rows 4 banks apart
 
 struct TcShared {
-  float epi[EPI_WARPS][32][EPI_PITCH];  // per epilogue warp: one 32x32 accumulator block being transposed
   uint64_t full[STAGES];
   uint64_t empty[STAGES];
   uint64_t acc_full[2];
@@ -447,6 +446,7 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc_kernel(const __grid_const
                                                               int dbg) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ TcShared sh;
+  __shared__ __align__(16) float epi_stage[EPI_WARPS][32][EPI_PITCH];   // per epilogue warp: a 32x32 accumulator block being transposed
   uint8_t* smem = align_1024(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 #ifdef MPQE_TC_STATS
@@ -647,7 +647,7 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc_kernel(const __grid_const
       // TMEM gives each thread one accumulator ROW; a 32x32 block per warp is transposed through shared memory so
       // that every global store instruction writes 4 full 128-byte row segments (instead of 32 scattered 16-byte
       // pieces, which kept the load/store pipe busier than the tensor pipe).
-      float* stage = &sh.epi[warp][0][0];
+      float* stage = &epi_stage[warp][0][0];
 #pragma unroll 1
       for (int c0 = 0; c0 < D; c0 += 32) {
         // the fetched block: bias scaled, mask compressed to one bit per element; then the next block's loads go out
@@ -778,6 +778,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
                                                               const __grid_constant__ Schedule S, int total_units) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ TcShared sh;
+  __shared__ __align__(16) float epi_stage[EPI_WARPS][32][EPI_PITCH];
   uint8_t* smem = align_1024(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   setup(sh, warp, tid, PROD_THREADS);
@@ -868,7 +869,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
       mbar_wait(smem_u32(&sh.acc_full[ab]), (uc >> 1) & 1);
       tc_fence_after();
       float* P = L.partials + (int64_t)unit * D * D;   // units are numbered destination-major, chunk-minor
-      float* stage = &sh.epi[warp][0][0];
+      float* stage = &epi_stage[warp][0][0];
       const int cq = (lane & 7) * 4;
 #pragma unroll 1
       for (int c0 = 0; c0 < D; c0 += 32) {
@@ -929,16 +930,20 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const __grid_constant
 // Full-entity rank counts on tensor cores (mpqe_rank_counts_table, use_tensor_cores = 1).
 // D[candidate, query] = table_row . q  for a 128-candidate x 128-query tile, K = 128; both operands are K-major as
 // stored.  A CTA owns one (query tile, slice of the candidate range): the query tile is split into tf32 hi/lo ONCE
-// and stays resident in shared memory (128 KB), candidate tiles stream through 2 x 32 KB stages.  The epilogue scales
+// and stays resident in shared memory (128 KB); the candidate rows are pre-split once per call into tile images
+// (pack_rows_kernel) and stream through 3 x 32 KB stages as bulk copies issued by one thread -- no per-tile
+// conversion work (re-splitting every candidate tile for each of the B/128 query tiles kept the tensor pipe at
+// ~40 %).  The epilogue scales
 // by 1/||row|| and 1/max(||q||,eps), compares with the positive score and counts with warp ballots; only integer
 // atomics touch global memory.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int RANK_STAGES = 2;
+constexpr int RANK_STAGES = 3;
 constexpr int RANK_A_STAGE = 2 * TILE_BYTES;                       // A_hi | A_lo
 constexpr size_t RANK_SMEM = size_t(D / KC) * 2 * TILE_BYTES + size_t(RANK_STAGES) * RANK_A_STAGE + 1024;
 
 struct RankLaunch {
   const float* table;      // rows [row_begin, row_begin + rows)
+  const float* packed;     // [candidate tile][k chunk][hi 16 KB | lo 16 KB] images of those rows
   int64_t row_begin, rows;
   const float* inv_norm;   // [rows]
   const float* q;          // [B, D]
@@ -949,6 +954,27 @@ struct RankLaunch {
   unsigned long long* right;
   int splits;              // candidate-range slices per query tile
 };
+
+// rows [rows][D] (row-major, K contiguous) -> per 128-row tile and 32-k chunk the [hi | lo] K-major tile images.
+// Thread e of a (tile, chunk) block writes the e-th 16-byte unit of the image (coalesced stores); rows past the end
+// are zero (the epilogue masks them).
+__global__ void __launch_bounds__(256) pack_rows_kernel(const float* __restrict__ rows_base, int64_t rows,
+                                                        float* __restrict__ out) {
+  const int kcb = blockIdx.x;
+  const int64_t tile = blockIdx.y;
+  float* hi_tile = out + (tile * (D / KC) + kcb) * (2 * TILE_BYTES / 4);
+  float* lo_tile = hi_tile + TILE_BYTES / 4;
+  for (int e = threadIdx.x; e < 128 * 8; e += 256) {
+    const int r = (e >> 6) * 8 + (e & 7), kq = (e >> 3) & 7;
+    const int64_t row = tile * BM + r;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < rows) x = *reinterpret_cast<const float4*>(rows_base + row * D + kcb * KC + kq * 4);
+    float4 hi, lo;
+    split_tf32(x, hi, lo);
+    *reinterpret_cast<float4*>(hi_tile + e * 4) = hi;   // e == ((r/8)*1024 + kq*128 + (r%8)*16) / 16
+    *reinterpret_cast<float4*>(lo_tile + e * 4) = lo;
+  }
+}
 
 __device__ __forceinline__ void load_rows_kmajor(Frag& f, const float* base, int64_t first_row, int64_t num_rows,
                                                  int kc, int pw, int lane) {
@@ -972,7 +998,7 @@ __global__ void __launch_bounds__(THREADS, 1) rank_tc_kernel(const __grid_consta
   uint8_t* astage = smem + (D / KC) * 2 * TILE_BYTES;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) mbar_init(smem_u32(&bres_full), PROD_THREADS);
-  setup(sh, warp, tid, PROD_THREADS);
+  setup(sh, warp, tid, 1);                                          // a stage is filled by one bulk copy
   const uint32_t tmem = sh.tmem_base;
 
   const int qt = blockIdx.x / R.splits, split = blockIdx.x % R.splits;
@@ -991,34 +1017,17 @@ __global__ void __launch_bounds__(THREADS, 1) rank_tc_kernel(const __grid_consta
     }
     fence_proxy_async();
     mbar_arrive(smem_u32(&bres_full));
-    uint32_t it = 0;
-    Frag f0, f1;
-    const int total = num_units * (D / KC);
-    auto ld = [&](Frag& fr, int step) {
-      load_rows_kmajor(fr, R.table + R.row_begin * D, (t0 + step / (D / KC)) * BM, R.rows, (step % (D / KC)) * KC, pw,
-                       lane);
-    };
-    auto put = [&](const Frag& fr) {
-      const int s = it % RANK_STAGES;
-      const uint32_t use = it / RANK_STAGES;
-      if (use > 0) mbar_wait(smem_u32(&sh.empty[s]), (use - 1) & 1);
-      uint8_t* st = astage + s * RANK_A_STAGE;
-      store_kmajor(fr, st, st + TILE_BYTES, pw, lane);
-    };
-    if (total > 0) ld(f0, 0);
-    if (total > 1) ld(f1, 1);
-    for (int step = 0; step < total; step += 2) {
-      put(f0);
-      if (step + 2 < total) ld(f0, step + 2);
-      fence_proxy_async();
-      mbar_arrive(smem_u32(&sh.full[it % RANK_STAGES]));
-      ++it;
-      if (step + 1 >= total) break;
-      put(f1);
-      if (step + 3 < total) ld(f1, step + 3);
-      fence_proxy_async();
-      mbar_arrive(smem_u32(&sh.full[it % RANK_STAGES]));
-      ++it;
+    if (pw == 0 && lane == 0) {                                     // candidate tiles: one 32 KB bulk copy per stage
+      const int total = num_units * (D / KC);
+      const float* src = R.packed + t0 * (int64_t)(D / KC) * (2 * TILE_BYTES / 4);
+      for (int it = 0; it < total; ++it) {
+        const int s = it % RANK_STAGES;
+        const uint32_t use = it / RANK_STAGES;
+        if (use > 0) mbar_wait(smem_u32(&sh.empty[s]), (use - 1) & 1);
+        const uint32_t bar = smem_u32(&sh.full[s]);
+        mbar_arrive_expect_tx(bar, 2 * TILE_BYTES);
+        bulk_copy_g2s(smem_u32(astage + s * RANK_A_STAGE), src + (int64_t)it * (2 * TILE_BYTES / 4), 2 * TILE_BYTES, bar);
+      }
     }
   } else if (warp == MMA_WARP) {
     if (lane == 0) {
@@ -1228,9 +1237,11 @@ int layer_wgrad_tc_launch(const WgradLaunch& launch, int total_chunks, cudaStrea
   return 0;
 }
 
+size_t rank_packed_bytes(int64_t rows) { return (size_t)((rows + BM - 1) / BM) * (D / KC) * 2 * TILE_BYTES; }
+
 int rank_counts_table_tc(const float* table, int64_t row_begin, int64_t rows, const float* inv_norm, const float* q,
                          const float* qinv, const float* pos, int64_t B, unsigned long long* left,
-                         unsigned long long* right, cudaStream_t stream) {
+                         unsigned long long* right, float* packed, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     MPQE_CUDA(cudaFuncSetAttribute(rank_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RANK_SMEM));
@@ -1238,12 +1249,20 @@ int rank_counts_table_tc(const float* table, int64_t row_begin, int64_t rows, co
   }
   RankLaunch R;
   R.table = table; R.row_begin = row_begin; R.rows = rows; R.inv_norm = inv_norm; R.q = q; R.qinv = qinv; R.pos = pos;
-  R.B = B; R.left = left; R.right = right;
+  R.B = B; R.left = left; R.right = right; R.packed = packed;
   const int64_t qtiles = (B + BM - 1) / BM;
   const int64_t ctiles = (rows + BM - 1) / BM;
-  int64_t splits = (num_sms() + qtiles - 1) / qtiles;
-  if (splits > ctiles) splits = ctiles;
-  if (splits < 1) splits = 1;
+  MPQE_CHECK_ARG(ctiles <= 65535, "mpqe_rank_counts_table: too many candidate rows per call (%lld)", (long long)rows);
+  pack_rows_kernel<<<dim3(D / KC, (unsigned)ctiles), 256, 0, stream>>>(table + row_begin * D, rows, packed);
+  MPQE_CHECK_LAUNCH("pack_rows_kernel");
+  // candidate-range slices per query tile: minimise waves x (tiles per CTA + start-up), one CTA per SM at a time
+  // (rounding the CTA count UP to the SM count, e.g. 160 CTAs on 148 SMs, doubles the run time)
+  int64_t splits = 1, best = -1;
+  for (int64_t sp = 1; sp <= ctiles && sp <= 4 * num_sms(); ++sp) {
+    const int64_t waves = (qtiles * sp + num_sms() - 1) / num_sms();
+    const int64_t cost = waves * ((ctiles + sp - 1) / sp + 6);      // + ~6 tile times to stage the query tile
+    if (best < 0 || cost < best) best = cost, splits = sp;
+  }
   R.splits = (int)splits;
   MPQE_CHECK_ARG(qtiles * splits < (1ll << 31), "mpqe_rank_counts_table: too many tiles");
   rank_tc_kernel<<<(unsigned)(qtiles * splits), THREADS, RANK_SMEM, stream>>>(R);

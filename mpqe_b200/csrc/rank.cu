@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(THREADS, 2) rank_counts_table_kernel(
 }
 
 struct RankWs {
-  float *qt, *qinv, *inv_norm;
+  float *qt, *qinv, *inv_norm, *packed;
   int64_t Bp;
   size_t bytes;
 };
@@ -184,6 +184,8 @@ RankWs carve_rank(void* ws, int64_t B, int64_t rows) {
   w.qt = (float*)(p + off); off += align_up((size_t)D * w.Bp * sizeof(float), 256);
   w.qinv = (float*)(p + off); off += align_up((size_t)w.Bp * sizeof(float), 256);
   w.inv_norm = (float*)(p + off); off += align_up((size_t)(rows > 0 ? rows : 1) * sizeof(float), 256);
+  off = align_up(off, 1024);
+  w.packed = (float*)(p + off); off += rank_packed_bytes(rows);   // tf32 hi/lo tile images of the candidate rows
   w.bytes = off;
   return w;
 }
@@ -220,7 +222,7 @@ extern "C" int mpqe_rank_counts_table(const float* q, int64_t B, const float* po
   MPQE_CHECK_LAUNCH("row_inv_norm_kernel");
   if (use_tensor_cores)
     return rank_counts_table_tc(table, row_begin, rows, w.inv_norm, q, w.qinv, pos, B, (unsigned long long*)left,
-                                (unsigned long long*)right, st);
+                                (unsigned long long*)right, w.packed, st);
   dim3 grid((unsigned)((rows + BM - 1) / BM), (unsigned)(w.Bp / BN));
   MPQE_CHECK_ARG(grid.y <= 65535, "mpqe_rank_counts_table: too many queries (%lld)", (long long)B);
   rank_counts_table_kernel<<<grid, THREADS, RANK_SMEM, st>>>(table, row_begin, rows, w.inv_norm, w.qt, w.Bp, w.qinv,
