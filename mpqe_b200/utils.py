@@ -13,6 +13,28 @@ import torch
 from . import ops
 
 
+def export_embeddings(enc_dec, entity_ids, path=None, batch_size=65536):
+    """The `embeddings.npy` array the reference writes after training for its node-classification script
+    (train.py:147-163): one row `[entity id, unit-norm embedding]` per value of `entity_ids` (dict or iterable, in
+    iteration order); an id found in no mode's `graph.full_sets` keeps a zero row, the last matching mode wins, as in
+    the reference loop.  Rows are gathered and normalised on the device, `batch_size` ids per launch."""
+    ids = list(entity_ids.values()) if hasattr(entity_ids, 'values') else list(entity_ids)
+    dim = enc_dec.emb_dim
+    out = np.zeros((len(ids), 1 + dim))
+    device = enc_dec.mode_embeddings.weight.device
+    for mode, members in enc_dec.graph.full_sets.items():
+        pos = [i for i, e in enumerate(ids) if e in members]
+        for lo in range(0, len(pos), batch_size):
+            sel = pos[lo:lo + batch_size]
+            nodes = torch.tensor([ids[i] for i in sel], dtype=torch.int64, device=device)
+            emb = enc_dec.enc(nodes, mode).detach().t().cpu().numpy()      # enc returns [d, n]
+            out[sel, 0] = [ids[i] for i in sel]
+            out[sel, 1:] = emb
+    if path is not None:
+        np.save(path, out)
+    return out
+
+
 def auc_from_scores(labels, scores):
     """roc_auc_score(labels, nan_to_num(scores)) via the Mann-Whitney identity (average ranks for ties)."""
     labels = np.asarray(labels).astype(bool)

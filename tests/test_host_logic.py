@@ -96,6 +96,33 @@ def test_adaptive_needs_enough_layers(emu):
         model.margin_loss(queries[0].formula, queries, hard_negatives=True)
 
 
+def test_export_embeddings_matches_reference_loop(emu, tmp_path):
+    """`embeddings.npy` export (reference train.py:147-163): [id, unit-norm embedding] per entity, zero row for ids in
+    no mode; checked against the reference's one-id-at-a-time loop restated on the oracle's tables."""
+    from mpqe_b200 import synthetic
+    from mpqe_b200.utils import export_embeddings
+    kg = synthetic.make_kg('tiny', seed=5)
+    rels, _, node_maps = kg.raw()
+    cfg = O.Config(readout='sum', num_layers=2)
+    params = O.init_params(rels, node_maps, cfg, seed=1)
+    model = build_model(kg.raw(), cfg, params, 'cpu')
+    ids = sorted({int(i) for m in node_maps for i in node_maps[m]})
+    entity_ids = {('e%d' % k): i for k, i in enumerate(ids[::3] + [10 ** 6])}      # one id that no mode contains
+    path = str(tmp_path / 'embeddings.npy')
+    got = export_embeddings(model, entity_ids, path, batch_size=7)
+    assert got.shape == (len(entity_ids), 129) and np.array_equal(np.load(path), got)
+    id2row = O.id_to_row(node_maps)
+    for k, ent in enumerate(entity_ids.values()):
+        modes = [m for m in model.graph.full_sets if ent in model.graph.full_sets[m]]
+        if not modes:
+            assert not got[k].any()
+            continue
+        row = params['enc.feat-%s.weight' % modes[-1]][id2row[ent]]
+        want = (row / row.norm()).numpy()
+        assert got[k, 0] == ent
+        np.testing.assert_allclose(got[k, 1:], want, rtol=1e-6, atol=1e-7)
+
+
 def test_unknown_readout_and_scatter():
     from mpqe_b200 import synthetic
     kg = synthetic.make_kg('tiny', seed=5)
