@@ -298,6 +298,15 @@ MPQE_API int mpqe_sparse_rows_plan(const int64_t* rows_id, int64_t count, int64_
 MPQE_API int mpqe_sparse_rows_apply(const float* rows, int64_t count, int64_t table_rows, int64_t pad_id, float scale,
                            int64_t* unique_ids, float* unique_rows, const int64_t* num_unique,
                            void* workspace, size_t workspace_bytes, void* stream);
+/* Data-parallel form of `apply`: the pairs of `world` ranks (plan built over the rank-major concatenation of their
+ * ids, `per_rank_count` each) are summed straight out of the ranks' own row buffers -- peer_rows_host[r] is rank r's
+ * buffer as mapped into THIS process (peer memory over NVLink / NVSwitch).  Gather and combine are one kernel: a
+ * remote row crosses NVLink once and is never staged locally (replaces an NCCL all-gather of the rows + apply). */
+#define MPQE_MAX_PEERS 16
+MPQE_API int mpqe_sparse_rows_apply_peers(const float* const* peer_rows_host, int32_t world, int64_t per_rank_count,
+                                 int64_t table_rows, int64_t pad_id, float scale, int64_t* unique_ids,
+                                 float* unique_rows, const int64_t* num_unique, void* workspace,
+                                 size_t workspace_bytes, void* stream);
 /* dense[ids[i], :] (+)= rows[i, :] for i < *num (ids unique) */
 MPQE_API int mpqe_scatter_rows(const int64_t* ids, const float* rows, const int64_t* num, int64_t max_count,
                       float* dense, int32_t accumulate, void* stream);

@@ -95,6 +95,7 @@ SIGNATURES = {
     'mpqe_sparse_rows_combine': (I32, [P, P, I64, I64, I64, P, P, P, P, SZ, P]),
     'mpqe_sparse_rows_plan': (I32, [P, I64, I64, P, P, SZ, P]),
     'mpqe_sparse_rows_apply': (I32, [P, I64, I64, I64, F32, P, P, P, P, SZ, P]),
+    'mpqe_sparse_rows_apply_peers': (I32, [P, I32, I64, I64, I64, F32, P, P, P, P, SZ, P]),
     'mpqe_scatter_rows': (I32, [P, P, P, I64, P, I32, P]),
     'mpqe_adam_dense': (I32, [P, P, P, P, I64, F32, F32, F32, F32, I32, P]),
     'mpqe_pack_weights': (I32, [P, I32, P, P]),

@@ -362,6 +362,45 @@ __global__ void __launch_bounds__(256) segment_sum_kernel(const uint32_t* __rest
   if (lane == 0) unique_ids[u] = (int64_t)sorted_key[i0];
 }
 
+// The same summation with the pairs of `world` ranks read IN PLACE from their buffers (peer-mapped memory over NVLink):
+// pair i lives in rank i / per_rank, row i % per_rank.  Gather and sum are one kernel: every remote row crosses
+// NVLink once and is never staged in local memory.
+struct PeerRows {
+  const float* rows[MPQE_MAX_PEERS];
+};
+__global__ void __launch_bounds__(256) segment_sum_peers_kernel(const uint32_t* __restrict__ sorted_key,
+                                                                const uint32_t* __restrict__ sorted_val,
+                                                                const int32_t* __restrict__ seg_start,
+                                                                const int64_t* __restrict__ num_unique, int64_t n,
+                                                                const __grid_constant__ PeerRows P, uint32_t per_rank,
+                                                                int64_t* __restrict__ unique_ids,
+                                                                float* __restrict__ unique_rows, int64_t pad_id,
+                                                                uint32_t sentinel, float scale) {
+  const int lane = threadIdx.x & 31;
+  const int64_t u = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int64_t nu = *num_unique;
+  if (u >= nu) {
+    if (u < n) {
+      *reinterpret_cast<float4*>(unique_rows + u * D + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (lane == 0) unique_ids[u] = pad_id;
+    }
+    return;
+  }
+  const int64_t nu_all = nu + (sorted_key[n - 1] >= sentinel ? 1 : 0);
+  const int64_t i0 = seg_start[u];
+  const int64_t i1 = (u + 1 < nu_all) ? seg_start[u + 1] : n;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t i = i0; i < i1; ++i) {  // ascending pair index (rank-major, the sort is stable): fixed summation order
+    const uint32_t idx = sorted_val[i];
+    const uint32_t r = idx / per_rank, local = idx - r * per_rank;
+    const float4 v = *reinterpret_cast<const float4*>(P.rows[r] + (int64_t)local * D + lane * 4);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  *reinterpret_cast<float4*>(unique_rows + u * D + lane * 4) =
+      make_float4(acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale);
+  if (lane == 0) unique_ids[u] = (int64_t)sorted_key[i0];
+}
+
 __global__ void __launch_bounds__(256) scatter_rows_kernel(const int64_t* __restrict__ ids,
                                                            const float* __restrict__ rows,
                                                            const int64_t* __restrict__ num, int64_t max_count,
@@ -509,6 +548,30 @@ extern "C" int mpqe_sparse_rows_apply(const float* rows, int64_t count, int64_t 
                                       void* workspace, size_t workspace_bytes, void* stream) {
   return sparse_rows_apply(rows, count, table_rows, pad_id, scale, unique_ids, unique_rows, num_unique, workspace,
                            workspace_bytes, stream, PLAN_DIGIT_BITS);
+}
+
+extern "C" int mpqe_sparse_rows_apply_peers(const float* const* peer_rows_host, int32_t world, int64_t per_rank_count,
+                                            int64_t table_rows, int64_t pad_id, float scale, int64_t* unique_ids,
+                                            float* unique_rows, const int64_t* num_unique, void* workspace,
+                                            size_t workspace_bytes, void* stream) {
+  MPQE_CHECK_ARG(peer_rows_host && world >= 1 && world <= MPQE_MAX_PEERS && per_rank_count >= 1,
+                 "mpqe_sparse_rows_apply_peers: world must be in [1,%d]", MPQE_MAX_PEERS);
+  const int64_t count = (int64_t)world * per_rank_count;
+  MPQE_CHECK_ARG(unique_ids && unique_rows && num_unique && count < (1ll << 31) && table_rows >= 1 &&
+                     table_rows < (1ll << 32),
+                 "mpqe_sparse_rows_apply_peers: bad argument");
+  MPQE_CHECK_ARG(workspace && workspace_bytes >= mpqe_sparse_rows_workspace_bytes(count),
+                 "mpqe_sparse_rows_apply_peers: workspace too small");
+  PeerRows P;
+  for (int r = 0; r < MPQE_MAX_PEERS; ++r) P.rows[r] = r < world ? peer_rows_host[r] : nullptr;
+  for (int r = 0; r < world; ++r)
+    MPQE_CHECK_ARG(P.rows[r] != nullptr, "mpqe_sparse_rows_apply_peers: null buffer of rank %d", r);
+  CombineBuffers c = carve_combine(workspace, count, table_rows, PLAN_DIGIT_BITS);
+  segment_sum_peers_kernel<<<blocks_for(count, 8), 256, 0, (cudaStream_t)stream>>>(
+      c.rk, c.rv, c.seg_start, num_unique, count, P, (uint32_t)per_rank_count, unique_ids, unique_rows, pad_id,
+      (uint32_t)table_rows, scale);
+  MPQE_CHECK_LAUNCH("segment_sum_peers_kernel");
+  return 0;
 }
 
 extern "C" int mpqe_sparse_rows_combine(const int64_t* rows_id, const float* rows, int64_t count, int64_t table_rows,

@@ -742,14 +742,15 @@ class RowGrads(object):
     Per mode by default; with `table_offsets` ({mode: first global row}) all modes share ONE buffer and the kernels
     emit global row ids (mode offset + row), so a step needs a single sort/combine and a single all-gather."""
 
-    def __init__(self, capacities, device, table_offsets=None):
+    def __init__(self, capacities, device, table_offsets=None, rows_buffer=None):
         self.buf = {}
         self.table_offsets = table_offsets
         self.planned = False     # True: every slot was reserved (and its row ids emitted) before the backward
         if table_offsets is not None:
             cap = sum(capacities.values())
-            self.shared = [torch.empty(cap, D, dtype=torch.float32, device=device),
-                           torch.empty(cap, dtype=torch.int64, device=device), 0]
+            # rows_buffer(cap) -> [>= cap, D] tensor: lets the caller place the rows in peer-visible memory
+            rows = rows_buffer(cap) if rows_buffer is not None else torch.empty(cap, D, dtype=torch.float32, device=device)
+            self.shared = [rows, torch.empty(cap, dtype=torch.int64, device=device), 0]
             return
         for mode, cap in capacities.items():
             if cap > 0:
@@ -1006,14 +1007,15 @@ def loss_forward(model, jobs, targets, negatives, margin, need_grad, grad_losses
     return losses, W
 
 
-def plan_rows(model, jobs, targets, negatives, table_offsets):
+def plan_rows(model, jobs, targets, negatives, table_offsets, rows_buffer=None):
     """Reserves every row-gradient slot of a step in the shared (row id, row) buffer BEFORE the forward and emits the
     row ids with one launch, so that the id-only half of the combine (`ops.SparseRowsPlan`) can overlap the step.
-    The reservations are left on the jobs (`margin_res`, `anchor_res`) for `loss_backward(..., rows=...)`."""
+    The reservations are left on the jobs (`margin_res`, `anchor_res`) for `loss_backward(..., rows=...)`.
+    `rows_buffer(capacity)` may supply the gradient-row buffer (peer-visible memory in data-parallel training)."""
     device = jobs[0].anchor_ids.device
     enc = model.enc
     cap = model._row_capacities(jobs, [(job.target_mode, 2 * job.B) for job in jobs])
-    R = RowGrads(cap, device, table_offsets)
+    R = RowGrads(cap, device, table_offsets, rows_buffer)
     items = []
     for job, tgt, neg in zip(jobs, targets, negatives):
         res = job.margin_res = R.reserve(job.target_mode, 2 * job.B)

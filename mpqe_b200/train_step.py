@@ -60,6 +60,7 @@ class TrainStep(object):
         self._layouts = {}
         self.adam_state = None
         self._side = None   # second stream for the id-only half of the row-gradient combine
+        self._sym_rows = self._sym_hdl = self._peer_ptrs = None   # peer-visible gradient-row buffer (world > 1)
         self.steps = 0
         # all entity tables as one id space: global row = table_offsets[mode] + row
         self.table_offsets, off = {}, 0
@@ -148,6 +149,23 @@ class TrainStep(object):
         if dev.type == 'cuda':
             torch.cuda.current_stream(dev).wait_stream(self._side)
 
+    def _peer_rows_buffer(self, cap):
+        """[>= cap, D] gradient-row buffer in memory that every rank of the group can address (torch symmetric memory:
+        cuMem allocations exchanged at a rendezvous).  Allocated once (a collective; never during graph capture)."""
+        if self._sym_rows is None or self._sym_rows.shape[0] < cap:
+            if torch.cuda.is_current_stream_capturing():
+                raise ops._lib.MpqeError('the peer-visible row buffer must be allocated before graph capture')
+            import torch.distributed._symmetric_memory as symm_mem
+            dev = self.model.mode_embeddings.weight.device
+            buf = symm_mem.empty(int(cap), D, dtype=torch.float32, device=dev)
+            hdl = symm_mem.rendezvous(buf, self.pg if self.pg is not None else torch.distributed.group.WORLD)
+            self._sym_rows, self._sym_hdl, self._peer_ptrs = buf, hdl, [int(p) for p in hdl.buffer_ptrs]
+        return self._sym_rows
+
+    def _use_peer_rows(self, dev):
+        import os
+        return self.world > 1 and dev.type == 'cuda' and os.environ.get('MPQE_PEER_ROWS', '1') != '0'
+
     def sync(self, G, sparse):
         """Data-parallel exchange: all-reduce(dense bucket), all-gather of the ranks' raw (row id, gradient row) pairs
         and ONE combine of all of them, identical on every rank (rank order + stable sort => same bits).  The ids
@@ -159,9 +177,21 @@ class TrainStep(object):
         dev = ids.device
         cap = ids.numel()
         all_ids = torch.empty(self.world * cap, dtype=torch.int64, device=dev)
-        all_rows = torch.empty(self.world * cap, D, dtype=torch.float32, device=dev)
         dist.all_gather_into_tensor(all_ids, ids, group=self.pg)
         plan = self._plan_on_side_stream(all_ids, dev)
+        if self._peer_ptrs is not None and rows.data_ptr() == self._sym_rows.data_ptr():
+            # Peer-memory path: every rank's rows sit in a buffer mapped into all processes (torch symmetric memory).
+            # The id all-gather above completes only after every rank has finished its local step, so the peers' rows
+            # are final; ONE kernel then gathers and sums them in place over NVLink (no NCCL all-gather of 54 MB per
+            # rank, no local staging).  The dense all-reduce comes last and doubles as the closing barrier: no rank
+            # starts overwriting its rows (next step) before every rank has finished reading them.
+            self._join_side(dev)
+            out = plan.apply_peers(self._peer_ptrs, cap, pad_id=self.total_rows, scale=scale)
+            dist.all_reduce(G.flat, group=self.pg)
+            if scale != 1.0:
+                G.flat.mul_(scale)
+            return out
+        all_rows = torch.empty(self.world * cap, D, dtype=torch.float32, device=dev)
         dist.all_reduce(G.flat, group=self.pg)
         if scale != 1.0:
             G.flat.mul_(scale)
@@ -182,7 +212,8 @@ class TrainStep(object):
         # With several ranks the pairs are exchanged raw and combined once, after the all-gather (see `sync`).
         # The per-step weight preparation (transposes, tf32 tile images, summed matrices) goes to that stream too, ahead
         # of the sort: it overlaps the input gather; the first layer launch waits for its event.
-        R = plan_rows(m, jobs, tg, ng, self.table_offsets)
+        R = plan_rows(m, jobs, tg, ng, self.table_offsets,
+                      rows_buffer=self._peer_rows_buffer if self._use_peer_rows(dev) else None)
         rows, ids, used = R.shared
         W = self._weights_on_side_stream(jobs, dev)
         plan = self._plan_on_side_stream(ids[:used], dev) if self.world == 1 else None

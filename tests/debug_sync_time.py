@@ -25,7 +25,7 @@ def timeit(name, fn, n=10):
     for _ in range(n): fn()
     torch.cuda.synchronize()
     if rank == 0: print('%-28s %.3f ms' % (name, (time.perf_counter() - t0) / n * 1e3), flush=True)
-uid, urows, num = res.sparse
+uid, urows = res.sparse[0], res.sparse[1]
 cap = uid.numel()
 if rank == 0: print('cap rows', cap, 'flat MB', res.dense.flat.numel() * 4 / 1e6, 'rows MB', urows.numel() * 4 / 1e6)
 all_ids = torch.empty(world * cap, dtype=torch.int64, device=dev)
@@ -36,6 +36,11 @@ timeit('allgather ids', lambda: dist.all_gather_into_tensor(all_ids, uid))
 timeit('allgather rows', lambda: dist.all_gather_into_tensor(all_rows, urows))
 timeit('torch.empty rows', lambda: torch.empty(world * cap, 128, dtype=torch.float32, device=dev))
 timeit('combine gathered', lambda: ops.sparse_rows_combine(all_ids, all_rows, ts.total_rows))
+def plan_apply():
+    plan = ops.SparseRowsPlan(all_ids, ts.total_rows)
+    return plan.apply(all_rows, pad_id=ts.total_rows, scale=0.5)
+timeit('plan+apply same stream', plan_apply)
+timeit('plan only', lambda: ops.SparseRowsPlan(all_ids, ts.total_rows))
 timeit('full sync()', lambda: ts.sync(res.dense, res.sparse))
 timeit('replay()+sync', lambda: ts.replay())
 dist.destroy_process_group()
