@@ -1007,7 +1007,7 @@ def loss_forward(model, jobs, targets, negatives, margin, need_grad, grad_losses
     return losses, W
 
 
-def plan_rows(model, jobs, targets, negatives, table_offsets, rows_buffer=None):
+def plan_rows(model, jobs, targets, negatives, table_offsets, rows_buffer=None, launch=True):
     """Reserves every row-gradient slot of a step in the shared (row id, row) buffer BEFORE the forward and emits the
     row ids with one launch, so that the id-only half of the combine (`ops.SparseRowsPlan`) can overlap the step.
     The reservations are left on the jobs (`margin_res`, `anchor_res`) for `loss_backward(..., rows=...)`.
@@ -1030,7 +1030,9 @@ def plan_rows(model, jobs, targets, negatives, table_offsets, rows_buffer=None):
             res = job.anchor_res[i] = R.reserve(mode, job.B)
             items.append(ops.GatherItem(enc.table(mode), enc.node_maps, job.anchor_ids, job.B, ids_offset=i,
                                         ids_stride=job.t.num_anchors, rows_id=res[1], rows_offset=res[2], id_offset=res[3]))
-    ops.gather_multi(items, backward='ids')
+    R.id_items = items
+    if launch:
+        ops.gather_multi(items, backward='ids')
     R.planned = True
     return R
 

@@ -570,6 +570,25 @@ def gather_multi(items, backward=False):
         _count()
 
 
+class GatherLaunch(object):
+    """A pre-marshalled `gather_multi` call for items whose tensors stay put (the static buffers of graph mode): the
+    per-step host cost is one ctypes call per chunk instead of rebuilding the item structs."""
+
+    def __init__(self, items, backward=False):
+        self.mode = 2 if backward == 'ids' else int(bool(backward))
+        self.keep = list(items)
+        self.chunks = []
+        for i in range(0, len(self.keep), _lib.MAX_GATHER_ITEMS):
+            chunk = self.keep[i:i + _lib.MAX_GATHER_ITEMS]
+            self.chunks.append(((_lib.GatherItem * len(chunk))(*[it.to_c() for it in chunk]), len(chunk)))
+
+    def launch(self):
+        lib = _lib.load()
+        for arr, n in self.chunks:
+            _lib.check(lib.mpqe_gather_multi(arr, n, self.mode, _stream()), 'mpqe_gather_multi')
+            _count()
+
+
 class MarginItem(object):
     """One formula group of `cosine_margin_multi` (see mpqe_margin_item_t)."""
 

@@ -61,6 +61,7 @@ class TrainStep(object):
         self.adam_state = None
         self._side = None   # second stream for the id-only half of the row-gradient combine
         self._sym_rows = self._sym_hdl = self._peer_ptrs = None   # peer-visible gradient-row buffer (world > 1)
+        self._early_cache = None                                  # marshalled id-emitting launch of the static batches
         self.steps = 0
         # all entity tables as one id space: global row = table_offsets[mode] + row
         self.table_offsets, off = {}, 0
@@ -110,19 +111,50 @@ class TrainStep(object):
         `.sparse = (unique global row ids, summed rows, num_unique)` with global row = table_offsets[mode] + row."""
         dev = self.model.mode_embeddings.weight.device
         with ops.device_guard(dev):
+            early = self._early_plan(batches) if self._use_peer_rows(dev) else None
             res = self._local_step(batches)
             if self.world > 1:
-                res = StepResult(res.losses, res.weights, res.dense, self.sync(res.dense, res.sparse))
+                res = StepResult(res.losses, res.weights, res.dense, self.sync(res.dense, res.sparse, early))
         return res
 
-    def _plan_on_side_stream(self, ids, dev):
-        """ops.SparseRowsPlan(ids) on the second stream (joined by `_join_side`); plain call on the CPU emulator."""
+    def _early_plan(self, batches, defer=False):
+        """Data-parallel, peer-memory path: the row ids of EVERY rank's step are known before any rank computes --
+        emit them (one small launch), all-gather them (0.8 MB per rank) and build the global combine plan on the second
+        stream, under the local step.  The all-gather is also the step's opening barrier: it completes only when every
+        rank has finished reading the others' gradient rows of the previous step, after which they may be overwritten."""
+        m = self.model
+        cache = self._early_cache
+        if cache is None or cache[0] is not batches:
+            # the id-emitting launch is marshalled once per batch list: in graph mode the same static batches come
+            # back every step and the per-step host cost is a single ctypes call
+            jobs = [b.job for b in batches]
+            R0 = plan_rows(m, jobs, [b.targets for b in batches], [b.negatives for b in batches], self.table_offsets,
+                           rows_buffer=lambda cap: None, launch=False)
+            cache = (batches, ops.GatherLaunch(R0.id_items, 'ids'), R0)
+            self._early_cache = cache if batches is getattr(self, '_static', None) else None
+        cache[1].launch()
+        _, ids0, used = cache[2].shared
+        dev = ids0.device
+        all_ids = torch.empty(self.world * used, dtype=torch.int64, device=dev)
+        torch.distributed.all_gather_into_tensor(all_ids, ids0[:used], group=self.pg)
+        if defer:      # graph mode: the caller enqueues the graph first, then the plan (ordered after this event only)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            return (lambda: self._plan_on_side_stream(all_ids, dev, after=ev)), used
+        return self._plan_on_side_stream(all_ids, dev), used
+
+    def _plan_on_side_stream(self, ids, dev, after=None):
+        """ops.SparseRowsPlan(ids) on the second stream (joined by `_join_side`); plain call on the CPU emulator.
+        `after`: an event to order the plan after, instead of everything enqueued on the current stream so far."""
         if dev.type != 'cuda':
             return ops.SparseRowsPlan(ids, self.total_rows)
         cur = torch.cuda.current_stream(dev)
         if self._side is None:
             self._side = torch.cuda.Stream(device=dev)
-        self._side.wait_stream(cur)
+        if after is not None:
+            self._side.wait_event(after)
+        else:
+            self._side.wait_stream(cur)
         with torch.cuda.stream(self._side):
             plan = ops.SparseRowsPlan(ids, self.total_rows)
         plan.ws.record_stream(cur)
@@ -166,16 +198,28 @@ class TrainStep(object):
         import os
         return self.world > 1 and dev.type == 'cuda' and os.environ.get('MPQE_PEER_ROWS', '1') != '0'
 
-    def sync(self, G, sparse):
+    def sync(self, G, sparse, early=None):
         """Data-parallel exchange: all-reduce(dense bucket), all-gather of the ranks' raw (row id, gradient row) pairs
         and ONE combine of all of them, identical on every rank (rank order + stable sort => same bits).  The ids
         travel first (0.8 MB per rank) so that their sort runs on the second stream under the all-gather of the rows
-        (54 MB per rank at the bench shape); the 1/world averaging is folded into the row summation."""
+        (54 MB per rank at the bench shape); the 1/world averaging is folded into the row summation.
+        `early` = (plan, pairs per rank) from `_early_plan`: the global plan was built under the local step."""
         dist = torch.distributed
         scale = 1.0 / self.world if self.average else 1.0
         ids, rows, _ = sparse
         dev = ids.device
         cap = ids.numel()
+        if (early is not None and early[1] == cap and self._peer_ptrs is not None and
+                rows.data_ptr() == self._sym_rows.data_ptr()):
+            # Peer-memory path.  The dense all-reduce completes only when every rank has finished its local step (its
+            # gradient rows are final) -- the barrier the gather needs; then ONE kernel gathers and sums all ranks'
+            # rows in place over NVLink (no NCCL all-gather of 54 MB per rank, no local staging).  The next step's id
+            # all-gather (`_early_plan`) keeps any rank from overwriting its rows before all have read them.
+            dist.all_reduce(G.flat, group=self.pg)
+            if scale != 1.0:
+                G.flat.mul_(scale)
+            self._join_side(dev)
+            return early[0].apply_peers(self._peer_ptrs, cap, pad_id=self.total_rows, scale=scale)
         all_ids = torch.empty(self.world * cap, dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(all_ids, ids, group=self.pg)
         plan = self._plan_on_side_stream(all_ids, dev)
@@ -267,6 +311,7 @@ class TrainStep(object):
                 self._static.append(self.to_device(hb, tuple(v[1] for v in views)))
             self._dev_ids.copy_(self._host_ids, non_blocking=True)
             self._wts = None
+            self._early_cache = None
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
@@ -292,11 +337,21 @@ class TrainStep(object):
                     st.targets.copy_(hb.targets)
                     st.negatives.copy_(hb.negatives)
             self._dev_ids.copy_(self._host_ids, non_blocking=True)
+        dev = self._dev_ids.device
+        early = None
+        if self._use_peer_rows(dev):
+            with ops.device_guard(dev):
+                # (defer=True would enqueue the plan after the graph launch: less host latency in front of the graph,
+                # +12 % end-to-end at N=2, but the plan then overlaps the graph's kernels worse: -12 % device-timed)
+                early = self._early_plan(self._static, defer=False)
         self._graph.replay()
+        if early is not None and callable(early[0]):     # deferred plan: enqueued after the graph launch, ordered only
+            with ops.device_guard(dev):                  # after the id all-gather
+                early = (early[0](), early[1])
         res = self._graph_res
         if self.world > 1:
             with ops.device_guard(res.dense.flat.device):
-                res = StepResult(res.losses, res.weights, res.dense, self.sync(res.dense, res.sparse))
+                res = StepResult(res.losses, res.weights, res.dense, self.sync(res.dense, res.sparse, early))
         return res
 
     def staging(self):
