@@ -187,16 +187,25 @@ class TrainStep(object):
         if self._sym_rows is None or self._sym_rows.shape[0] < cap:
             if torch.cuda.is_current_stream_capturing():
                 raise ops._lib.MpqeError('the peer-visible row buffer must be allocated before graph capture')
-            import torch.distributed._symmetric_memory as symm_mem
             dev = self.model.mode_embeddings.weight.device
-            buf = symm_mem.empty(int(cap), D, dtype=torch.float32, device=dev)
-            hdl = symm_mem.rendezvous(buf, self.pg if self.pg is not None else torch.distributed.group.WORLD)
-            self._sym_rows, self._sym_hdl, self._peer_ptrs = buf, hdl, [int(p) for p in hdl.buffer_ptrs]
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                buf = symm_mem.empty(int(cap), D, dtype=torch.float32, device=dev)
+                hdl = symm_mem.rendezvous(buf, self.pg if self.pg is not None else torch.distributed.group.WORLD)
+                self._sym_rows, self._sym_hdl, self._peer_ptrs = buf, hdl, [int(p) for p in hdl.buffer_ptrs]
+            except Exception as exc:      # no peer mapping on this system: NCCL all-gather of the rows from now on
+                import warnings
+                warnings.warn('mpqe_b200: symmetric (peer-mapped) memory unavailable (%r); the row-gradient exchange '
+                              'falls back to an NCCL all-gather' % (exc,))
+                self._peers_off = True
+                self._sym_rows = self._sym_hdl = self._peer_ptrs = None
+                return torch.empty(int(cap), D, dtype=torch.float32, device=dev)
         return self._sym_rows
 
     def _use_peer_rows(self, dev):
         import os
-        return self.world > 1 and dev.type == 'cuda' and os.environ.get('MPQE_PEER_ROWS', '1') != '0'
+        return (self.world > 1 and dev.type == 'cuda' and not getattr(self, '_peers_off', False) and
+                os.environ.get('MPQE_PEER_ROWS', '1') != '0')
 
     def sync(self, G, sparse, early=None):
         """Data-parallel exchange: all-reduce(dense bucket), all-gather of the ranks' raw (row id, gradient row) pairs
