@@ -78,8 +78,9 @@ class RGCNConv(nn.Module):
         if edge_norm is not None:
             raise NotImplementedError('edge_norm is never passed by MPQE (model.py:436, 441)')
         if graph is None:
-            raise NotImplementedError('RGCNConv on an arbitrary edge list needs the template that produced it: pass '
-                                      'graph=<QueryGraphBatch> (general graphs are outside the MPQE hot path)')
+            # the reference's call signature (model.py:269): recover the template from the edge list itself.  Costs a
+            # device -> host copy of the indices; callers on the hot path pass the QueryGraphBatch instead.
+            graph = infer_template_batch(x.shape[0], edge_index, edge_type)
         if self.in_channels != D or self.out_channels != D:
             raise ValueError('kernels are specialised for %d channels' % D)
         return _ConvFn.apply(x, self.relation_weights(), self.root, self.bias, graph)
@@ -87,6 +88,45 @@ class RGCNConv(nn.Module):
     def __repr__(self):
         return '{}({}, {}, num_relations={})'.format(self.__class__.__name__, self.in_channels, self.out_channels,
                                                      self.num_relations)
+
+
+class _InferredTemplate(object):
+    def __init__(self, num_nodes, src, dst):
+        self.num_nodes, self.num_edges, self.src, self.dst = int(num_nodes), len(src), list(src), list(dst)
+
+
+class _InferredBatch(object):
+    """What `_ConvFn` needs of a QueryGraphBatch, recovered from (edge_index, edge_type)."""
+
+    def __init__(self, template, edge_rel_ids, num_graphs):
+        self.template, self.edge_rel_ids, self.num_graphs = template, list(edge_rel_ids), int(num_graphs)
+
+
+def infer_template_batch(num_rows, edge_index, edge_type):
+    """A PyG-style batch of B identical graphs (`Batch.from_data_list`, reference data_utils.py:402-405) is B copies of
+    one template with node offsets b*n: find the largest B for which (edge_index, edge_type) has that form and return
+    the template.  Raises NotImplementedError for edge lists that are not such a batch (general graphs are outside
+    the MPQE path) or whose template exceeds the kernels' limits."""
+    ei = edge_index.detach().cpu().numpy()
+    et = edge_type.detach().cpu().numpy()
+    total_e = int(ei.shape[1])
+    if ei.ndim != 2 or ei.shape[0] != 2 or et.shape[0] != total_e or total_e == 0 or num_rows == 0:
+        raise NotImplementedError('RGCNConv: expected edge_index [2, E] and edge_type [E] of a non-empty batch')
+    g = math.gcd(int(num_rows), total_e)
+    for B in sorted((b for b in range(1, g + 1) if g % b == 0), reverse=True):
+        n, E = num_rows // B, total_e // B
+        if n > ops.MAX_SLOTS or E + n > ops.MAX_TERMS:
+            break      # smaller B only makes the template larger
+        src, dst, rel = ei[0, :E], ei[1, :E], et[:E]
+        if src.max() >= n or dst.max() >= n or src.min() < 0 or dst.min() < 0:
+            continue
+        offs = (torch.arange(B).repeat_interleave(E) * n).numpy()
+        if ((ei[0] == (offs + list(src) * B)).all() and (ei[1] == (offs + list(dst) * B)).all() and
+                (et == list(rel) * B).all()):
+            return _InferredBatch(_InferredTemplate(n, src.tolist(), dst.tolist()), rel.tolist(), B)
+    raise NotImplementedError('RGCNConv: the edge list is not a batch of identical query templates with at most %d '
+                              'nodes and %d edge + node terms (general graphs are outside the MPQE hot path)'
+                              % (ops.MAX_SLOTS, ops.MAX_TERMS))
 
 
 def _conv_terms(t, rels, x, n, w, root):

@@ -123,6 +123,37 @@ def test_export_embeddings_matches_reference_loop(emu, tmp_path):
         np.testing.assert_allclose(got[k, 1:], want, rtol=1e-6, atol=1e-7)
 
 
+def test_rgcn_conv_reference_signature_infers_the_template(emu):
+    """`RGCNConv.forward(x, edge_index, edge_type)` exactly as the reference calls it (model.py:269): the template of
+    the batched query graphs is recovered from the edge list; anything that is not such a batch is refused."""
+    from mpqe_b200.model import RGCNConv, infer_template_batch
+    from mpqe_b200.data_utils import QueryGraphBatch, template_of
+    torch.manual_seed(0)
+    conv = RGCNConv(128, 128, 6, 0)
+    for qt, rels, B in (('3-chain_inter', [4, 1, 2], 13), ('1-chain', [3], 5), ('3-inter', [0, 0, 5], 1)):
+        t = template_of(qt)
+        g = QueryGraphBatch(t, rels, B)
+        inferred = infer_template_batch(B * t.num_nodes, g.edge_index, g.edge_type)
+        assert inferred.num_graphs == B and inferred.template.num_nodes == t.num_nodes
+        assert inferred.template.src == list(t.src) and inferred.template.dst == list(t.dst)
+        assert inferred.edge_rel_ids == rels
+        x = torch.randn(B * t.num_nodes, 128, requires_grad=True)
+        out = conv(x, g.edge_index, g.edge_type)
+        pc = {k: v.detach().clone().requires_grad_(True) for k, v in conv.named_parameters()}
+        xc = x.detach().clone().requires_grad_(True)
+        want = O.rgcn_conv(xc, g.edge_index, g.edge_type, pc['basis'], pc['root'], pc['bias'])
+        assert_close(out.detach().numpy(), want.detach().numpy(), 1e-5, 1e-5, qt + ' conv out')
+        w = torch.randn_like(want)
+        conv.zero_grad()
+        (out * w).sum().backward()
+        (want * w).sum().backward()
+        assert_close(x.grad.numpy(), xc.grad.numpy(), 1e-4, 1e-5, qt + ' dx')
+        for k, prm in conv.named_parameters():
+            assert_close(prm.grad.numpy(), pc[k].grad.numpy(), 1e-3, 1e-4, qt + ' d' + k)
+    with pytest.raises(NotImplementedError, match='not a batch of identical query templates'):
+        infer_template_batch(40, torch.randint(0, 40, (2, 30)), torch.randint(0, 6, (30,)))
+
+
 def test_unknown_readout_and_scatter():
     from mpqe_b200 import synthetic
     kg = synthetic.make_kg('tiny', seed=5)
