@@ -301,6 +301,10 @@ class TrainStep(object):
         Later steps with batches of the same formulas and sizes call `replay(host_batches)`."""
         m = self.model
         dev = m.mode_embeddings.weight.device
+        if self._use_peer_rows(dev):
+            # the warm-up steps below overwrite this rank's peer-visible gradient rows without the opening barrier of a
+            # regular step: first let every rank finish reading them (previous step's gather)
+            torch.distributed.barrier(group=self.pg)
         with ops.device_guard(dev):
             # all ids of a step live in ONE device buffer mirrored by ONE pinned host buffer: a step's input is a
             # single H2D copy instead of three small copies per formula batch
