@@ -154,6 +154,30 @@ def test_rgcn_conv_reference_signature_infers_the_template(emu):
         infer_template_batch(40, torch.randint(0, 40, (2, 30)), torch.randint(0, 6, (30,)))
 
 
+def test_rgcn_conv_basis_decomposition(emu):
+    """`num_bases > 0` (reference model.py:243-248, 281-284): W_r = sum_b att[r, b] basis[b]; output and the gradients
+    of `att` and `basis` against the oracle."""
+    from mpqe_b200.model import RGCNConv
+    from mpqe_b200.data_utils import QueryGraphBatch, template_of
+    torch.manual_seed(1)
+    conv = RGCNConv(128, 128, 7, 3)
+    assert conv.att.shape == (7, 3) and conv.basis.shape == (3, 128, 128)
+    t = template_of('3-inter_chain')
+    g = QueryGraphBatch(t, [6, 2, 0], 11)
+    x = torch.randn(11 * t.num_nodes, 128, requires_grad=True)
+    out = conv(x, g.edge_index, g.edge_type, graph=g)
+    pc = {k: v.detach().clone().requires_grad_(True) for k, v in conv.named_parameters()}
+    xc = x.detach().clone().requires_grad_(True)
+    want = O.rgcn_conv(xc, g.edge_index, g.edge_type, pc['basis'], pc['root'], pc['bias'], att=pc['att'])
+    assert_close(out.detach().numpy(), want.detach().numpy(), 1e-5, 1e-5, 'conv out (bases)')
+    w = torch.randn_like(want)
+    (out * w).sum().backward()
+    (want * w).sum().backward()
+    assert_close(x.grad.numpy(), xc.grad.numpy(), 1e-4, 1e-5, 'dx')
+    for k, prm in conv.named_parameters():
+        assert_close(prm.grad.numpy(), pc[k].grad.numpy(), 1e-3, 1e-4, 'd' + k)
+
+
 def test_unknown_readout_and_scatter():
     from mpqe_b200 import synthetic
     kg = synthetic.make_kg('tiny', seed=5)
