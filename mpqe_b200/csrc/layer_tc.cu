@@ -187,18 +187,6 @@ struct Frag {  // one pipeline stage worth of one operand, per producer thread
 };
 
 // rows = queries (K-major source): idx = pw*4+i -> row group idx/2, k half idx%2   (pw = producer warp 0..7)
-__device__ __forceinline__ void load_kmajor(Frag& f, const mpqe_term_t& T, int64_t q0, int64_t B, int kc, int pw,
-                                            int lane) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int idx = pw * 4 + i;
-    const int row = (idx >> 1) * 8 + (lane & 7);
-    const int kq = (idx & 1) * 4 + (lane >> 3);
-    int64_t q = q0 + row;
-    if (q >= B) q = B - 1;
-    f.v[i] = *reinterpret_cast<const float4*>(T.a + (q * T.a_slots + T.a_slot) * (int64_t)D + kc + kq * 4);
-  }
-}
 __device__ __forceinline__ void store_kmajor(const Frag& f, uint8_t* hi_tile, uint8_t* lo_tile, int pw, int lane) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
