@@ -178,6 +178,76 @@ def test_rgcn_conv_basis_decomposition(emu):
         assert_close(prm.grad.numpy(), pc[k].grad.numpy(), 1e-3, 1e-4, 'd' + k)
 
 
+@pytest.mark.parametrize('readout,num_layers,adaptive,shared,scatter_op',
+                         [('sum', 2, False, False, 'add'), ('sum', 3, False, True, 'add'), ('mp', 3, True, False, 'add'),
+                          ('max', 2, False, False, 'add'), ('concat', 2, False, False, 'mean'),
+                          ('targetmlp', 2, False, False, 'max')])
+def test_fused_train_step_host_logic_vs_oracle(emu, readout, num_layers, adaptive, shared, scatter_op):
+    """The host side of the fused multi-batch step (planned row slots, margin backward inside the forward, collapsed
+    last pass, batch-constant rows) with emulated kernels: losses, dense gradients summed over the seven formula
+    batches and the combined row-sparse entity gradients against the oracle."""
+    from mpqe_b200 import synthetic
+    from mpqe_b200.graph import Formula
+    from mpqe_b200.train_step import HostBatch, TrainStep
+    from tests.model_utils import oracle_loss_and_grads
+    kg = synthetic.make_kg('tiny', seed=5)
+    rels, _, node_maps = kg.raw()
+    cfg = O.Config(readout=readout, num_layers=num_layers, adaptive=adaptive, shared_layers=shared,
+                   scatter_op=scatter_op, weight_decay=0.0)
+    params = O.init_params(rels, node_maps, cfg, d=128, seed=1)
+    mode_ids, rel_ids = O.schema_ids(rels)
+    id2row = O.id_to_row(node_maps)
+    model = build_model(kg.raw(), cfg, params, 'cpu', sparse_grad=True)
+    frng, rng = np.random.RandomState(0), np.random.RandomState(1)
+    want_losses, want, host = [], {}, []
+    for qt in synthetic.QUERY_TYPES:
+        frm_rels = kg.sample_formula(qt, frng)
+        formula = Formula(qt, frm_rels)
+        a, t, n = synthetic.sample_id_batch(kg, formula, 9, rng)
+        host.append(HostBatch(formula, torch.from_numpy(a), torch.from_numpy(t), torch.from_numpy(n)))
+        loss, grads = oracle_loss_and_grads(params, cfg, O.formula_spec(qt, frm_rels), torch.from_numpy(a), rel_ids,
+                                            mode_ids, id2row, torch.from_numpy(t), torch.from_numpy(n))
+        want_losses.append(loss)
+        for k, g in grads.items():
+            want[k] = want.get(k, 0) + g
+    ts = TrainStep(model)
+    res = ts.forward_backward([ts.to_device(hb) for hb in host])
+    assert_close(res.losses.numpy(), np.array(want_losses, dtype=np.float32), 1e-5, 1e-5, 'losses')
+    G = res.dense
+    got = {}
+    for name, prm in model.named_parameters():
+        for li, layer in enumerate(model.distinct_layers()):
+            if prm is layer.basis:
+                got[name] = G.dw[li]
+            elif prm is layer.root:
+                got[name] = G.droot[li]
+            elif prm is layer.bias:
+                got[name] = G.dbias[li]
+        if prm is model.mode_embeddings.weight:
+            got[name] = G.dmode
+    if isinstance(model.readout, torch.nn.Module):
+        lin1, lin2 = model.readout.layers[0], model.readout.layers[2]
+        for name, prm in model.named_parameters():
+            if prm is lin1.weight:
+                got[name] = G.dw1t.t()
+            elif prm is lin2.weight:
+                got[name] = G.dw2t.t()
+            elif prm is lin1.bias:
+                got[name] = G.db1
+            elif prm is lin2.bias:
+                got[name] = G.db2
+    uid, urows, num = res.sparse
+    k = int(num)
+    tables = torch.zeros(ts.total_rows, 128)
+    tables[uid[:k]] = urows[:k]
+    for mode, off in ts.table_offsets.items():
+        got['enc.feat-%s.weight' % mode] = tables[off:off + model.enc.table(mode).shape[0]]
+    for name, g in want.items():
+        assert got.get(name) is not None, name
+        g = np.asarray(g)
+        assert_close(got[name].detach().numpy(), g, 1e-3, 3e-5 * max(np.abs(g).max(), 1e-12), 'grad ' + name)
+
+
 def test_unknown_readout_and_scatter():
     from mpqe_b200 import synthetic
     kg = synthetic.make_kg('tiny', seed=5)
