@@ -91,3 +91,29 @@ def test_negatives_come_from_each_querys_list(query_sets):
     it = ts.batches(8, rng, full_lists=full_lists)
     sizes = [next(it).targets.numel() for _ in range(6)]
     assert all(1 <= s <= 8 for s in sizes)
+
+
+def test_template_inference_reproduces_any_batched_edge_list():
+    """Property: for a batch of B copies of ANY small template, `infer_template_batch` returns a template (possibly a
+    finer one, when the template itself repeats) whose B' copies are exactly the given edge list."""
+    from hypothesis import given, settings, strategies as st
+    from mpqe_b200.model import infer_template_batch
+
+    @settings(max_examples=120, deadline=None)
+    @given(st.integers(1, 6), st.integers(1, 6), st.integers(1, 9), st.randoms(use_true_random=False))
+    def check(n, E, B, rnd):
+        src = [rnd.randrange(n) for _ in range(E)]
+        dst = [rnd.randrange(n) for _ in range(E)]
+        rel = [rnd.randrange(5) for _ in range(E)]
+        ei = torch.tensor([[s + b * n for b in range(B) for s in src], [d + b * n for b in range(B) for d in dst]])
+        et = torch.tensor(rel * B)
+        got = infer_template_batch(B * n, ei, et)
+        t = got.template
+        assert got.num_graphs * t.num_nodes == B * n and got.num_graphs * t.num_edges == B * E
+        assert got.num_graphs >= B      # the largest decomposition is preferred
+        re_src = [s + b * t.num_nodes for b in range(got.num_graphs) for s in t.src]
+        re_dst = [d + b * t.num_nodes for b in range(got.num_graphs) for d in t.dst]
+        assert re_src == ei[0].tolist() and re_dst == ei[1].tolist()
+        assert got.edge_rel_ids * got.num_graphs == et.tolist()
+
+    check()
