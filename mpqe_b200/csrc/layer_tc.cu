@@ -173,7 +173,7 @@ __device__ __forceinline__ void split_tf32(const float4& x, float4& hi, float4& 
 
 // Every operand tile is K-major [128 rows][32 k]: element (row, k) at (row/8)*1024 + (k/4)*128 + (row%8)*16 + (k%4)*4
 // bytes; descriptor for k-step j (k = 8j..8j+7): start + j*256, LBO = 128 (next 4 k), SBO = 1024 (next 8 rows).
-// (Probed on B200 with tests/tc_probe.cu: K-major tf32 operands are exact with and without the 128-byte swizzle and
+// (Probed on B200 with tools/tc_probe.cu: K-major tf32 operands are exact with and without the 128-byte swizzle and
 // run at the same ~160 cycles per 128x128x8 MMA; with either MN-major bit of the instruction descriptor set, every
 // canonical MN-major layout tried -- no swizzle and 128-byte swizzle, LBO/SBO in both orders -- accumulates exact
 // zeros, even on an all-ones operand: kind::tf32 takes K-major operands only here.)

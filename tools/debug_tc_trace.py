@@ -1,4 +1,4 @@
-"""Debug tool: event trace of CTA 0 of the tcgen05 layer kernel (python tests/debug_tc_trace.py)."""
+"""Debug tool: event trace of CTA 0 of the tcgen05 layer kernel (python tools/debug_tc_trace.py)."""
 import ctypes
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -2,7 +2,7 @@
 // The HOST builds the byte image of the A and B tiles under a hypothesised canonical layout; the kernel copies
 // the images to shared memory verbatim, issues the MMAs with the given descriptor parameters and dumps the 128x128
 // accumulator.  The host compares with the exact product and reports which hypotheses hold.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o tests/_probe/tc_probe tests/tc_probe.cu
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o tools/_build/tc_probe tools/tc_probe.cu
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
