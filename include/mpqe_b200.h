@@ -98,7 +98,7 @@ typedef struct {
 MPQE_API const char* mpqe_b200_last_error(void);
 MPQE_API int mpqe_b200_version(void);
 /* sizeof the ABI structs (0: term, 1: layer group, 2: wgrad dest, 3: wgrad operand, 4: gather item, 5: margin item,
- * 6: colsum item, 7: matsum item) so bindings can self-check */
+ * 6: colsum item, 7: matsum item, 8: l2 item, 9: adam item, 10: adam table) so bindings can self-check */
 MPQE_API int mpqe_b200_sizeof(int which);
 /* 1 if the library was built with the tcgen05 (sm_100a tensor core) layer kernels */
 MPQE_API int mpqe_b200_has_tcgen05(void);
@@ -314,6 +314,76 @@ MPQE_API int mpqe_scatter_rows(const int64_t* ids, const float* rows, const int6
 /* ---- optimiser (train.py:86-88, torch.optim.Adam defaults; caller of the hot path, row (f)) -------------- */
 MPQE_API int mpqe_adam_dense(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel,
                     float lr, float beta1, float beta2, float eps, int32_t step, void* stream);
+
+/* ---- L2 term of margin_loss over the readout-MLP parameters (model.py:487-492) -----------------------------------
+ * loss += weight_decay * sum_i ||param_i||_2  (un-squared norms, one term per margin_loss call).  For every item
+ * grad_i += grad_scale * weight_decay * param_i / ||param_i|| (grad_scale = sum of d total / d loss_j over the step's
+ * batches; `grad` is laid out like `param`), every losses[j < num_losses] += weight_decay * sum_i ||param_i||, and
+ * norms[i] (optional) receives ||param_i||.  One CTA, fixed summation order: bit-reproducible. */
+#define MPQE_MAX_L2_ITEMS 8
+typedef struct {
+  const float* param;
+  float* grad;     /* may be NULL (loss only) */
+  int64_t numel;
+} mpqe_l2_item_t;
+MPQE_API int mpqe_l2_reg_multi(const mpqe_l2_item_t* items_host, int32_t n, float weight_decay, float grad_scale,
+                      float* losses, int32_t num_losses, float* norms, void* stream);
+
+/* Adam over up to MPQE_MAX_ADAM_ITEMS dense tensors in one launch (torch/optim/adam.py single-tensor formula:
+ * exp_avg.lerp_, exp_avg_sq.mul_.addcmul_, bias corrections in double, param.addcdiv_). */
+#define MPQE_MAX_ADAM_ITEMS 32
+typedef struct {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t numel;
+} mpqe_adam_item_t;
+/* Device-resident optimiser clock, so that a captured CUDA graph can be replayed step after step: `mpqe_adam_tick`
+ * (one thread) increments `step` and recomputes the bias corrections; the Adam entry points below read them from
+ * `state` when it is non-NULL (their `step` argument is then ignored). */
+typedef struct {
+  int32_t step;        /* optimiser steps completed (after a tick: the step being applied) */
+  float step_size;     /* lr / (1 - beta1^step) */
+  float bc2_sqrt;      /* sqrt(1 - beta2^step) */
+  int32_t reserved;
+} mpqe_adam_state_t;
+MPQE_API int mpqe_adam_tick(mpqe_adam_state_t* state, float lr, float beta1, float beta2, void* stream);
+MPQE_API int mpqe_adam_multi(const mpqe_adam_item_t* items_host, int32_t n, float lr, float beta1, float beta2, float eps,
+                    int32_t step, const mpqe_adam_state_t* state, void* stream);
+
+/* Adam over the entity tables from the row-sparse gradient of a step, trajectory-equivalent to the reference's DENSE
+ * Adam (train.py:86-88): a row that a step does not touch still moves through its momentum under dense Adam; those
+ * zero-gradient steps are applied lazily by `catchup` -- called with the ids a step is about to read, BEFORE its
+ * forward pass, with upto_step = step - 1 -- and `apply` then performs step `step` on the combined (unique) gradient
+ * rows.  `last_step` is an int32 array over the global row id space (table t owns ids [row_begin, row_begin+rows)),
+ * zero-initialised.  catchup with ids == NULL brings rows [0, count) of the id space up to date (before an
+ * evaluation, a checkpoint or an export).  Duplicate ids are fine in catchup (claimed once).  With a device `state`
+ * catchup runs up to state->step (call it BEFORE the step's tick) and apply performs step state->step (after it). */
+#define MPQE_MAX_TABLES 16
+typedef struct {
+  float* table;       /* [rows, d] */
+  float* exp_avg;     /* [rows, d] */
+  float* exp_avg_sq;  /* [rows, d] */
+  int64_t row_begin;  /* first global row id of this table */
+  int64_t rows;
+} mpqe_adam_table_t;
+MPQE_API int mpqe_adam_rows_catchup(const mpqe_adam_table_t* tables_host, int32_t num_tables, const int64_t* ids,
+                           int64_t count, int32_t upto_step, float lr, float beta1, float beta2, float eps,
+                           const mpqe_adam_state_t* state, int32_t* last_step, void* stream);
+MPQE_API int mpqe_adam_rows_apply(const mpqe_adam_table_t* tables_host, int32_t num_tables, const int64_t* ids,
+                         const float* rows, const int64_t* num, int64_t max_count, int32_t step, float lr, float beta1,
+                         float beta2, float eps, const mpqe_adam_state_t* state, int32_t* last_step, void* stream);
+
+/* ---- negative sampling on the device (model.py:470-476: random.choice over each query's stored negatives) --------
+ * out[i] = candidates[offsets[q] + r % (offsets[q+1] - offsets[q])] with q = query_index ? query_index[i]
+ * : (first_query + i) % num_queries_total (the reference's contiguous batch slice with wrap-around,
+ * data_utils.py:300-308) and r = splitmix64(seed, step, i): a counter-based draw, reproducible for a given
+ * (seed, step) whatever the launch geometry.  offsets == NULL: all queries share candidates[0 .. shared_count)
+ * (1-chain negatives are drawn from the whole target mode, model.py:472-473).  A query without candidates gets -1. */
+MPQE_API int mpqe_sample_negatives(const int64_t* candidates, const int64_t* offsets, const int64_t* query_index,
+                          int64_t first_query, int64_t num_queries_total, int64_t shared_count, int64_t count,
+                          uint64_t seed, uint64_t step, int64_t* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -58,9 +58,27 @@ class MatsumItem(C.Structure):
                 ('accumulate', C.c_int32)]
 
 
-ABI_STRUCTS = (Term, LayerGroup, WgradDest, WgradOperand, GatherItem, MarginItem, ColsumItem, MatsumItem)
+MAX_L2_ITEMS, MAX_ADAM_ITEMS, MAX_TABLES = 8, 32, 16
 
-P, I32, I64, F32, SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
+
+class L2Item(C.Structure):
+    _fields_ = [('param', C.c_void_p), ('grad', C.c_void_p), ('numel', C.c_int64)]
+
+
+class AdamItem(C.Structure):
+    _fields_ = [('param', C.c_void_p), ('grad', C.c_void_p), ('exp_avg', C.c_void_p), ('exp_avg_sq', C.c_void_p),
+                ('numel', C.c_int64)]
+
+
+class AdamTable(C.Structure):
+    _fields_ = [('table', C.c_void_p), ('exp_avg', C.c_void_p), ('exp_avg_sq', C.c_void_p), ('row_begin', C.c_int64),
+                ('rows', C.c_int64)]
+
+
+ABI_STRUCTS = (Term, LayerGroup, WgradDest, WgradOperand, GatherItem, MarginItem, ColsumItem, MatsumItem, L2Item,
+               AdamItem, AdamTable)
+
+P, I32, I64, F32, SZ, U64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t, C.c_uint64
 
 # name -> (restype, argtypes); mirrors include/mpqe_b200.h one to one (tests/test_abi.py checks both directions)
 SIGNATURES = {
@@ -103,6 +121,12 @@ SIGNATURES = {
     'mpqe_cosine_margin_multi': (I32, [P, I32, F32, I32, P]),
     'mpqe_colsum_multi_workspace_bytes': (SZ, [P, I32]),
     'mpqe_colsum_multi': (I32, [P, I32, P, SZ, P]),
+    'mpqe_l2_reg_multi': (I32, [P, I32, F32, F32, P, I32, P, P]),
+    'mpqe_adam_tick': (I32, [P, F32, F32, F32, P]),
+    'mpqe_adam_multi': (I32, [P, I32, F32, F32, F32, F32, I32, P, P]),
+    'mpqe_adam_rows_catchup': (I32, [P, I32, P, I64, I32, F32, F32, F32, F32, P, P, P]),
+    'mpqe_adam_rows_apply': (I32, [P, I32, P, P, P, I64, I32, F32, F32, F32, F32, P, P, P]),
+    'mpqe_sample_negatives': (I32, [P, P, P, I64, I64, I64, I64, U64, U64, P, P]),
 }
 
 _lib = None

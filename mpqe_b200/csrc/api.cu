@@ -26,6 +26,9 @@ extern "C" int mpqe_b200_sizeof(int which) {
     case 5: return (int)sizeof(mpqe_margin_item_t);
     case 6: return (int)sizeof(mpqe_colsum_item_t);
     case 7: return (int)sizeof(mpqe_matsum_item_t);
+    case 8: return (int)sizeof(mpqe_l2_item_t);
+    case 9: return (int)sizeof(mpqe_adam_item_t);
+    case 10: return (int)sizeof(mpqe_adam_table_t);
     default: return -1;
   }
 }

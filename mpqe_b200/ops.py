@@ -643,3 +643,115 @@ def colsum_multi(items, device):
         ws = workspace(lib.mpqe_colsum_multi_workspace_bytes(arr, len(chunk)), device, 'colsum')
         _lib.check(lib.mpqe_colsum_multi(arr, len(chunk), _ptr(ws), ws.numel(), _stream()), 'mpqe_colsum_multi')
         _count(2)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Regulariser, optimiser and negative sampling of the fused training step (csrc/optim.cu)
+# ---------------------------------------------------------------------------------------------------------------
+def l2_reg(params, grads, weight_decay, grad_scale, losses=None, norms=None):
+    """model.py:487-492 on the device: losses[:] += weight_decay * sum_i ||params[i]||, and
+    grads[i] += grad_scale * weight_decay * params[i] / ||params[i]|| (grads[i] laid out like params[i], or None)."""
+    lib = _lib.load()
+    arr = (_lib.L2Item * len(params))()
+    for i, (p, g) in enumerate(zip(params, grads)):
+        arr[i].param = _chk(p, torch.float32, 'param').data_ptr()
+        arr[i].grad = _chk(g, torch.float32, 'grad').data_ptr() if g is not None else 0
+        if g is not None and g.numel() != p.numel():
+            raise _lib.MpqeError('l2_reg: gradient and parameter sizes differ')
+        arr[i].numel = p.numel()
+    _lib.check(lib.mpqe_l2_reg_multi(arr, len(params), float(weight_decay), float(grad_scale), _ptr(losses),
+                                     losses.numel() if losses is not None else 0, _ptr(norms), _stream()),
+               'mpqe_l2_reg_multi')
+    _count()
+
+
+def adam_state(device):
+    """Device-resident optimiser clock (mpqe_adam_state_t: step, lr / bias correction 1, sqrt(bias correction 2))."""
+    return torch.zeros(4, dtype=torch.int32, device=device)
+
+
+def adam_tick(state, lr, beta1, beta2):
+    lib = _lib.load()
+    _lib.check(lib.mpqe_adam_tick(_ptr(state), lr, beta1, beta2, _stream()), 'mpqe_adam_tick')
+    _count()
+
+
+def adam_multi(items, lr, beta1, beta2, eps, step=0, state=None):
+    """One torch.optim.Adam step over [(param, grad, exp_avg, exp_avg_sq)] dense tensors, <= 32 per launch.
+    `state`: device clock from `adam_state` (graph-capturable) instead of the host `step`."""
+    lib = _lib.load()
+    for i in range(0, len(items), _lib.MAX_ADAM_ITEMS):
+        chunk = items[i:i + _lib.MAX_ADAM_ITEMS]
+        arr = (_lib.AdamItem * len(chunk))()
+        for j, (p, g, m, v) in enumerate(chunk):
+            for t, name in ((p, 'param'), (g, 'grad'), (m, 'exp_avg'), (v, 'exp_avg_sq')):
+                _chk(t, torch.float32, name)
+                if t.numel() != p.numel():
+                    raise _lib.MpqeError('adam_multi: %s has %d elements, param %d' % (name, t.numel(), p.numel()))
+            arr[j].param, arr[j].grad, arr[j].exp_avg, arr[j].exp_avg_sq = (p.data_ptr(), g.data_ptr(), m.data_ptr(),
+                                                                            v.data_ptr())
+            arr[j].numel = p.numel()
+        _lib.check(lib.mpqe_adam_multi(arr, len(chunk), lr, beta1, beta2, eps, int(step), _ptr(state), _stream()),
+                   'mpqe_adam_multi')
+        _count()
+
+
+class RowAdam(object):
+    """torch.optim.Adam over the entity tables driven by row-sparse gradients, trajectory-equivalent to the dense
+    optimiser of the reference (train.py:86-88): see mpqe_adam_rows_catchup / mpqe_adam_rows_apply.
+    `tables` = [(table tensor [rows, D], first global row id)]."""
+
+    def __init__(self, tables, lr=0.01, betas=(0.9, 0.999), eps=1e-8):
+        self.hyper = (float(lr), float(betas[0]), float(betas[1]), float(eps))
+        self.tables = [(t, int(begin)) for t, begin in tables]
+        if len(self.tables) > _lib.MAX_TABLES:
+            raise _lib.MpqeError('RowAdam: at most %d tables' % _lib.MAX_TABLES)
+        dev = self.tables[0][0].device
+        self.exp_avg = [torch.zeros_like(t) for t, _ in self.tables]
+        self.exp_avg_sq = [torch.zeros_like(t) for t, _ in self.tables]
+        self.total_rows = max(begin + t.shape[0] for t, begin in self.tables)
+        self.last = torch.zeros(self.total_rows, dtype=torch.int32, device=dev)
+        self.arr = (_lib.AdamTable * len(self.tables))()
+        for i, (t, begin) in enumerate(self.tables):
+            _chk(t, torch.float32, 'table')
+            self.arr[i].table, self.arr[i].exp_avg = t.data_ptr(), self.exp_avg[i].data_ptr()
+            self.arr[i].exp_avg_sq, self.arr[i].row_begin, self.arr[i].rows = self.exp_avg_sq[i].data_ptr(), begin, t.shape[0]
+
+    def catchup(self, ids, upto_step=0, state=None):
+        """Zero-gradient steps up to `upto_step` (or the device clock `state`) for the rows `ids` (global row ids,
+        duplicates allowed) -- call with the ids a step is about to read, before its forward and before the step's
+        tick.  ids=None: every row (before eval / export)."""
+        lib = _lib.load()
+        lr, b1, b2, eps = self.hyper
+        count = ids.numel() if ids is not None else self.total_rows
+        _lib.check(lib.mpqe_adam_rows_catchup(self.arr, len(self.tables), _ptr(ids), count, int(upto_step), lr, b1, b2,
+                                              eps, _ptr(state), _ptr(self.last), _stream()), 'mpqe_adam_rows_catchup')
+        _count()
+
+    def apply(self, ids, rows, num, step=0, state=None):
+        """Adam step `step` (or the device clock) on the combined (unique ids, summed rows, device count) gradient."""
+        lib = _lib.load()
+        lr, b1, b2, eps = self.hyper
+        _lib.check(lib.mpqe_adam_rows_apply(self.arr, len(self.tables), _ptr(_chk(ids, torch.int64, 'ids')),
+                                            _ptr(_chk(rows, torch.float32, 'rows')), _ptr(num), ids.numel(), int(step),
+                                            lr, b1, b2, eps, _ptr(state), _ptr(self.last), _stream()),
+                   'mpqe_adam_rows_apply')
+        _count()
+
+
+def sample_negatives(candidates, offsets, count, seed, step, first_query=0, num_queries_total=None, query_index=None,
+                     out=None):
+    """Device-side negative draw (model.py:470-476): one candidate per batch position from the CSR (candidates,
+    offsets) of the stored query set, or from the shared list `candidates` when offsets is None (1-chain)."""
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty(count, dtype=torch.int64, device=candidates.device)
+    if num_queries_total is None:
+        num_queries_total = offsets.numel() - 1 if offsets is not None else count
+    shared = candidates.numel() if offsets is None else 0
+    _lib.check(lib.mpqe_sample_negatives(_ptr(_chk(candidates, torch.int64, 'candidates')), _ptr(offsets),
+                                         _ptr(query_index), int(first_query), int(num_queries_total), int(shared),
+                                         int(count), int(seed), int(step), _ptr(_chk(out, torch.int64, 'out')),
+                                         _stream()), 'mpqe_sample_negatives')
+    _count()
+    return out

@@ -144,10 +144,8 @@ class TrainStep(object):
         return self._plan_on_side_stream(all_ids, dev), used
 
     def _plan_on_side_stream(self, ids, dev, after=None):
-        """ops.SparseRowsPlan(ids) on the second stream (joined by `_join_side`); plain call on the CPU emulator.
+        """ops.SparseRowsPlan(ids) on the second stream (joined by `_join_side`).
         `after`: an event to order the plan after, instead of everything enqueued on the current stream so far."""
-        if dev.type != 'cuda':
-            return ops.SparseRowsPlan(ids, self.total_rows)
         cur = torch.cuda.current_stream(dev)
         if self._side is None:
             self._side = torch.cuda.Stream(device=dev)
@@ -157,15 +155,15 @@ class TrainStep(object):
             self._side.wait_stream(cur)
         with torch.cuda.stream(self._side):
             plan = ops.SparseRowsPlan(ids, self.total_rows)
+        # the ids are read by the sort on the second stream: keep the caching allocator from handing their block to
+        # the main stream's next allocation while those kernels are still pending
+        ids.record_stream(self._side)
         plan.ws.record_stream(cur)
         plan.num.record_stream(cur)
         return plan
 
     def _weights_on_side_stream(self, jobs, dev):
-        """`Weights` + `Engine.prepare` on the second stream; `W.ready_event` orders the first layer launch after it.
-        (None on the CPU emulator: `loss_forward` then builds the weights itself.)"""
-        if dev.type != 'cuda':
-            return None
+        """`Weights` + `Engine.prepare` on the second stream; `W.ready_event` orders the first layer launch after it."""
         cur = torch.cuda.current_stream(dev)
         if self._side is None:
             self._side = torch.cuda.Stream(device=dev)
@@ -178,8 +176,13 @@ class TrainStep(object):
         return W
 
     def _join_side(self, dev):
-        if dev.type == 'cuda':
-            torch.cuda.current_stream(dev).wait_stream(self._side)
+        torch.cuda.current_stream(dev).wait_stream(self._side)
+
+    def _on_side_stream(self, dev, fn):
+        """Runs fn() on the second stream, ordered after everything enqueued on the current stream so far."""
+        self._side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(self._side):
+            fn()
 
     def _peer_rows_buffer(self, cap):
         """[>= cap, D] gradient-row buffer in memory that every rank of the group can address (torch symmetric memory:
@@ -276,23 +279,30 @@ class TrainStep(object):
             wts = self._wts = (key, torch.tensor(key, dtype=torch.float32, device=dev))
         # d total / d loss_i = the batch weights, known now: the margin backward rides on the margin forward
         losses, W = loss_forward(m, jobs, tg, ng, self.margin, True, grad_losses=wts[1], W=W)
-        overlap_tail = plan is not None and dev.type == 'cuda'
+        overlap_tail = plan is not None
         G = loss_backward(m, jobs, W, tg, ng, self.margin, wts[1], self.table_offsets, rows=R,
                           defer_constant=overlap_tail)
+        self._weight_decay(W, G, losses, sum(key))
         if plan is not None:
             self._join_side(dev)
-            if overlap_tail:
-                # the batch-constant tail of the backward (five small latency-bound launches) runs on the second
-                # stream under the row summation, which does not depend on it
-                self._side.wait_stream(torch.cuda.current_stream(dev))
-                with torch.cuda.stream(self._side):
-                    G.finish()
+            # the batch-constant tail of the backward (five small latency-bound launches) runs on the second
+            # stream under the row summation, which does not depend on it
+            self._on_side_stream(dev, G.finish)
             sparse = plan.apply(rows[:used], pad_id=self.total_rows)
-            if overlap_tail:
-                self._join_side(dev)
+            self._join_side(dev)
         else:
             sparse = (ids[:used], rows[:used], None)
         return StepResult(losses, wts[1], G, sparse)
+
+    def _weight_decay(self, W, G, losses, weight_sum):
+        """The L2 term of every margin_loss call of the step (reference model.py:487-492: weight_decay * sum of the
+        un-squared norms of the readout-MLP parameters, once per formula batch): each loss gets the term, the readout
+        gradients get (sum of the batch weights) * weight_decay * p / ||p||.  The transposed copies W.w1t / W.w2t have
+        the layout of the gradient buffers and the same norms as the parameters."""
+        wd = float(self.model.weight_decay)
+        if W.ro is None or wd <= 0:
+            return
+        ops.l2_reg([W.w1t, W.b1, W.w2t, W.b2], [G.dw1t, G.db1, G.dw2t, G.db2], wd, float(weight_sum), losses=losses)
 
     # ---- CUDA-graph mode: the whole local step becomes one graph launch --------------------------------------
     @torch.no_grad()
@@ -382,25 +392,68 @@ class TrainStep(object):
             res = self.forward_backward([self.to_device(hb) for hb in host_batches])
         return res, res.losses.cpu()
 
-    # ---- optional fused optimiser over the dense bucket (torch.optim.Adam defaults, train.py:86-88) -----
-    @torch.no_grad()
-    def adam_step_dense(self, res, lr=0.01, betas=(0.9, 0.999), eps=1e-8):
-        """Adam on the dense parameters straight from the flat gradient bucket (entity tables are left to the caller:
-        the reference's dense Adam keeps moving rows after they were touched)."""
+    # ---- fused optimiser (torch.optim.Adam defaults, reference train.py:86-88) ------------------------------
+    def _adam_setup(self, lr, betas, eps):
         m = self.model
-        W_params = []
         for layer in m.distinct_layers():
-            W_params.append(layer.basis)
-        for layer in m.distinct_layers():
-            W_params.append(layer.root)
-        for layer in m.distinct_layers():
-            W_params.append(layer.bias)
-        W_params.append(m.mode_embeddings.weight)
-        G = res.dense
+            if layer.att is not None:
+                raise ops._lib.MpqeError('TrainStep.adam_step does not handle a basis decomposition (num_bases > 0); '
+                                         'use torch.optim with margin_loss instead')
+        dev = m.mode_embeddings.weight.device
+        params = [l.basis for l in m.distinct_layers()] + [l.root for l in m.distinct_layers()]
+        params += [l.bias for l in m.distinct_layers()] + [m.mode_embeddings.weight]
+        if isinstance(m.readout, torch.nn.Module):
+            lin1, lin2 = m.readout.layers[0], m.readout.layers[2]
+            params += [lin1.weight, lin2.weight, lin1.bias, lin2.bias]
+        self.adam_params = [p.data for p in params]
+        self.adam_state = [(torch.zeros_like(p), torch.zeros_like(p)) for p in self.adam_params]
+        self.adam_hyper = (float(lr), float(betas[0]), float(betas[1]), float(eps))
+        self.adam_clock = ops.adam_state(dev)
+        self.row_adam = ops.RowAdam([(module.weight.data, self.table_offsets[mode])
+                                     for mode, module in m.enc.feature_modules.items()], lr, betas, eps)
+
+    def _dense_grads(self, G):
         grads = list(G.dw) + list(G.droot) + list(G.dbias) + [G.dmode]
+        if isinstance(self.model.readout, torch.nn.Module):
+            # the readout gradients are kept transposed (the layout the kernels produce): bring them to the parameters'
+            grads += [ops.transpose(G.dw1t), ops.transpose(G.dw2t), G.db1, G.db2]
+        return grads
+
+    @torch.no_grad()
+    def catchup_rows(self, batches=None):
+        """Row-sparse Adam bookkeeping BEFORE a step's forward: the rows this step reads receive the zero-gradient
+        Adam steps they skipped since they were last touched, so the forward sees exactly what dense Adam would have
+        stored (see mpqe_adam_rows_catchup).  batches=None: every row (before evaluation / checkpoint / export)."""
         if self.adam_state is None:
-            self.adam_state = [(torch.zeros_like(p.data), torch.zeros_like(p.data)) for p in W_params]
-        self.steps += 1
+            return
+        dev = self.model.mode_embeddings.weight.device
+        with ops.device_guard(dev):
+            if batches is None:
+                self.row_adam.catchup(None, state=self.adam_clock)
+                return
+            from .model import plan_rows
+            R0 = plan_rows(self.model, [b.job for b in batches], [b.targets for b in batches],
+                           [b.negatives for b in batches], self.table_offsets)
+            _, ids, used = R0.shared
+            self.row_adam.catchup(ids[:used], state=self.adam_clock)
+
+    @torch.no_grad()
+    def adam_step(self, res, lr=0.01, betas=(0.9, 0.999), eps=1e-8):
+        """One torch.optim.Adam step on EVERY parameter from a StepResult: the dense parameters (layers, mode
+        embeddings, readout MLP) in one launch from the flat gradient bucket, the entity tables from the combined
+        row-sparse gradient.  Call `catchup_rows(batches)` before the step's forward: with it the trajectory equals
+        the reference's dense Adam over the tables (rows a step does not touch are brought up to date lazily)."""
+        if self.adam_state is None:
+            self._adam_setup(lr, betas, eps)
+        lr, b1, b2, eps = self.adam_hyper
+        G = res.dense
         with ops.device_guard(G.flat.device):
-            for p, g, (m1, m2) in zip(W_params, grads, self.adam_state):
-                ops.adam_dense(p.data, g.contiguous(), m1, m2, lr, betas[0], betas[1], eps, self.steps)
+            ops.adam_tick(self.adam_clock, lr, b1, b2)
+            items = [(p, g.contiguous(), m1, m2) for p, g, (m1, m2) in
+                     zip(self.adam_params, self._dense_grads(G), self.adam_state)]
+            ops.adam_multi(items, lr, b1, b2, eps, state=self.adam_clock)
+            uid, urows, num = res.sparse
+            self.row_adam.apply(uid, urows, num, state=self.adam_clock)
+        self.steps += 1
+
+    adam_step_dense = adam_step     # round-1 name

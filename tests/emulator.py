@@ -273,10 +273,37 @@ def install(monkeypatch):
                  'cosine_scores', 'cosine_scores_bwd', 'rank_counts_ragged', 'rank_counts_table',
                  'build_query_graph', 'relation_sort', 'sparse_rows_combine', 'SparseRowsPlan', 'scatter_rows',
                  'gather_multi', 'matrix_sum_multi',
-                 'cosine_margin_multi', 'colsum_multi'):
+                 'cosine_margin_multi', 'colsum_multi', 'l2_reg'):
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(ops, 'device_guard', lambda device: contextlib.nullcontext())
     monkeypatch.setattr(ops, 'tensor_cores_default', lambda: False)
+    # the fused training step orders its work over two CUDA streams; on the CPU everything simply runs in order
+    from mpqe_b200 import model as M
+    from mpqe_b200.train_step import TrainStep
+
+    def weights_now(self, jobs, dev):
+        W = M.Weights(self.model, True)
+        self.model._engine.prepare(jobs, W)
+        return W
+
+    monkeypatch.setattr(TrainStep, '_plan_on_side_stream',
+                        lambda self, ids, dev, after=None: ops.SparseRowsPlan(ids, self.total_rows))
+    monkeypatch.setattr(TrainStep, '_weights_on_side_stream', weights_now)
+    monkeypatch.setattr(TrainStep, '_join_side', lambda self, dev: None)
+    monkeypatch.setattr(TrainStep, '_on_side_stream', lambda self, dev, fn: fn())
+
+
+def l2_reg(params, grads, weight_decay, grad_scale, losses=None, norms=None):
+    total = 0.0
+    for i, (p, g) in enumerate(zip(params, grads)):
+        nrm = torch.sqrt((p * p).sum())
+        total = total + nrm
+        if g is not None and float(nrm) > 0:
+            g += (grad_scale * weight_decay / nrm) * p.reshape(g.shape)
+        if norms is not None:
+            norms[i] = nrm
+    if losses is not None:
+        losses += weight_decay * total
 
 
 def gather_multi(items, backward=False):

@@ -66,3 +66,24 @@ def assert_close(actual, expected, rtol, atol, what=''):
         i = np.unravel_index(np.argmax(err - tol), err.shape)
         raise AssertionError('%s: max violation at %s: got %r want %r (|err|=%.3e, tol=%.3e)' % (
             what, i, actual[i], expected[i], err[i], tol[i]))
+
+
+# ---- stated fp32 tolerances ---------------------------------------------------------------
+# Gradients are sums over the batch: the error of a tensor is measured against that tensor's largest entry.
+#   strict-fp32 FFMA kernels ........ max|err| <= 1e-5 * max|g|
+#   tcgen05 3xTF32 kernels .......... max|err| <= 5e-5 * max|g|   (the split drops the lo*lo products)
+GRAD_TOL = {'ffma': 1e-5, 'tcgen05': 5e-5}
+OBSERVED = {}     # what -> largest normalised error seen in this session (written out by conftest at exit)
+
+
+def assert_grad_close(got, want, mode, what):
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    scale = max(np.abs(want).max(), 1e-30)
+    err = np.abs(got - want).max() / scale
+    key = '%s %s' % (mode, what.split(' ')[0])
+    OBSERVED[key] = max(OBSERVED.get(key, 0.0), float(err))
+    assert np.isfinite(got).all(), '%s: non-finite gradient' % what
+    assert err <= GRAD_TOL[mode], '%s: max|err| = %.3e * max|g| exceeds the %s bound %.1e' % (
+        what, err, mode, GRAD_TOL[mode])

@@ -67,3 +67,40 @@ def model_grads(model):
         else:
             out[k] = (g.to_dense() if g.is_sparse else g).detach().cpu().numpy()
     return out
+
+
+def train_step_grads(ts, model, res, device):
+    """{state_dict name: gradient tensor} of a TrainStep result: views of the flat dense bucket plus the combined
+    row-sparse entity gradients scattered back into dense tables (global row = table offset + row)."""
+    G = res.dense
+    got = {}
+    layers = model.distinct_layers()
+    for name, prm in model.named_parameters():
+        for li, layer in enumerate(layers):
+            if prm is layer.basis:
+                got[name] = G.dw[li]
+            elif prm is layer.root:
+                got[name] = G.droot[li]
+            elif prm is layer.bias:
+                got[name] = G.dbias[li]
+        if prm is model.mode_embeddings.weight:
+            got[name] = G.dmode
+    if isinstance(model.readout, torch.nn.Module):
+        lin1, lin2 = model.readout.layers[0], model.readout.layers[2]
+        for name, prm in model.named_parameters():
+            if prm is lin1.weight:
+                got[name] = G.dw1t.t()
+            elif prm is lin2.weight:
+                got[name] = G.dw2t.t()
+            elif prm is lin1.bias:
+                got[name] = G.db1
+            elif prm is lin2.bias:
+                got[name] = G.db2
+    uid, urows, num = res.sparse
+    k = int(num)
+    dense_tables = torch.zeros(ts.total_rows, urows.shape[1], device=device)
+    dense_tables[uid[:k]] = urows[:k]
+    for mode, off in ts.table_offsets.items():
+        rows = model.enc.table(mode).shape[0]
+        got['enc.feat-%s.weight' % mode] = dense_tables[off:off + rows]
+    return got, uid[:k]

@@ -1,0 +1,125 @@
+"""Parity of the CUDA path with the CPU oracle ON THE CONFIGURATIONS BASELINE.json NAMES, at the batch sizes it names:
+
+  config 2  MPQE-TM  (--readout mp --adaptive, 3 layers) on the AIFB-shaped graph
+  config 3  MPQE-max and MPQE-concat (2 layers) on the MUTAG-shaped graph
+  config 4  MPQE-sum (2 layers) on the AM-shaped graph (the bench workload)
+
+each with all 7 query types at B = 512 and B = 4096 queries per type, on the strict-fp32 FFMA kernels and on the
+tcgen05 3xTF32 kernels.  Compared: the loss of every formula batch, EVERY parameter gradient (entity tables
+included, made dense) and the set of touched entity rows.  The oracle (reference arithmetic: per-edge weight gather
++ bmm + scatter, two encoder passes) is evaluated once per case and shared by both kernel modes.
+Tolerances: tests/helpers.py (GRAD_TOL) and DESIGN.md section 5.
+"""
+import functools
+
+import numpy as np
+import pytest
+import torch
+
+from mpqe_b200 import synthetic
+from mpqe_b200.graph import Formula
+from oracle import mpqe_oracle as O
+from tests.helpers import assert_close, assert_grad_close
+from tests.model_utils import build_model, model_grads, oracle_loss_and_grads, queries_from_ids, train_step_grads
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+# name -> (graph shape, readout, layers, adaptive)
+CASES = {
+    'aifb_tm': ('aifb', 'mp', 3, True),
+    'mutag_max': ('mutag', 'max', 2, False),
+    'mutag_concat': ('mutag', 'concat', 2, False),
+    'am_sum': ('am', 'sum', 2, False),
+}
+
+
+@functools.lru_cache(maxsize=None)
+def world(case):
+    shape, readout, layers, adaptive = CASES[case]
+    kg = synthetic.make_kg(shape, seed=0)
+    rels, _, node_maps = kg.raw()
+    cfg = O.Config(readout=readout, num_layers=layers, adaptive=adaptive, weight_decay=1e-3)
+    params = O.init_params(rels, node_maps, cfg, d=128, seed=1)
+    mode_ids, rel_ids = O.schema_ids(rels)
+    frng = np.random.RandomState(0)
+    formulas = [Formula(qt, kg.sample_formula(qt, frng)) for qt in synthetic.QUERY_TYPES]
+    return kg, cfg, params, mode_ids, rel_ids, O.id_to_row(node_maps), formulas
+
+
+@functools.lru_cache(maxsize=None)
+def oracle_case(case, B):
+    """[(formula, anchors, targets, negatives, oracle loss, oracle gradients)] for the 7 query types."""
+    kg, cfg, params, mode_ids, rel_ids, id2row, formulas = world(case)
+    rng = np.random.RandomState(B)
+    out = []
+    for f in formulas:
+        a, t, n = synthetic.sample_id_batch(kg, f, B, rng)
+        spec = O.formula_spec(f.query_type, f.rels)
+        loss, grads = oracle_loss_and_grads(params, cfg, spec, torch.from_numpy(a), rel_ids, mode_ids, id2row,
+                                            torch.from_numpy(t), torch.from_numpy(n))
+        out.append((f, a, t, n, loss, grads))
+    return out
+
+
+@pytest.fixture(params=['ffma', 'tcgen05'])
+def mode(request):
+    from mpqe_b200 import _lib, ops
+    tc = request.param == 'tcgen05'
+    if tc and not _lib.load().mpqe_b200_has_tcgen05():
+        pytest.skip('library built without tcgen05 kernels')
+    ops.set_tensor_cores(tc)
+    yield request.param
+    ops.set_tensor_cores(False)
+
+
+def touched_rows(model, ts, formula, anchors, targets, negatives):
+    """Global table rows (table offset + row) a formula batch touches: anchors, targets, negatives."""
+    id2row = model.enc.node_maps.cpu().numpy()
+    rows = [ts.table_offsets[m] + id2row[anchors[:, i]] for i, m in enumerate(formula.anchor_modes)]
+    rows += [ts.table_offsets[formula.target_mode] + id2row[targets], ts.table_offsets[formula.target_mode] + id2row[negatives]]
+    return np.concatenate(rows)
+
+
+@pytest.mark.parametrize('B', [512, 4096])
+@pytest.mark.parametrize('case', sorted(CASES))
+def test_fused_step_vs_oracle(case, B, mode):
+    """The fused training step (all 7 formula batches in one pass: the bench path) against the oracle."""
+    from mpqe_b200.train_step import HostBatch, TrainStep
+    kg, cfg, params, mode_ids, rel_ids, id2row, formulas = world(case)
+    model = build_model(kg.raw(), cfg, params, DEV, sparse_grad=True)
+    ts = TrainStep(model)
+    want_losses, want, host, touched = [], {}, [], []
+    for f, a, t, n, loss, grads in oracle_case(case, B):
+        host.append(HostBatch(f, torch.from_numpy(a), torch.from_numpy(t), torch.from_numpy(n)))
+        want_losses.append(loss)
+        for k, g in grads.items():
+            want[k] = want.get(k, 0) + g
+        touched.append(touched_rows(model, ts, f, a, t, n))
+    res = ts.forward_backward([ts.to_device(hb) for hb in host])
+    torch.cuda.synchronize()
+    atol = 1e-5 if mode == 'tcgen05' else 2e-6        # cosine scores live in [-1, 1]; the loss is their batch mean
+    assert_close(res.losses.cpu().numpy(), np.array(want_losses, dtype=np.float32), 1e-5, atol, 'losses')
+    got, uid = train_step_grads(ts, model, res, DEV)
+    # integer artefact: the combined row set is exactly the set of rows the batches touch, ascending, no duplicates
+    assert np.array_equal(uid.cpu().numpy(), np.unique(np.concatenate(touched)))
+    for name, g in want.items():
+        assert got.get(name) is not None, name
+        assert_grad_close(got[name].detach().cpu().numpy(), g, mode, '%s:B%d grad %s' % (case, B, name))
+
+
+@pytest.mark.parametrize('case', sorted(CASES))
+def test_margin_loss_api_vs_oracle(case, mode):
+    """The reference-shaped API (`margin_loss` + autograd `backward`, one formula batch per call) at B = 512."""
+    kg, cfg, params, mode_ids, rel_ids, id2row, formulas = world(case)
+    model = build_model(kg.raw(), cfg, params, DEV, sparse_grad=True)
+    atol = 1e-5 if mode == 'tcgen05' else 2e-6
+    for f, a, t, n, want_loss, want in oracle_case(case, 512):
+        queries = queries_from_ids(f.query_type, f.rels, a, t)
+        model.zero_grad()
+        loss = model.margin_loss_ids(queries[0].formula, queries, torch.from_numpy(t), torch.from_numpy(n))
+        assert_close(loss.item(), want_loss, 1e-5, atol, '%s %s loss' % (case, f.query_type))
+        loss.backward()
+        got = model_grads(model)
+        for k, g in want.items():
+            assert_grad_close(got[k], g, mode, '%s:api grad %s (%s)' % (case, k, f.query_type))

@@ -174,7 +174,7 @@ def test_train_step_gradients_match_oracle(readout, num_layers, adaptive, shared
     kg = synthetic.make_kg('tiny', seed=5)
     rels, _, node_maps = kg.raw()
     cfg = O.Config(readout=readout, num_layers=num_layers, adaptive=adaptive, shared_layers=shared,
-                   scatter_op=scatter_op, weight_decay=0.0)
+                   scatter_op=scatter_op, weight_decay=1e-3)
     params = O.init_params(rels, node_maps, cfg, d=128, seed=1)
     mode_ids, rel_ids = O.schema_ids(rels)
     id2row = O.id_to_row(node_maps)
@@ -198,42 +198,8 @@ def test_train_step_gradients_match_oracle(readout, num_layers, adaptive, shared
     torch.cuda.synchronize()
     assert_close(res.losses.cpu().numpy(), np.array(want_losses, dtype=np.float32), 1e-5, 1e-5, 'losses')
     assert_close(float(res.total), float(np.sum(want_losses)), 1e-5, 1e-5, 'total')
-    G = res.dense
-    W = None
-    got = {}
-    for name, prm in model.named_parameters():
-        got[name] = None
-    layers = model.distinct_layers()
-    for li, layer in enumerate(layers):
-        for name, prm in model.named_parameters():
-            if prm is layer.basis:
-                got[name] = G.dw[li]
-            elif prm is layer.root:
-                got[name] = G.droot[li]
-            elif prm is layer.bias:
-                got[name] = G.dbias[li]
-    for name, prm in model.named_parameters():
-        if prm is model.mode_embeddings.weight:
-            got[name] = G.dmode
-    if isinstance(model.readout, torch.nn.Module):
-        lin1, lin2 = model.readout.layers[0], model.readout.layers[2]
-        for name, prm in model.named_parameters():
-            if prm is lin1.weight:
-                got[name] = G.dw1t.t()
-            elif prm is lin2.weight:
-                got[name] = G.dw2t.t()
-            elif prm is lin1.bias:
-                got[name] = G.db1
-            elif prm is lin2.bias:
-                got[name] = G.db2
-    uid, urows, num = res.sparse
-    k = int(num)
-    total_rows = ts.total_rows
-    dense_tables = torch.zeros(total_rows, 128, device=DEV)
-    dense_tables[uid[:k]] = urows[:k]
-    for mode, off in ts.table_offsets.items():
-        rows = model.enc.table(mode).shape[0]
-        got['enc.feat-%s.weight' % mode] = dense_tables[off:off + rows]
+    from tests.model_utils import train_step_grads
+    got, _ = train_step_grads(ts, model, res, DEV)
     for name, g in want.items():
         if shared and name.startswith('layers.') and not name.startswith('layers.0.'):
             continue      # shared layers: the oracle reports the one parameter set under layers.0

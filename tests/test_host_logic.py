@@ -193,7 +193,7 @@ def test_fused_train_step_host_logic_vs_oracle(emu, readout, num_layers, adaptiv
     kg = synthetic.make_kg('tiny', seed=5)
     rels, _, node_maps = kg.raw()
     cfg = O.Config(readout=readout, num_layers=num_layers, adaptive=adaptive, shared_layers=shared,
-                   scatter_op=scatter_op, weight_decay=0.0)
+                   scatter_op=scatter_op, weight_decay=1e-3)
     params = O.init_params(rels, node_maps, cfg, d=128, seed=1)
     mode_ids, rel_ids = O.schema_ids(rels)
     id2row = O.id_to_row(node_maps)
