@@ -228,6 +228,11 @@ typedef struct {
   int64_t id_offset;
   int32_t normalize;
   int32_t reserved;
+  /* data-parallel training with row-range-owned tables: peer_tables (DEVICE array of world pointers, entry r = rank r's
+   * full-size copy of `table` as mapped into this process) and peer_chunk = ceil(table_rows / world); a normalised row
+   * is then read from its owner's copy (peer_tables[row / peer_chunk]).  NULL: read `table`. */
+  const float* const* peer_tables;
+  int64_t peer_chunk;
 } mpqe_gather_item_t;
 MPQE_API int mpqe_gather_multi(const mpqe_gather_item_t* items_host, int32_t n, int32_t backward, void* stream);
 
@@ -251,6 +256,8 @@ typedef struct {
   float* rows_out;
   int64_t* rows_id;
   int64_t id_offset;
+  const float* const* peer_tables;   /* as in mpqe_gather_item_t */
+  int64_t peer_chunk;
 } mpqe_margin_item_t;
 MPQE_API int mpqe_cosine_margin_multi(const mpqe_margin_item_t* items_host, int32_t n, float margin, int32_t backward,
                                       void* stream);
@@ -307,6 +314,26 @@ MPQE_API int mpqe_sparse_rows_apply_peers(const float* const* peer_rows_host, in
                                  int64_t table_rows, int64_t pad_id, float scale, int64_t* unique_ids,
                                  float* unique_rows, const int64_t* num_unique, void* workspace,
                                  size_t workspace_bytes, void* stream);
+/* ---- data-parallel exchange over peer-mapped memory (new capability; the reference is single-process) ------------
+ * `peer_*_host[r]` is rank r's buffer as mapped into THIS process (e.g. torch symmetric memory); all ranks call the
+ * same sequence of these entry points on their streams. */
+/* flag barrier: peer_flags_host[r] = rank r's int32[MPQE_MAX_PEERS] flag array (zero-initialised), `epoch` a
+ * zero-initialised device int32 private to the rank.  Everything the stream did before the barrier is visible to the
+ * peers after it.  Graph-capturable (the epoch lives on the device). */
+MPQE_API int mpqe_peer_barrier(const void* const* peer_flags_host, int32_t rank, int32_t world, int32_t* epoch,
+                      void* stream);
+/* out[i] = scale * sum_r peer_bufs[r][i] in rank order (identical bits on every rank); numel % 4 == 0 */
+MPQE_API int mpqe_allreduce_peers(const void* const* peer_bufs_host, int32_t world, int64_t numel, float scale, float* out,
+                         void* stream);
+/* Owner-side plan of the row-gradient exchange.  The entity tables are owned row-range-wise: rank r owns rows
+ * [r*ceil(rows_t/world), (r+1)*ceil(rows_t/world)) of every table t (global row id = table_begin[t] + row).  The ids
+ * every rank emitted for its step (per_rank_count each, mpqe_gather_multi mode 2) are read in place; ids this rank
+ * does not own are dropped; the rest is planned exactly like mpqe_sparse_rows_plan over the rank-major concatenation,
+ * so that mpqe_sparse_rows_apply_peers then sums the owned rows out of the peers' row buffers. */
+MPQE_API int mpqe_sparse_rows_plan_owner(const void* const* peer_ids_host, int32_t world, int32_t rank,
+                                int64_t per_rank_count, const int64_t* table_begin_host,
+                                const int64_t* table_rows_host, int32_t num_tables, int64_t total_rows,
+                                int64_t* num_unique, void* workspace, size_t workspace_bytes, void* stream);
 /* dense[ids[i], :] (+)= rows[i, :] for i < *num (ids unique) */
 MPQE_API int mpqe_scatter_rows(const int64_t* ids, const float* rows, const int64_t* num, int64_t max_count,
                       float* dense, int32_t accumulate, void* stream);

@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, '_C', 'libmpqe_b200.so')
+LIB_PATH = os.environ.get('MPQE_LIB_PATH') or os.path.join(HERE, '_C', 'libmpqe_b200.so')
 
 MAX_GROUPS, MAX_TERMS, MAX_SLOTS, MAX_DESTS, D = 8, 16, 8, 64, 128
 EPI_NONE, EPI_RELU, EPI_MASK = 0, 1, 2
@@ -34,14 +34,16 @@ class GatherItem(C.Structure):
     _fields_ = [('table', C.c_void_p), ('table_rows', C.c_int64), ('id2row', C.c_void_p), ('ids', C.c_void_p),
                 ('ids_stride', C.c_int64), ('count', C.c_int64), ('out', C.c_void_p), ('out_stride', C.c_int64),
                 ('grad', C.c_void_p), ('grad_stride', C.c_int64), ('rows_out', C.c_void_p), ('rows_id', C.c_void_p),
-                ('id_offset', C.c_int64), ('normalize', C.c_int32), ('reserved', C.c_int32)]
+                ('id_offset', C.c_int64), ('normalize', C.c_int32), ('reserved', C.c_int32),
+                ('peer_tables', C.c_void_p), ('peer_chunk', C.c_int64)]
 
 
 class MarginItem(C.Structure):
     _fields_ = [('q', C.c_void_p), ('B', C.c_int64), ('table', C.c_void_p), ('id2row', C.c_void_p),
                 ('ids_pos', C.c_void_p), ('ids_neg', C.c_void_p), ('score_pos', C.c_void_p), ('score_neg', C.c_void_p),
                 ('hinge', C.c_void_p), ('loss', C.c_void_p), ('grad_loss', C.c_void_p), ('dq', C.c_void_p),
-                ('rows_out', C.c_void_p), ('rows_id', C.c_void_p), ('id_offset', C.c_int64)]
+                ('rows_out', C.c_void_p), ('rows_id', C.c_void_p), ('id_offset', C.c_int64),
+                ('peer_tables', C.c_void_p), ('peer_chunk', C.c_int64)]
 
 
 class ColsumItem(C.Structure):
@@ -58,7 +60,7 @@ class MatsumItem(C.Structure):
                 ('accumulate', C.c_int32)]
 
 
-MAX_L2_ITEMS, MAX_ADAM_ITEMS, MAX_TABLES = 8, 32, 16
+MAX_L2_ITEMS, MAX_ADAM_ITEMS, MAX_TABLES, MAX_PEERS = 8, 32, 16, 16
 
 
 class L2Item(C.Structure):
@@ -114,6 +116,9 @@ SIGNATURES = {
     'mpqe_sparse_rows_plan': (I32, [P, I64, I64, P, P, SZ, P]),
     'mpqe_sparse_rows_apply': (I32, [P, I64, I64, I64, F32, P, P, P, P, SZ, P]),
     'mpqe_sparse_rows_apply_peers': (I32, [P, I32, I64, I64, I64, F32, P, P, P, P, SZ, P]),
+    'mpqe_peer_barrier': (I32, [P, I32, I32, P, P]),
+    'mpqe_allreduce_peers': (I32, [P, I32, I64, F32, P, P]),
+    'mpqe_sparse_rows_plan_owner': (I32, [P, I32, I32, I64, P, P, I32, I64, P, P, SZ, P]),
     'mpqe_scatter_rows': (I32, [P, P, P, I64, P, I32, P]),
     'mpqe_adam_dense': (I32, [P, P, P, P, I64, F32, F32, F32, F32, I32, P]),
     'mpqe_pack_weights': (I32, [P, I32, P, P]),

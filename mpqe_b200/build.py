@@ -11,7 +11,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-OUT_DIR = os.path.join(HERE, '_C')
+OUT_DIR = os.environ.get('MPQE_BUILD_DIR') or os.path.join(HERE, '_C')   # (debug builds go to a directory of their own)
 LIB_PATH = os.path.join(OUT_DIR, 'libmpqe_b200.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '--use_fast_math=false',

@@ -534,7 +534,9 @@ extern "C" int mpqe_layer_forward(const mpqe_layer_group_t* groups_host, int32_t
   bool rows_only = true;
   for (int i = 0; i < num_groups; ++i) rows_only = rows_only && groups_host[i].num_queries == 1;
   if (rows_only) return layer_forward_rows(groups_host, num_groups, (cudaStream_t)stream);
-  if (use_tensor_cores) return layer_forward_tc(groups_host, num_groups, (cudaStream_t)stream);
+  if (use_tensor_cores)
+    return tc_generation() == 2 ? layer_forward_tc2(groups_host, num_groups, (cudaStream_t)stream)
+                                : layer_forward_tc(groups_host, num_groups, (cudaStream_t)stream);
   return layer_forward_simt(groups_host, num_groups, (cudaStream_t)stream);
 }
 

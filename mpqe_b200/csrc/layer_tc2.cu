@@ -1,0 +1,502 @@
+// Fused R-GCN layer on tcgen05, second generation: the QUERIES are the N side of the MMA (N = 256) and the weight
+// matrix the M side (M = 128 output features), i.e. the accumulator in tensor memory is D[feature, query].
+//
+// Why (measured on B200 with tools/tc_rate_probe.cu, profiles/r02_tc_rate_probe.txt): one tcgen05.mma.kind::tf32
+// costs ~130-160 cycles whether N is 128 or 256, so a 128 x 128 x 8 instruction (the first-generation kernel,
+// layer_tc.cu) runs the tensor pipe at 40 % of its rate and a 128 x 256 x 8 one at 80-90 %.  The contraction width of
+// this model is fixed (d = 128 features in, 128 out), so the only dimension that can fill N = 256 is the batch:
+//   D[n, q] (+)= sum_k Wt[n, k] * X[q, k],    Wt[n, k] = M[k, n]   (out[q, :] = X[q, :] @ M)
+// Same contract as layer_simt.cu / layer_tc.cu (term lists, see include/mpqe_b200.h); the reference lines replaced
+// are /root/reference/mpqe/model.py:292-294 (index_select + bmm), :277 (gather + scatter_add), :301-304 (root,
+// bias), :437 (relu) and their autograd.  fp32 accuracy through the 3xTF32 split, as before.
+//
+// Persistent, warp-specialised CTA per SM (13 warps), unit = (group, out slot, 256-query tile):
+//   warps 4-11  producers : activation rows global --ld.global.v4 (3 stages of loads in flight per thread)--> split
+//                           hi/lo --> st.shared in the canonical K-major no-swizzle layout; one thread stages the
+//                           stage's weight chunk (pre-split image, mpqe_pack_weights) with a 16 KB bulk copy
+//   warp  12    MMA issuer: per stage (16 k) 2 k-steps x 3 products (lo*hi, hi*lo, hi*hi) of 128 x 256 x 8,
+//                           tcgen05.commit -> empty[stage]; after the unit's last stage -> acc_full[buffer]
+//   warps 0-3   epilogue  : thread = output feature (TMEM lane), 32 queries per tcgen05.ld; a warp's store of one
+//                           query is 128 contiguous bytes of the output row, the four warps complete its 512 bytes --
+//                           no shared-memory transpose.  Two 256-column accumulators ping-pong (all 512 TMEM columns).
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace mpqe {
+
+namespace {
+
+using namespace tc;
+
+constexpr int EPI_WARPS = 4;
+constexpr int PROD_WARPS = 8;
+constexpr int PROD_THREADS = PROD_WARPS * 32;
+constexpr int MMA_WARP = EPI_WARPS + PROD_WARPS;
+constexpr int THREADS = (MMA_WARP + 1) * 32;     // 416
+constexpr int BQ = 256;                          // queries per unit = UMMA N
+constexpr int KC = 16;                           // k per pipeline stage = 2 UMMA k-steps of 8
+constexpr int STAGES = 4;
+constexpr int LOADS_AHEAD = 3;                   // stages of activation loads in flight per producer thread
+constexpr int W_TILE = 128 * KC * 4;             // 8 KB: weight chunk, hi or lo      [128 n][16 k]
+constexpr int X_TILE = BQ * KC * 4;              // 16 KB: activation chunk, hi or lo [256 q][16 k]
+constexpr int STAGE_BYTES = 2 * W_TILE + 2 * X_TILE;   // W_hi | W_lo | X_hi | X_lo = 48 KB
+constexpr int TMEM_COLS = 512;                   // two 256-column fp32 accumulators
+constexpr size_t TC2_SMEM = size_t(STAGES) * STAGE_BYTES + 1024;
+// both operands K-major: element (row, k) of a [rows][16 k] chunk at (row/8)*512 + (k/4)*128 + (row%8)*16 + (k%4)*4;
+// descriptor of k-step j (k = 8j .. 8j+7): start + j*256, LBO = 128 (next 4 k), SBO = 512 (next 8 rows)
+constexpr uint32_t LBO = 128, SBO = 512;
+// instruction descriptor: c = f32, a = b = tf32, both K-major, N = 256, M = 128
+constexpr uint32_t IDESC2 = (1u << 4) | (2u << 7) | (2u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+
+struct Shared2 {
+  uint64_t full[STAGES];
+  uint64_t empty[STAGES];
+  uint64_t acc_full[2];
+  uint64_t acc_empty[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint8_t* align_1024(uint8_t* p) {
+  return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023));
+}
+
+struct Unit2 {
+  int gi, slot;
+  int64_t q0;
+};
+
+// k-th unit of this CTA from the host-built schedule (see tc_common.cuh): tile = 256-query tile index
+__device__ __forceinline__ bool next_unit(const Schedule& S, int k, Unit2& U, uint32_t& mask) {
+  const int i = S.start[blockIdx.x] + k;
+  if (i >= S.start[blockIdx.x + 1]) return false;
+  const uint32_t g = S.gsm[i];
+  U.gi = (int)(g >> 24);
+  U.slot = (int)((g >> 16) & 0xffu);
+  U.q0 = (int64_t)S.tile[i] * BQ;
+  mask = g & 0xffffu;
+  return true;
+}
+
+struct Frag4 {
+  float4 v[4];
+};
+
+// ---- optional per-role cycle accounting (debug builds: -DMPQE_TC_STATS + mpqe_debug_set_stats2) ---------------------
+#ifdef MPQE_TC_STATS
+__device__ long long* g_stats2 = nullptr;   // [CTA][16] cycle totals
+__device__ int g_dbg2 = 0;                  // timing experiments: 1 = no epilogue stores, 2 = no tensor-memory loads
+#define ST_DECL long long st_t0 = 0, st_acc[4] = {0, 0, 0, 0}
+#define ST_BEGIN() st_t0 = clock64()
+#define ST_END(i) st_acc[i] += clock64() - st_t0
+#define ST_FLUSH(base, n)                                                             \
+  if (g_stats2 != nullptr)                                                            \
+    for (int i_ = 0; i_ < (n); ++i_) g_stats2[(long long)blockIdx.x * 16 + (base) + i_] = st_acc[i_]
+#else
+#define ST_DECL
+#define ST_BEGIN()
+#define ST_END(i)
+#define ST_FLUSH(base, n)
+#endif
+
+__global__ void __launch_bounds__(THREADS, 1) layer_tc2_kernel(const __grid_constant__ LayerLaunch L,
+                                                               const __grid_constant__ Schedule S) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ Shared2 sh;
+  uint8_t* smem = align_1024(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef MPQE_TC_STATS
+  const long long kernel_t0 = clock64();
+#endif
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&sh.full[s]), PROD_THREADS + 1);   // + the thread that arms the weight bulk copy
+      mbar_init(smem_u32(&sh.empty[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&sh.acc_full[b]), 1);
+      mbar_init(smem_u32(&sh.acc_empty[b]), EPI_WARPS * 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&sh.tmem_base), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sh.tmem_base;
+
+  if (warp >= EPI_WARPS && warp < MMA_WARP) {
+    // ===== producers ==================================================================================================
+    // Thread (pw, lane) owns, in every stage, rows  8*(4 pw + i) + (lane & 7), i = 0..3,  and the k-quad  lane >> 3:
+    // a warp instruction reads 8 rows x 64 contiguous bytes and writes 512 contiguous bytes of the tile (conflict-free).
+    const int pw = warp - EPI_WARPS;
+    const int kq = lane >> 3;
+    uint32_t it = 0;                 // stage counter (stores)
+    // load-side iterator over (unit, term, k chunk); everything a stage needs sits in registers per term
+    int uk = 0;
+    uint32_t mask = 0u;
+    int kc = D - KC;
+    bool alive = true;
+    Unit2 U{0, 0, 0};
+    const float* rowp[4] = {nullptr, nullptr, nullptr, nullptr};
+    const float* packed_base = nullptr;
+    auto advance = [&](const float*& packed) -> bool {
+      if (!alive) return false;
+      kc += KC;
+      if (kc >= D) {
+        kc = 0;
+        mask &= mask - 1;
+        while (mask == 0) {
+          if (!next_unit(S, uk++, U, mask)) {
+            alive = false;
+            return false;
+          }
+        }
+        const mpqe_layer_group_t& G = L.g[U.gi];
+        const mpqe_term_t& T = G.terms[__ffs(mask) - 1];
+        const float* a = T.a;
+        const int64_t a_slots = T.a_slots, a_slot = T.a_slot, nq = G.num_queries;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          int64_t q = U.q0 + (pw * 4 + i) * 8 + (lane & 7);
+          if (q >= nq) q = nq - 1;                      // rows past the end repeat the last row (never stored)
+          rowp[i] = a + (q * a_slots + a_slot) * (int64_t)D + kq * 4;
+        }
+        packed_base = T.m_packed;
+      }
+      packed = packed_base + (kc / KC) * (2 * W_TILE / 4);
+      return true;
+    };
+    auto issue = [&](Frag4& f) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) f.v[i] = *reinterpret_cast<const float4*>(rowp[i] + kc);
+    };
+    ST_DECL;
+    auto put = [&](const Frag4& f, const float* packed) {
+      const int s = it % STAGES;
+      const uint32_t use = it / STAGES;
+      ST_BEGIN();
+      if (use > 0) mbar_wait(smem_u32(&sh.empty[s]), (use - 1) & 1);
+      ST_END(0);   // waiting for a free stage
+      ST_BEGIN();
+      uint8_t* st = smem + s * STAGE_BYTES;
+      if (pw == 0 && lane == 0) {
+        const uint32_t bar = smem_u32(&sh.full[s]);
+        mbar_arrive_expect_tx(bar, 2 * W_TILE);
+        bulk_copy_g2s(smem_u32(st), packed, 2 * W_TILE, bar);
+      }
+      uint8_t* xh = st + 2 * W_TILE;
+      uint8_t* xl = xh + X_TILE;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int off = (pw * 4 + i) * 512 + kq * 128 + (lane & 7) * 16;
+        float4 hi, lo;
+        split_tf32(f.v[i], hi, lo);
+        *reinterpret_cast<float4*>(xh + off) = hi;
+        *reinterpret_cast<float4*>(xl + off) = lo;
+      }
+      ST_END(1);   // waiting for the loaded rows + split + stores
+      ST_BEGIN();
+      fence_proxy_async();
+      mbar_arrive(smem_u32(&sh.full[s]));
+      ST_END(2);   // fence + arrive
+      ++it;
+    };
+    // software pipeline over LOADS_AHEAD = 3 register sets: set j holds the loads of stage (it + j)
+    Frag4 f0, f1, f2;
+    const float *p0 = nullptr, *p1 = nullptr, *p2 = nullptr;
+    bool h0 = advance(p0);
+    if (h0) issue(f0);
+    bool h1 = h0 && advance(p1);
+    if (h1) issue(f1);
+    bool h2 = h1 && advance(p2);
+    if (h2) issue(f2);
+    while (h0) {
+      put(f0, p0);
+      h0 = h2 && advance(p0);
+      if (h0) issue(f0);
+      if (!h1) break;
+      put(f1, p1);
+      h1 = h0 && advance(p1);
+      if (h1) issue(f1);
+      if (!h2) break;
+      put(f2, p2);
+      h2 = h1 && advance(p2);
+      if (h2) issue(f2);
+    }
+    if (pw == 0 && lane == 0) { ST_FLUSH(0, 3); }
+  } else if (warp == MMA_WARP) {
+    // ===== MMA issuer (one thread) ====================================================================================
+    if (lane == 0) {
+      uint32_t it = 0;
+      int uc = 0;
+      Unit2 U{0, 0, 0};
+      const uint32_t base = smem_u32(smem);
+      ST_DECL;
+      for (uint32_t umask; next_unit(S, uc, U, umask); ++uc) {
+        const int nsteps = __popc(umask) * (D / KC);
+        const int ab = uc & 1, use = uc >> 1;
+        ST_BEGIN();
+        if (use > 0) mbar_wait(smem_u32(&sh.acc_empty[ab]), (use - 1) & 1);   // epilogue drained this accumulator
+        ST_END(0);
+        tc_fence_after();
+        const uint32_t acc = tmem + ab * BQ;
+        for (int step = 0; step < nsteps; ++step, ++it) {
+          const int s = it % STAGES;
+          ST_BEGIN();
+          mbar_wait(smem_u32(&sh.full[s]), (it / STAGES) & 1);
+          ST_END(1);
+          ST_BEGIN();
+          tc_fence_after();
+          const uint32_t w_hi = base + s * STAGE_BYTES, w_lo = w_hi + W_TILE, x_hi = w_hi + 2 * W_TILE,
+                         x_lo = x_hi + X_TILE;
+#pragma unroll
+          for (int j = 0; j < KC / 8; ++j) {
+            const uint64_t dwh = make_desc(w_hi + j * 256, LBO, SBO), dwl = make_desc(w_lo + j * 256, LBO, SBO);
+            const uint64_t dxh = make_desc(x_hi + j * 256, LBO, SBO), dxl = make_desc(x_lo + j * 256, LBO, SBO);
+            umma_tf32(acc, dwl, dxh, IDESC2, (step == 0 && j == 0) ? 0u : 1u);   // small products first
+            umma_tf32(acc, dwh, dxl, IDESC2, 1u);
+            umma_tf32(acc, dwh, dxh, IDESC2, 1u);
+          }
+          umma_commit(smem_u32(&sh.empty[s]));      // frees the stage when the MMAs have read it
+          ST_END(2);
+        }
+        umma_commit(smem_u32(&sh.acc_full[ab]));    // accumulator complete
+      }
+#ifdef MPQE_TC_STATS
+      st_acc[3] = it;
+      ST_FLUSH(4, 4);
+      if (g_stats2 != nullptr) g_stats2[(long long)blockIdx.x * 16 + 8] = uc;
+#endif
+    }
+  } else {
+    // ===== epilogue: thread = output feature ==========================================================================
+    int uc = 0;
+    Unit2 U{0, 0, 0};
+    const int n = warp * 32 + lane;                 // this thread's feature = its TMEM lane
+    ST_DECL;
+    for (uint32_t umask; next_unit(S, uc, U, umask); ++uc) {
+      const mpqe_layer_group_t& G = L.g[U.gi];
+      const int nsteps = __popc(umask) * (D / KC);
+      const int ab = uc & 1;
+      const int oslot = G.out_slot_map[U.slot];
+      const int epi = G.epilogue;
+      const bool masked = epi == MPQE_EPI_MASK;
+      const int64_t rows_left = G.num_queries - U.q0;             // query c of the tile exists iff c < rows_left
+      const int64_t out_step = (int64_t)G.out_slots * D;
+      float* outp = G.out + (U.q0 * (int64_t)G.out_slots + oslot) * (int64_t)D + n;
+      const int64_t mask_step = (int64_t)G.mask_slots * D;
+      const float* maskp = masked ? G.mask + (U.q0 * (int64_t)G.mask_slots + oslot) * (int64_t)D + n : nullptr;
+      float bv = 0.f;
+      if (G.bias != nullptr) bv = G.bias_scale[U.slot] * __ldg(G.bias + (int64_t)U.slot * G.bias_slot_stride + n);
+      // the ReLU mask of a 32-query block is fetched one block ahead (read-only path): inside the store loop the loads
+      // could not be hoisted above the stores and every query would pay a full memory round trip
+      float mk[32];
+      auto fetch = [&](int c0) {
+        if (masked) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mk[i] = c0 + i < rows_left ? __ldg(maskp + (int64_t)(c0 + i) * mask_step) : 0.f;
+        }
+      };
+      fetch(0);
+      ST_BEGIN();
+      mbar_wait(smem_u32(&sh.acc_full[ab]), (uc >> 1) & 1);
+      ST_END(0);
+      ST_BEGIN();
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BQ; c0 += 32) {
+        if (c0 >= rows_left) break;
+        uint32_t v[32];
+#ifdef MPQE_TC_STATS
+        const long long tl0 = clock64();
+        if (!(g_dbg2 & 2))
+#endif
+        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + ab * BQ + c0, v);
+#ifdef MPQE_TC_STATS
+        st_acc[2] += clock64() - tl0;
+#endif
+        uint32_t keep = 0xffffffffu;
+        if (masked) {
+          keep = 0u;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) keep |= (mk[i] > 0.f ? 1u : 0u) << i;
+          if (c0 + 32 < BQ) fetch(c0 + 32);
+        }
+        float* o = outp + (int64_t)c0 * out_step;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float x = nsteps == 0 ? 0.f : __uint_as_float(v[i]);
+          x += bv;
+          if (epi == MPQE_EPI_RELU) x = fmaxf(x, 0.f);
+          if (!((keep >> i) & 1u)) x = 0.f;
+#ifdef MPQE_TC_STATS
+          if (g_dbg2 & 1) continue;
+#endif
+          if (c0 + i < rows_left) o[(int64_t)i * out_step] = x;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(&sh.acc_empty[ab]));
+      ST_END(1);
+    }
+    if (tid == 0) { ST_FLUSH(9, 2); }
+#ifdef MPQE_TC_STATS
+    if (tid == 0 && g_stats2 != nullptr) g_stats2[(long long)blockIdx.x * 16 + 12] = st_acc[2];
+#endif
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+#ifdef MPQE_TC_STATS
+  if (tid == 0 && g_stats2 != nullptr) g_stats2[(long long)blockIdx.x * 16 + 11] = clock64() - kernel_t0;
+#endif
+}
+
+// Pre-split weights for this kernel: out[m][16-k chunk c] = [hi 8 KB | lo 8 KB] of Wt[n][k] = M[k][n], the byte image
+// of the shared-memory operand chunk (element (n, kk) at (n/8)*512 + (kk/4)*128 + (n%8)*16 + (kk%4)*4).
+constexpr int PACK_MAX = 256;
+struct PackLaunch2 {
+  const float* m[PACK_MAX];
+};
+
+__global__ void __launch_bounds__(256) pack_weights2_kernel(const __grid_constant__ PackLaunch2 P,
+                                                            float* __restrict__ out) {
+  const float* M = P.m[blockIdx.y];
+  const int c = blockIdx.x;                          // k chunk (16 k)
+  float* hi_tile = out + ((int64_t)blockIdx.y * (D / KC) + c) * (2 * W_TILE / 4);
+  float* lo_tile = hi_tile + W_TILE / 4;
+  for (int e = threadIdx.x; e < 128 * 4; e += 256) {   // e -> (n, k quad): lanes run over n (coalesced reads of M rows)
+    const int n = e & 127, q = e >> 7;
+    float4 x;
+    x.x = M[(int64_t)(c * KC + q * 4 + 0) * D + n];
+    x.y = M[(int64_t)(c * KC + q * 4 + 1) * D + n];
+    x.z = M[(int64_t)(c * KC + q * 4 + 2) * D + n];
+    x.w = M[(int64_t)(c * KC + q * 4 + 3) * D + n];
+    float4 hi, lo;
+    split_tf32(x, hi, lo);
+    const int off = ((n >> 3) * 512 + q * 128 + (n & 7) * 16) / 4;
+    *reinterpret_cast<float4*>(hi_tile + off) = hi;
+    *reinterpret_cast<float4*>(lo_tile + off) = lo;
+  }
+}
+
+int sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+}  // namespace
+
+static int launch_tc2(const mpqe_layer_group_t* groups, int num_groups, cudaStream_t stream) {
+  static thread_local LayerLaunch L;
+  memset(&L, 0, sizeof(L));
+  L.num_groups = num_groups;
+  int64_t units = 0;
+  for (int i = 0; i < num_groups; ++i) {
+    L.g[i] = groups[i];
+    units += (groups[i].num_queries + BQ - 1) / BQ * groups[i].num_out_slots;
+  }
+  const int grid = units < sm_count() ? (int)units : sm_count();
+  MPQE_CHECK_ARG(grid <= SCHED_MAX_CTAS, "mpqe_layer_forward (tcgen05): %d SMs", grid);
+  // longest-processing-time-first assignment of units to the persistent CTAs (cost = terms of the unit's slot)
+  static thread_local Schedule S;
+  static thread_local int cost[SCHED_MAX_UNITS];
+  static thread_local uint16_t tile_of[SCHED_MAX_UNITS];
+  static thread_local uint32_t gsm_of[SCHED_MAX_UNITS];
+  int u = 0;
+  for (int i = 0; i < num_groups; ++i) {
+    const int tiles = (int)((groups[i].num_queries + BQ - 1) / BQ);
+    for (int slot = 0; slot < groups[i].num_out_slots; ++slot) {
+      int nt = 0;
+      uint32_t mask = 0;
+      for (int t = 0; t < groups[i].num_terms; ++t)
+        if (groups[i].terms[t].out_slot == slot) ++nt, mask |= 1u << t;
+      for (int k = 0; k < tiles; ++k) {
+        cost[u] = nt;
+        tile_of[u] = (uint16_t)k;
+        gsm_of[u] = ((uint32_t)i << 24) | ((uint32_t)slot << 16) | mask;
+        ++u;
+      }
+    }
+  }
+  build_lpt(S, cost, (int)units, grid);
+  for (int pos = 0; pos < (int)units; ++pos) {
+    S.tile[pos] = tile_of[S.unit[pos]];
+    S.gsm[pos] = gsm_of[S.unit[pos]];
+  }
+  layer_tc2_kernel<<<grid, THREADS, TC2_SMEM, stream>>>(L, S);
+  MPQE_CHECK_LAUNCH("layer_tc2_kernel");
+  return 0;
+}
+
+int layer_forward_tc2(const mpqe_layer_group_t* groups, int num_groups, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    MPQE_CUDA(cudaFuncSetAttribute(layer_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC2_SMEM));
+    configured = true;
+  }
+  int slots = 0;
+  int64_t longest = 0;
+  for (int i = 0; i < num_groups; ++i) {
+    slots += groups[i].num_out_slots;
+    if (groups[i].num_queries > longest) longest = groups[i].num_queries;
+    for (int t = 0; t < groups[i].num_terms; ++t)
+      MPQE_CHECK_ARG(groups[i].terms[t].m_packed != nullptr,
+                     "mpqe_layer_forward (tcgen05): group %d term %d has no packed weight image (mpqe_pack_weights)", i, t);
+  }
+  if (slots == 0 || longest == 0) return 0;
+  // the per-launch schedule holds SCHED_MAX_UNITS units: longer batches go through in slices of whole 256-query tiles
+  const int64_t tiles_per_launch = SCHED_MAX_UNITS / slots;
+  MPQE_CHECK_ARG(tiles_per_launch >= 1, "mpqe_layer_forward (tcgen05): too many output slots");
+  const int64_t slice = tiles_per_launch * BQ;
+  for (int64_t q0 = 0; q0 < longest; q0 += slice) {
+    mpqe_layer_group_t part[MPQE_MAX_GROUPS];
+    int n = 0;
+    for (int i = 0; i < num_groups; ++i) {
+      if (groups[i].num_queries <= q0) continue;
+      mpqe_layer_group_t g = groups[i];
+      g.num_queries = groups[i].num_queries - q0 < slice ? groups[i].num_queries - q0 : slice;
+      for (int t = 0; t < g.num_terms; ++t) g.terms[t].a += q0 * g.terms[t].a_slots * (int64_t)D;
+      g.out += q0 * g.out_slots * (int64_t)D;
+      if (g.mask != nullptr) g.mask += q0 * g.mask_slots * (int64_t)D;
+      part[n++] = g;
+    }
+    if (int rc = launch_tc2(part, n, stream)) return rc;
+  }
+  return 0;
+}
+
+int pack_weights_tc2(const float* const* mats_host, int32_t count, float* packed, cudaStream_t stream) {
+  for (int base = 0; base < count; base += PACK_MAX) {
+    static thread_local PackLaunch2 P;
+    const int n = count - base < PACK_MAX ? count - base : PACK_MAX;
+    for (int i = 0; i < n; ++i) {
+      MPQE_CHECK_ARG(mats_host[base + i] != nullptr, "mpqe_pack_weights: matrix %d is null", base + i);
+      P.m[i] = mats_host[base + i];
+    }
+    pack_weights2_kernel<<<dim3(D / KC, n), 256, 0, stream>>>(P, packed + (int64_t)base * MPQE_PACKED_FLOATS);
+    MPQE_CHECK_LAUNCH("pack_weights2_kernel");
+  }
+  return 0;
+}
+
+}  // namespace mpqe
+
+#ifdef MPQE_TC_STATS
+// debug only (not part of the public header): [148][16] int64 device buffer receiving per-CTA cycle totals
+extern "C" __attribute__((visibility("default"))) int mpqe_debug_set_stats2(void* buf) {
+  return (int)cudaMemcpyToSymbol(mpqe::g_stats2, &buf, sizeof(buf));
+}
+extern "C" __attribute__((visibility("default"))) int mpqe_debug_set_dbg2(int bits) {
+  return (int)cudaMemcpyToSymbol(mpqe::g_dbg2, &bits, sizeof(bits));
+}
+#endif

@@ -497,17 +497,11 @@ CombineBuffers carve_combine(void* workspace, int64_t count, int64_t table_rows,
 
 // The part of the combine that needs only the row ids: stable sort, segment heads, number of distinct rows.  It can
 // run (on another stream) while the gradient rows are still being computed; mpqe_sparse_rows_apply then sums them.
-static int sparse_rows_plan(const int64_t* rows_id, int64_t count, int64_t table_rows, int64_t* num_unique,
-                            void* workspace, size_t workspace_bytes, void* stream, int digit_bits) {
-  MPQE_CHECK_ARG(rows_id && num_unique && count >= 1 && count < (1ll << 31) && table_rows >= 1 &&
-                     table_rows < (1ll << 32),
-                 "mpqe_sparse_rows_plan: bad argument");
-  MPQE_CHECK_ARG(workspace && workspace_bytes >= mpqe_sparse_rows_workspace_bytes(count),
-                 "mpqe_sparse_rows_plan: workspace too small");
+// sort + segmentation of `count` keys already narrowed (uint32, sentinel = table_rows) into the sort's first buffer
+static int plan_sorted(int64_t count, int64_t table_rows, int64_t* num_unique, void* workspace, void* stream,
+                       int digit_bits) {
   cudaStream_t st = (cudaStream_t)stream;
   CombineBuffers c = carve_combine(workspace, count, table_rows, digit_bits);
-  narrow_keys_kernel<<<blocks_for(count, 256), 256, 0, st>>>(rows_id, count, c.s.k0, table_rows);
-  MPQE_CHECK_LAUNCH("narrow_keys_kernel");
   uint32_t *rk, *rv;
   if (radix_sort(c.s, count, bits_for(table_rows + 1), st, &rk, &rv, digit_bits)) return 2;
   MPQE_CHECK_ARG(rk == c.rk && rv == c.rv, "mpqe_sparse_rows_plan: internal buffer parity mismatch");
@@ -520,6 +514,29 @@ static int sparse_rows_plan(const int64_t* rows_id, int64_t count, int64_t table
   MPQE_CHECK_LAUNCH("segment_starts_kernel");
   return 0;
 }
+
+static int sparse_rows_plan(const int64_t* rows_id, int64_t count, int64_t table_rows, int64_t* num_unique,
+                            void* workspace, size_t workspace_bytes, void* stream, int digit_bits) {
+  MPQE_CHECK_ARG(rows_id && num_unique && count >= 1 && count < (1ll << 31) && table_rows >= 1 &&
+                     table_rows < (1ll << 32),
+                 "mpqe_sparse_rows_plan: bad argument");
+  MPQE_CHECK_ARG(workspace && workspace_bytes >= mpqe_sparse_rows_workspace_bytes(count),
+                 "mpqe_sparse_rows_plan: workspace too small");
+  CombineBuffers c = carve_combine(workspace, count, table_rows, digit_bits);
+  narrow_keys_kernel<<<blocks_for(count, 256), 256, 0, (cudaStream_t)stream>>>(rows_id, count, c.s.k0, table_rows);
+  MPQE_CHECK_LAUNCH("narrow_keys_kernel");
+  return plan_sorted(count, table_rows, num_unique, workspace, stream, digit_bits);
+}
+
+// entry points for peer.cu (owner-filtered keys are written straight into the sort's first key buffer)
+namespace mpqe {
+uint32_t* sparse_rows_key_buffer(void* workspace, int64_t count) { return carve_sort(workspace, count).k0; }
+int sparse_rows_plan_prepared(int64_t count, int64_t table_rows, int64_t* num_unique, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  (void)workspace_bytes;
+  return plan_sorted(count, table_rows, num_unique, workspace, stream, PLAN_DIGIT_BITS);
+}
+}  // namespace mpqe
 
 static int sparse_rows_apply(const float* rows, int64_t count, int64_t table_rows, int64_t pad_id, float scale,
                              int64_t* unique_ids, float* unique_rows, const int64_t* num_unique, void* workspace,

@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(ROW_THREADS) gather_fwd_multi_kernel(const __g
   if (row < 0 || row >= T.table_rows) {
     y = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F);
   } else if (T.normalize) {
-    normalize_row(T.table, row, lane, y);
+    normalize_row(table_of_row(T.table, T.peer_tables, T.peer_chunk, row), row, lane, y);
   } else {
     y = *reinterpret_cast<const float4*>(T.table + row * D + lane * 4);
   }
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(ROW_THREADS) gather_bwd_multi_kernel(const __g
   const mpqe_gather_item_t& T = L.it[item];
   const int64_t row = resolve_row(T.id2row, T.ids, T.ids_stride, i);
   float4 y;
-  const float nrm = normalize_row(T.table, row, lane, y);
+  const float nrm = normalize_row(table_of_row(T.table, T.peer_tables, T.peer_chunk, row), row, lane, y);
   const float4 g = *reinterpret_cast<const float4*>(T.grad + i * T.grad_stride + lane * 4);
   *reinterpret_cast<float4*>(T.rows_out + i * D + lane * 4) = normalize_bwd(g, y, nrm);
   if (lane == 0) T.rows_id[i] = row + T.id_offset;
@@ -107,8 +107,9 @@ __global__ void __launch_bounds__(ROW_THREADS) margin_fwd_multi_kernel(const __g
   const mpqe_margin_item_t& T = L.it[item];
   const float4 qv = *reinterpret_cast<const float4*>(T.q + b * D + lane * 4);
   float4 yp, yn;
-  normalize_row(T.table, resolve_row(T.id2row, T.ids_pos, 1, b), lane, yp);
-  normalize_row(T.table, resolve_row(T.id2row, T.ids_neg, 1, b), lane, yn);
+  const int64_t rp = resolve_row(T.id2row, T.ids_pos, 1, b), rn = resolve_row(T.id2row, T.ids_neg, 1, b);
+  normalize_row(table_of_row(T.table, T.peer_tables, T.peer_chunk, rp), rp, lane, yp);
+  normalize_row(table_of_row(T.table, T.peer_tables, T.peer_chunk, rn), rn, lane, yn);
   const float sp = cosine(qv, yp).score, sn = cosine(qv, yn).score;
   if (lane == 0) {
     if (T.score_pos != nullptr) T.score_pos[b] = sp;
@@ -142,8 +143,8 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) margin_bwd_multi_kernel(const 
   const float4 qv = *reinterpret_cast<const float4*>(T.q + b * D + lane * 4);
   const int64_t rp = resolve_row(T.id2row, T.ids_pos, 1, b), rn = resolve_row(T.id2row, T.ids_neg, 1, b);
   float4 yp, yn;
-  const float np_ = normalize_row(T.table, rp, lane, yp);
-  const float nn_ = normalize_row(T.table, rn, lane, yn);
+  const float np_ = normalize_row(table_of_row(T.table, T.peer_tables, T.peer_chunk, rp), rp, lane, yp);
+  const float nn_ = normalize_row(table_of_row(T.table, T.peer_tables, T.peer_chunk, rn), rn, lane, yn);
   const Cos cp = cosine(qv, yp), cn = cosine(qv, yn);
   const float active = (L.margin - (cp.score - cn.score)) >= 0.f ? 1.f : 0.f;
   const float g = active * T.grad_loss[0] / (float)B;

@@ -14,6 +14,14 @@ __device__ __forceinline__ int64_t resolve_row(const int64_t* id2row, const int6
   return id2row != nullptr ? id2row[id] : id;
 }
 
+// Base address of the table that holds `row`.  With peer tables (data-parallel training, entity tables owned
+// row-range-wise: rank r owns rows [r*chunk, (r+1)*chunk)) the row is read from its OWNER's copy -- peers[r] is rank r's
+// full-size table as mapped into this process -- so a rank always sees the owner's latest update; otherwise `table`.
+__device__ __forceinline__ const float* table_of_row(const float* table, const float* const* peers, int64_t chunk,
+                                                     int64_t row) {
+  return peers != nullptr ? peers[row / chunk] : table;
+}
+
 __device__ __forceinline__ float4 scale4(const float4& v, float s) { return make_float4(v.x * s, v.y * s, v.z * s, v.w * s); }
 __device__ __forceinline__ float4 div4(const float4& v, float s) { return make_float4(v.x / s, v.y / s, v.z / s, v.w / s); }
 

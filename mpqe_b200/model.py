@@ -242,6 +242,7 @@ class Weights(object):
         # tcgen05 path: tf32 hi/lo tile images of every matrix, staged by the kernel with one bulk copy per tile;
         # all matrices of the step are packed by ONE launch
         self.wp = self.rootp = self.wtp = self.roottp = None
+        self.w1tp = self.w2tp = self.w2p = self.w1bp = None
         if ops.tensor_cores_default():
             mats = []
             for li in range(len(self.w)):
@@ -262,6 +263,15 @@ class Weights(object):
                     off += R + 1
             if not need_grad:
                 self.wtp = self.roottp = None
+            if ro is not None:
+                # readout MLP: W1^T blocks and W2^T (forward), W2 and the W1 blocks (their input gradients)
+                mats = [self.w1t[b * D:(b + 1) * D] for b in range(self.blocks)] + [self.w2t]
+                if need_grad:
+                    mats += [self.w2] + [self.w1b[b] for b in range(self.blocks)]
+                packed = ops.pack_weights([m.contiguous() for m in mats])
+                self.w1tp, self.w2tp = packed[:self.blocks], packed[self.blocks]
+                if need_grad:
+                    self.w2p, self.w1bp = packed[self.blocks + 1], packed[self.blocks + 2:]
 
 
 def _needed_slots(job, readout):
@@ -522,15 +532,16 @@ class Engine(object):
             units = self.mlp_inputs(job)
             nu = len(units)
             dev = job.anchor_ids.device
-            terms = [Term(a, s, j, W.w1t[b * D:(b + 1) * D], k) for k, srcs in enumerate(units) for (a, s, j, b) in srcs]
+            terms = [Term(a, s, j, W.w1t[b * D:(b + 1) * D], k, W.w1tp[b] if W.w1tp is not None else None)
+                     for k, srcs in enumerate(units) for (a, s, j, b) in srcs]
             job.u = torch.empty(job.B, nu, D, dtype=torch.float32, device=dev)
             job.mlp1 = Group(job.B, terms, nu, job.u, nu, epilogue=EPI_RELU, bias=W.b1)
             if self.m.scatter_op == 'max':     # per-unit outputs, then the per-feature max over the query's units
                 job.z2 = torch.empty(job.B, nu, D, dtype=torch.float32, device=dev)
-                job.mlp2 = Group(job.B, [Term(job.u, nu, k, W.w2t, k) for k in range(nu)], nu, job.z2, nu, bias=W.b2)
+                job.mlp2 = Group(job.B, [Term(job.u, nu, k, W.w2t, k, W.w2tp) for k in range(nu)], nu, job.z2, nu, bias=W.b2)
             else:                              # add / mean: the second linear layer sums over the units directly
                 job.q = torch.empty(job.B, D, dtype=torch.float32, device=dev)
-                job.mlp2 = Group(job.B, [Term(job.u, nu, k, W.w2t, 0) for k in range(nu)], 1, job.q, 1,
+                job.mlp2 = Group(job.B, [Term(job.u, nu, k, W.w2t, 0, W.w2tp) for k in range(nu)], 1, job.q, 1,
                                  out_slot_map=[0], bias=W.b2, bias_scale=[float(nu)])
             g1.append(job.mlp1)
             g2.append(job.mlp2)
@@ -642,7 +653,8 @@ class Engine(object):
                     terms += [Term(g, g_slots, smap[okey[s]], W.roott[li], pos[s], rtp) for s in outs if s in pos]
                 if readout == 'concat' and p > 0:
                     # h_p also feeds block p-1 of the concat MLP
-                    terms += [Term(job.du, n, j, W.w1b[p - 1], pos[j]) for j in range(n)]
+                    terms += [Term(job.du, n, j, W.w1b[p - 1], pos[j], W.w1bp[p - 1] if W.w1bp is not None else None)
+                              for j in range(n)]
                 dx = torch.empty(job.B, n, D, dtype=torch.float32, device=g.device)
                 if p > 0:
                     groups.append(Group(job.B, terms, len(ins), dx, n, out_slot_map=ins, epilogue=EPI_MASK,
@@ -748,7 +760,7 @@ class Engine(object):
                 g2.append((dq, 1, [0] * nu))
             g, gs, smap = g2[-1]
             # dU[:, k] = (dZ2[:, k] @ W2) * (u > 0)       (W2 is stored [out, in] = the matrix this product needs)
-            g_du.append(Group(job.B, [Term(g, gs, smap[k], W.w2, k) for k in range(nu)], nu, job.du, nu,
+            g_du.append(Group(job.B, [Term(g, gs, smap[k], W.w2, k, W.w2p) for k in range(nu)], nu, job.du, nu,
                               epilogue=EPI_MASK, mask=job.u, mask_slots=nu))
         ops.layer_forward(g_du)
         for i in range(0, len(jobs), ops.MAX_GROUPS):
@@ -768,10 +780,12 @@ class Engine(object):
             gz = torch.empty(job.B, n, D, dtype=torch.float32, device=g.device)
             if ro == 'targetmlp':
                 others = [j for j in range(n) if j != t.target_slot]
-                terms = [Term(job.du, nu, k, W.w1b[0], t.target_slot) for k in range(nu)]
-                terms += [Term(job.du, nu, k, W.w1b[1], j) for k, j in enumerate(others)]
+                bp = W.w1bp if W.w1bp is not None else [None] * W.blocks
+                terms = [Term(job.du, nu, k, W.w1b[0], t.target_slot, bp[0]) for k in range(nu)]
+                terms += [Term(job.du, nu, k, W.w1b[1], j, bp[1]) for k, j in enumerate(others)]
             else:
-                terms = [Term(job.du, nu, j, W.w1b[W.blocks - 1], j) for j in range(n)]
+                bp = W.w1bp if W.w1bp is not None else [None] * W.blocks
+                terms = [Term(job.du, nu, j, W.w1b[W.blocks - 1], j, bp[W.blocks - 1]) for j in range(n)]
             g_last.append(Group(job.B, terms, n, gz, n))
             last[job] = (gz, n, list(range(n)))
         ops.layer_forward(g_last)
@@ -782,15 +796,17 @@ class RowGrads(object):
     Per mode by default; with `table_offsets` ({mode: first global row}) all modes share ONE buffer and the kernels
     emit global row ids (mode offset + row), so a step needs a single sort/combine and a single all-gather."""
 
-    def __init__(self, capacities, device, table_offsets=None, rows_buffer=None):
+    def __init__(self, capacities, device, table_offsets=None, rows_buffer=None, ids_buffer=None):
         self.buf = {}
         self.table_offsets = table_offsets
         self.planned = False     # True: every slot was reserved (and its row ids emitted) before the backward
         if table_offsets is not None:
             cap = sum(capacities.values())
-            # rows_buffer(cap) -> [>= cap, D] tensor: lets the caller place the rows in peer-visible memory
+            # rows_buffer(cap) -> [>= cap, D] tensor, ids_buffer(cap) -> [>= cap] int64: let the caller place the pairs
+            # in peer-visible memory
             rows = rows_buffer(cap) if rows_buffer is not None else torch.empty(cap, D, dtype=torch.float32, device=device)
-            self.shared = [rows, torch.empty(cap, dtype=torch.int64, device=device), 0]
+            ids = ids_buffer(cap) if ids_buffer is not None else torch.empty(cap, dtype=torch.int64, device=device)
+            self.shared = [rows, ids, 0]
             return
         for mode, cap in capacities.items():
             if cap > 0:
@@ -809,7 +825,7 @@ class RowGrads(object):
 class Grads(object):
     """Dense gradient buffers (zero-initialised, kernels accumulate) + the row-gradient collector."""
 
-    def __init__(self, model, W, row_capacities, device, table_offsets=None, rows=None):
+    def __init__(self, model, W, row_capacities, device, table_offsets=None, rows=None, flat=None):
         self.device = device
         self.colsums, self.gathers, self.keep = [], [], []
         # one flat zeroed bucket: a single memset here, a single NCCL all-reduce in data-parallel training
@@ -818,17 +834,34 @@ class Grads(object):
         if W.ro is not None:
             shapes += [tuple(W.w1t.shape), tuple(W.w2t.shape), (D,), (D,)]
         sizes = [int(torch.Size(s).numel()) for s in shapes]
-        self.flat = torch.zeros(sum(sizes), dtype=torch.float32, device=device)
+        if flat is not None:       # caller-provided bucket (peer-visible memory in data-parallel training)
+            if flat.numel() != sum(sizes):
+                raise ops._lib.MpqeError('dense gradient bucket has %d elements, need %d' % (flat.numel(), sum(sizes)))
+            self.flat = flat.zero_()
+        else:
+            self.flat = torch.zeros(sum(sizes), dtype=torch.float32, device=device)
+        self._layout = (shapes, sizes, len(W.w), W.ro is not None)
+        self._bind(self.flat)
+        self.rows = rows if rows is not None else RowGrads(row_capacities, device, table_offsets)
+
+    def _bind(self, flat):
+        shapes, sizes, L, has_ro = self._layout
         views, off = [], 0
         for s, k in zip(shapes, sizes):
-            views.append(self.flat[off:off + k].view(s))
+            views.append(flat[off:off + k].view(s))
             off += k
-        L = len(W.w)
         self.dw, self.droot, self.dbias = views[:L], views[L:2 * L], views[2 * L:3 * L]
         self.dmode = views[3 * L]
-        if W.ro is not None:
+        if has_ro:
             self.dw1t, self.dw2t, self.db1, self.db2 = views[3 * L + 1:3 * L + 5]
-        self.rows = rows if rows is not None else RowGrads(row_capacities, device, table_offsets)
+
+    def over(self, flat):
+        """The same views over another bucket of the same layout (the all-reduced copy of a data-parallel step)."""
+        other = object.__new__(Grads)
+        other.device, other.colsums, other.gathers, other.keep = self.device, [], [], []
+        other._layout, other.flat, other.rows = self._layout, flat, self.rows
+        other._bind(flat)
+        return other
 
     def colsum(self, src, rows, stride, dst, scale=1.0):
         """Deferred dst += scale * column-sum(src): all of a backward's reductions run in one multi-item launch."""
@@ -1047,7 +1080,7 @@ def loss_forward(model, jobs, targets, negatives, margin, need_grad, grad_losses
     return losses, W
 
 
-def plan_rows(model, jobs, targets, negatives, table_offsets, rows_buffer=None, launch=True):
+def plan_rows(model, jobs, targets, negatives, table_offsets, rows_buffer=None, launch=True, ids_buffer=None):
     """Reserves every row-gradient slot of a step in the shared (row id, row) buffer BEFORE the forward and emits the
     row ids with one launch, so that the id-only half of the combine (`ops.SparseRowsPlan`) can overlap the step.
     The reservations are left on the jobs (`margin_res`, `anchor_res`) for `loss_backward(..., rows=...)`.
@@ -1055,7 +1088,7 @@ def plan_rows(model, jobs, targets, negatives, table_offsets, rows_buffer=None, 
     device = jobs[0].anchor_ids.device
     enc = model.enc
     cap = model._row_capacities(jobs, [(job.target_mode, 2 * job.B) for job in jobs])
-    R = RowGrads(cap, device, table_offsets, rows_buffer)
+    R = RowGrads(cap, device, table_offsets, rows_buffer, ids_buffer)
     items = []
     for job, tgt, neg in zip(jobs, targets, negatives):
         res = job.margin_res = R.reserve(job.target_mode, 2 * job.B)
@@ -1078,14 +1111,14 @@ def plan_rows(model, jobs, targets, negatives, table_offsets, rows_buffer=None, 
 
 
 def loss_backward(model, jobs, W, targets, negatives, margin, grad_losses, table_offsets=None, rows=None,
-                  defer_constant=False):
+                  defer_constant=False, flat=None):
     """Backward of `loss_forward` for d(total)/d(loss_i) = grad_losses[i] (device tensor [len(jobs)]).
     Returns the filled `Grads` (dense bucket + (row id, gradient row) pairs, not yet combined).  `rows`: a RowGrads
     from `plan_rows` (slots reserved and ids already emitted).  `defer_constant`: leave the batch-constant tail of the
     backward to the caller as `G.finish()` (the dense gradients are complete only after it)."""
     device = jobs[0].anchor_ids.device
     cap = model._row_capacities(jobs, [(job.target_mode, 2 * job.B) for job in jobs]) if rows is None else None
-    G = Grads(model, W, cap, device, table_offsets, rows)
+    G = Grads(model, W, cap, device, table_offsets, rows, flat)
     dqs, items = [], []
     for i, (job, tgt, neg) in enumerate(zip(jobs, targets, negatives)):
         if G.rows.planned and getattr(job, 'dq', None) is not None:

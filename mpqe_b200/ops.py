@@ -172,11 +172,33 @@ def layer_forward(groups, use_tensor_cores=None):
     tc = tensor_cores_default() if use_tensor_cores is None else bool(use_tensor_cores)
     for i in range(0, len(groups), MAX_GROUPS):
         chunk = groups[i:i + MAX_GROUPS]
-        arr = (_lib.LayerGroup * len(chunk))(*[g.to_c() for g in chunk])
         rows_only = all(g.num_queries == 1 for g in chunk)     # batch-constant rows: the one-row kernel
+        if tc and not rows_only:
+            _ensure_packed(chunk)
+        arr = (_lib.LayerGroup * len(chunk))(*[g.to_c() for g in chunk])
         with _Profiled('layer_rows' if rows_only else 'layer', chunk):
             _lib.check(lib.mpqe_layer_forward(arr, len(chunk), int(tc), _stream()), 'mpqe_layer_forward')
         _count()
+
+
+def _ensure_packed(groups):
+    """The tcgen05 layer kernel stages every weight matrix as a pre-split tile image: matrices that reach a launch
+    without one (stand-alone RGCNConv calls; the per-step weights arrive packed from `model.Weights`) are packed here,
+    all in one launch."""
+    missing = {}
+    for g in groups:
+        for t in g.terms:
+            if t.mp is None:
+                missing.setdefault(t.m.data_ptr(), t.m)
+    if not missing:
+        return
+    keys = list(missing)
+    packed = pack_weights([missing[k] for k in keys])
+    image = {k: packed[j] for j, k in enumerate(keys)}
+    for g in groups:
+        for t in g.terms:
+            if t.mp is None:
+                t.mp = image[t.m.data_ptr()]
 
 
 def layer_wgrad(groups, grad_operands, dests, ctas_hint=296, use_tensor_cores=None):
@@ -500,6 +522,7 @@ class SparseRowsPlan(object):
         device address of rank r's rows in this process (torch symmetric memory); the plan must have been built over
         the rank-major concatenation of the ranks' ids (mpqe_sparse_rows_apply_peers)."""
         lib = _lib.load()
+        peer_ptrs = [p.data_ptr() if torch.is_tensor(p) else p for p in peer_ptrs]     # (tensors: gathered local copies)
         world = len(peer_ptrs)
         if world * per_rank_count != self.count:
             raise _lib.MpqeError('apply_peers: plan covers %d pairs, peers provide %d' % (self.count, world * per_rank_count))
@@ -535,6 +558,18 @@ def _addr(t, elem_offset=0):
     return t.data_ptr() + elem_offset * t.element_size() if t is not None else 0
 
 
+PEER_TABLES = {}   # table data_ptr -> (device int64 tensor of the ranks' table addresses, rows per owner)
+
+
+def _peer_tables(table):
+    """(device pointer to the peers' addresses of this table, rows per owner) when the table is owned row-range-wise
+    across a data-parallel group (see train_step.TrainStep.shard_tables), else (0, 0): read the local table."""
+    ent = PEER_TABLES.get(table.data_ptr())
+    if ent is None:
+        return 0, 0
+    return ent[0].data_ptr(), ent[1]
+
+
 class GatherItem(object):
     """One (group, node slot) work item of `gather_multi` (see mpqe_gather_item_t); tensors + element offsets."""
 
@@ -556,6 +591,7 @@ class GatherItem(object):
         it.grad, it.grad_stride = _addr(self.grad, self.grad_offset), self.grad_stride
         it.rows_out, it.rows_id = _addr(self.rows_out, self.rows_offset * D), _addr(self.rows_id, self.rows_offset)
         it.id_offset, it.normalize = self.id_offset, int(self.normalize)
+        it.peer_tables, it.peer_chunk = _peer_tables(self.table)
         return it
 
 
@@ -606,6 +642,7 @@ class MarginItem(object):
         it.hinge, it.loss, it.grad_loss, it.dq = _addr(self.hinge), _addr(self.loss), _addr(self.grad_loss), _addr(self.dq)
         it.rows_out, it.rows_id = _addr(self.rows_out, self.rows_offset * D), _addr(self.rows_id, self.rows_offset)
         it.id_offset = self.id_offset
+        it.peer_tables, it.peer_chunk = _peer_tables(self.table)
         return it
 
 
@@ -755,3 +792,47 @@ def sample_negatives(candidates, offsets, count, seed, step, first_query=0, num_
                                          _stream()), 'mpqe_sample_negatives')
     _count()
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Data-parallel exchange over peer-mapped memory (csrc/peer.cu)
+# ---------------------------------------------------------------------------------------------------------------
+def _ptr_array(ptrs):
+    return (C.c_void_p * len(ptrs))(*[int(p) for p in ptrs])
+
+
+def peer_barrier(flag_ptrs, rank, epoch):
+    """Flag barrier across the ranks of a peer group, on the current stream (graph-capturable)."""
+    lib = _lib.load()
+    _lib.check(lib.mpqe_peer_barrier(_ptr_array(flag_ptrs), int(rank), len(flag_ptrs), _ptr(epoch), _stream()),
+               'mpqe_peer_barrier')
+    _count()
+
+
+def allreduce_peers(buf_ptrs, numel, scale, out):
+    """out = scale * sum over ranks of their buffers (read in place over NVLink, rank order)."""
+    lib = _lib.load()
+    _lib.check(lib.mpqe_allreduce_peers(_ptr_array(buf_ptrs), len(buf_ptrs), int(numel), float(scale),
+                                        _ptr(_chk(out, torch.float32, 'out')), _stream()), 'mpqe_allreduce_peers')
+    _count()
+
+
+def owner_plan(id_ptrs, rank, per_rank_count, table_begin, table_rows, total_rows, device):
+    """SparseRowsPlan over the ids of all ranks (read in place from `id_ptrs`), restricted to the rows `rank` owns."""
+    lib = _lib.load()
+    id_ptrs = [_chk(p, torch.int64, 'ids').data_ptr() if torch.is_tensor(p) else p for p in id_ptrs]
+    world = len(id_ptrs)
+    plan = object.__new__(SparseRowsPlan)
+    plan.count, plan.table_rows = world * int(per_rank_count), int(total_rows)
+    plan.num = torch.empty(1, dtype=torch.int64, device=device)
+    plan.nbytes = lib.mpqe_sparse_rows_workspace_bytes(plan.count)
+    plan.ws = torch.empty(plan.nbytes, dtype=torch.uint8, device=device)
+    nt = len(table_begin)
+    _lib.check(lib.mpqe_sparse_rows_plan_owner(_ptr_array(id_ptrs), world, int(rank), int(per_rank_count),
+                                               (C.c_int64 * nt)(*[int(x) for x in table_begin]),
+                                               (C.c_int64 * nt)(*[int(x) for x in table_rows]), nt, int(total_rows),
+                                               _ptr(plan.num), _ptr(plan.ws), plan.nbytes, _stream()),
+               'mpqe_sparse_rows_plan_owner')
+    passes = (max(1, plan.table_rows.bit_length()) + 6) // 7
+    _count(7 + 4 * passes)
+    return plan

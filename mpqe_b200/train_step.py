@@ -5,9 +5,22 @@ This is the caller-side row (f)1 of SURVEY.md section 8 (`run_train` / `run_batc
 train_helpers.py:76-120): the reference issues up to 11 `margin_loss` calls per step, one per query type, each
 a separate pair of encoder forwards; here all batches of a step go through the same per-pass launches.
 
-Multi-GPU (one process per GPU, torch.distributed): query batches are data-parallel.  Per step there is exactly one
-exchange: an all-reduce of the flat dense-gradient bucket and an all-gather of the per-mode (row id, gradient row)
-pairs, followed by the same deterministic combine on every rank, so that all ranks apply identical updates.
+Multi-GPU (one process per GPU, torch.distributed for the rendezvous): query batches are data-parallel, dense
+parameters are replicated, and the entity tables are OWNED row-range-wise: rank r owns rows [r*ceil(rows/N),
+(r+1)*ceil(rows/N)) of every table.  All buffers the ranks exchange live in peer-mapped (symmetric) memory, and the whole
+step -- exchange included -- is one stream of kernels (one CUDA graph), with no host-side collective call:
+  forward   the gather / margin kernels read every entity row from its owner's copy of the table over NVLink;
+  B1        flag barrier: every rank has emitted its row ids and finished the previous step;
+  side      the owner plan: all ranks' ids are read in place, the ones this rank owns are sorted and segmented;
+  backward  gradient rows and the dense bucket land in this rank's peer-visible buffers;
+  B2        flag barrier: all rows and buckets are final;
+  exchange  one-shot all-reduce of the dense bucket (rank order: identical bits everywhere) and ONE kernel that sums
+            the owned rows straight out of the peers' buffers.  Per GPU and step (N-1)/N of one rank's gradient rows
+            cross NVLink once, plus the entity rows its batch reads.
+The result of a step on rank r is the dense gradient (replicated) and the combined row gradient OF THE ROWS r OWNS;
+the ranks' partitions are disjoint and their union is the single-process result on the concatenated batch.
+Without peer-mapped memory (CPU / gloo tests, or when symmetric memory cannot be set up) the same kernels run on
+buffers assembled with torch.distributed all_gather / all_reduce.
 """
 import torch
 
@@ -50,6 +63,38 @@ class StepResult(object):
         return (self.losses * self.weights).sum()
 
 
+class PeerGroup(object):
+    """Peer-mapped buffers of one data-parallel group (torch symmetric memory: cuMem allocations exchanged at a
+    rendezvous and mapped into every process) and the flag barrier over them."""
+
+    def __init__(self, pg, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        self._symm = symm_mem
+        self.pg = pg if pg is not None else torch.distributed.group.WORLD
+        self.rank = torch.distributed.get_rank(self.pg)
+        self.world = torch.distributed.get_world_size(self.pg)
+        self.device = device
+        self._keep = []
+        self.flags, self.flag_ptrs = self.alloc((ops._lib.MAX_PEERS,), torch.int32, zero=True)
+        self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        torch.distributed.barrier(group=self.pg)     # every rank's flags are zero before the first device barrier
+
+    def alloc(self, shape, dtype, zero=False):
+        """(local tensor, [address of every rank's tensor in this process]).  A collective: never during capture."""
+        if torch.cuda.is_current_stream_capturing():
+            raise ops._lib.MpqeError('peer-visible buffers must be allocated before graph capture')
+        buf = self._symm.empty(*shape, dtype=dtype, device=self.device)
+        if zero:
+            buf.zero_()
+        hdl = self._symm.rendezvous(buf, self.pg)
+        self._keep.append((buf, hdl))
+        return buf, [int(p) for p in hdl.buffer_ptrs]
+
+    def barrier(self):
+        ops.peer_barrier(self.flag_ptrs, self.rank, self.epoch)
+
+
 class TrainStep(object):
     def __init__(self, model, margin=1.0, process_group=None, average=True):
         self.model = model
@@ -60,8 +105,10 @@ class TrainStep(object):
         self._layouts = {}
         self.adam_state = None
         self._side = None   # second stream for the id-only half of the row-gradient combine
-        self._sym_rows = self._sym_hdl = self._peer_ptrs = None   # peer-visible gradient-row buffer (world > 1)
-        self._early_cache = None                                  # marshalled id-emitting launch of the static batches
+        self.rank = torch.distributed.get_rank(process_group) if self._dist() else 0
+        self.peers = None        # PeerGroup (world > 1, peer-mapped memory available)
+        self._xcap = None        # pairs per rank the exchange buffers were set up for
+        self._xrows = self._xids = self._xflat = self._dense_out = None
         self.steps = 0
         # all entity tables as one id space: global row = table_offsets[mode] + row
         self.table_offsets, off = {}, 0
@@ -106,58 +153,27 @@ class TrainStep(object):
     # ---- the step -------------------------------------------------------------------------------------
     @torch.no_grad()
     def forward_backward(self, batches):
-        """Returns StepResult: per-batch losses, weighted total (device scalars), the flat dense gradient bucket
-        (`.dense.flat`, views per parameter in `.dense`) and the row-sparse entity gradient
-        `.sparse = (unique global row ids, summed rows, num_unique)` with global row = table_offsets[mode] + row."""
+        """Returns StepResult: per-batch losses (device scalars), the flat dense gradient bucket (`.dense.flat`, views
+        per parameter in `.dense`; averaged over the ranks) and the row-sparse entity gradient `.sparse = (unique global
+        row ids, summed rows, num_unique)` with global row = table_offsets[mode] + row.  With several ranks `.sparse`
+        covers the rows THIS rank owns (see the module docstring)."""
         dev = self.model.mode_embeddings.weight.device
         with ops.device_guard(dev):
-            early = self._early_plan(batches) if self._use_peer_rows(dev) else None
-            res = self._local_step(batches)
-            if self.world > 1:
-                res = StepResult(res.losses, res.weights, res.dense, self.sync(res.dense, res.sparse, early))
-        return res
+            return self._local_step(batches)
 
-    def _early_plan(self, batches, defer=False):
-        """Data-parallel, peer-memory path: the row ids of EVERY rank's step are known before any rank computes --
-        emit them (one small launch), all-gather them (0.8 MB per rank) and build the global combine plan on the second
-        stream, under the local step.  The all-gather is also the step's opening barrier: it completes only when every
-        rank has finished reading the others' gradient rows of the previous step, after which they may be overwritten."""
-        m = self.model
-        cache = self._early_cache
-        if cache is None or cache[0] is not batches:
-            # the id-emitting launch is marshalled once per batch list: in graph mode the same static batches come
-            # back every step and the per-step host cost is a single ctypes call
-            jobs = [b.job for b in batches]
-            R0 = plan_rows(m, jobs, [b.targets for b in batches], [b.negatives for b in batches], self.table_offsets,
-                           rows_buffer=lambda cap: None, launch=False)
-            cache = (batches, ops.GatherLaunch(R0.id_items, 'ids'), R0)
-            self._early_cache = cache if batches is getattr(self, '_static', None) else None
-        cache[1].launch()
-        _, ids0, used = cache[2].shared
-        dev = ids0.device
-        all_ids = torch.empty(self.world * used, dtype=torch.int64, device=dev)
-        torch.distributed.all_gather_into_tensor(all_ids, ids0[:used], group=self.pg)
-        if defer:      # graph mode: the caller enqueues the graph first, then the plan (ordered after this event only)
-            ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream(dev))
-            return (lambda: self._plan_on_side_stream(all_ids, dev, after=ev)), used
-        return self._plan_on_side_stream(all_ids, dev), used
-
-    def _plan_on_side_stream(self, ids, dev, after=None):
-        """ops.SparseRowsPlan(ids) on the second stream (joined by `_join_side`).
-        `after`: an event to order the plan after, instead of everything enqueued on the current stream so far."""
+    def _plan_on_side_stream(self, make_plan, dev, keep=()):
+        """make_plan() -> ops.SparseRowsPlan, run on the second stream (joined by `_join_side`).  `keep`: tensors the
+        plan kernels read, allocated on the current stream."""
         cur = torch.cuda.current_stream(dev)
         if self._side is None:
             self._side = torch.cuda.Stream(device=dev)
-        if after is not None:
-            self._side.wait_event(after)
-        else:
-            self._side.wait_stream(cur)
+        self._side.wait_stream(cur)
         with torch.cuda.stream(self._side):
-            plan = ops.SparseRowsPlan(ids, self.total_rows)
-        # the ids are read by the sort on the second stream: keep the caching allocator from handing their block to
-        # the main stream's next allocation while those kernels are still pending
-        ids.record_stream(self._side)
+            plan = make_plan()
+        for t in keep:
+            # read by the sort on the second stream: keep the caching allocator from handing the block to the main
+            # stream's next allocation while those kernels are still pending
+            t.record_stream(self._side)
         plan.ws.record_stream(cur)
         plan.num.record_stream(cur)
         return plan
@@ -184,114 +200,185 @@ class TrainStep(object):
         with torch.cuda.stream(self._side):
             fn()
 
-    def _peer_rows_buffer(self, cap):
-        """[>= cap, D] gradient-row buffer in memory that every rank of the group can address (torch symmetric memory:
-        cuMem allocations exchanged at a rendezvous).  Allocated once (a collective; never during graph capture)."""
-        if self._sym_rows is None or self._sym_rows.shape[0] < cap:
-            if torch.cuda.is_current_stream_capturing():
-                raise ops._lib.MpqeError('the peer-visible row buffer must be allocated before graph capture')
-            dev = self.model.mode_embeddings.weight.device
-            try:
-                import torch.distributed._symmetric_memory as symm_mem
-                buf = symm_mem.empty(int(cap), D, dtype=torch.float32, device=dev)
-                hdl = symm_mem.rendezvous(buf, self.pg if self.pg is not None else torch.distributed.group.WORLD)
-                self._sym_rows, self._sym_hdl, self._peer_ptrs = buf, hdl, [int(p) for p in hdl.buffer_ptrs]
-            except Exception as exc:      # no peer mapping on this system: NCCL all-gather of the rows from now on
-                import warnings
-                warnings.warn('mpqe_b200: symmetric (peer-mapped) memory unavailable (%r); the row-gradient exchange '
-                              'falls back to an NCCL all-gather' % (exc,))
-                self._peers_off = True
-                self._sym_rows = self._sym_hdl = self._peer_ptrs = None
-                return torch.empty(int(cap), D, dtype=torch.float32, device=dev)
-        return self._sym_rows
+    # ---- data-parallel exchange: buffers ---------------------------------------------------------------
+    def _table_ranges(self):
+        """[(mode, first global row, rows)] in table_offsets order."""
+        m = self.model
+        return [(mode, self.table_offsets[mode], m.enc.feature_modules[mode].weight.shape[0]) for mode in
+                m.enc.feature_modules]
 
-    def _use_peer_rows(self, dev):
+    def owned_rows(self, rank=None):
+        """[(mode, first owned row, one past the last)] of `rank` (default: this rank)."""
+        rank = self.rank if rank is None else rank
+        out = []
+        for mode, _, rows in self._table_ranges():
+            chunk = (rows + self.world - 1) // self.world
+            out.append((mode, min(rank * chunk, rows), min((rank + 1) * chunk, rows)))
+        return out
+
+    def _use_peer_memory(self, dev):
         import os
         return (self.world > 1 and dev.type == 'cuda' and not getattr(self, '_peers_off', False) and
                 os.environ.get('MPQE_PEER_ROWS', '1') != '0')
 
-    def sync(self, G, sparse, early=None):
-        """Data-parallel exchange: all-reduce(dense bucket), all-gather of the ranks' raw (row id, gradient row) pairs
-        and ONE combine of all of them, identical on every rank (rank order + stable sort => same bits).  The ids
-        travel first (0.8 MB per rank) so that their sort runs on the second stream under the all-gather of the rows
-        (54 MB per rank at the bench shape); the 1/world averaging is folded into the row summation.
-        `early` = (plan, pairs per rank) from `_early_plan`: the global plan was built under the local step."""
+    def setup_exchange(self, batches):
+        """Allocates the peer-visible buffers of the data-parallel exchange for steps shaped like `batches` (row
+        gradients, their ids, the dense bucket), moves the entity tables into peer-visible memory and registers them as
+        owner-read tables.  A collective over the process group (rendezvous): called automatically by the first step,
+        and before graph capture.  All ranks must run steps with the same number of (row id, row) pairs -- batches of
+        the same formulas and sizes -- which is checked here."""
+        m = self.model
+        dev = m.mode_embeddings.weight.device
+        jobs = [b.job for b in batches]
+        cap = sum(m._row_capacities(jobs, [(job.target_mode, 2 * job.B) for job in jobs]).values())
         dist = torch.distributed
-        scale = 1.0 / self.world if self.average else 1.0
-        ids, rows, _ = sparse
-        dev = ids.device
-        cap = ids.numel()
-        if (early is not None and early[1] == cap and self._peer_ptrs is not None and
-                rows.data_ptr() == self._sym_rows.data_ptr()):
-            # Peer-memory path.  The dense all-reduce completes only when every rank has finished its local step (its
-            # gradient rows are final) -- the barrier the gather needs; then ONE kernel gathers and sums all ranks'
-            # rows in place over NVLink (no NCCL all-gather of 54 MB per rank, no local staging).  The next step's id
-            # all-gather (`_early_plan`) keeps any rank from overwriting its rows before all have read them.
-            dist.all_reduce(G.flat, group=self.pg)
-            if scale != 1.0:
-                G.flat.mul_(scale)
-            self._join_side(dev)
-            return early[0].apply_peers(self._peer_ptrs, cap, pad_id=self.total_rows, scale=scale)
-        all_ids = torch.empty(self.world * cap, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(all_ids, ids, group=self.pg)
-        plan = self._plan_on_side_stream(all_ids, dev)
-        if self._peer_ptrs is not None and rows.data_ptr() == self._sym_rows.data_ptr():
-            # Peer-memory path: every rank's rows sit in a buffer mapped into all processes (torch symmetric memory).
-            # The id all-gather above completes only after every rank has finished its local step, so the peers' rows
-            # are final; ONE kernel then gathers and sums them in place over NVLink (no NCCL all-gather of 54 MB per
-            # rank, no local staging).  The dense all-reduce comes last and doubles as the closing barrier: no rank
-            # starts overwriting its rows (next step) before every rank has finished reading them.
-            self._join_side(dev)
-            out = plan.apply_peers(self._peer_ptrs, cap, pad_id=self.total_rows, scale=scale)
-            dist.all_reduce(G.flat, group=self.pg)
-            if scale != 1.0:
-                G.flat.mul_(scale)
-            return out
-        all_rows = torch.empty(self.world * cap, D, dtype=torch.float32, device=dev)
-        dist.all_reduce(G.flat, group=self.pg)
-        if scale != 1.0:
-            G.flat.mul_(scale)
-        dist.all_gather_into_tensor(all_rows, rows, group=self.pg)
-        self._join_side(dev)
-        return plan.apply(all_rows, pad_id=self.total_rows, scale=scale)
+        caps = [None] * self.world
+        dist.all_gather_object(caps, int(cap), group=self.pg)
+        if len(set(caps)) != 1:
+            raise ops._lib.MpqeError('data-parallel step: ranks differ in their (row id, row) pair counts %r; every rank '
+                                     'must run batches of the same formulas and sizes' % (caps,))
+        dense_numel = sum(int(p.numel()) for p in self._dense_shapes())
+        self._xcap, self._xdense = cap, dense_numel
+        self._dense_out = None
+        if not self._use_peer_memory(dev):
+            self.peers = None
+            self._xrows = self._xids = self._xflat = None
+            return
+        try:
+            if self.peers is None:
+                self.peers = PeerGroup(self.pg, dev)
+            self._xrows, self._row_ptrs = self.peers.alloc((cap, D), torch.float32)
+            self._xids, self._id_ptrs = self.peers.alloc((cap,), torch.int64)
+            self._xflat, self._flat_ptrs = self.peers.alloc((dense_numel,), torch.float32)
+            self.shard_tables()
+            torch.cuda.synchronize(dev)
+            dist.barrier(group=self.pg)
+        except Exception as exc:      # no peer mapping on this system: torch.distributed collectives from now on
+            import warnings
+            warnings.warn('mpqe_b200: symmetric (peer-mapped) memory unavailable (%r); the gradient exchange falls '
+                          'back to torch.distributed all_gather / all_reduce' % (exc,))
+            self._peers_off = True
+            self.peers = None
+            self._xrows = self._xids = self._xflat = None
 
+    def _dense_shapes(self):
+        m = self.model
+        ps = []
+        for layer in m.distinct_layers():
+            ps += [layer.relation_weights(), layer.root, layer.bias]
+        ps.append(m.mode_embeddings.weight)
+        if isinstance(m.readout, torch.nn.Module):
+            ps += [m.readout.layers[0].weight, m.readout.layers[2].weight, m.readout.layers[0].bias,
+                   m.readout.layers[2].bias]
+        return ps
+
+    def shard_tables(self):
+        """Moves every entity table into peer-visible memory and registers it with the row kernels as owner-read: row r
+        of a table is read from rank (r // ceil(rows / world))'s copy.  Replicas start identical; after that only the
+        owner's range of a copy is authoritative (an optimiser updates the rows it owns), until `gather_tables()`."""
+        if getattr(self, '_sharded', False):
+            return
+        dev = self.model.mode_embeddings.weight.device
+        for mode, module in self.model.enc.feature_modules.items():
+            w = module.weight
+            buf, ptrs = self.peers.alloc(tuple(w.shape), torch.float32)
+            buf.copy_(w.data)
+            w.data = buf
+            chunk = (w.shape[0] + self.world - 1) // self.world
+            ops.PEER_TABLES[buf.data_ptr()] = (torch.tensor(ptrs, dtype=torch.int64, device=dev), chunk)
+        self._sharded = True
+
+    @torch.no_grad()
+    def gather_tables(self):
+        """Every rank's copy of every entity table receives the owners' rows (before a checkpoint, an export or an
+        evaluation that reads tables locally)."""
+        if self.world == 1:
+            return
+        for (mode, _, rows), (_, lo, hi) in zip(self._table_ranges(), self.owned_rows()):
+            w = self.model.enc.feature_modules[mode].weight.data
+            chunk = (rows + self.world - 1) // self.world
+            mine = torch.zeros(chunk, w.shape[1], dtype=w.dtype, device=w.device)
+            mine[:hi - lo] = w[lo:hi]
+            full = torch.empty(self.world * chunk, w.shape[1], dtype=w.dtype, device=w.device)
+            torch.distributed.all_gather_into_tensor(full, mine, group=self.pg)
+            w.copy_(full[:rows])
+
+    # ---- the step proper -------------------------------------------------------------------------------
     def _local_step(self, batches):
-        """forward + backward + local row-gradient combine (no cross-rank exchange): the part that is graph-captured."""
+        """forward + backward + row-gradient combine (+ the cross-rank exchange): everything here is enqueued on the
+        current stream and one helper stream, with no host synchronisation -- the part that is graph-captured."""
         m = self.model
         dev = m.mode_embeddings.weight.device
         jobs = [self.refresh(b).job for b in batches]
         tg = [b.targets for b in batches]
         ng = [b.negatives for b in batches]
+        multi = self.world > 1
+        if multi and getattr(self, '_xcap', None) is None:
+            self.setup_exchange(batches)
+        peer = multi and self.peers is not None
         # The row ids of the step's entity gradients depend only on the batch ids: emit them first and run the id-only
-        # half of the combine (stable sort + segmentation, ~10 small latency-bound launches) on a second stream, under
+        # half of the combine (stable sort + segmentation, ~20 small latency-bound launches) on a second stream, under
         # the forward and backward; only the final row summation waits for the gradient rows.
-        # With several ranks the pairs are exchanged raw and combined once, after the all-gather (see `sync`).
         # The per-step weight preparation (transposes, tf32 tile images, summed matrices) goes to that stream too, ahead
         # of the sort: it overlaps the input gather; the first layer launch waits for its event.
         R = plan_rows(m, jobs, tg, ng, self.table_offsets,
-                      rows_buffer=self._peer_rows_buffer if self._use_peer_rows(dev) else None)
+                      rows_buffer=(lambda cap: self._xrows) if peer else None,
+                      ids_buffer=(lambda cap: self._xids) if peer else None)
         rows, ids, used = R.shared
+        if multi and used != self._xcap:
+            raise ops._lib.MpqeError('data-parallel step: %d (row id, row) pairs, the exchange was set up for %d; call '
+                                     'setup_exchange(batches) when the batch shapes change' % (used, self._xcap))
+        ranges = self._table_ranges()
+        if peer:
+            self.peers.barrier()      # B1: all ranks' ids are in place and every rank is done with the previous step
         W = self._weights_on_side_stream(jobs, dev)
-        plan = self._plan_on_side_stream(ids[:used], dev) if self.world == 1 else None
+        all_ids = None
+        if not multi:
+            plan = self._plan_on_side_stream(lambda: ops.SparseRowsPlan(ids[:used], self.total_rows), dev, keep=(ids,))
+        else:
+            if peer:
+                id_src = self._id_ptrs
+            else:     # ids through torch.distributed; the same owner plan then reads the gathered copy
+                all_ids = torch.empty(self.world * used, dtype=torch.int64, device=ids.device)
+                torch.distributed.all_gather_into_tensor(all_ids, ids[:used].contiguous(), group=self.pg)
+                id_src = [all_ids[r * used:(r + 1) * used] for r in range(self.world)]
+            plan = self._plan_on_side_stream(
+                lambda: ops.owner_plan(id_src, self.rank, used, [r[1] for r in ranges], [r[2] for r in ranges],
+                                       self.total_rows, ids.device), dev, keep=() if all_ids is None else (all_ids,))
         key = tuple(b.weight for b in batches)
         wts = getattr(self, '_wts', None)
         if wts is None or wts[0] != key:
             wts = self._wts = (key, torch.tensor(key, dtype=torch.float32, device=dev))
         # d total / d loss_i = the batch weights, known now: the margin backward rides on the margin forward
         losses, W = loss_forward(m, jobs, tg, ng, self.margin, True, grad_losses=wts[1], W=W)
-        overlap_tail = plan is not None
         G = loss_backward(m, jobs, W, tg, ng, self.margin, wts[1], self.table_offsets, rows=R,
-                          defer_constant=overlap_tail)
+                          defer_constant=not multi, flat=self._xflat if peer else None)
         self._weight_decay(W, G, losses, sum(key))
-        if plan is not None:
+        if not multi:
             self._join_side(dev)
             # the batch-constant tail of the backward (five small latency-bound launches) runs on the second
             # stream under the row summation, which does not depend on it
             self._on_side_stream(dev, G.finish)
             sparse = plan.apply(rows[:used], pad_id=self.total_rows)
             self._join_side(dev)
-        else:
-            sparse = (ids[:used], rows[:used], None)
+            return StepResult(losses, wts[1], G, sparse)
+        scale = 1.0 / self.world if self.average else 1.0
+        if peer:
+            self.peers.barrier()      # B2: every rank's gradient rows and dense bucket are final
+            if self._dense_out is None:
+                self._dense_out = torch.empty_like(self._xflat)
+            ops.allreduce_peers(self._flat_ptrs, self._xdense, scale, self._dense_out)
+            self._join_side(dev)
+            sparse = plan.apply_peers(self._row_ptrs, used, pad_id=self.total_rows, scale=scale)
+            return StepResult(losses, wts[1], G.over(self._dense_out), sparse)
+        torch.distributed.all_reduce(G.flat, group=self.pg)
+        if scale != 1.0:
+            G.flat.mul_(scale)
+        all_rows = torch.empty(self.world * used, D, dtype=torch.float32, device=rows.device)
+        torch.distributed.all_gather_into_tensor(all_rows, rows[:used].contiguous(), group=self.pg)
+        self._join_side(dev)
+        sparse = plan.apply_peers([all_rows[r * used:(r + 1) * used] for r in range(self.world)], used,
+                                  pad_id=self.total_rows, scale=scale)
         return StepResult(losses, wts[1], G, sparse)
 
     def _weight_decay(self, W, G, losses, weight_sum):
@@ -304,17 +391,14 @@ class TrainStep(object):
             return
         ops.l2_reg([W.w1t, W.b1, W.w2t, W.b2], [G.dw1t, G.db1, G.dw2t, G.db2], wd, float(weight_sum), losses=losses)
 
-    # ---- CUDA-graph mode: the whole local step becomes one graph launch --------------------------------------
+    # ---- CUDA-graph mode: the whole step (exchange included) becomes one graph launch --------------------------
     @torch.no_grad()
     def capture(self, host_batches):
-        """Stages `host_batches` into static device buffers, warms up and captures the local step into a CUDA graph.
-        Later steps with batches of the same formulas and sizes call `replay(host_batches)`."""
+        """Stages `host_batches` into static device buffers, warms up and captures the step into a CUDA graph.
+        Later steps with batches of the same formulas and sizes call `replay(host_batches)`.  With several ranks the
+        graph contains the flag barriers and the peer-memory exchange: every rank must capture and replay in step."""
         m = self.model
         dev = m.mode_embeddings.weight.device
-        if self._use_peer_rows(dev):
-            # the warm-up steps below overwrite this rank's peer-visible gradient rows without the opening barrier of a
-            # regular step: first let every rank finish reading them (previous step's gather)
-            torch.distributed.barrier(group=self.pg)
         with ops.device_guard(dev):
             # all ids of a step live in ONE device buffer mirrored by ONE pinned host buffer: a step's input is a
             # single H2D copy instead of three small copies per formula batch
@@ -334,7 +418,13 @@ class TrainStep(object):
                 self._static.append(self.to_device(hb, tuple(v[1] for v in views)))
             self._dev_ids.copy_(self._host_ids, non_blocking=True)
             self._wts = None
-            self._early_cache = None
+            if self.world > 1:
+                self.setup_exchange(self._static)     # collective: peer-visible buffers exist before the capture
+                if self.peers is None:
+                    # torch.distributed fallback: the collectives stay eager, the step is not captured
+                    self._graph = None
+                    self._graph_res = self._local_step(self._static)
+                    return self._graph_res
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
@@ -360,22 +450,12 @@ class TrainStep(object):
                     st.targets.copy_(hb.targets)
                     st.negatives.copy_(hb.negatives)
             self._dev_ids.copy_(self._host_ids, non_blocking=True)
-        dev = self._dev_ids.device
-        early = None
-        if self._use_peer_rows(dev):
-            with ops.device_guard(dev):
-                # (defer=True would enqueue the plan after the graph launch: less host latency in front of the graph,
-                # +12 % end-to-end at N=2, but the plan then overlaps the graph's kernels worse: -12 % device-timed)
-                early = self._early_plan(self._static, defer=False)
-        self._graph.replay()
-        if early is not None and callable(early[0]):     # deferred plan: enqueued after the graph launch, ordered only
-            with ops.device_guard(dev):                  # after the id all-gather
-                early = (early[0](), early[1])
-        res = self._graph_res
-        if self.world > 1:
-            with ops.device_guard(res.dense.flat.device):
-                res = StepResult(res.losses, res.weights, res.dense, self.sync(res.dense, res.sparse, early))
-        return res
+        if self._graph is None:
+            with ops.device_guard(self._dev_ids.device):
+                self._graph_res = self._local_step(self._static)
+        else:
+            self._graph.replay()
+        return self._graph_res
 
     def staging(self):
         """Graph mode: HostBatch objects whose id tensors are views of the step's single pinned host buffer.  A data
@@ -386,7 +466,7 @@ class TrainStep(object):
     @torch.no_grad()
     def run_host(self, host_batches):
         """End-to-end step from pinned host ids: H2D copies, forward+backward(+sync), D2H of the losses."""
-        if getattr(self, '_graph', None) is not None:
+        if getattr(self, '_static', None) is not None:
             res = self.replay(host_batches)
         else:
             res = self.forward_backward([self.to_device(hb) for hb in host_batches])

@@ -258,6 +258,22 @@ class SparseRowsPlan(object):
         uid, urows, num = sparse_rows_combine(self.rows_id, rows, self.table_rows, pad_id)
         return uid, urows * scale, num
 
+    def apply_peers(self, peer_rows, per_rank_count, pad_id=0, scale=1.0):
+        return self.apply(torch.cat([r[:per_rank_count] for r in peer_rows]), pad_id, scale)
+
+
+def owner_plan(id_sources, rank, per_rank_count, table_begin, table_rows, total_rows, device):
+    """mpqe_sparse_rows_plan_owner: ids of all ranks, those `rank` does not own clamped to the sentinel."""
+    world = len(id_sources)
+    ids = torch.cat([t[:per_rank_count] for t in id_sources]).clone()
+    owned = torch.zeros_like(ids, dtype=torch.bool)
+    for begin, rows in zip(table_begin, table_rows):
+        chunk = (rows + world - 1) // world
+        inside = (ids >= begin) & (ids < begin + rows)
+        owned |= inside & (((ids - begin) // chunk) == rank)
+    ids[~owned] = total_rows
+    return SparseRowsPlan(ids, total_rows)
+
 
 def scatter_rows(ids, rows, num, dense, accumulate=False):
     k = int(num.item()) if num is not None else ids.numel()
@@ -273,7 +289,7 @@ def install(monkeypatch):
                  'cosine_scores', 'cosine_scores_bwd', 'rank_counts_ragged', 'rank_counts_table',
                  'build_query_graph', 'relation_sort', 'sparse_rows_combine', 'SparseRowsPlan', 'scatter_rows',
                  'gather_multi', 'matrix_sum_multi',
-                 'cosine_margin_multi', 'colsum_multi', 'l2_reg'):
+                 'cosine_margin_multi', 'colsum_multi', 'l2_reg', 'owner_plan'):
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(ops, 'device_guard', lambda device: contextlib.nullcontext())
     monkeypatch.setattr(ops, 'tensor_cores_default', lambda: False)
@@ -286,8 +302,7 @@ def install(monkeypatch):
         self.model._engine.prepare(jobs, W)
         return W
 
-    monkeypatch.setattr(TrainStep, '_plan_on_side_stream',
-                        lambda self, ids, dev, after=None: ops.SparseRowsPlan(ids, self.total_rows))
+    monkeypatch.setattr(TrainStep, '_plan_on_side_stream', lambda self, make_plan, dev, keep=(): make_plan())
     monkeypatch.setattr(TrainStep, '_weights_on_side_stream', weights_now)
     monkeypatch.setattr(TrainStep, '_join_side', lambda self, dev: None)
     monkeypatch.setattr(TrainStep, '_on_side_stream', lambda self, dev, fn: fn())

@@ -1,5 +1,7 @@
 """Data-parallel gradient exchange on CPU: 2 gloo ranks (kernels emulated) must reproduce the 1-rank gradients of
-the concatenated batch: dense bucket within fp32 tolerance, touched-row id set bit-exact, identical bits on both ranks."""
+the concatenated batch: dense bucket within fp32 tolerance and identical bits on both ranks; the row-sparse entity
+gradient arrives partitioned by row OWNER -- each rank holds exactly the rows it owns, the partitions are disjoint and
+their union is the single-process result (touched-row id set bit-exact)."""
 import os
 import sys
 
@@ -50,7 +52,9 @@ def _worker(rank, world, port, out):
     res = ts.forward_backward([ts.to_device(hb) for hb in host])
     u, r, k = res.sparse
     sparse = {'all': (u[:int(k)].clone(), r[:int(k)].clone())}
-    torch.save({'flat': res.dense.flat.clone(), 'sparse': sparse, 'losses': res.losses.clone()}, out % rank)
+    owned = [(ts.table_offsets[mode] + lo, ts.table_offsets[mode] + hi) for mode, lo, hi in ts.owned_rows()]
+    torch.save({'flat': res.dense.flat.clone(), 'sparse': sparse, 'losses': res.losses.clone(), 'owned': owned},
+               out % rank)
     dist.destroy_process_group()
 
 
@@ -60,8 +64,19 @@ def test_two_rank_gradients_equal_single_rank(tmp_path, monkeypatch):
     mp.start_processes(_worker, args=(2, port, out), nprocs=2, join=True, start_method='spawn')
     r0, r1 = torch.load(out % 0), torch.load(out % 1)
     assert torch.equal(r0['flat'], r1['flat']), 'all ranks must hold identical dense gradients'
-    for m in r0['sparse']:
-        assert torch.equal(r0['sparse'][m][0], r1['sparse'][m][0]) and torch.equal(r0['sparse'][m][1], r1['sparse'][m][1])
+    # every rank holds exactly the rows it owns
+    for r in (r0, r1):
+        ids = r['sparse']['all'][0]
+        inside = torch.zeros_like(ids, dtype=torch.bool)
+        for lo, hi in r['owned']:
+            inside |= (ids >= lo) & (ids < hi)
+        assert bool(inside.all()) and ids.numel() > 0
+    # the union of the partitions, in id order (ownership ranges interleave over the tables)
+    ids_all = torch.cat([r0['sparse']['all'][0], r1['sparse']['all'][0]])
+    rows_all = torch.cat([r0['sparse']['all'][1], r1['sparse']['all'][1]])
+    assert ids_all.unique().numel() == ids_all.numel(), 'the owners' + "'" + ' partitions must be disjoint'
+    order = torch.argsort(ids_all)
+    r0['sparse']['all'] = (ids_all[order], rows_all[order])
 
     # single process on the concatenated batch (mean over 2B == average of the two ranks' means)
     from tests import emulator

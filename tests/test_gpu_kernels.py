@@ -50,7 +50,7 @@ def need_tc(tc):
 
 
 @pytest.mark.parametrize('tc', [False, True])
-@pytest.mark.parametrize('B', [1, 63, 64, 65, 300, 4096])
+@pytest.mark.parametrize('B', [1, 63, 64, 65, 255, 257, 300, 4096])
 @pytest.mark.parametrize('epi', [ops.EPI_NONE, ops.EPI_RELU, ops.EPI_MASK])
 def test_layer_forward_matches_cpu(B, epi, tc):
     need_tc(tc)
@@ -73,6 +73,26 @@ def test_layer_forward_matches_cpu(B, epi, tc):
     print('tc=%s max abs err %.3e (max |out| %.3f)' % (tc, float((got - out).abs().max()), float(out.abs().max())))
     # fp32 tolerance: K=128..512 products of O(1)*O(0.05) -> abs error ~1e-6 (FFMA and 3xTF32 alike)
     assert_close(got.numpy(), out.numpy(), 1e-5, 2e-5, 'layer out')
+
+
+@pytest.mark.parametrize('tc', [False, True])
+@pytest.mark.parametrize('B', [40, 513])
+def test_layer_forward_slot_without_terms_and_per_slot_bias(B, tc):
+    """An output slot no term writes to receives only its bias (batch-constant contributions arrive that way), and
+    `bias_slot_stride` selects a bias vector per slot."""
+    need_tc(tc)
+    x = rnd(B, 3, D, seed=1)
+    w = rnd(2, D, D, seed=2, scale=0.05)
+    bias = rnd(3, D, seed=3)
+    out = torch.full((B, 3, D), float('nan'))
+    g = ops.Group(B, [ops.Term(x, 3, 0, w[0], 2), ops.Term(x, 3, 1, w[1], 2), ops.Term(x, 3, 2, w[1], 0)], 3, out, 3,
+                  epilogue=ops.EPI_RELU, bias=bias, bias_scale=[1.0, -2.0, 0.5], bias_slot_stride=D)
+    E.layer_forward([g])
+    gg = run_layer([g])
+    gg[0].bias_slot_stride = D
+    gg[0].out.fill_(float('nan'))
+    ops.layer_forward(gg, use_tensor_cores=tc)
+    assert_close(gg[0].out.cpu().numpy(), out.numpy(), 1e-5, 2e-5, 'layer out')
 
 
 @pytest.mark.parametrize('tc', [False, True])
