@@ -77,6 +77,13 @@ typedef struct {
   int32_t mask_slots;
   int32_t bias_slot_stride;              /* 0: one bias vector for all slots; d: a vector per out slot (used for the
                                             contribution of batch-constant input rows, computed once per group) */
+  /* ReLU sign bits, an optional 32x smaller form of the ReLU-backward mask.  Word ((q/32)*S + slot)*d + c holds, for
+   * feature c of node slot `slot`, bit (q%32) = (value of query q > 0); S = out_slots (written) / mask_slots (read).
+   * relu_bits_out (EPI_RELU launches): the kernel also writes the words of the slots it stores, [ceil(B/32), out_slots,
+   * d]; mask_bits (EPI_MASK launches): used instead of reading `mask` when non-NULL (`mask` must still be given: kernels
+   * without a bit path read it).  Only the tcgen05 kernel produces / consumes the bits. */
+  uint32_t* relu_bits_out;
+  const uint32_t* mask_bits;
 } mpqe_layer_group_t;
 
 /* One weight-gradient destination: dM = sum over every term (of every group) whose `m` equals `m_fwd` of
@@ -286,6 +293,16 @@ MPQE_API size_t mpqe_rank_counts_table_workspace_bytes(int64_t B, int64_t rows);
 MPQE_API int mpqe_rank_counts_table(const float* q, int64_t B, const float* pos, const float* table,
                            int64_t row_begin, int64_t row_end, int64_t* left, int64_t* right,
                            void* workspace, size_t workspace_bytes, int32_t use_tensor_cores, void* stream);
+/* The same in two phases, for an evaluation that ranks many batches against one table shard: `prepare` computes the
+ * table-dependent half once (1/||row|| and, for the tensor-core kernel, the pre-split tile images of the shard) into
+ * `table_ws`; `mpqe_rank_counts_prepared` then does only the per-batch work.  Prepare again when the table changes. */
+MPQE_API size_t mpqe_rank_table_workspace_bytes(int64_t rows, int32_t use_tensor_cores);
+MPQE_API int mpqe_rank_table_prepare(const float* table, int64_t row_begin, int64_t row_end, void* table_ws,
+                            size_t table_ws_bytes, int32_t use_tensor_cores, void* stream);
+MPQE_API size_t mpqe_rank_query_workspace_bytes(int64_t B);
+MPQE_API int mpqe_rank_counts_prepared(const float* q, int64_t B, const float* pos, const float* table,
+                              int64_t row_begin, int64_t row_end, const void* table_ws, int64_t* left, int64_t* right,
+                              void* query_ws, size_t query_ws_bytes, int32_t use_tensor_cores, void* stream);
 
 /* ---- a16: row-sparse embedding gradients ----------------------------------------------------------------
  * Combine `count` (row id, gradient row) pairs: unique_ids ascending, rows summed in ascending pair order

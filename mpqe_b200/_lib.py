@@ -19,7 +19,7 @@ class LayerGroup(C.Structure):
                 ('terms', Term * MAX_TERMS), ('out', C.c_void_p), ('out_slots', C.c_int32),
                 ('epilogue', C.c_int32), ('bias', C.c_void_p), ('bias_scale', C.c_float * MAX_SLOTS),
                 ('out_slot_map', C.c_int16 * MAX_SLOTS), ('mask', C.c_void_p), ('mask_slots', C.c_int32),
-                ('bias_slot_stride', C.c_int32)]
+                ('bias_slot_stride', C.c_int32), ('relu_bits_out', C.c_void_p), ('mask_bits', C.c_void_p)]
 
 
 class WgradDest(C.Structure):
@@ -111,6 +111,10 @@ SIGNATURES = {
     'mpqe_rank_counts_ragged': (I32, [P, P, P, I64, P, P, P]),
     'mpqe_rank_counts_table_workspace_bytes': (SZ, [I64, I64]),
     'mpqe_rank_counts_table': (I32, [P, I64, P, P, I64, I64, P, P, P, SZ, I32, P]),
+    'mpqe_rank_table_workspace_bytes': (SZ, [I64, I32]),
+    'mpqe_rank_table_prepare': (I32, [P, I64, I64, P, SZ, I32, P]),
+    'mpqe_rank_query_workspace_bytes': (SZ, [I64]),
+    'mpqe_rank_counts_prepared': (I32, [P, I64, P, P, I64, I64, P, P, P, P, SZ, I32, P]),
     'mpqe_sparse_rows_workspace_bytes': (SZ, [I64]),
     'mpqe_sparse_rows_combine': (I32, [P, P, I64, I64, I64, P, P, P, P, SZ, P]),
     'mpqe_sparse_rows_plan': (I32, [P, I64, I64, P, P, SZ, P]),

@@ -92,15 +92,15 @@ struct Frag {  // one pipeline stage worth of one operand, per producer thread
 };
 
 // rows = queries (K-major source): idx = pw*4+i -> row group idx/2, k half idx%2   (pw = producer warp 0..7)
-__device__ __forceinline__ void store_kmajor(const Frag& f, uint8_t* hi_tile, uint8_t* lo_tile, int pw, int lane) {
+__device__ __forceinline__ void store_kmajor(const Frag& f, uint32_t hi_tile, uint32_t lo_tile, int pw, int lane) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int idx = pw * 4 + i;
     const int off = (idx >> 1) * 1024 + ((idx & 1) * 4 + (lane >> 3)) * 128 + (lane & 7) * 16;
     float4 hi, lo;
     split_tf32(f.v[i], hi, lo);
-    *reinterpret_cast<float4*>(hi_tile + off) = hi;
-    *reinterpret_cast<float4*>(lo_tile + off) = lo;
+    sts128(hi_tile + off, hi);     // (explicit shared-window stores: see sts128)
+    sts128(lo_tile + off, lo);
   }
 }
 // Column-gather stage: the source is row-major [32 k][128 mn] (pitch floats between k rows) but the tile wants mn as
@@ -121,7 +121,7 @@ __device__ __forceinline__ void load_columns_at(Frag& f, const float* col, int64
 __device__ __forceinline__ void load_columns(Frag& f, const float* src, int64_t pitch, int k_valid, int pw, int lane) {
   load_columns_at(f, src + 32 * (pw & 3) + lane, pitch, k_valid, pw);
 }
-__device__ __forceinline__ void store_columns(const Frag& f, uint8_t* hi_tile, uint8_t* lo_tile, int pw, int lane) {
+__device__ __forceinline__ void store_columns(const Frag& f, uint32_t hi_tile, uint32_t lo_tile, int pw, int lane) {
   const int mn = 32 * (pw & 3) + lane;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -129,8 +129,8 @@ __device__ __forceinline__ void store_columns(const Frag& f, uint8_t* hi_tile, u
     const int off = (mn >> 3) * 1024 + kq * 128 + (mn & 7) * 16;
     float4 hi, lo;
     split_tf32(f.v[i], hi, lo);
-    *reinterpret_cast<float4*>(hi_tile + off) = hi;
-    *reinterpret_cast<float4*>(lo_tile + off) = lo;
+    sts128(hi_tile + off, hi);
+    sts128(lo_tile + off, lo);
   }
 }
 
@@ -153,7 +153,7 @@ __device__ __forceinline__ float pick4(const float4& v, int j) {
   const float lo = (j & 1) ? v.y : v.x, hi = (j & 1) ? v.w : v.z;
   return (j & 2) ? hi : lo;
 }
-__device__ __forceinline__ void store_block4(const Frag& f, uint8_t* hi_tile, uint8_t* lo_tile, int pw, int lane) {
+__device__ __forceinline__ void store_block4(const Frag& f, uint32_t hi_tile, uint32_t lo_tile, int pw, int lane) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int j = (i + (lane >> 1)) & 3;
@@ -162,8 +162,8 @@ __device__ __forceinline__ void store_block4(const Frag& f, uint8_t* hi_tile, ui
     const float4 x = make_float4(pick4(f.v[0], j), pick4(f.v[1], j), pick4(f.v[2], j), pick4(f.v[3], j));
     float4 hi, lo;
     split_tf32(x, hi, lo);
-    *reinterpret_cast<float4*>(hi_tile + off) = hi;
-    *reinterpret_cast<float4*>(lo_tile + off) = lo;
+    sts128(hi_tile + off, hi);
+    sts128(lo_tile + off, lo);
   }
 }
 
@@ -251,11 +251,11 @@ __device__ __forceinline__ void mma_unit(TcShared& sh, uint32_t smem_base, uint3
 }
 
 // producer-side stage acquisition: stage index + wait until the MMAs that read it last have completed
-__device__ __forceinline__ uint8_t* acquire_stage(TcShared& sh, uint8_t* smem, uint32_t it) {
+__device__ __forceinline__ uint32_t acquire_stage(TcShared& sh, uint8_t* smem, uint32_t it) {
   const int s = it % STAGES;
   const uint32_t use = it / STAGES;
   if (use > 0) mbar_wait(smem_u32(&sh.empty[s]), (use - 1) & 1);
-  return smem + s * STAGE_BYTES;
+  return smem_u32(smem) + s * STAGE_BYTES;
 }
 __device__ __forceinline__ void publish_stage(TcShared& sh, uint32_t it) {
   fence_proxy_async();                                                  // generic-proxy stores -> async proxy (UMMA)
@@ -400,14 +400,14 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc_kernel(const __grid_const
     STAT_DECL;
     auto put = [&](const Frag& fa, const Frag& fb, const float* packed) {
       STAT_BEGIN();
-      uint8_t* st = acquire_stage(sh, smem, it);
+      const uint32_t st = acquire_stage(sh, smem, it);
       STAT_END(0);   // waiting for a free stage
       STAT_BEGIN();
       if (pw == 0 && lane == 0) {    // the B tiles: one 32 KB bulk copy, or (unpacked weights) a plain arrival
         const uint32_t bar = smem_u32(&sh.full[it % STAGES]);
         if (packed != nullptr) {
           mbar_arrive_expect_tx(bar, 2 * TILE_BYTES);
-          bulk_copy_g2s(smem_u32(st + 2 * TILE_BYTES), packed, 2 * TILE_BYTES, bar);
+          bulk_copy_g2s(st + 2 * TILE_BYTES, packed, 2 * TILE_BYTES, bar);
         } else {
           mbar_arrive(bar);
         }
@@ -709,7 +709,7 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
       return true;
     };
     auto put = [&](const Frag& fa, const Frag& fb) {
-      uint8_t* st = acquire_stage(sh, smem, it);
+      const uint32_t st = acquire_stage(sh, smem, it);
       store_block4(fa, st, st + TILE_BYTES, pw, lane);
       store_block4(fb, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, pw, lane);
     };
@@ -893,7 +893,7 @@ __global__ void __launch_bounds__(THREADS, 1) rank_tc_kernel(const __grid_consta
     Frag f;
     for (int kcb = 0; kcb < D / KC; ++kcb) {                        // resident query tile
       load_rows_kmajor(f, R.q, b0, R.B, kcb * KC, pw, lane);
-      store_kmajor(f, bres + kcb * 2 * TILE_BYTES, bres + kcb * 2 * TILE_BYTES + TILE_BYTES, pw, lane);
+      store_kmajor(f, smem_u32(bres) + kcb * 2 * TILE_BYTES, smem_u32(bres) + kcb * 2 * TILE_BYTES + TILE_BYTES, pw, lane);
     }
     fence_proxy_async();
     mbar_arrive(smem_u32(&bres_full));
@@ -1094,22 +1094,28 @@ int layer_wgrad_tc_launch(const WgradLaunch& launch, int total_chunks, cudaStrea
 
 size_t rank_packed_bytes(int64_t rows) { return (size_t)((rows + BM - 1) / BM) * (D / KC) * 2 * TILE_BYTES; }
 
-int rank_counts_table_tc(const float* table, int64_t row_begin, int64_t rows, const float* inv_norm, const float* q,
-                         const float* qinv, const float* pos, int64_t B, unsigned long long* left,
-                         unsigned long long* right, float* packed, cudaStream_t stream) {
+// candidate rows [row_begin, row_begin + rows) of `table` -> tf32 hi/lo tile images (once per table shard)
+int rank_pack_rows(const float* table, int64_t row_begin, int64_t rows, float* packed, cudaStream_t stream) {
+  const int64_t ctiles = (rows + BM - 1) / BM;
+  MPQE_CHECK_ARG(ctiles <= 65535, "mpqe_rank_counts_table: too many candidate rows per call (%lld)", (long long)rows);
+  pack_rows_kernel<<<dim3(D / KC, (unsigned)ctiles), 256, 0, stream>>>(table + row_begin * D, rows, packed);
+  MPQE_CHECK_LAUNCH("pack_rows_kernel");
+  return 0;
+}
+
+int rank_counts_packed_tc(int64_t rows, const float* inv_norm, const float* q, const float* qinv, const float* pos,
+                          int64_t B, unsigned long long* left, unsigned long long* right, const float* packed,
+                          cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     MPQE_CUDA(cudaFuncSetAttribute(rank_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RANK_SMEM));
     configured = true;
   }
   RankLaunch R;
-  R.table = table; R.row_begin = row_begin; R.rows = rows; R.inv_norm = inv_norm; R.q = q; R.qinv = qinv; R.pos = pos;
+  R.table = nullptr; R.row_begin = 0; R.rows = rows; R.inv_norm = inv_norm; R.q = q; R.qinv = qinv; R.pos = pos;
   R.B = B; R.left = left; R.right = right; R.packed = packed;
   const int64_t qtiles = (B + BM - 1) / BM;
   const int64_t ctiles = (rows + BM - 1) / BM;
-  MPQE_CHECK_ARG(ctiles <= 65535, "mpqe_rank_counts_table: too many candidate rows per call (%lld)", (long long)rows);
-  pack_rows_kernel<<<dim3(D / KC, (unsigned)ctiles), 256, 0, stream>>>(table + row_begin * D, rows, packed);
-  MPQE_CHECK_LAUNCH("pack_rows_kernel");
   // candidate-range slices per query tile: minimise waves x (tiles per CTA + start-up), one CTA per SM at a time
   // (rounding the CTA count UP to the SM count, e.g. 160 CTAs on 148 SMs, doubles the run time)
   int64_t splits = 1, best = -1;
@@ -1123,6 +1129,13 @@ int rank_counts_table_tc(const float* table, int64_t row_begin, int64_t rows, co
   rank_tc_kernel<<<(unsigned)(qtiles * splits), THREADS, RANK_SMEM, stream>>>(R);
   MPQE_CHECK_LAUNCH("rank_tc_kernel");
   return 0;
+}
+
+int rank_counts_table_tc(const float* table, int64_t row_begin, int64_t rows, const float* inv_norm, const float* q,
+                         const float* qinv, const float* pos, int64_t B, unsigned long long* left,
+                         unsigned long long* right, float* packed, cudaStream_t stream) {
+  if (int rc = rank_pack_rows(table, row_begin, rows, packed, stream)) return rc;
+  return rank_counts_packed_tc(rows, inv_norm, q, qinv, pos, B, left, right, packed, stream);
 }
 
 }  // namespace mpqe

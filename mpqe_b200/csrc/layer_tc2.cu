@@ -10,10 +10,10 @@
 // are /root/reference/mpqe/model.py:292-294 (index_select + bmm), :277 (gather + scatter_add), :301-304 (root,
 // bias), :437 (relu) and their autograd.  fp32 accuracy through the 3xTF32 split, as before.
 //
-// Persistent, warp-specialised CTA per SM (13 warps), unit = (group, out slot, 256-query tile):
+// Persistent, warp-specialised CTA per SM (14 warps), unit = (group, out slot, 256-query tile):
 //   warps 4-11  producers : activation rows global --ld.global.v4 (3 stages of loads in flight per thread)--> split
-//                           hi/lo --> st.shared in the canonical K-major no-swizzle layout; one thread stages the
-//                           stage's weight chunk (pre-split image, mpqe_pack_weights) with a 16 KB bulk copy
+//                           hi/lo --> st.shared in the canonical K-major no-swizzle layout
+//   warp  13    one thread stages the stage's weight chunk (pre-split image, mpqe_pack_weights): a 16 KB bulk copy
 //   warp  12    MMA issuer: per stage (16 k) 2 k-steps x 3 products (lo*hi, hi*lo, hi*hi) of 128 x 256 x 8,
 //                           tcgen05.commit -> empty[stage]; after the unit's last stage -> acc_full[buffer]
 //   warps 0-3   epilogue  : thread = output feature (TMEM lane), 32 queries per tcgen05.ld; a warp's store of one
@@ -34,16 +34,19 @@ constexpr int EPI_WARPS = 4;
 constexpr int PROD_WARPS = 8;
 constexpr int PROD_THREADS = PROD_WARPS * 32;
 constexpr int MMA_WARP = EPI_WARPS + PROD_WARPS;
-constexpr int THREADS = (MMA_WARP + 1) * 32;     // 416
+constexpr int TMA_WARP = MMA_WARP + 1;             // one thread of it stages the weight chunks (bulk copies)
+constexpr int THREADS = (TMA_WARP + 1) * 32;     // 448
 constexpr int BQ = 256;                          // queries per unit = UMMA N
 constexpr int KC = 16;                           // k per pipeline stage = 2 UMMA k-steps of 8
-constexpr int STAGES = 4;
-constexpr int LOADS_AHEAD = 3;                   // stages of activation loads in flight per producer thread
+constexpr int STAGES = 3;
+constexpr int LOADS_AHEAD = 3;                   // stages of activation rows in flight (cp.async) ahead of the stores
+constexpr int RING = LOADS_AHEAD + 1;            // raw-row ring slots
+constexpr int RING_SLOT = 256 * 4 * 16;          // 16 KB: one stage of raw rows, [i][thread] 16-byte pieces
 constexpr int W_TILE = 128 * KC * 4;             // 8 KB: weight chunk, hi or lo      [128 n][16 k]
 constexpr int X_TILE = BQ * KC * 4;              // 16 KB: activation chunk, hi or lo [256 q][16 k]
 constexpr int STAGE_BYTES = 2 * W_TILE + 2 * X_TILE;   // W_hi | W_lo | X_hi | X_lo = 48 KB
 constexpr int TMEM_COLS = 512;                   // two 256-column fp32 accumulators
-constexpr size_t TC2_SMEM = size_t(STAGES) * STAGE_BYTES + 1024;
+constexpr size_t TC2_SMEM = size_t(STAGES) * STAGE_BYTES + size_t(RING) * RING_SLOT + 1024;
 // both operands K-major: element (row, k) of a [rows][16 k] chunk at (row/8)*512 + (k/4)*128 + (row%8)*16 + (k%4)*4;
 // descriptor of k-step j (k = 8j .. 8j+7): start + j*256, LBO = 128 (next 4 k), SBO = 512 (next 8 rows)
 constexpr uint32_t LBO = 128, SBO = 512;
@@ -79,14 +82,27 @@ __device__ __forceinline__ bool next_unit(const Schedule& S, int k, Unit2& U, ui
   return true;
 }
 
-struct Frag4 {
-  float4 v[4];
-};
+// x = hi + lo with hi = x rounded to tf32 (nearest, ties away from zero -- cvt.rna.tf32.f32 for finite x) in two integer
+// instructions instead of the five of the cvt (which also handles NaN / infinity): activations are finite
+__device__ __forceinline__ void split_tf32_fast(const float4& x, float4& hi, float4& lo) {
+  hi.x = __uint_as_float((__float_as_uint(x.x) + 0x1000u) & 0xffffe000u);
+  hi.y = __uint_as_float((__float_as_uint(x.y) + 0x1000u) & 0xffffe000u);
+  hi.z = __uint_as_float((__float_as_uint(x.z) + 0x1000u) & 0xffffe000u);
+  hi.w = __uint_as_float((__float_as_uint(x.w) + 0x1000u) & 0xffffe000u);
+  lo = make_float4(x.x - hi.x, x.y - hi.y, x.z - hi.z, x.w - hi.w);
+}
+
+// timing experiments (debug builds only; results are wrong when non-zero): 4 = no producer stores, 8 = no MMAs,
+// 16 = no weight bulk copies, 32 = no epilogue stores
+#ifndef MPQE_TC2_ABLATE
+#define MPQE_TC2_ABLATE 0
+#endif
 
 // ---- optional per-role cycle accounting (debug builds: -DMPQE_TC_STATS + mpqe_debug_set_stats2) ---------------------
 #ifdef MPQE_TC_STATS
 __device__ long long* g_stats2 = nullptr;   // [CTA][16] cycle totals
-__device__ int g_dbg2 = 0;                  // timing experiments: 1 = no epilogue stores, 2 = no tensor-memory loads
+__device__ int g_dbg2 = 0;                  // timing experiments (wrong results): 4 = no producer stores, 8 = no MMAs,
+                                            // 16 = no weight bulk copies
 #define ST_DECL long long st_t0 = 0, st_acc[4] = {0, 0, 0, 0}
 #define ST_BEGIN() st_t0 = clock64()
 #define ST_END(i) st_acc[i] += clock64() - st_t0
@@ -100,6 +116,26 @@ __device__ int g_dbg2 = 0;                  // timing experiments: 1 = no epilog
 #define ST_FLUSH(base, n)
 #endif
 
+// One 32-query block of the epilogue for one output feature: v[i] = accumulator of query i.  MODE 0: + bias;
+// 1: + bias, ReLU (BITS: also returns the sign bits); 2: + bias, keep where bit i of `keep` is set (ReLU backward).
+// Kept to ~5 instructions per element: there is one epilogue warp per scheduler, so its instruction count is the
+// epilogue's run time (the first version spent ~30 instructions per element on 64-bit address products and
+// per-element branches: 18 k cycles per unit, more than the unit's MMAs).
+template <int MODE, bool BITS>
+__device__ __forceinline__ uint32_t epi_block(const uint32_t (&v)[32], float bv, uint32_t keep, float* o, int out_step,
+                                              int valid) {
+  uint32_t pos = 0u;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    float t = __uint_as_float(v[i]) + bv;
+    if (MODE == 1) t = fmaxf(t, 0.f);
+    if (MODE == 2) t = ((keep >> i) & 1u) ? t : 0.f;
+    if (BITS) pos |= (t > 0.f ? 1u : 0u) << i;
+    if (i < valid) o[i * out_step] = t;
+  }
+  return pos;
+}
+
 __global__ void __launch_bounds__(THREADS, 1) layer_tc2_kernel(const __grid_constant__ LayerLaunch L,
                                                                const __grid_constant__ Schedule S) {
   extern __shared__ uint8_t smem_raw[];
@@ -112,7 +148,7 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc2_kernel(const __grid_cons
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(smem_u32(&sh.full[s]), PROD_THREADS + 1);   // + the thread that arms the weight bulk copy
+      mbar_init(smem_u32(&sh.full[s]), PROD_THREADS + 1);   // producers + the weight stager
       mbar_init(smem_u32(&sh.empty[s]), 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -129,104 +165,130 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc2_kernel(const __grid_cons
 
   if (warp >= EPI_WARPS && warp < MMA_WARP) {
     // ===== producers ==================================================================================================
-    // Thread (pw, lane) owns, in every stage, rows  8*(4 pw + i) + (lane & 7), i = 0..3,  and the k-quad  lane >> 3:
-    // a warp instruction reads 8 rows x 64 contiguous bytes and writes 512 contiguous bytes of the tile (conflict-free).
+    // The activation rows come from HBM with ~1000 cycles of latency (measured: with everything else switched off the
+    // wait for the rows alone set the stage time).  They are therefore fetched LOADS_AHEAD stages ahead with cp.async
+    // (global -> shared without registers) into a thread-private ring -- a thread later reads back exactly the 16-byte
+    // pieces it copied, so cp.async.wait_group is the only synchronisation the ring needs -- and one copy of the stage
+    // code (load back, split hi/lo, store into the operand tiles) serves all stages: with 14 warps in four roles the
+    // kernel is sensitive to instruction-cache footprint, a software pipeline over register sets tripled it.
+    // Thread (pw, lane) owns rows  8*(4 pw + i) + (lane & 7), i = 0..3,  and the k-quad  lane >> 3 of every stage:
+    // a warp instruction reads 8 rows x 64 contiguous bytes and writes 512 contiguous bytes of the tile.
     const int pw = warp - EPI_WARPS;
     const int kq = lane >> 3;
-    uint32_t it = 0;                 // stage counter (stores)
-    // load-side iterator over (unit, term, k chunk); everything a stage needs sits in registers per term
+    const int ptid = tid - EPI_WARPS * 32;                                // 0..255
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t my_off = pw * 4 * 512 + kq * 128 + (lane & 7) * 16;   // this thread's 16 bytes of row group 4 pw
+    const uint32_t ring = smem_base + STAGES * STAGE_BYTES + ptid * 16;  // raw ring: [slot][i][thread] 16-byte pieces
+    // load-side iterator over (unit, term, k chunk), LOADS_AHEAD stages ahead of the stores
     int uk = 0;
     uint32_t mask = 0u;
     int kc = D - KC;
     bool alive = true;
     Unit2 U{0, 0, 0};
-    const float* rowp[4] = {nullptr, nullptr, nullptr, nullptr};
-    const float* packed_base = nullptr;
-    auto advance = [&](const float*& packed) -> bool {
-      if (!alive) return false;
-      kc += KC;
-      if (kc >= D) {
-        kc = 0;
-        mask &= mask - 1;
-        while (mask == 0) {
-          if (!next_unit(S, uk++, U, mask)) {
-            alive = false;
-            return false;
+    uint32_t row_off[4];          // element offset of this thread's four rows (k-quad included) in the term's operand
+    const float* a = nullptr;
+    uint32_t issued = 0;
+    auto fetch_next = [&]() {     // cp.async of the next stage's rows into ring slot issued % RING; always commits
+      if (alive) {
+        kc += KC;
+        if (kc >= D) {
+          kc = 0;
+          mask &= mask - 1;
+          while (mask == 0 && alive) alive = next_unit(S, uk++, U, mask);
+          if (alive) {
+            const mpqe_layer_group_t& G = L.g[U.gi];
+            const mpqe_term_t& T = G.terms[__ffs(mask) - 1];
+            a = T.a;
+            const int64_t a_slots = T.a_slots, a_slot = T.a_slot, nq = G.num_queries;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              int64_t q = U.q0 + (pw * 4 + i) * 8 + (lane & 7);
+              if (q >= nq) q = nq - 1;                    // rows past the end repeat the last row (never stored)
+              row_off[i] = (uint32_t)((q * a_slots + a_slot) * (int64_t)D + kq * 4);
+            }
           }
         }
-        const mpqe_layer_group_t& G = L.g[U.gi];
-        const mpqe_term_t& T = G.terms[__ffs(mask) - 1];
-        const float* a = T.a;
-        const int64_t a_slots = T.a_slots, a_slot = T.a_slot, nq = G.num_queries;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          int64_t q = U.q0 + (pw * 4 + i) * 8 + (lane & 7);
-          if (q >= nq) q = nq - 1;                      // rows past the end repeat the last row (never stored)
-          rowp[i] = a + (q * a_slots + a_slot) * (int64_t)D + kq * 4;
-        }
-        packed_base = T.m_packed;
       }
-      packed = packed_base + (kc / KC) * (2 * W_TILE / 4);
-      return true;
-    };
-    auto issue = [&](Frag4& f) {
+      if (alive) {
+        const uint32_t dst = ring + (issued % RING) * RING_SLOT;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) f.v[i] = *reinterpret_cast<const float4*>(rowp[i] + kc);
+        for (int i = 0; i < 4; ++i)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * (PROD_THREADS * 16)),
+                       "l"(a + row_off[i] + kc)
+                       : "memory");
+        ++issued;
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
     };
+#pragma unroll 1
+    for (int j = 0; j < LOADS_AHEAD; ++j) fetch_next();
     ST_DECL;
-    auto put = [&](const Frag4& f, const float* packed) {
+#pragma unroll 1
+    for (uint32_t it = 0;; ++it) {
+      fetch_next();                                                        // stage it + LOADS_AHEAD
+      if (it >= issued) break;                                             // nothing left: all issued stages stored
+      ST_BEGIN();
+      asm volatile("cp.async.wait_group %0;" ::"n"(LOADS_AHEAD) : "memory");   // stage `it` has landed (own pieces)
+      ST_END(3);   // waiting for the rows
       const int s = it % STAGES;
       const uint32_t use = it / STAGES;
       ST_BEGIN();
       if (use > 0) mbar_wait(smem_u32(&sh.empty[s]), (use - 1) & 1);
       ST_END(0);   // waiting for a free stage
       ST_BEGIN();
-      uint8_t* st = smem + s * STAGE_BYTES;
-      if (pw == 0 && lane == 0) {
-        const uint32_t bar = smem_u32(&sh.full[s]);
-        mbar_arrive_expect_tx(bar, 2 * W_TILE);
-        bulk_copy_g2s(smem_u32(st), packed, 2 * W_TILE, bar);
-      }
-      uint8_t* xh = st + 2 * W_TILE;
-      uint8_t* xl = xh + X_TILE;
+      const uint32_t src = ring + (it % RING) * RING_SLOT;
+      const uint32_t xh = smem_base + s * STAGE_BYTES + 2 * W_TILE + my_off;
+#if !(MPQE_TC2_ABLATE & 4)
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int off = (pw * 4 + i) * 512 + kq * 128 + (lane & 7) * 16;
-        float4 hi, lo;
-        split_tf32(f.v[i], hi, lo);
-        *reinterpret_cast<float4*>(xh + off) = hi;
-        *reinterpret_cast<float4*>(xl + off) = lo;
+        float4 x, hi, lo;
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
+                     : "r"(src + i * (PROD_THREADS * 16)));
+        split_tf32_fast(x, hi, lo);
+        sts128(xh + i * 512, hi);
+        sts128(xh + i * 512 + X_TILE, lo);
       }
-      ST_END(1);   // waiting for the loaded rows + split + stores
+#else
+      (void)src; (void)xh;
+#endif
+      ST_END(1);   // load back + split + stores
       ST_BEGIN();
       fence_proxy_async();
       mbar_arrive(smem_u32(&sh.full[s]));
       ST_END(2);   // fence + arrive
-      ++it;
-    };
-    // software pipeline over LOADS_AHEAD = 3 register sets: set j holds the loads of stage (it + j)
-    Frag4 f0, f1, f2;
-    const float *p0 = nullptr, *p1 = nullptr, *p2 = nullptr;
-    bool h0 = advance(p0);
-    if (h0) issue(f0);
-    bool h1 = h0 && advance(p1);
-    if (h1) issue(f1);
-    bool h2 = h1 && advance(p2);
-    if (h2) issue(f2);
-    while (h0) {
-      put(f0, p0);
-      h0 = h2 && advance(p0);
-      if (h0) issue(f0);
-      if (!h1) break;
-      put(f1, p1);
-      h1 = h0 && advance(p1);
-      if (h1) issue(f1);
-      if (!h2) break;
-      put(f2, p2);
-      h2 = h1 && advance(p2);
-      if (h2) issue(f2);
     }
-    if (pw == 0 && lane == 0) { ST_FLUSH(0, 3); }
+    if (pw == 0 && lane == 0) { ST_FLUSH(0, 4); }
+  } else if (warp == TMA_WARP) {
+    // ===== weight stager (one thread): one 16 KB bulk copy of the pre-split chunk per stage ===========================
+    // (a thread of its own: issued from a producer warp, the copy instruction held that warp -- and with it every
+    // stage -- for ~1000 cycles)
+    if (lane == 0) {
+      uint32_t it = 0;
+      int uc = 0;
+      Unit2 U{0, 0, 0};
+      const uint32_t base = smem_u32(smem);
+      for (uint32_t umask; next_unit(S, uc, U, umask); ++uc) {
+        const mpqe_layer_group_t& G = L.g[U.gi];
+        for (uint32_t m = umask; m != 0; m &= m - 1) {
+          const float* packed = G.terms[__ffs(m) - 1].m_packed;
+          for (int c = 0; c < D / KC; ++c, ++it) {
+            const int s = it % STAGES;
+            const uint32_t use = it / STAGES;
+            if (use > 0) mbar_wait(smem_u32(&sh.empty[s]), (use - 1) & 1);
+            const uint32_t bar = smem_u32(&sh.full[s]);
+#if MPQE_TC2_ABLATE & 16
+            mbar_arrive(bar);
+            (void)packed;
+            (void)base;
+#else
+            mbar_arrive_expect_tx(bar, 2 * W_TILE);
+            bulk_copy_g2s(base + s * STAGE_BYTES, packed + c * (2 * W_TILE / 4), 2 * W_TILE, bar);
+#endif
+          }
+        }
+      }
+    }
   } else if (warp == MMA_WARP) {
     // ===== MMA issuer (one thread) ====================================================================================
     if (lane == 0) {
@@ -252,6 +314,7 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc2_kernel(const __grid_cons
           tc_fence_after();
           const uint32_t w_hi = base + s * STAGE_BYTES, w_lo = w_hi + W_TILE, x_hi = w_hi + 2 * W_TILE,
                          x_lo = x_hi + X_TILE;
+#if !(MPQE_TC2_ABLATE & 8)
 #pragma unroll
           for (int j = 0; j < KC / 8; ++j) {
             const uint64_t dwh = make_desc(w_hi + j * 256, LBO, SBO), dwl = make_desc(w_lo + j * 256, LBO, SBO);
@@ -260,6 +323,9 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc2_kernel(const __grid_cons
             umma_tf32(acc, dwh, dxl, IDESC2, 1u);
             umma_tf32(acc, dwh, dxh, IDESC2, 1u);
           }
+#else
+          (void)w_lo; (void)x_lo; (void)acc;
+#endif
           umma_commit(smem_u32(&sh.empty[s]));      // frees the stage when the MMAs have read it
           ST_END(2);
         }
@@ -284,20 +350,31 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc2_kernel(const __grid_cons
       const int oslot = G.out_slot_map[U.slot];
       const int epi = G.epilogue;
       const bool masked = epi == MPQE_EPI_MASK;
-      const int64_t rows_left = G.num_queries - U.q0;             // query c of the tile exists iff c < rows_left
-      const int64_t out_step = (int64_t)G.out_slots * D;
+      const int64_t left64 = G.num_queries - U.q0;                // query c of the tile exists iff c < rows_left
+      const int rows_left = left64 < BQ ? (int)left64 : BQ;
+      // Strides as 32-bit element counts: with 64-bit products the address chain of every store (three IMADs, two LEAs
+      // behind a branch) ran at ~70 cycles per store on the one epilogue warp of each scheduler -- 18 k cycles per
+      // unit, more than the unit's MMAs
+      const int out_step = G.out_slots * D, mask_step = G.mask_slots * D;
       float* outp = G.out + (U.q0 * (int64_t)G.out_slots + oslot) * (int64_t)D + n;
-      const int64_t mask_step = (int64_t)G.mask_slots * D;
       const float* maskp = masked ? G.mask + (U.q0 * (int64_t)G.mask_slots + oslot) * (int64_t)D + n : nullptr;
       float bv = 0.f;
       if (G.bias != nullptr) bv = G.bias_scale[U.slot] * __ldg(G.bias + (int64_t)U.slot * G.bias_slot_stride + n);
-      // the ReLU mask of a 32-query block is fetched one block ahead (read-only path): inside the store loop the loads
-      // could not be hoisted above the stores and every query would pay a full memory round trip
+      // ReLU-backward mask.  Preferred form: the sign bits written by the forward launch (one word per 32 queries and
+      // feature: 8 loads per unit, all issued up front).  Otherwise the fp32 activations, a 32-query block fetched one
+      // block ahead through the read-only path (inside the store loop the loads could not be hoisted above the stores).
+      const uint32_t* bitsp = masked && G.mask_bits != nullptr
+                                  ? G.mask_bits + ((U.q0 / 32) * (int64_t)G.mask_slots + oslot) * (int64_t)D + n : nullptr;
+      uint32_t* bits_out = epi == MPQE_EPI_RELU && G.relu_bits_out != nullptr
+                               ? G.relu_bits_out + ((U.q0 / 32) * (int64_t)G.out_slots + oslot) * (int64_t)D + n : nullptr;
+      uint32_t kb = bitsp != nullptr ? __ldg(bitsp) : 0u;       // sign bits of the current block (next one prefetched)
       float mk[32];
       auto fetch = [&](int c0) {
-        if (masked) {
+        if (masked && bitsp == nullptr) {
+          const float* mp = maskp + c0 * mask_step;
+          const int valid = rows_left - c0;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mk[i] = c0 + i < rows_left ? __ldg(maskp + (int64_t)(c0 + i) * mask_step) : 0.f;
+          for (int i = 0; i < 32; ++i) mk[i] = i < valid ? __ldg(mp + i * mask_step) : 0.f;
         }
       };
       fetch(0);
@@ -307,35 +384,39 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc2_kernel(const __grid_cons
       ST_BEGIN();
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < BQ; c0 += 32) {
+      for (int j = 0; j < BQ / 32; ++j) {
+        const int c0 = 32 * j;
         if (c0 >= rows_left) break;
         uint32_t v[32];
-#ifdef MPQE_TC_STATS
-        const long long tl0 = clock64();
-        if (!(g_dbg2 & 2))
-#endif
         tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + ab * BQ + c0, v);
-#ifdef MPQE_TC_STATS
-        st_acc[2] += clock64() - tl0;
-#endif
+        if (nsteps == 0) {                       // a slot no term writes to: bias only
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0u;
+        }
         uint32_t keep = 0xffffffffu;
-        if (masked) {
+        if (bitsp != nullptr) {
+          keep = kb;
+          if (c0 + 32 < rows_left) kb = __ldg(bitsp + (j + 1) * mask_step);
+        } else if (masked) {
           keep = 0u;
 #pragma unroll
           for (int i = 0; i < 32; ++i) keep |= (mk[i] > 0.f ? 1u : 0u) << i;
-          if (c0 + 32 < BQ) fetch(c0 + 32);
+          if (c0 + 32 < rows_left) fetch(c0 + 32);
         }
-        float* o = outp + (int64_t)c0 * out_step;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float x = nsteps == 0 ? 0.f : __uint_as_float(v[i]);
-          x += bv;
-          if (epi == MPQE_EPI_RELU) x = fmaxf(x, 0.f);
-          if (!((keep >> i) & 1u)) x = 0.f;
-#ifdef MPQE_TC_STATS
-          if (g_dbg2 & 1) continue;
-#endif
-          if (c0 + i < rows_left) o[(int64_t)i * out_step] = x;
+        float* o = outp + c0 * out_step;
+        const int valid = (MPQE_TC2_ABLATE & 32) ? 0 : rows_left - c0;     // >= 32 for whole blocks
+        if (epi == MPQE_EPI_RELU) {
+          if (bits_out != nullptr) {
+            uint32_t pos = epi_block<1, true>(v, bv, keep, o, out_step, valid);
+            if (valid < 32) pos &= (1u << valid) - 1u;
+            bits_out[j * out_step] = pos;
+          } else {
+            epi_block<1, false>(v, bv, keep, o, out_step, valid);
+          }
+        } else if (masked) {
+          epi_block<2, false>(v, bv, keep, o, out_step, valid);
+        } else {
+          epi_block<0, false>(v, bv, keep, o, out_step, valid);
         }
       }
       tc_fence_before();

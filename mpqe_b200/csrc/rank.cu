@@ -195,6 +195,99 @@ RankWs carve_rank(void* ws, int64_t B, int64_t rows) {
 
 using namespace mpqe;
 
+// ---- two-phase form: the table-dependent half (1/||row||, tf32 hi/lo tile images of the shard) is prepared ONCE and
+// reused by every batch of an evaluation; only the query-dependent half runs per batch --------------------------------
+namespace {
+struct TableWs {
+  float* inv_norm;
+  float* packed;
+  size_t bytes;
+};
+TableWs carve_table(void* ws, int64_t rows, int use_tc) {
+  TableWs w;
+  char* p = (char*)ws;
+  size_t off = 0;
+  w.inv_norm = (float*)(p + off); off += align_up((size_t)(rows > 0 ? rows : 1) * sizeof(float), 1024);
+  w.packed = (float*)(p + off); off += use_tc ? rank_packed_bytes(rows) : 0;
+  w.bytes = off;
+  return w;
+}
+struct QueryWs {
+  float *qt, *qinv;
+  int64_t Bp;
+  size_t bytes;
+};
+QueryWs carve_query(void* ws, int64_t B) {
+  QueryWs w;
+  w.Bp = (B + BN - 1) / BN * BN;
+  char* p = (char*)ws;
+  size_t off = 0;
+  w.qt = (float*)(p + off); off += align_up((size_t)D * w.Bp * sizeof(float), 256);
+  w.qinv = (float*)(p + off); off += align_up((size_t)w.Bp * sizeof(float), 256);
+  w.bytes = off;
+  return w;
+}
+}  // namespace
+
+namespace mpqe {
+int rank_pack_rows(const float* table, int64_t row_begin, int64_t rows, float* packed, cudaStream_t stream);
+int rank_counts_packed_tc(int64_t rows, const float* inv_norm, const float* q, const float* qinv, const float* pos,
+                          int64_t B, unsigned long long* left, unsigned long long* right, const float* packed,
+                          cudaStream_t stream);
+}
+
+extern "C" size_t mpqe_rank_table_workspace_bytes(int64_t rows, int32_t use_tensor_cores) {
+  return carve_table(nullptr, rows, use_tensor_cores).bytes;
+}
+
+extern "C" int mpqe_rank_table_prepare(const float* table, int64_t row_begin, int64_t row_end, void* table_ws,
+                                       size_t table_ws_bytes, int32_t use_tensor_cores, void* stream) {
+  MPQE_CHECK_ARG(table && row_begin >= 0 && row_end >= row_begin, "mpqe_rank_table_prepare: bad argument");
+  const int64_t rows = row_end - row_begin;
+  if (rows == 0) return 0;
+  TableWs w = carve_table(table_ws, rows, use_tensor_cores);
+  MPQE_CHECK_ARG(table_ws && table_ws_bytes >= w.bytes, "mpqe_rank_table_prepare: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  row_inv_norm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(table, row_begin, rows, w.inv_norm);
+  MPQE_CHECK_LAUNCH("row_inv_norm_kernel");
+  if (use_tensor_cores) return rank_pack_rows(table, row_begin, rows, w.packed, st);
+  return 0;
+}
+
+extern "C" size_t mpqe_rank_query_workspace_bytes(int64_t B) { return carve_query(nullptr, B).bytes; }
+
+extern "C" int mpqe_rank_counts_prepared(const float* q, int64_t B, const float* pos, const float* table,
+                                         int64_t row_begin, int64_t row_end, const void* table_ws, int64_t* left,
+                                         int64_t* right, void* query_ws, size_t query_ws_bytes,
+                                         int32_t use_tensor_cores, void* stream) {
+  MPQE_CHECK_ARG(q && pos && table && table_ws && left && right && B >= 1 && row_begin >= 0 && row_end >= row_begin,
+                 "mpqe_rank_counts_prepared: bad argument");
+  const int64_t rows = row_end - row_begin;
+  if (rows == 0) return 0;
+  TableWs tw = carve_table(const_cast<void*>(table_ws), rows, use_tensor_cores);
+  QueryWs qw = carve_query(query_ws, B);
+  MPQE_CHECK_ARG(query_ws && query_ws_bytes >= qw.bytes, "mpqe_rank_counts_prepared: query workspace too small");
+  static bool configured = false;
+  if (!configured) {
+    MPQE_CUDA(cudaFuncSetAttribute(rank_counts_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)RANK_SMEM));
+    configured = true;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  prep_queries_kernel<<<(unsigned)((qw.Bp + 7) / 8), 256, 0, st>>>(q, B, qw.Bp, qw.qt, qw.qinv);
+  MPQE_CHECK_LAUNCH("prep_queries_kernel");
+  if (use_tensor_cores)
+    return rank_counts_packed_tc(rows, tw.inv_norm, q, qw.qinv, pos, B, (unsigned long long*)left,
+                                 (unsigned long long*)right, tw.packed, st);
+  dim3 grid((unsigned)((rows + BM - 1) / BM), (unsigned)(qw.Bp / BN));
+  MPQE_CHECK_ARG(grid.y <= 65535, "mpqe_rank_counts_prepared: too many queries (%lld)", (long long)B);
+  rank_counts_table_kernel<<<grid, THREADS, RANK_SMEM, st>>>(table, row_begin, rows, tw.inv_norm, qw.qt, qw.Bp, qw.qinv,
+                                                            pos, B, (unsigned long long*)left,
+                                                            (unsigned long long*)right);
+  MPQE_CHECK_LAUNCH("rank_counts_table_kernel");
+  return 0;
+}
+
 extern "C" size_t mpqe_rank_counts_table_workspace_bytes(int64_t B, int64_t rows) {
   return carve_rank(nullptr, B, rows).bytes;
 }

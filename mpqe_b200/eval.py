@@ -15,40 +15,78 @@ from .model import Weights
 from .utils import percentile_from_counts
 
 
-def shard_rows(num_rows, rank, world):
-    """Row range [begin, end) of rank `rank` (contiguous, balanced)."""
-    base, rem = divmod(num_rows, world)
-    begin = rank * base + min(rank, rem)
-    return begin, begin + base + (1 if rank < rem else 0)
+def shard_rows(num_rows, rank, world, table_rows=None):
+    """Row range [begin, end) of rank `rank`: the rows of the table the rank OWNS in data-parallel training (ranges of
+    ceil(table_rows / world) rows, see train_step.TrainStep), clipped to the `num_rows` candidate rows -- so that a
+    rank always ranks against rows whose latest values it holds."""
+    table_rows = num_rows if table_rows is None else table_rows
+    chunk = (table_rows + world - 1) // world
+    return min(rank * chunk, num_rows), min((rank + 1) * chunk, num_rows)
+
+
+class RankIndex(object):
+    """Everything of a full-entity ranking evaluation that does not depend on the batch, cached across batches: the
+    per-step weight layouts of the encoder (`Weights`: transposes, tf32 tile images) and, per target mode, the prepared
+    table shard of this rank (1/||row||, pre-split tile images).  Parameters are frozen during an evaluation
+    (`torch.no_grad`); entries are rebuilt when a parameter's version counter has moved."""
+
+    def __init__(self, model, process_group=None, use_tensor_cores=None, distributed=None):
+        dist = torch.distributed
+        if distributed is None:
+            distributed = dist.is_available() and dist.is_initialized()
+        self.model, self.pg, self.distributed = model, process_group, bool(distributed)
+        self.rank = dist.get_rank(process_group) if self.distributed else 0
+        self.world = dist.get_world_size(process_group) if self.distributed else 1
+        self.tc = ops.tensor_cores_default() if use_tensor_cores is None else bool(use_tensor_cores)
+        self._weights = None
+        self._tables = {}
+
+    def _param_version(self):
+        return tuple(p._version for p in self.model.parameters())
+
+    def weights(self):
+        v = self._param_version()
+        if self._weights is None or self._weights[0] != v:
+            self._weights = (v, Weights(self.model, False))
+        return self._weights[1]
+
+    def table(self, mode):
+        table = self.model.enc.table(mode)
+        ent = self._tables.get(mode)
+        if ent is None or ent.version != table._version or ent.table.data_ptr() != table.data_ptr():
+            num_entities = table.shape[0] - 1          # the spare last row (data_utils.py:31) is not a candidate
+            begin, end = shard_rows(num_entities, self.rank, self.world, table.shape[0])
+            ent = self._tables[mode] = ops.RankTable(table, begin, end, self.tc)
+        return ent
+
+    @torch.no_grad()
+    def counts(self, formula, queries, target_nodes, anchor_ids=None, var_ids=None, q_graphs=None):
+        """(count_lt, count_le, positive scores, N) of one formula batch, merged over the ranks."""
+        model = self.model
+        job = model.make_job(formula, queries, anchor_ids, var_ids, q_graphs)
+        device = job.anchor_ids.device
+        table = model.enc.table(formula.target_mode)
+        with ops.device_guard(device):
+            W = self.weights()
+            W.prepared = None
+            model._engine.encode([job], W)
+            tgt = model.enc.ids_on_device(target_nodes, device).reshape(-1)
+            pos = ops.cosine_scores(job.q, table, model.enc.node_maps, tgt)
+            both = torch.zeros(2, job.B, dtype=torch.int64, device=device)
+            self.table(formula.target_mode).counts(job.q, pos, both[0], both[1])
+            if self.world > 1:
+                torch.distributed.all_reduce(both, group=self.pg)     # integer sum: exact, order independent
+        return both[0], both[1], pos, table.shape[0] - 1
 
 
 @torch.no_grad()
 def full_rank_counts(model, formula, queries, target_nodes, anchor_ids=None, var_ids=None, q_graphs=None,
-                     process_group=None, use_tensor_cores=None):
+                     process_group=None, use_tensor_cores=None, index=None):
     """(count_lt, count_le, positive scores, N): counts of entities of the target mode scoring below / not above each
-    query's positive.  The spare last table row (data_utils.py:31) is not a candidate."""
-    dist = torch.distributed
-    distributed = dist.is_available() and dist.is_initialized()
-    rank = dist.get_rank(process_group) if distributed else 0
-    world = dist.get_world_size(process_group) if distributed else 1
-    job = model.make_job(formula, queries, anchor_ids, var_ids, q_graphs)
-    device = job.anchor_ids.device
-    table = model.enc.table(formula.target_mode)
-    num_entities = table.shape[0] - 1
-    with ops.device_guard(device):
-        model._engine.encode([job], Weights(model, False))
-        tgt = model.enc.ids_on_device(target_nodes, device).reshape(-1)
-        pos = ops.cosine_scores(job.q, table, model.enc.node_maps, tgt)
-        left = torch.zeros(job.B, dtype=torch.int64, device=device)
-        right = torch.zeros(job.B, dtype=torch.int64, device=device)
-        begin, end = shard_rows(num_entities, rank, world)
-        tc = ops.tensor_cores_default() if use_tensor_cores is None else bool(use_tensor_cores)
-        ops.rank_counts_table(job.q, pos, table, begin, end, left, right, use_tensor_cores=tc)
-        if world > 1:
-            both = torch.stack((left, right))
-            dist.all_reduce(both, group=process_group)     # integer sum: exact, order independent
-            left, right = both[0], both[1]
-    return left, right, pos, num_entities
+    query's positive.  Pass a `RankIndex` as `index` to reuse the prepared weights and table shards across batches."""
+    if index is None:
+        index = RankIndex(model, process_group, use_tensor_cores)
+    return index.counts(formula, queries, target_nodes, anchor_ids, var_ids, q_graphs)
 
 
 def ranking_metrics(left, right, num_entities):
@@ -64,11 +102,11 @@ def ranking_metrics(left, right, num_entities):
 def eval_full_rank(model, test_queries, batch_size=4096, process_group=None, use_tensor_cores=None):
     """{formula: [queries]} -> overall APR / MRR against all entities of each target mode."""
     lefts, rights, ns = [], [], []
+    index = RankIndex(model, process_group, use_tensor_cores)
     for formula, formula_queries in test_queries.items():
         for off in range(0, len(formula_queries), batch_size):
             batch = formula_queries[off:off + batch_size]
-            l, r, _, n = full_rank_counts(model, formula, batch, [q.target_node for q in batch],
-                                          process_group=process_group, use_tensor_cores=use_tensor_cores)
+            l, r, _, n = index.counts(formula, batch, [q.target_node for q in batch])
             lefts.append(l.cpu().numpy())
             rights.append(r.cpu().numpy())
             ns.append(np.full(len(batch), n, dtype=np.float64))

@@ -306,6 +306,7 @@ class Engine(object):
                 items.append(ops.GatherItem(enc.table(mode), enc.node_maps, job.anchor_ids, B, ids_offset=i,
                                             ids_stride=t.num_anchors, out=x, out_offset=i * D, out_stride=n * D))
             job.acts = [x]
+            job.act_bits = {}
         ops.gather_multi(items)
 
     def layer_index(self, p, P):
@@ -495,9 +496,12 @@ class Engine(object):
                     bias, bias_scale, stride = job.const_fwd.out, [1.0] * nb, D
                 if p < job.P - 1:
                     h = torch.empty(B, n, D, dtype=torch.float32, device=dev)
+                    # the tcgen05 kernel also leaves the ReLU sign bits (1/32 of h) for the backward's mask
+                    bits = ops.relu_bits(B, n, dev) if ops.tensor_cores_default() and W.need_grad else None
                     g = Group(B, terms, nb, h, n, out_slot_map=outs, epilogue=EPI_RELU, bias=bias, bias_scale=bias_scale,
-                              bias_slot_stride=stride)
+                              bias_slot_stride=stride, bits_out=bits)
                     job.acts.append(h)
+                    job.act_bits[p + 1] = bits
                 elif fused:
                     job.q = torch.empty(B, D, dtype=torch.float32, device=dev)
                     g = Group(B, terms, 1, job.q, 1, out_slot_map=[0], bias=bias, bias_scale=bias_scale)
@@ -535,7 +539,8 @@ class Engine(object):
             terms = [Term(a, s, j, W.w1t[b * D:(b + 1) * D], k, W.w1tp[b] if W.w1tp is not None else None)
                      for k, srcs in enumerate(units) for (a, s, j, b) in srcs]
             job.u = torch.empty(job.B, nu, D, dtype=torch.float32, device=dev)
-            job.mlp1 = Group(job.B, terms, nu, job.u, nu, epilogue=EPI_RELU, bias=W.b1)
+            job.u_bits = ops.relu_bits(job.B, nu, dev) if ops.tensor_cores_default() and W.need_grad else None
+            job.mlp1 = Group(job.B, terms, nu, job.u, nu, epilogue=EPI_RELU, bias=W.b1, bits_out=job.u_bits)
             if self.m.scatter_op == 'max':     # per-unit outputs, then the per-feature max over the query's units
                 job.z2 = torch.empty(job.B, nu, D, dtype=torch.float32, device=dev)
                 job.mlp2 = Group(job.B, [Term(job.u, nu, k, W.w2t, k, W.w2tp) for k in range(nu)], nu, job.z2, nu, bias=W.b2)
@@ -658,7 +663,7 @@ class Engine(object):
                 dx = torch.empty(job.B, n, D, dtype=torch.float32, device=g.device)
                 if p > 0:
                     groups.append(Group(job.B, terms, len(ins), dx, n, out_slot_map=ins, epilogue=EPI_MASK,
-                                        mask=job.acts[p], mask_slots=n))
+                                        mask=job.acts[p], mask_slots=n, mask_bits=job.act_bits.get(p)))
                 else:
                     groups.append(Group(job.B, terms, len(ins), dx, n, out_slot_map=ins))
                 nxt[job] = (dx, n, ins)
@@ -761,7 +766,7 @@ class Engine(object):
             g, gs, smap = g2[-1]
             # dU[:, k] = (dZ2[:, k] @ W2) * (u > 0)       (W2 is stored [out, in] = the matrix this product needs)
             g_du.append(Group(job.B, [Term(g, gs, smap[k], W.w2, k, W.w2p) for k in range(nu)], nu, job.du, nu,
-                              epilogue=EPI_MASK, mask=job.u, mask_slots=nu))
+                              epilogue=EPI_MASK, mask=job.u, mask_slots=nu, mask_bits=getattr(job, 'u_bits', None)))
         ops.layer_forward(g_du)
         for i in range(0, len(jobs), ops.MAX_GROUPS):
             chunk = jobs[i:i + ops.MAX_GROUPS]

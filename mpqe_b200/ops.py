@@ -93,7 +93,7 @@ class Group(object):
     """One formula group of a layer launch (see mpqe_layer_group_t)."""
 
     def __init__(self, num_queries, terms, num_out_slots, out, out_slots, out_slot_map=None, epilogue=EPI_NONE,
-                 bias=None, bias_scale=None, mask=None, mask_slots=0, bias_slot_stride=0):
+                 bias=None, bias_scale=None, mask=None, mask_slots=0, bias_slot_stride=0, bits_out=None, mask_bits=None):
         self.num_queries, self.terms, self.num_out_slots = int(num_queries), list(terms), int(num_out_slots)
         self.out, self.out_slots = out, int(out_slots)
         self.out_slot_map = list(out_slot_map) if out_slot_map is not None else list(range(num_out_slots))
@@ -101,6 +101,8 @@ class Group(object):
         self.bias_scale = list(bias_scale) if bias_scale is not None else [1.0] * num_out_slots
         self.mask, self.mask_slots = mask, int(mask_slots)
         self.bias_slot_stride = int(bias_slot_stride)   # 0: one bias vector; D: bias is [num_out_slots, D]
+        # ReLU sign bits (int32 [ceil(B/32), slots, D]): written by an EPI_RELU launch / read by an EPI_MASK launch
+        self.bits_out, self.mask_bits = bits_out, mask_bits
 
     def to_c(self):
         if len(self.terms) > MAX_TERMS or self.num_out_slots > MAX_SLOTS:
@@ -124,6 +126,8 @@ class Group(object):
         g.mask = _chk(self.mask, torch.float32, 'mask').data_ptr() if self.mask is not None else 0
         g.mask_slots = self.mask_slots
         g.bias_slot_stride = self.bias_slot_stride
+        g.relu_bits_out = _chk(self.bits_out, torch.int32, 'bits_out').data_ptr() if self.bits_out is not None else 0
+        g.mask_bits = _chk(self.mask_bits, torch.int32, 'mask_bits').data_ptr() if self.mask_bits is not None else 0
         return g
 
 
@@ -199,6 +203,11 @@ def _ensure_packed(groups):
         for t in g.terms:
             if t.mp is None:
                 t.mp = image[t.m.data_ptr()]
+
+
+def relu_bits(num_queries, slots, device):
+    """Buffer for the ReLU sign bits of a [num_queries, slots, D] activation (see mpqe_layer_group_t.relu_bits_out)."""
+    return torch.empty((num_queries + 31) // 32, slots, D, dtype=torch.int32, device=device)
 
 
 def layer_wgrad(groups, grad_operands, dests, ctas_hint=296, use_tensor_cores=None):
@@ -439,6 +448,34 @@ def rank_counts_table(q, pos, table, row_begin, row_end, left, right, use_tensor
                                           _ptr(ws), ws.numel(), int(use_tensor_cores), _stream()),
                'mpqe_rank_counts_table')
     _count(3)
+
+
+class RankTable(object):
+    """The table-dependent half of the full-entity ranking, prepared once per table shard (mpqe_rank_table_prepare:
+    1/||row|| and the pre-split tile images of rows [row_begin, row_end)) and reused by every batch."""
+
+    def __init__(self, table, row_begin, row_end, use_tensor_cores):
+        lib = _lib.load()
+        self.table, self.row_begin, self.row_end = _chk(table, torch.float32, 'table'), int(row_begin), int(row_end)
+        self.tc = bool(use_tensor_cores)
+        self.version = table._version
+        nbytes = lib.mpqe_rank_table_workspace_bytes(self.row_end - self.row_begin, int(self.tc))
+        self.ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=table.device)
+        _lib.check(lib.mpqe_rank_table_prepare(_ptr(table), self.row_begin, self.row_end, _ptr(self.ws), self.ws.numel(),
+                                               int(self.tc), _stream()), 'mpqe_rank_table_prepare')
+        _count(2 if self.tc else 1)
+
+    def counts(self, q, pos, left, right):
+        """Accumulates (count_lt, count_le) of the shard's rows against each query's positive into left/right."""
+        lib = _lib.load()
+        B = q.shape[0]
+        ws = workspace(lib.mpqe_rank_query_workspace_bytes(B), q.device, 'rankq')
+        _lib.check(lib.mpqe_rank_counts_prepared(_ptr(_chk(q, torch.float32, 'q')), B, _ptr(_chk(pos, torch.float32, 'pos')),
+                                                 _ptr(self.table), self.row_begin, self.row_end, _ptr(self.ws),
+                                                 _ptr(_chk(left, torch.int64, 'left')),
+                                                 _ptr(_chk(right, torch.int64, 'right')), _ptr(ws), ws.numel(),
+                                                 int(self.tc), _stream()), 'mpqe_rank_counts_prepared')
+        _count(2)
 
 
 # ---------------------------------------------------------------------------------------------------------------

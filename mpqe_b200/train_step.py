@@ -96,10 +96,12 @@ class PeerGroup(object):
 
 
 class TrainStep(object):
-    def __init__(self, model, margin=1.0, process_group=None, average=True):
+    def __init__(self, model, margin=1.0, process_group=None, average=True, data_parallel=True):
+        """data_parallel=False: a single-rank step even inside an initialised process group (reference runs, checks)."""
         self.model = model
         self.margin = float(margin)
         self.pg = process_group
+        self._dp = bool(data_parallel)
         self.world = torch.distributed.get_world_size(process_group) if self._dist() else 1
         self.average = average
         self._layouts = {}
@@ -118,7 +120,7 @@ class TrainStep(object):
         self.total_rows = off
 
     def _dist(self):
-        return torch.distributed.is_available() and torch.distributed.is_initialized()
+        return self._dp and torch.distributed.is_available() and torch.distributed.is_initialized()
 
     # ---- batch construction ---------------------------------------------------------------------------
     def layout(self, formula):
@@ -281,6 +283,8 @@ class TrainStep(object):
         dev = self.model.mode_embeddings.weight.device
         for mode, module in self.model.enc.feature_modules.items():
             w = module.weight
+            if w.data_ptr() in ops.PEER_TABLES:      # already owner-read (another TrainStep of the same model)
+                continue
             buf, ptrs = self.peers.alloc(tuple(w.shape), torch.float32)
             buf.copy_(w.data)
             w.data = buf

@@ -95,6 +95,41 @@ def test_layer_forward_slot_without_terms_and_per_slot_bias(B, tc):
     assert_close(gg[0].out.cpu().numpy(), out.numpy(), 1e-5, 2e-5, 'layer out')
 
 
+@pytest.mark.parametrize('B', [70, 256, 1000])
+def test_relu_sign_bits_replace_the_fp32_mask(B):
+    """tcgen05 kernel: an EPI_RELU launch also writes the ReLU sign bits (1 bit per element, word per 32 queries); an
+    EPI_MASK launch that reads them gives the same bits as one that reads the fp32 activations."""
+    need_tc(True)
+    n = 3
+    x = rnd(B, n, D, seed=1).to(DEV)
+    w = (rnd(4, D, D, seed=2, scale=0.05)).to(DEV)
+    bias = rnd(D, seed=3).to(DEV)
+    h = torch.empty(B, n, D, device=DEV)
+    bits = ops.relu_bits(B, n, torch.device(DEV))
+    bits.fill_(-1)
+    fwd = ops.Group(B, [ops.Term(x, n, 0, w[0], 1), ops.Term(x, n, 1, w[1], 1), ops.Term(x, n, 2, w[2], 0)], 2, h, n,
+                    out_slot_map=[0, 2], epilogue=ops.EPI_RELU, bias=bias, bits_out=bits)
+    ops.layer_forward([fwd], use_tensor_cores=True)
+    torch.cuda.synchronize()
+    # the words of the written slots spell (h > 0); queries past B read as 0
+    hb = torch.zeros((B + 31) // 32 * 32, n, D, dtype=torch.bool, device=DEV)
+    hb[:B] = h > 0
+    want = (hb.view(-1, 32, n, D).to(torch.int64) << torch.arange(32, device=DEV).view(1, 32, 1, 1)).sum(1)
+    got = bits.to(torch.int64) & 0xffffffff
+    for slot in (0, 2):
+        assert torch.equal(got[:, slot], want[:, slot])
+    g = rnd(B, n, D, seed=5).to(DEV)
+    outs = []
+    for mb in (None, bits):
+        dx = torch.full((B, n, D), float('nan'), device=DEV)
+        back = ops.Group(B, [ops.Term(g, n, 2, w[3], 0), ops.Term(g, n, 0, w[1], 1)], 2, dx, n, out_slot_map=[0, 2],
+                         epilogue=ops.EPI_MASK, mask=h, mask_slots=n, mask_bits=mb)
+        ops.layer_forward([back], use_tensor_cores=True)
+        outs.append(dx)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0][:, 0], outs[1][:, 0]) and torch.equal(outs[0][:, 2], outs[1][:, 2])
+
+
 @pytest.mark.parametrize('tc', [False, True])
 def test_layer_forward_multi_group_slot_maps_and_broadcast(tc):
     need_tc(tc)

@@ -45,13 +45,13 @@ def launches():
     return [('fwd pass 0', L1), ('fwd pass 1 (collapsed, fused sum)', L2), ('bwd pass 1 (masked)', L3), ('bwd pass 0', L4)]
 
 
-names = ['P wait empty', 'P data+stores', 'P fence+arrive', '-', 'M wait acc_empty', 'M wait full', 'M issue+commit',
+names = ['P wait empty', 'P data+stores', 'P fence+arrive', 'P wait data', 'M wait acc_empty', 'M wait full', 'M issue+commit',
          'stages', 'units', 'E wait acc_full', 'E work', 'CTA total', 'E tmem loads']
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 dbg = int(os.environ.get('DBG', '0'))
 if has_stats and dbg:
     lib.mpqe_debug_set_dbg2(dbg)
-    print('#### debug bits %d (1 = no epilogue stores, 2 = no tensor-memory loads)' % dbg)
+    print('#### debug bits %d (4 = no producer stores, 8 = no MMAs, 16 = no weight bulk copies)' % dbg)
 for name, groups in launches():
     for _ in range(3):
         ops.layer_forward(groups, use_tensor_cores=True)
@@ -82,7 +82,7 @@ for name, groups in launches():
         if nm != '-':
             print('   %-18s mean %9.0f  min %9.0f  max %9.0f' % (nm, st[:, i].mean(), st[:, i].min(), st[:, i].max()))
     stages = np.maximum(st[:, 7], 1)
-    print('   per stage: P wait empty %.0f, P data+stores %.0f, P publish %.0f | M wait full %.0f, M issue %.0f | CTA '
-          'total / stage %.0f' % tuple((st[:, i] / stages).mean() for i in (0, 1, 2, 5, 6, 11)))
+    print('   per stage: P wait empty %.0f, P data+stores %.0f (of which waiting for the rows %.0f), P publish %.0f | M wait '
+          'full %.0f, M issue %.0f | CTA total / stage %.0f' % tuple((st[:, i] / stages).mean() for i in (0, 1, 3, 2, 5, 6, 11)))
     units = np.maximum(st[:, 8], 1)
     print('   per unit: E wait %.0f, E work %.0f (tmem loads %.0f), M wait acc_empty %.0f' % tuple((st[:, i] / units).mean() for i in (9, 10, 12, 4)))
