@@ -344,9 +344,12 @@ def dp_check(run, dev, rank, world):
     ids_equal = got_ids.numel() == k1 and bool(torch.equal(got_ids, u1[:k1]))
     rows_err = float((got_rows - r1[:k1]).abs().max() / r1[:k1].abs().max().clamp_min(1e-30)) if ids_equal else None
     # sharded vs unsharded rank counts (same queries on every rank)
+    from mpqe_b200 import data_utils
     ef = run.formulas[4]
     ea, et_, _ = synthetic.sample_id_batch(run.kg, ef, 512, np.random.RandomState(9))
-    args_ = dict(anchor_ids=torch.from_numpy(ea))
+    t, var_ids, rels_e = data_utils.RGCNQueryDataset.formula_layout(ef, run.model.rel_ids, run.model.mode_ids)
+    args_ = dict(anchor_ids=torch.from_numpy(ea), var_ids=torch.tensor(var_ids, dtype=torch.int64),
+                 q_graphs=data_utils.QueryGraphBatch(t, rels_e, 512))
     ts_n.gather_tables()
     sharded = mp_eval.RankIndex(run.model).counts(ef, [None] * 512, torch.from_numpy(et_).to(dev), **args_)
     single = mp_eval.RankIndex(run.model, distributed=False).counts(ef, [None] * 512, torch.from_numpy(et_).to(dev),

@@ -368,11 +368,13 @@ class TrainStep(object):
             return StepResult(losses, wts[1], G, sparse)
         scale = 1.0 / self.world if self.average else 1.0
         if peer:
+            # the owner plan has finished reading the peers' ids before this rank signals B2: a rank that has passed B2
+            # may start its next step and overwrite its ids
+            self._join_side(dev)
             self.peers.barrier()      # B2: every rank's gradient rows and dense bucket are final
             if self._dense_out is None:
                 self._dense_out = torch.empty_like(self._xflat)
             ops.allreduce_peers(self._flat_ptrs, self._xdense, scale, self._dense_out)
-            self._join_side(dev)
             sparse = plan.apply_peers(self._row_ptrs, used, pad_id=self.total_rows, scale=scale)
             return StepResult(losses, wts[1], G.over(self._dense_out), sparse)
         torch.distributed.all_reduce(G.flat, group=self.pg)
