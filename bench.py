@@ -258,6 +258,13 @@ def timed_steps(run, args, dev, world, barrier, flush):
         ts.forward_backward(resident)
     barrier()
     prof, ops.profile = ops.profile, None
+    if os.environ.get('MPQE_DP_TRACE'):      # phase times of the eager data-parallel step (diagnostic)
+        ts.trace = []
+        for _ in range(5):
+            ts.forward_backward(resident)
+        rep = ts.trace_report()
+        ts.trace = None
+        sys.stderr.write('[rank %d] phases ms: %s\n' % (int(os.environ.get('RANK', '0')), json.dumps({k: round(v, 4) for k, v in rep.items()})))
     kernels = {}
     steps_prof = min(args.steps, 10)
     for kind in sorted({p[0] for p in prof}):

@@ -240,6 +240,10 @@ typedef struct {
    * is then read from its owner's copy (peer_tables[row / peer_chunk]).  NULL: read `table`. */
   const float* const* peer_tables;
   int64_t peer_chunk;
+  /* optional [count] row norms.  forward: written (||table[row]||).  backward: when non-NULL the table is NOT read
+   * again -- the normalised row y is taken from the forward output (`out`, `out_stride`) and the norm from here (same
+   * arithmetic, one gather of 512 bytes per row less; with owner-read tables one NVLink round trip less). */
+  float* norm;
 } mpqe_gather_item_t;
 MPQE_API int mpqe_gather_multi(const mpqe_gather_item_t* items_host, int32_t n, int32_t backward, void* stream);
 
@@ -342,6 +346,13 @@ MPQE_API int mpqe_peer_barrier(const void* const* peer_flags_host, int32_t rank,
 /* out[i] = scale * sum_r peer_bufs[r][i] in rank order (identical bits on every rank); numel % 4 == 0 */
 MPQE_API int mpqe_allreduce_peers(const void* const* peer_bufs_host, int32_t world, int64_t numel, float scale, float* out,
                          void* stream);
+/* The same all-reduce in two shots for larger groups: `reduce_scatter` sums float4 slice `rank` (slices of
+ * ceil(numel/4/world) float4) of all ranks' buffers, in rank order, IN PLACE into this rank's buffer; after a barrier
+ * `all_gather` reads every slice from its owner into `out`.  Per rank 2 (N-1)/N buckets cross NVLink instead of N-1. */
+MPQE_API int mpqe_reduce_scatter_peers(const void* const* peer_bufs_host, int32_t world, int32_t rank, int64_t numel,
+                              float scale, void* stream);
+MPQE_API int mpqe_all_gather_peers(const void* const* peer_bufs_host, int32_t world, int64_t numel, float* out,
+                          void* stream);
 /* Owner-side plan of the row-gradient exchange.  The entity tables are owned row-range-wise: rank r owns rows
  * [r*ceil(rows_t/world), (r+1)*ceil(rows_t/world)) of every table t (global row id = table_begin[t] + row).  The ids
  * every rank emitted for its step (per_rank_count each, mpqe_gather_multi mode 2) are read in place; ids this rank

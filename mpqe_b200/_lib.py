@@ -35,7 +35,7 @@ class GatherItem(C.Structure):
                 ('ids_stride', C.c_int64), ('count', C.c_int64), ('out', C.c_void_p), ('out_stride', C.c_int64),
                 ('grad', C.c_void_p), ('grad_stride', C.c_int64), ('rows_out', C.c_void_p), ('rows_id', C.c_void_p),
                 ('id_offset', C.c_int64), ('normalize', C.c_int32), ('reserved', C.c_int32),
-                ('peer_tables', C.c_void_p), ('peer_chunk', C.c_int64)]
+                ('peer_tables', C.c_void_p), ('peer_chunk', C.c_int64), ('norm', C.c_void_p)]
 
 
 class MarginItem(C.Structure):
@@ -122,6 +122,8 @@ SIGNATURES = {
     'mpqe_sparse_rows_apply_peers': (I32, [P, I32, I64, I64, I64, F32, P, P, P, P, SZ, P]),
     'mpqe_peer_barrier': (I32, [P, I32, I32, P, P]),
     'mpqe_allreduce_peers': (I32, [P, I32, I64, F32, P, P]),
+    'mpqe_reduce_scatter_peers': (I32, [P, I32, I32, I64, F32, P]),
+    'mpqe_all_gather_peers': (I32, [P, I32, I64, P, P]),
     'mpqe_sparse_rows_plan_owner': (I32, [P, I32, I32, I64, P, P, I32, I64, P, P, SZ, P]),
     'mpqe_scatter_rows': (I32, [P, P, P, I64, P, I32, P]),
     'mpqe_adam_dense': (I32, [P, P, P, P, I64, F32, F32, F32, F32, I32, P]),

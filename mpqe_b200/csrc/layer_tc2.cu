@@ -502,7 +502,8 @@ static int launch_tc2(const mpqe_layer_group_t* groups, int num_groups, cudaStre
       for (int t = 0; t < groups[i].num_terms; ++t)
         if (groups[i].terms[t].out_slot == slot) ++nt, mask |= 1u << t;
       for (int k = 0; k < tiles; ++k) {
-        cost[u] = nt;
+        // in stages: 8 per term, and the unit's epilogue (256 x 512 bytes of stores) costs about as much as one term
+        cost[u] = nt * (D / KC) + D / KC;
         tile_of[u] = (uint16_t)k;
         gsm_of[u] = ((uint32_t)i << 24) | ((uint32_t)slot << 16) | mask;
         ++u;

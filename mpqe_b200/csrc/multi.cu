@@ -54,7 +54,8 @@ __global__ void __launch_bounds__(ROW_THREADS) gather_fwd_multi_kernel(const __g
   if (row < 0 || row >= T.table_rows) {
     y = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F);
   } else if (T.normalize) {
-    normalize_row(table_of_row(T.table, T.peer_tables, T.peer_chunk, row), row, lane, y);
+    const float nrm = normalize_row(table_of_row(T.table, T.peer_tables, T.peer_chunk, row), row, lane, y);
+    if (T.norm != nullptr && lane == 0) T.norm[i] = nrm;
   } else {
     y = *reinterpret_cast<const float4*>(T.table + row * D + lane * 4);
   }
@@ -69,7 +70,13 @@ __global__ void __launch_bounds__(ROW_THREADS) gather_bwd_multi_kernel(const __g
   const mpqe_gather_item_t& T = L.it[item];
   const int64_t row = resolve_row(T.id2row, T.ids, T.ids_stride, i);
   float4 y;
-  const float nrm = normalize_row(table_of_row(T.table, T.peer_tables, T.peer_chunk, row), row, lane, y);
+  float nrm;
+  if (T.norm != nullptr) {      // the forward kept y (its output) and ||row||: no second gather
+    y = *reinterpret_cast<const float4*>(T.out + i * T.out_stride + lane * 4);
+    nrm = T.norm[i];
+  } else {
+    nrm = normalize_row(table_of_row(T.table, T.peer_tables, T.peer_chunk, row), row, lane, y);
+  }
   const float4 g = *reinterpret_cast<const float4*>(T.grad + i * T.grad_stride + lane * 4);
   *reinterpret_cast<float4*>(T.rows_out + i * D + lane * 4) = normalize_bwd(g, y, nrm);
   if (lane == 0) T.rows_id[i] = row + T.id_offset;
@@ -266,7 +273,8 @@ extern "C" int mpqe_gather_multi(const mpqe_gather_item_t* items_host, int32_t n
     if (backward == 2)
       MPQE_CHECK_ARG(T.rows_id != nullptr, "mpqe_gather_multi: item %d: ids mode without rows_id", i);
     else if (backward)
-      MPQE_CHECK_ARG(T.grad && T.rows_out && T.rows_id && T.grad_stride >= D, "mpqe_gather_multi: item %d: bad bwd argument", i);
+      MPQE_CHECK_ARG(T.grad && T.rows_out && T.rows_id && T.grad_stride >= D && (T.norm == nullptr || T.out != nullptr),
+                     "mpqe_gather_multi: item %d: bad bwd argument", i);
     else
       MPQE_CHECK_ARG(T.out && T.out_stride >= D, "mpqe_gather_multi: item %d: bad fwd argument", i);
     L.it[i] = T;

@@ -77,6 +77,37 @@ __global__ void __launch_bounds__(256) allreduce_peers_kernel(const __grid_const
   }
 }
 
+// Two-shot form for larger groups (every rank reads 2 (N-1)/N of a bucket instead of N-1 buckets):
+// reduce-scatter: rank r sums float4 slice r of all ranks' buffers (rank order) IN PLACE into its own buffer's slice r
+// (the peers read other slices of it, and only their owner writes a slice); after a barrier, all-gather: slice p is
+// read from rank p's buffer.
+__global__ void __launch_bounds__(256) reduce_slice_peers_kernel(const __grid_constant__ PeerPtrs bufs, int world, int rank,
+                                                                 int64_t begin4, int64_t end4, float scale) {
+  float4* mine = reinterpret_cast<float4*>(bufs.p[rank]);
+  for (int64_t i = begin4 + (int64_t)blockIdx.x * 256 + threadIdx.x; i < end4; i += (int64_t)gridDim.x * 256) {
+    float4 v[MPQE_MAX_PEERS];
+#pragma unroll
+    for (int r = 0; r < MPQE_MAX_PEERS; ++r)
+      if (r < world) v[r] = __ldcg(reinterpret_cast<const float4*>(bufs.p[r]) + i);
+    float4 acc = v[0];
+#pragma unroll
+    for (int r = 1; r < MPQE_MAX_PEERS; ++r)
+      if (r < world) {
+        acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w;
+      }
+    mine[i] = make_float4(acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale);
+  }
+}
+
+__global__ void __launch_bounds__(256) gather_slices_peers_kernel(const __grid_constant__ PeerPtrs bufs, int world,
+                                                                  int64_t n4, int64_t chunk4, float4* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) {
+    int owner = (int)(i / chunk4);
+    if (owner >= world) owner = world - 1;
+    out[i] = __ldcg(reinterpret_cast<const float4*>(bufs.p[owner]) + i);
+  }
+}
+
 struct Ownership {
   int num_tables, rank, world;
   int64_t begin[MPQE_MAX_TABLES];   // first global row id of table t
@@ -148,6 +179,39 @@ extern "C" int mpqe_allreduce_peers(const void* const* peer_bufs_host, int32_t w
   allreduce_peers_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(P, world, numel / 4, scale,
                                                                           reinterpret_cast<float4*>(out));
   MPQE_CHECK_LAUNCH("allreduce_peers_kernel");
+  return 0;
+}
+
+static int64_t slice_chunk4(int64_t n4, int world) { return (n4 + world - 1) / world; }
+
+extern "C" int mpqe_reduce_scatter_peers(const void* const* peer_bufs_host, int32_t world, int32_t rank, int64_t numel,
+                                         float scale, void* stream) {
+  PeerPtrs P;
+  if (int rc = fill_peers(P, peer_bufs_host, world, "mpqe_reduce_scatter_peers")) return rc;
+  MPQE_CHECK_ARG(rank >= 0 && rank < world && numel >= 0 && numel % 4 == 0, "mpqe_reduce_scatter_peers: bad argument");
+  const int64_t n4 = numel / 4, chunk4 = slice_chunk4(n4, world);
+  const int64_t begin4 = chunk4 * rank < n4 ? chunk4 * rank : n4;
+  const int64_t end4 = rank == world - 1 ? n4 : (chunk4 * (rank + 1) < n4 ? chunk4 * (rank + 1) : n4);
+  if (end4 <= begin4) return 0;
+  int64_t blocks = (end4 - begin4 + 255) / 256;
+  if (blocks > 2 * 148) blocks = 2 * 148;
+  reduce_slice_peers_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(P, world, rank, begin4, end4, scale);
+  MPQE_CHECK_LAUNCH("reduce_slice_peers_kernel");
+  return 0;
+}
+
+extern "C" int mpqe_all_gather_peers(const void* const* peer_bufs_host, int32_t world, int64_t numel, float* out,
+                                     void* stream) {
+  PeerPtrs P;
+  if (int rc = fill_peers(P, peer_bufs_host, world, "mpqe_all_gather_peers")) return rc;
+  MPQE_CHECK_ARG(out != nullptr && numel >= 0 && numel % 4 == 0, "mpqe_all_gather_peers: bad argument");
+  if (numel == 0) return 0;
+  const int64_t n4 = numel / 4;
+  int64_t blocks = (n4 + 255) / 256;
+  if (blocks > 4 * 148) blocks = 4 * 148;
+  gather_slices_peers_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(P, world, n4, slice_chunk4(n4, world),
+                                                                              reinterpret_cast<float4*>(out));
+  MPQE_CHECK_LAUNCH("gather_slices_peers_kernel");
   return 0;
 }
 

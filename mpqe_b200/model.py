@@ -302,9 +302,13 @@ class Engine(object):
         for job in jobs:
             t, B, n = job.t, job.B, job.t.num_nodes
             x = torch.empty(B, n, D, dtype=torch.float32, device=job.anchor_ids.device)
+            # ||row|| of every gathered anchor row: with it (and x itself) the backward needs no second gather
+            job.anchor_norm = torch.empty(t.num_anchors, B, dtype=torch.float32, device=job.anchor_ids.device) \
+                if W.need_grad else None
             for i, mode in enumerate(job.anchor_modes):
                 items.append(ops.GatherItem(enc.table(mode), enc.node_maps, job.anchor_ids, B, ids_offset=i,
-                                            ids_stride=t.num_anchors, out=x, out_offset=i * D, out_stride=n * D))
+                                            ids_stride=t.num_anchors, out=x, out_offset=i * D, out_stride=n * D,
+                                            norm=job.anchor_norm, norm_offset=i * B))
             job.acts = [x]
             job.act_bits = {}
         ops.gather_multi(items)
@@ -745,9 +749,12 @@ class Engine(object):
             if i not in ins:
                 continue
             rows, rows_id, off, id_off = planned[i] if planned is not None else G.rows.reserve(mode, B)
+            norm = getattr(job, 'anchor_norm', None)
             G.gathers.append(ops.GatherItem(enc.table(mode), enc.node_maps, job.anchor_ids, B, ids_offset=i,
                                             ids_stride=t.num_anchors, grad=dx, grad_offset=i * D, grad_stride=n * D,
-                                            rows_out=rows, rows_id=rows_id, rows_offset=off, id_offset=id_off))
+                                            rows_out=rows, rows_id=rows_id, rows_offset=off, id_offset=id_off,
+                                            out=job.acts[0] if norm is not None else None, out_offset=i * D,
+                                            out_stride=n * D, norm=norm, norm_offset=i * B))
 
     def mlp_backward(self, jobs, W, dqs, G, last):
         """Backward of the MLP readouts; fills last[job] (gradient wrt the last R-GCN pass output) and job.du."""

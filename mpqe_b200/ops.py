@@ -612,13 +612,14 @@ class GatherItem(object):
 
     def __init__(self, table, id2row, ids, count, ids_offset=0, ids_stride=1, out=None, out_offset=0, out_stride=D,
                  grad=None, grad_offset=0, grad_stride=D, rows_out=None, rows_id=None, rows_offset=0, id_offset=0,
-                 normalize=True):
+                 normalize=True, norm=None, norm_offset=0):
         self.table, self.id2row, self.ids, self.count = table, id2row, ids, int(count)
         self.ids_offset, self.ids_stride = int(ids_offset), int(ids_stride)
         self.out, self.out_offset, self.out_stride = out, int(out_offset), int(out_stride)
         self.grad, self.grad_offset, self.grad_stride = grad, int(grad_offset), int(grad_stride)
         self.rows_out, self.rows_id, self.rows_offset = rows_out, rows_id, int(rows_offset)
         self.id_offset, self.normalize = int(id_offset), bool(normalize)
+        self.norm, self.norm_offset = norm, int(norm_offset)   # [count] row norms: written forward, read backward
 
     def to_c(self):
         it = _lib.GatherItem()
@@ -629,6 +630,7 @@ class GatherItem(object):
         it.rows_out, it.rows_id = _addr(self.rows_out, self.rows_offset * D), _addr(self.rows_id, self.rows_offset)
         it.id_offset, it.normalize = self.id_offset, int(self.normalize)
         it.peer_tables, it.peer_chunk = _peer_tables(self.table)
+        it.norm = _addr(self.norm, self.norm_offset)
         return it
 
 
@@ -851,6 +853,22 @@ def allreduce_peers(buf_ptrs, numel, scale, out):
     lib = _lib.load()
     _lib.check(lib.mpqe_allreduce_peers(_ptr_array(buf_ptrs), len(buf_ptrs), int(numel), float(scale),
                                         _ptr(_chk(out, torch.float32, 'out')), _stream()), 'mpqe_allreduce_peers')
+    _count()
+
+
+def reduce_scatter_peers(buf_ptrs, rank, numel, scale):
+    """First half of the two-shot all-reduce: this rank's slice of every rank's buffer, summed in place into its own."""
+    lib = _lib.load()
+    _lib.check(lib.mpqe_reduce_scatter_peers(_ptr_array(buf_ptrs), len(buf_ptrs), int(rank), int(numel), float(scale),
+                                             _stream()), 'mpqe_reduce_scatter_peers')
+    _count()
+
+
+def all_gather_peers(buf_ptrs, numel, out):
+    """Second half: every slice read from its owner's buffer into `out` (after a barrier)."""
+    lib = _lib.load()
+    _lib.check(lib.mpqe_all_gather_peers(_ptr_array(buf_ptrs), len(buf_ptrs), int(numel),
+                                         _ptr(_chk(out, torch.float32, 'out')), _stream()), 'mpqe_all_gather_peers')
     _count()
 
 

@@ -316,6 +316,8 @@ class TrainStep(object):
         jobs = [self.refresh(b).job for b in batches]
         tg = [b.targets for b in batches]
         ng = [b.negatives for b in batches]
+        mark = self._mark
+        mark('start')
         multi = self.world > 1
         if multi and getattr(self, '_xcap', None) is None:
             self.setup_exchange(batches)
@@ -334,7 +336,9 @@ class TrainStep(object):
                                      'setup_exchange(batches) when the batch shapes change' % (used, self._xcap))
         ranges = self._table_ranges()
         if peer:
+            mark('ids emitted')
             self.peers.barrier()      # B1: all ranks' ids are in place and every rank is done with the previous step
+            mark('B1')
         W = self._weights_on_side_stream(jobs, dev)
         all_ids = None
         if not multi:
@@ -355,9 +359,11 @@ class TrainStep(object):
             wts = self._wts = (key, torch.tensor(key, dtype=torch.float32, device=dev))
         # d total / d loss_i = the batch weights, known now: the margin backward rides on the margin forward
         losses, W = loss_forward(m, jobs, tg, ng, self.margin, True, grad_losses=wts[1], W=W)
+        mark('forward')
         G = loss_backward(m, jobs, W, tg, ng, self.margin, wts[1], self.table_offsets, rows=R,
                           defer_constant=not multi, flat=self._xflat if peer else None)
         self._weight_decay(W, G, losses, sum(key))
+        mark('backward')
         if not multi:
             self._join_side(dev)
             # the batch-constant tail of the backward (five small latency-bound launches) runs on the second
@@ -371,11 +377,21 @@ class TrainStep(object):
             # the owner plan has finished reading the peers' ids before this rank signals B2: a rank that has passed B2
             # may start its next step and overwrite its ids
             self._join_side(dev)
+            mark('owner plan joined')
             self.peers.barrier()      # B2: every rank's gradient rows and dense bucket are final
+            mark('B2')
             if self._dense_out is None:
                 self._dense_out = torch.empty_like(self._xflat)
-            ops.allreduce_peers(self._flat_ptrs, self._xdense, scale, self._dense_out)
-            sparse = plan.apply_peers(self._row_ptrs, used, pad_id=self.total_rows, scale=scale)
+            if self.world < 4:        # one shot: every rank sums all buckets (N-1 buckets in, one kernel)
+                ops.allreduce_peers(self._flat_ptrs, self._xdense, scale, self._dense_out)
+                sparse = plan.apply_peers(self._row_ptrs, used, pad_id=self.total_rows, scale=scale)
+            else:                     # two shots around the row combine, which hides the third barrier's skew
+                ops.reduce_scatter_peers(self._flat_ptrs, self.rank, self._xdense, scale)
+                sparse = plan.apply_peers(self._row_ptrs, used, pad_id=self.total_rows, scale=scale)
+                mark('reduce-scatter + row combine')
+                self.peers.barrier()  # B3: every rank's slice of the bucket is reduced
+                ops.all_gather_peers(self._flat_ptrs, self._xdense, self._dense_out)
+            mark('exchange done')
             return StepResult(losses, wts[1], G.over(self._dense_out), sparse)
         torch.distributed.all_reduce(G.flat, group=self.pg)
         if scale != 1.0:
@@ -386,6 +402,25 @@ class TrainStep(object):
         sparse = plan.apply_peers([all_rows[r * used:(r + 1) * used] for r in range(self.world)], used,
                                   pad_id=self.total_rows, scale=scale)
         return StepResult(losses, wts[1], G, sparse)
+
+    def _mark(self, name):
+        """Phase tracing of eager steps (`self.trace = []` switches it on): CUDA events on the current stream."""
+        tr = getattr(self, 'trace', None)
+        if tr is not None and not torch.cuda.is_current_stream_capturing():
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            tr.append((name, ev))
+
+    def trace_report(self):
+        """{phase: mean ms since the previous mark} over the traced steps."""
+        tr, out, cnt = self.trace, {}, {}
+        torch.cuda.synchronize()
+        for (n0, e0), (n1, e1) in zip(tr[:-1], tr[1:]):
+            if n1 == 'start':
+                continue
+            out[n1] = out.get(n1, 0.0) + e0.elapsed_time(e1)
+            cnt[n1] = cnt.get(n1, 0) + 1
+        return {k: out[k] / cnt[k] for k in out}
 
     def _weight_decay(self, W, G, losses, weight_sum):
         """The L2 term of every margin_loss call of the step (reference model.py:487-492: weight_decay * sum of the

@@ -333,6 +333,9 @@ def gather_multi(items, backward=False):
         elif it.normalize:
             gather_normalize(it.table, it.id2row, it.ids, it.out, it.out_offset, it.out_stride, it.ids_offset,
                              it.ids_stride, it.count)
+            if getattr(it, 'norm', None) is not None:
+                idx = it.ids.reshape(-1)[it.ids_offset::max(it.ids_stride, 1)][:it.count]
+                it.norm.reshape(-1)[it.norm_offset:it.norm_offset + it.count] = it.table[_resolve(it.id2row, idx)].norm(dim=1)
         else:  # plain row copy; ids_stride 0 broadcasts one row
             row = it.ids.reshape(-1)[it.ids_offset]
             view = torch.as_strided(it.out, (it.count, D), (it.out_stride, 1), it.out.storage_offset() + it.out_offset)

@@ -138,8 +138,11 @@ def test_train_step_adam_follows_oracle_training():
     ref = {k: v.clone().requires_grad_(True) for k, v in params.items()}
     opt = torch.optim.Adam(list(ref.values()), lr=0.01)
     curve_ref, curve = [], []
+    # three batch sets taken in turn: the model can fit them (the loss falls), and every entity row sits out two of
+    # three steps, which is what the lazy catch-up has to get right
+    pool = [[synthetic.sample_id_batch(kg, f, 24, rng) for f in formulas] for _ in range(3)]
     for step in range(40):
-        data = [synthetic.sample_id_batch(kg, f, 24, rng) for f in formulas]
+        data = pool[step % 3]
         opt.zero_grad()
         total = 0
         for f, (a, t, n) in zip(formulas, data):
@@ -156,7 +159,7 @@ def test_train_step_adam_follows_oracle_training():
         curve.append(float(res.total))
         ts.adam_step(res, lr=0.01)
     ts.catchup_rows(None)
-    assert curve_ref[-1] < 0.8 * curve_ref[0], 'the reference run should be learning'
+    assert curve_ref[-1] < 0.9 * curve_ref[0], 'the reference run should be learning: %r' % (curve_ref[::8],)
     assert_close(np.array(curve), np.array(curve_ref), 1e-3, 1e-3, 'loss curve')
     # Adam divides by sqrt(v): an element whose gradient is at the level of fp32 rounding can move by lr in either
     # direction, so single elements may differ; the parameters as a whole must coincide

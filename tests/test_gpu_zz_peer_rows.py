@@ -80,6 +80,13 @@ def test_allreduce_peers_and_barrier():
     ops.allreduce_peers([b.data_ptr() for b in bufs], n, 0.25, out)
     want = ((bufs[0] + bufs[1]) + bufs[2] + bufs[3]) * 0.25
     assert torch.equal(out, want)
+    # two shots (every "rank" reduces its slice in place, then the slices are gathered) give the same bits
+    two = [b.clone() for b in bufs]
+    for r in range(world):
+        ops.reduce_scatter_peers([b.data_ptr() for b in two], r, n, 0.25)
+    out2 = torch.empty(n, device=DEV)
+    ops.all_gather_peers([b.data_ptr() for b in two], n, out2)
+    assert torch.equal(out2, want)
     flags = [torch.zeros(16, dtype=torch.int32, device=DEV) for _ in range(world)]
     epochs = [torch.zeros(1, dtype=torch.int32, device=DEV) for _ in range(world)]
     data = [torch.zeros(1024, device=DEV) for _ in range(world)]
