@@ -326,7 +326,9 @@ def dp_check(run, dev, rank, world):
     dist.all_gather(chks, chk)
     same_bits = all(int(c) == int(chks[0]) for c in chks)
     # the owners' partitions, gathered (padded to the common capacity)
-    cap = uid.numel()
+    capt = torch.tensor([uid.numel()], dtype=torch.int64, device=dev)
+    dist.all_reduce(capt, op=dist.ReduceOp.MAX)          # the owners' capacities differ by a few rows
+    cap = int(capt)
     ids_pad = torch.full((cap,), -1, dtype=torch.int64, device=dev)
     ids_pad[:k] = uid[:k]
     rows_pad = torch.zeros(cap, D, device=dev)

@@ -329,11 +329,13 @@ MPQE_API int mpqe_sparse_rows_apply(const float* rows, int64_t count, int64_t ta
 /* Data-parallel form of `apply`: the pairs of `world` ranks (plan built over the rank-major concatenation of their
  * ids, `per_rank_count` each) are summed straight out of the ranks' own row buffers -- peer_rows_host[r] is rank r's
  * buffer as mapped into THIS process (peer memory over NVLink / NVSwitch).  Gather and combine are one kernel: a
- * remote row crosses NVLink once and is never staged locally (replaces an NCCL all-gather of the rows + apply). */
+ * remote row crosses NVLink once and is never staged locally (replaces an NCCL all-gather of the rows + apply).
+ * unique_ids / unique_rows hold `out_capacity` entries (<= world * per_rank_count; with an owner plan the number of
+ * rows this rank owns bounds the distinct rows it can receive): entries in [*num_unique, out_capacity) are padding. */
 #define MPQE_MAX_PEERS 16
 MPQE_API int mpqe_sparse_rows_apply_peers(const float* const* peer_rows_host, int32_t world, int64_t per_rank_count,
                                  int64_t table_rows, int64_t pad_id, float scale, int64_t* unique_ids,
-                                 float* unique_rows, const int64_t* num_unique, void* workspace,
+                                 float* unique_rows, int64_t out_capacity, const int64_t* num_unique, void* workspace,
                                  size_t workspace_bytes, void* stream);
 /* ---- data-parallel exchange over peer-mapped memory (new capability; the reference is single-process) ------------
  * `peer_*_host[r]` is rank r's buffer as mapped into THIS process (e.g. torch symmetric memory); all ranks call the

@@ -119,7 +119,7 @@ SIGNATURES = {
     'mpqe_sparse_rows_combine': (I32, [P, P, I64, I64, I64, P, P, P, P, SZ, P]),
     'mpqe_sparse_rows_plan': (I32, [P, I64, I64, P, P, SZ, P]),
     'mpqe_sparse_rows_apply': (I32, [P, I64, I64, I64, F32, P, P, P, P, SZ, P]),
-    'mpqe_sparse_rows_apply_peers': (I32, [P, I32, I64, I64, I64, F32, P, P, P, P, SZ, P]),
+    'mpqe_sparse_rows_apply_peers': (I32, [P, I32, I64, I64, I64, F32, P, P, I64, P, P, SZ, P]),
     'mpqe_peer_barrier': (I32, [P, I32, I32, P, P]),
     'mpqe_allreduce_peers': (I32, [P, I32, I64, F32, P, P]),
     'mpqe_reduce_scatter_peers': (I32, [P, I32, I32, I64, F32, P]),

@@ -375,10 +375,11 @@ __global__ void __launch_bounds__(256) segment_sum_peers_kernel(const uint32_t* 
                                                                 const __grid_constant__ PeerRows P, uint32_t per_rank,
                                                                 int64_t* __restrict__ unique_ids,
                                                                 float* __restrict__ unique_rows, int64_t pad_id,
-                                                                uint32_t sentinel, float scale) {
+                                                                uint32_t sentinel, float scale, int64_t capacity) {
   const int lane = threadIdx.x & 31;
   const int64_t u = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int64_t nu = *num_unique;
+  if (u >= capacity) return;
   if (u >= nu) {
     if (u < n) {
       *reinterpret_cast<float4*>(unique_rows + u * D + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -569,9 +570,9 @@ extern "C" int mpqe_sparse_rows_apply(const float* rows, int64_t count, int64_t 
 
 extern "C" int mpqe_sparse_rows_apply_peers(const float* const* peer_rows_host, int32_t world, int64_t per_rank_count,
                                             int64_t table_rows, int64_t pad_id, float scale, int64_t* unique_ids,
-                                            float* unique_rows, const int64_t* num_unique, void* workspace,
-                                            size_t workspace_bytes, void* stream) {
-  MPQE_CHECK_ARG(peer_rows_host && world >= 1 && world <= MPQE_MAX_PEERS && per_rank_count >= 1,
+                                            float* unique_rows, int64_t out_capacity, const int64_t* num_unique,
+                                            void* workspace, size_t workspace_bytes, void* stream) {
+  MPQE_CHECK_ARG(peer_rows_host && world >= 1 && world <= MPQE_MAX_PEERS && per_rank_count >= 1 && out_capacity >= 1,
                  "mpqe_sparse_rows_apply_peers: world must be in [1,%d]", MPQE_MAX_PEERS);
   const int64_t count = (int64_t)world * per_rank_count;
   MPQE_CHECK_ARG(unique_ids && unique_rows && num_unique && count < (1ll << 31) && table_rows >= 1 &&
@@ -584,9 +585,10 @@ extern "C" int mpqe_sparse_rows_apply_peers(const float* const* peer_rows_host, 
   for (int r = 0; r < world; ++r)
     MPQE_CHECK_ARG(P.rows[r] != nullptr, "mpqe_sparse_rows_apply_peers: null buffer of rank %d", r);
   CombineBuffers c = carve_combine(workspace, count, table_rows, PLAN_DIGIT_BITS);
-  segment_sum_peers_kernel<<<blocks_for(count, 8), 256, 0, (cudaStream_t)stream>>>(
+  const int64_t cap = out_capacity < count ? out_capacity : count;
+  segment_sum_peers_kernel<<<blocks_for(cap, 8), 256, 0, (cudaStream_t)stream>>>(
       c.rk, c.rv, c.seg_start, num_unique, count, P, (uint32_t)per_rank_count, unique_ids, unique_rows, pad_id,
-      (uint32_t)table_rows, scale);
+      (uint32_t)table_rows, scale, cap);
   MPQE_CHECK_LAUNCH("segment_sum_peers_kernel");
   return 0;
 }

@@ -175,13 +175,19 @@ class _ConvFn(torch.autograd.Function):
 
 class MLPReadout(nn.Module):
     """Linear-ReLU-Linear on every node, then scatter over each query's nodes (reference model.py:497-515).
-    Inside RGCNEncoderDecoder the arithmetic runs in the fused kernels; this module owns the parameters."""
+    Inside RGCNEncoderDecoder the arithmetic runs in the fused step; called on its own -- with the reference's
+    signature, `readout(embs=, batch_idx=, batch_size=, num_nodes=, num_anchors=)` -- it runs the same CUDA kernels
+    (term-list launches for both linear layers, their input / weight gradients and the scatter) behind autograd."""
 
     def __init__(self, input_dim, output_dim, scatter_fn):
         super(MLPReadout, self).__init__()
         self.layers = nn.Sequential(nn.Linear(in_features=input_dim, out_features=output_dim), nn.ReLU(),
                                     nn.Linear(in_features=output_dim, out_features=output_dim))
         self.scatter_fn = scatter_fn
+
+    def forward(self, embs, batch_idx=None, batch_size=None, num_nodes=None, num_anchors=None, **kwargs):
+        return _readout_forward(self, 'concat' if self.layers[0].in_features > D else 'mlp', embs, batch_size,
+                                num_nodes, num_anchors)
 
 
 class TargetMLPReadout(nn.Module):
@@ -192,6 +198,115 @@ class TargetMLPReadout(nn.Module):
         self.layers = nn.Sequential(nn.Linear(in_features=2 * dim, out_features=dim), nn.ReLU(),
                                     nn.Linear(in_features=dim, out_features=dim))
         self.scatter_fn = scatter_fn
+
+    def forward(self, embs, batch_idx=None, batch_size=None, num_nodes=None, num_anchors=None, **kwargs):
+        return _readout_forward(self, 'targetmlp', embs, batch_size, num_nodes, num_anchors)
+
+
+def _scatter_name(fn):
+    name = fn if isinstance(fn, str) else getattr(fn, '__name__', str(fn))
+    for op in ('add', 'max', 'mean'):
+        if op in name:
+            return op
+    raise ValueError('Unknown scatter op %r' % (fn,))
+
+
+def _readout_forward(module, kind, embs, batch_size, num_nodes, num_anchors):
+    if batch_size is None or num_nodes is None:
+        raise ValueError('the readout needs batch_size and num_nodes (queries of a batch share one template)')
+    lin1, lin2 = module.layers[0], module.layers[2]
+    if lin1.out_features != D or lin1.in_features % D != 0:
+        raise ValueError('kernels are specialised for %d channels' % D)
+    return _ReadoutFn.apply(embs, lin1.weight, lin1.bias, lin2.weight, lin2.bias, kind, _scatter_name(module.scatter_fn),
+                            int(batch_size), int(num_nodes), int(num_anchors if num_anchors is not None else 0))
+
+
+class _ReadoutFn(torch.autograd.Function):
+    """A stand-alone MLP readout: embs [B*n, blocks*D] -> [B, D] (the per-module API of the reference's readouts)."""
+
+    @staticmethod
+    def _units(kind, n, target, blocks):
+        """[(unit k, [(node slot j, W1 block b)])]: which node rows feed MLP unit k, through which block of W1."""
+        if kind == 'targetmlp':
+            return [[(target, 0), (j, 1)] for j in range(n) if j != target]
+        return [[(j, b) for b in range(blocks)] for j in range(n)]
+
+    @staticmethod
+    def forward(ctx, embs, w1, b1, w2, b2, kind, op, B, n, a):
+        with ops.device_guard(embs.device):
+            blocks = w1.shape[1] // D
+            nb = blocks if kind != 'targetmlp' else 1            # feature blocks per node row of `embs`
+            x = embs.contiguous().view(B, n * nb, D)              # node j, block b -> slot j*nb + b
+            w1t = ops.transpose(w1.contiguous())                  # [blocks*D, D]
+            w2t = ops.transpose(w2.contiguous())
+            units = _ReadoutFn._units(kind, n, a, blocks)
+            nu = len(units)
+            slot = (lambda j, b: j * nb + b) if kind != 'targetmlp' else (lambda j, b: j)
+            u = torch.empty(B, nu, D, dtype=torch.float32, device=embs.device)
+            t1 = [Term(x, n * nb, slot(j, b), w1t[b * D:(b + 1) * D], k) for k, srcs in enumerate(units) for (j, b) in srcs]
+            g1 = Group(B, t1, nu, u, nu, epilogue=EPI_RELU, bias=b1)
+            ops.layer_forward([g1])
+            argmax = None
+            if op == 'max':
+                z2 = torch.empty(B, nu, D, dtype=torch.float32, device=embs.device)
+                g2 = Group(B, [Term(u, nu, k, w2t, k) for k in range(nu)], nu, z2, nu, bias=b2)
+                ops.layer_forward([g2])
+                q, argmax = ops.max_readout(z2, B, nu)
+            else:
+                q = torch.empty(B, D, dtype=torch.float32, device=embs.device)
+                g2 = Group(B, [Term(u, nu, k, w2t, 0) for k in range(nu)], 1, q, 1, out_slot_map=[0], bias=b2,
+                           bias_scale=[float(nu)])
+                ops.layer_forward([g2])
+                if op == 'mean':
+                    q = q * (1.0 / nu)
+        ctx.save_for_backward(x, u, w1, w2, w1t, w2t)
+        ctx.meta = (kind, op, B, n, a, nb, blocks, units, argmax, g1, g2, embs.shape)
+        return q
+
+    @staticmethod
+    def backward(ctx, dq):
+        x, u, w1, w2, w1t, w2t = ctx.saved_tensors
+        kind, op, B, n, a, nb, blocks, units, argmax, g1, g2, shape = ctx.meta
+        nu = len(units)
+        dev = dq.device
+        with ops.device_guard(dev):
+            dq = dq.contiguous()
+            if op == 'max':
+                gt, gs, smap = ops.max_readout_bwd(dq, argmax, B, nu), nu, list(range(nu))
+            else:
+                gt, gs, smap = (dq * (1.0 / nu) if op == 'mean' else dq), 1, [0] * nu
+            du = torch.empty_like(u)       # dU[:, k] = (dZ2[:, k] @ W2) * (u > 0)
+            ops.layer_forward([Group(B, [Term(gt, gs, smap[k], w2.contiguous(), k) for k in range(nu)], nu, du, nu,
+                                     epilogue=EPI_MASK, mask=u, mask_slots=nu)])
+            dw1t, dw2t = torch.zeros_like(w1t), torch.zeros_like(w2t)
+            ops.layer_wgrad([g2], [(gt, gs, smap)], [(w2t, dw2t, 1)])
+            ops.layer_wgrad([g1], [(du, nu, list(range(nu)))],
+                            [(w1t[b * D:(b + 1) * D], dw1t[b * D:(b + 1) * D], 1) for b in range(blocks)])
+            db1 = torch.empty(D, dtype=torch.float32, device=dev)
+            db2 = torch.empty(D, dtype=torch.float32, device=dev)
+            ops.colsum(du, B * nu, D, db1)
+            ops.colsum(gt, B * gs, D, db2, scale=float(nu) if gs == 1 else 1.0)
+            # d embs: node slot (j, b) collects dU of the units it feeds, through block b of W1
+            w1b = ops.transpose(w1t.view(blocks, D, D))
+            dx = torch.zeros_like(x)
+            slot = (lambda j, b: j * nb + b) if kind != 'targetmlp' else (lambda j, b: j)
+            feeds = {}
+            for k, srcs in enumerate(units):
+                for (j, b) in srcs:
+                    feeds.setdefault(slot(j, b), []).append((k, b))
+            slots = sorted(feeds)
+            for lo in range(0, len(slots), ops.MAX_SLOTS):
+                part = slots[lo:lo + ops.MAX_SLOTS]
+                terms = [Term(du, nu, k, w1b[b], i) for i, sl in enumerate(part) for (k, b) in feeds[sl]]
+                for t0 in range(0, len(terms), ops.MAX_TERMS):     # accumulate over term chunks via separate passes
+                    chunk = terms[t0:t0 + ops.MAX_TERMS]
+                    if t0 == 0:
+                        ops.layer_forward([Group(B, chunk, len(part), dx, x.shape[1], out_slot_map=part)])
+                    else:
+                        extra = torch.zeros_like(dx)
+                        ops.layer_forward([Group(B, chunk, len(part), extra, x.shape[1], out_slot_map=part)])
+                        dx += extra
+        return (dx.view(shape), ops.transpose(dw1t), db1, ops.transpose(dw2t), db2, None, None, None, None, None)
 
 
 # ===============================================================================================================

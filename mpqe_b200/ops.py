@@ -554,7 +554,7 @@ class SparseRowsPlan(object):
         _count()
         return uid, urows, self.num
 
-    def apply_peers(self, peer_ptrs, per_rank_count, pad_id=0, scale=1.0):
+    def apply_peers(self, peer_ptrs, per_rank_count, pad_id=0, scale=1.0, capacity=None):
         """`apply` over the row buffers of all ranks read in place through peer-mapped memory: `peer_ptrs[r]` is the
         device address of rank r's rows in this process (torch symmetric memory); the plan must have been built over
         the rank-major concatenation of the ranks' ids (mpqe_sparse_rows_apply_peers)."""
@@ -564,12 +564,15 @@ class SparseRowsPlan(object):
         if world * per_rank_count != self.count:
             raise _lib.MpqeError('apply_peers: plan covers %d pairs, peers provide %d' % (self.count, world * per_rank_count))
         dev = self.num.device
-        uid = torch.empty(self.count, dtype=torch.int64, device=dev)
-        urows = torch.empty(self.count, D, dtype=torch.float32, device=dev)
+        # `capacity`: an upper bound of the distinct rows the plan can hold (the rows this rank owns, for an owner
+        # plan): outputs and padding writes are sized by it instead of by the total number of pairs
+        cap = self.count if capacity is None else max(1, min(int(capacity), self.count))
+        uid = torch.empty(cap, dtype=torch.int64, device=dev)
+        urows = torch.empty(cap, D, dtype=torch.float32, device=dev)
         ptrs = (C.c_void_p * world)(*[int(p) for p in peer_ptrs])
         _lib.check(lib.mpqe_sparse_rows_apply_peers(ptrs, world, int(per_rank_count), self.table_rows, pad_id,
-                                                    float(scale), _ptr(uid), _ptr(urows), _ptr(self.num), _ptr(self.ws),
-                                                    self.nbytes, _stream()), 'mpqe_sparse_rows_apply_peers')
+                                                    float(scale), _ptr(uid), _ptr(urows), cap, _ptr(self.num),
+                                                    _ptr(self.ws), self.nbytes, _stream()), 'mpqe_sparse_rows_apply_peers')
         _count()
         return uid, urows, self.num
 

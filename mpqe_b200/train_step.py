@@ -373,6 +373,7 @@ class TrainStep(object):
             self._join_side(dev)
             return StepResult(losses, wts[1], G, sparse)
         scale = 1.0 / self.world if self.average else 1.0
+        owned = sum(hi - lo for _, lo, hi in self.owned_rows())     # bound of the distinct rows this rank can receive
         if peer:
             # the owner plan has finished reading the peers' ids before this rank signals B2: a rank that has passed B2
             # may start its next step and overwrite its ids
@@ -384,10 +385,10 @@ class TrainStep(object):
                 self._dense_out = torch.empty_like(self._xflat)
             if self.world < 4:        # one shot: every rank sums all buckets (N-1 buckets in, one kernel)
                 ops.allreduce_peers(self._flat_ptrs, self._xdense, scale, self._dense_out)
-                sparse = plan.apply_peers(self._row_ptrs, used, pad_id=self.total_rows, scale=scale)
+                sparse = plan.apply_peers(self._row_ptrs, used, pad_id=self.total_rows, scale=scale, capacity=owned)
             else:                     # two shots around the row combine, which hides the third barrier's skew
                 ops.reduce_scatter_peers(self._flat_ptrs, self.rank, self._xdense, scale)
-                sparse = plan.apply_peers(self._row_ptrs, used, pad_id=self.total_rows, scale=scale)
+                sparse = plan.apply_peers(self._row_ptrs, used, pad_id=self.total_rows, scale=scale, capacity=owned)
                 mark('reduce-scatter + row combine')
                 self.peers.barrier()  # B3: every rank's slice of the bucket is reduced
                 ops.all_gather_peers(self._flat_ptrs, self._xdense, self._dense_out)
@@ -400,7 +401,7 @@ class TrainStep(object):
         torch.distributed.all_gather_into_tensor(all_rows, rows[:used].contiguous(), group=self.pg)
         self._join_side(dev)
         sparse = plan.apply_peers([all_rows[r * used:(r + 1) * used] for r in range(self.world)], used,
-                                  pad_id=self.total_rows, scale=scale)
+                                  pad_id=self.total_rows, scale=scale, capacity=owned)
         return StepResult(losses, wts[1], G, sparse)
 
     def _mark(self, name):

@@ -258,8 +258,11 @@ class SparseRowsPlan(object):
         uid, urows, num = sparse_rows_combine(self.rows_id, rows, self.table_rows, pad_id)
         return uid, urows * scale, num
 
-    def apply_peers(self, peer_rows, per_rank_count, pad_id=0, scale=1.0):
-        return self.apply(torch.cat([r[:per_rank_count] for r in peer_rows]), pad_id, scale)
+    def apply_peers(self, peer_rows, per_rank_count, pad_id=0, scale=1.0, capacity=None):
+        uid, urows, num = self.apply(torch.cat([r[:per_rank_count] for r in peer_rows]), pad_id, scale)
+        cap = uid.numel() if capacity is None else max(1, min(int(capacity), uid.numel()))
+        assert int(num) <= cap
+        return uid[:cap], urows[:cap], num
 
 
 def owner_plan(id_sources, rank, per_rank_count, table_begin, table_rows, total_rows, device):

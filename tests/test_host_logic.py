@@ -270,3 +270,36 @@ def test_no_cpu_fallback():
     queries = queries_from_ids('2-inter', frm_rels, [p[2] for p in parsed], [p[3] for p in parsed])
     with pytest.raises(_lib.MpqeError, match='no CPU fallback'):
         model.margin_loss_ids(queries[0].formula, queries, [p[3] for p in parsed], [p[3] for p in parsed])
+
+
+@pytest.mark.parametrize('kind,op', [('mlp', 'add'), ('concat', 'add'), ('concat', 'max'), ('targetmlp', 'mean'),
+                                     ('targetmlp', 'add')])
+def test_readout_modules_forward_with_the_reference_signature(kind, op, monkeypatch):
+    """`MLPReadout` / `TargetMLPReadout` called on their own, `readout(embs=, batch_idx=, batch_size=, num_nodes=,
+    num_anchors=)` (reference model.py:447-449, 506-515, 531-553), against the oracle's restatement: value and every
+    gradient."""
+    import torch
+    from mpqe_b200 import model as M
+    emulator.install(monkeypatch)
+    torch.manual_seed(0)
+    B, n, a, d = 7, 4, 2, 128
+    blocks = {'mlp': 1, 'concat': 2, 'targetmlp': 1}[kind]
+    mod = M.TargetMLPReadout(d, op) if kind == 'targetmlp' else M.MLPReadout(d * blocks, d, op)
+    embs = torch.randn(B * n, d * blocks, requires_grad=True)
+    batch_idx = torch.arange(B).repeat_interleave(n)
+    out = mod(embs=embs, batch_idx=batch_idx, batch_size=B, num_nodes=n, num_anchors=a)
+    p = {'readout.layers.0.weight': mod.layers[0].weight.detach().clone().requires_grad_(True),
+         'readout.layers.0.bias': mod.layers[0].bias.detach().clone().requires_grad_(True),
+         'readout.layers.2.weight': mod.layers[2].weight.detach().clone().requires_grad_(True),
+         'readout.layers.2.bias': mod.layers[2].bias.detach().clone().requires_grad_(True)}
+    e2 = embs.detach().clone().requires_grad_(True)
+    want, _ = O.readout(kind, e2, batch_idx, B, n, a, p, op)
+    assert out.shape == (B, d)
+    np.testing.assert_allclose(out.detach().numpy(), want.detach().numpy(), rtol=1e-5, atol=1e-5)
+    w = torch.randn(B, d)
+    (out * w).sum().backward()
+    (want * w).sum().backward()
+    np.testing.assert_allclose(embs.grad.numpy(), e2.grad.numpy(), rtol=1e-4, atol=1e-5)
+    for name, prm in (('readout.layers.0.weight', mod.layers[0].weight), ('readout.layers.0.bias', mod.layers[0].bias),
+                      ('readout.layers.2.weight', mod.layers[2].weight), ('readout.layers.2.bias', mod.layers[2].bias)):
+        np.testing.assert_allclose(prm.grad.numpy(), p[name].grad.numpy(), rtol=1e-4, atol=1e-5)
