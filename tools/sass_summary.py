@@ -35,7 +35,7 @@ def main():
             name = m.group(1)
             counts[name] = collections.Counter()
             continue
-        m = re.search(r'/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)', line)
+        m = re.search(r'/\*[0-9a-f]{4,6}\*/\s+(?:@!?U?P[T\d]+\s+)?([A-Z0-9_.]+)', line)
         if m and name:
             op = m.group(1)
             counts[name]['total'] += 1
@@ -45,7 +45,7 @@ def main():
     print('SASS summary of %s (cuobjdump -sass; sm_100a)' % os.path.relpath(LIB, ROOT))
     print('columns: instructions | registers, static shared bytes | watched mnemonics (count)')
     for name, c in counts.items():
-        m = re.search(r'\d+_(?:cu|cuh)_[0-9a-f]+(\d\d)([a-z_0-9]+?)E', name)
+        m = re.search(r'_cu_[0-9a-f]{8}(\d\d)([A-Za-z_0-9]+)', name)
         short = m.group(2)[:int(m.group(1))] if m else name
         if pat and not pat.search(short):
             continue
