@@ -391,11 +391,25 @@ __global__ void __launch_bounds__(256) segment_sum_peers_kernel(const uint32_t* 
   const int64_t i0 = seg_start[u];
   const int64_t i1 = (u + 1 < nu_all) ? seg_start[u + 1] : n;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int64_t i = i0; i < i1; ++i) {  // ascending pair index (rank-major, the sort is stable): fixed summation order
-    const uint32_t idx = sorted_val[i];
-    const uint32_t r = idx / per_rank, local = idx - r * per_rank;
-    const float4 v = *reinterpret_cast<const float4*>(P.rows[r] + (int64_t)local * D + lane * 4);
-    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  // ascending pair index (rank-major, the sort is stable): fixed summation order.  Four rows are requested before the
+  // first is added: a remote row is a ~2 us round trip over NVLink, and a row with several pairs would otherwise pay
+  // it once per pair, one after the other.
+  for (int64_t i = i0; i < i1; i += 4) {
+    float4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i + k < i1) {
+        const uint32_t idx = sorted_val[i + k];
+        const uint32_t r = idx / per_rank, local = idx - r * per_rank;
+        v[k] = __ldcg(reinterpret_cast<const float4*>(P.rows[r] + (int64_t)local * D + lane * 4));
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (i + k < i1) {
+        acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w;
+      }
   }
   *reinterpret_cast<float4*>(unique_rows + u * D + lane * 4) =
       make_float4(acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale);

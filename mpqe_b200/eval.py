@@ -61,8 +61,25 @@ class RankIndex(object):
 
     @torch.no_grad()
     def counts(self, formula, queries, target_nodes, anchor_ids=None, var_ids=None, q_graphs=None):
-        """(count_lt, count_le, positive scores, N) of one formula batch, merged over the ranks."""
+        """(count_lt, count_le, positive scores, N) of one formula batch, merged over the ranks.
+        With several ranks the batch is also SPLIT for the encoder: every rank encodes B / world of the queries and
+        scores them against their positives, the query embeddings and positive scores are all-gathered (B x 516
+        bytes), and every rank then ranks all B queries against the rows of the table it owns."""
+        from .data_utils import QueryGraphBatch
         model = self.model
+        B = len(queries)
+        lo, hi = 0, B
+        split = self.world > 1 and B % self.world == 0 and B >= self.world
+        if split:
+            per = B // self.world
+            lo, hi = self.rank * per, (self.rank + 1) * per
+            queries = queries[lo:hi]
+            if anchor_ids is not None:
+                anchor_ids = anchor_ids[lo:hi]
+            if isinstance(q_graphs, QueryGraphBatch):
+                q_graphs = QueryGraphBatch(q_graphs.template, q_graphs.edge_rel_ids, hi - lo)
+            elif q_graphs is not None:
+                anchor_ids = var_ids = q_graphs = None      # rebuild the layout of the slice from the queries
         job = model.make_job(formula, queries, anchor_ids, var_ids, q_graphs)
         device = job.anchor_ids.device
         table = model.enc.table(formula.target_mode)
@@ -70,10 +87,17 @@ class RankIndex(object):
             W = self.weights()
             W.prepared = None
             model._engine.encode([job], W)
-            tgt = model.enc.ids_on_device(target_nodes, device).reshape(-1)
+            tgt = model.enc.ids_on_device(target_nodes, device).reshape(-1)[lo:hi].contiguous()
             pos = ops.cosine_scores(job.q, table, model.enc.node_maps, tgt)
-            both = torch.zeros(2, job.B, dtype=torch.int64, device=device)
-            self.table(formula.target_mode).counts(job.q, pos, both[0], both[1])
+            q = job.q
+            if split:
+                q_all = torch.empty(B, q.shape[1], dtype=q.dtype, device=device)
+                pos_all = torch.empty(B, dtype=pos.dtype, device=device)
+                torch.distributed.all_gather_into_tensor(q_all, q.contiguous(), group=self.pg)
+                torch.distributed.all_gather_into_tensor(pos_all, pos.contiguous(), group=self.pg)
+                q, pos = q_all, pos_all
+            both = torch.zeros(2, B, dtype=torch.int64, device=device)
+            self.table(formula.target_mode).counts(q, pos, both[0], both[1])
             if self.world > 1:
                 torch.distributed.all_reduce(both, group=self.pg)     # integer sum: exact, order independent
         return both[0], both[1], pos, table.shape[0] - 1

@@ -117,6 +117,28 @@ def test_training_loop_runs_and_loss_decreases():
     assert np.isfinite(after) and after < before
 
 
+def test_fused_training_loop_runs_and_loss_decreases():
+    """`run_train_fused`: the reference's loop structure on the fused step -- pre-tensorised query sets on the device,
+    negatives drawn on the device, fused Adam, no per-step loss read-back."""
+    from mpqe_b200.tensor_queries import TensorQuerySet
+    kg, cfg, params, model, qsets = setup(per_formula=64)
+    train = {qt: {Query.deserialize(raw[0]).formula: [Query.deserialize(r) for r in raw]}
+             for qt, groups in qsets.items() for (_, raw) in groups}
+    evalq = {'one_neg': {qt: {f: qs[:8] for f, qs in d.items()} for qt, d in train.items()},
+             'full_neg': {qt: {f: qs[:8] for f, qs in d.items()} for qt, d in train.items()}}
+    sets = {qt: TensorQuerySet.from_queries(d) for qt, d in train.items()}
+    log = logging.getLogger('mpqe_test')
+    frm = next(iter(train['1-chain']))
+    qs = train['1-chain'][frm]
+    with torch.no_grad():
+        before = float(model.margin_loss_ids(frm, qs, [q.target_node for q in qs], [q.neg_samples[0] for q in qs]))
+    train_helpers.run_train_fused(model, sets, evalq, evalq, log, full_lists=model.graph.full_lists, max_burn_in=3,
+                                  batch_size=32, log_every=5, val_every=1000, max_iter=14)
+    with torch.no_grad():
+        after = float(model.margin_loss_ids(frm, qs, [q.target_node for q in qs], [q.neg_samples[0] for q in qs]))
+    assert np.isfinite(after) and after < before
+
+
 def test_train_step_graph_replay_equals_eager():
     """The CUDA-graph step (row (f)1) gives the same bits as the eager step, and follows new ids copied into the
     static buffers."""
