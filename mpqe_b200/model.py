@@ -679,8 +679,11 @@ class Engine(object):
                 job.q.mul_(1.0 / nu)
 
     # ---- backward -----------------------------------------------------------------------------------------
-    def backward(self, jobs, W, dqs, G, defer_constant=False):
-        """dqs[i] = d loss / d job.q.  Accumulates dense gradients into `G` (a Grads) and row gradients into G.rows."""
+    def backward(self, jobs, W, dqs, G, defer_constant=False, side=None):
+        """dqs[i] = d loss / d job.q.  Accumulates dense gradients into `G` (a Grads) and row gradients into G.rows.
+        `side` = (run, join): run(fn) executes fn() on a second stream forked from the current one, join() makes the
+        current stream wait for it.  The weight-gradient launches of a pass then run next to its input-gradient
+        launch, which does not depend on them -- one kernel's write-bound tail overlaps the other's main loop."""
         readout = self.m.readout_str
         # gradient wrt the last pass output, as (tensor, slots, slot_map over outs[P-1])
         last = {}
@@ -703,6 +706,7 @@ class Engine(object):
             for job in active:
                 by_layer.setdefault(self.layer_index(p, job.P), []).append(job)
             spread = {}    # (layer, parameter key) -> gradients of the summed matrices it is a summand of
+            launches = []  # (forward groups, gradient operands, destinations) per weight-gradient launch
             for li, ljobs in by_layer.items():
                 chunk, dests = [], {}
                 for job in ljobs + [None]:
@@ -710,14 +714,23 @@ class Engine(object):
                     if chunk and (job is None or len(chunk) == ops.MAX_GROUPS or
                                   len(set(dests) | set(jd)) > ops.MAX_DESTS):
                         if dests:
-                            ops.layer_wgrad([j.fwd_groups[p] for j in chunk], [cur[j] for j in chunk],
-                                            list(dests.values()))
+                            launches.append(([j.fwd_groups[p] for j in chunk], [cur[j] for j in chunk],
+                                             list(dests.values())))
                         chunk, dests = [], {}
                     if job is not None:
                         chunk.append(job)
                         dests.update(jd)
-            if spread:     # d(root + sum basis[rel]) goes to every summand, in a fixed order
-                ops.matrix_sum_multi([(self._pgrad(G, li, key), srcs, True) for (li, key), srcs in spread.items()])
+            G.keep.append(launches)   # the operands stay alive until the caller has joined the second stream
+
+            def weight_gradients(launches=launches, spread=spread):
+                for fwd, operands, dests in launches:
+                    ops.layer_wgrad(fwd, operands, dests)
+                if spread:     # d(root + sum basis[rel]) goes to every summand, in a fixed order
+                    ops.matrix_sum_multi([(self._pgrad(G, li, key), srcs, True) for (li, key), srcs in spread.items()])
+            if side is not None:
+                side[0](weight_gradients)
+            else:
+                weight_gradients()
             for li, ljobs in by_layer.items():
                 for job in ljobs:
                     if p == 0 and job.const_fwd is not None:
@@ -797,6 +810,8 @@ class Engine(object):
                 else:
                     self.input_backward(job, dx, ins, G)
         G.flush()
+        if side is not None:    # the dense gradients below accumulate into the same matrices
+            side[1]()
         if defer_constant:      # the caller runs it (e.g. on another stream, under independent work)
             G.finish = lambda: self.constant_backward(jobs, W, G)
         else:
@@ -1238,7 +1253,7 @@ def plan_rows(model, jobs, targets, negatives, table_offsets, rows_buffer=None, 
 
 
 def loss_backward(model, jobs, W, targets, negatives, margin, grad_losses, table_offsets=None, rows=None,
-                  defer_constant=False, flat=None):
+                  defer_constant=False, flat=None, side=None):
     """Backward of `loss_forward` for d(total)/d(loss_i) = grad_losses[i] (device tensor [len(jobs)]).
     Returns the filled `Grads` (dense bucket + (row id, gradient row) pairs, not yet combined).  `rows`: a RowGrads
     from `plan_rows` (slots reserved and ids already emitted).  `defer_constant`: leave the batch-constant tail of the
@@ -1259,7 +1274,7 @@ def loss_backward(model, jobs, W, targets, negatives, margin, grad_losses, table
         dqs.append(dq)
     if items:
         ops.cosine_margin_multi(items, margin, backward=True)
-    model._engine.backward(jobs, W, dqs, G, defer_constant=defer_constant)
+    model._engine.backward(jobs, W, dqs, G, defer_constant=defer_constant, side=side)
     return G
 
 

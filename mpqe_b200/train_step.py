@@ -22,6 +22,8 @@ the ranks' partitions are disjoint and their union is the single-process result 
 Without peer-mapped memory (CPU / gloo tests, or when symmetric memory cannot be set up) the same kernels run on
 buffers assembled with torch.distributed all_gather / all_reduce.
 """
+import os
+
 import torch
 
 from . import ops
@@ -107,6 +109,8 @@ class TrainStep(object):
         self._layouts = {}
         self.adam_state = None
         self._side = None   # second stream for the id-only half of the row-gradient combine
+        self._wgrad_stream = None   # third stream: weight gradients next to the input-gradient launches
+        self.overlap_wgrad = os.environ.get('MPQE_OVERLAP_WGRAD', '1') != '0'
         self.rank = torch.distributed.get_rank(process_group) if self._dist() else 0
         self.peers = None        # PeerGroup (world > 1, peer-mapped memory available)
         self._xcap = None        # pairs per rank the exchange buffers were set up for
@@ -201,6 +205,17 @@ class TrainStep(object):
         self._side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(self._side):
             fn()
+
+    def _on_wgrad_stream(self, dev, fn):
+        if self._wgrad_stream is None:
+            self._wgrad_stream = torch.cuda.Stream(device=dev)
+        self._wgrad_stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(self._wgrad_stream):
+            fn()
+
+    def _join_wgrad(self, dev):
+        if self._wgrad_stream is not None:
+            torch.cuda.current_stream(dev).wait_stream(self._wgrad_stream)
 
     # ---- data-parallel exchange: buffers ---------------------------------------------------------------
     def _table_ranges(self):
@@ -360,8 +375,9 @@ class TrainStep(object):
         # d total / d loss_i = the batch weights, known now: the margin backward rides on the margin forward
         losses, W = loss_forward(m, jobs, tg, ng, self.margin, True, grad_losses=wts[1], W=W)
         mark('forward')
+        side = (lambda fn: self._on_wgrad_stream(dev, fn), lambda: self._join_wgrad(dev)) if self.overlap_wgrad else None
         G = loss_backward(m, jobs, W, tg, ng, self.margin, wts[1], self.table_offsets, rows=R,
-                          defer_constant=not multi, flat=self._xflat if peer else None)
+                          defer_constant=not multi, flat=self._xflat if peer else None, side=side)
         self._weight_decay(W, G, losses, sum(key))
         mark('backward')
         if not multi:

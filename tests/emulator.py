@@ -309,6 +309,8 @@ def install(monkeypatch):
     monkeypatch.setattr(TrainStep, '_weights_on_side_stream', weights_now)
     monkeypatch.setattr(TrainStep, '_join_side', lambda self, dev: None)
     monkeypatch.setattr(TrainStep, '_on_side_stream', lambda self, dev, fn: fn())
+    monkeypatch.setattr(TrainStep, '_on_wgrad_stream', lambda self, dev, fn: fn())
+    monkeypatch.setattr(TrainStep, '_join_wgrad', lambda self, dev: None)
 
 
 def l2_reg(params, grads, weight_decay, grad_scale, losses=None, norms=None):

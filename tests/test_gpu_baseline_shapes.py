@@ -81,6 +81,59 @@ def touched_rows(model, ts, formula, anchors, targets, negatives):
     return np.concatenate(rows)
 
 
+def discontinuity_events(case, B, batches, mode):
+    """Number of ReLU signs / arg-maxes of the CUDA step that differ from the oracle's, after asserting that each of
+    them is a near-tie in the oracle's own values and that they are a vanishing fraction of all decisions."""
+    import torch.nn.functional as F
+    kg, cfg, params, mode_ids, rel_ids, id2row, formulas = world(case)
+    rel = 2e-5 if mode == 'tcgen05' else 4e-6
+    events = total = 0
+    for b_, (f, a, t, n, loss, grads) in zip(batches, oracle_case(case, B)):
+        job = b_.job
+        spec = O.formula_spec(f.query_type, f.rels)
+        a_ids, var_ids, ei, et, batch = O.query_graph(spec, a.tolist(), rel_ids, mode_ids)
+        conv_out, hidden = [], []
+        conv, mlp = O.rgcn_conv, O.mlp
+
+        def spy_conv(*args, **kw):
+            conv_out.append(conv(*args, **kw))
+            return conv_out[-1]
+
+        def spy_mlp(x, p, prefix='readout.layers.'):
+            hidden.append(F.linear(x, p[prefix + '0.weight'], p[prefix + '0.bias']))
+            return mlp(x, p, prefix)
+
+        O.rgcn_conv, O.mlp = spy_conv, spy_mlp
+        try:
+            with torch.no_grad():
+                _, arg_want = O.encode_queries(params, cfg, spec, a_ids, var_ids, ei, et, batch, id2row, want_argmax=True)
+        finally:
+            O.rgcn_conv, O.mlp = conv, mlp
+        # ReLU between the passes: job.acts[k + 1] = relu(pass k), every pass but the last
+        # (the target-message readout prunes the slots that cannot reach the target: nothing to compare there)
+        signs = [(job.acts[k + 1], conv_out[k]) for k in range(len(conv_out) - 1)] if cfg.readout != 'mp' else []
+        if hidden:
+            signs.append((job.u, hidden[0]))
+        for got_act, pre in signs:
+            got_pos = (got_act.cpu().reshape(pre.shape) > 0)
+            differ = got_pos != (pre > 0)
+            total += pre.numel()
+            events += int(differ.sum())
+            if differ.any():
+                worst = float(pre[differ].abs().max())
+                assert worst <= rel * float(pre.abs().max()), ('ReLU sign differs on a clearly non-zero value', worst)
+        if cfg.readout == 'max':
+            got_arg, z = job.argmax.cpu(), job.z.cpu().reshape(-1, 128)
+            differ = (got_arg != arg_want).nonzero()
+            total += got_arg.numel()
+            events += differ.shape[0]
+            for q_, c_ in differ.tolist():
+                v_got, v_want = float(z[got_arg[q_, c_], c_]), float(z[arg_want[q_, c_], c_])
+                assert abs(v_got - v_want) <= 4e-6 * abs(v_want) + 2e-7, ('argmax differs on a clear maximum', q_, c_)
+    assert events <= 1e-4 * total, 'too many discontinuity events: %d of %d' % (events, total)
+    return events
+
+
 @pytest.mark.parametrize('B', [512, 4096])
 @pytest.mark.parametrize('case', sorted(CASES))
 def test_fused_step_vs_oracle(case, B, mode):
@@ -104,39 +157,21 @@ def test_fused_step_vs_oracle(case, B, mode):
     got, uid = train_step_grads(ts, model, res, DEV)
     # integer artefact: the combined row set is exactly the set of rows the batches touch, ascending, no duplicates
     assert np.array_equal(uid.cpu().numpy(), np.unique(np.concatenate(touched)))
-    # The max readout routes each feature's gradient to the node attaining the maximum.  Where two nodes' values agree
-    # to fp32 rounding the choice depends on the summation order, and a different (equally valid) choice moves O(1) of
-    # that feature's gradient to another node.  At B = 4096 a handful of the 3.7 M arg-maxes are such near-ties
-    # (checked below: every index that differs from the oracle's is a near-tie in the kernel's own values), so the
-    # gradients of that configuration are compared with a bound that admits them.
-    # The readout MLP of `concat` has its own ReLU on B x n x 128 pre-activations: at B = 4096 one or two of the 15 M
-    # lie within fp32 rounding of zero, and whether a gradient flows through such an element depends on the summation
-    # order (observed: identical 2.3e-4 deviations on the FFMA and the tcgen05 path, none at B = 512).
-    # For these two configurations at B = 4096 the outer bounds are therefore relaxed, and instead the bulk of every
-    # tensor (median deviation) must meet the tight bound -- a systematic error would move most entries.
-    fro_tol = max_tol = median_tol = None
-    if cfg.readout in ('max', 'concat') and B >= 4096:
-        fro_tol, max_tol = 2e-3, 2e-2
-        median_tol = GRAD_TOL[mode] if cfg.readout == 'concat' else None   # (an arg-max flip moves a whole column)
-    if cfg.readout == 'max' and B >= 4096:
-        flips = total = 0
-        for b_, (f, a, t, n, loss, grads) in zip(batches, oracle_case(case, B)):
-            spec = O.formula_spec(f.query_type, f.rels)
-            a_ids, var_ids, ei, et, batch = O.query_graph(spec, a.tolist(), rel_ids, mode_ids)
-            with torch.no_grad():
-                _, arg_want = O.encode_queries(params, cfg, spec, a_ids, var_ids, ei, et, batch, id2row, want_argmax=True)
-            got_arg, z = b_.job.argmax.cpu(), b_.job.z.cpu().reshape(-1, 128)
-            differ = (got_arg != arg_want).nonzero()
-            total += got_arg.numel()
-            flips += differ.shape[0]
-            for q_, c_ in differ.tolist():
-                v_got, v_want = float(z[got_arg[q_, c_], c_]), float(z[arg_want[q_, c_], c_])
-                assert abs(v_got - v_want) <= 4e-6 * abs(v_want) + 2e-7, ('argmax differs on a clear maximum', q_, c_)
-        assert flips <= 1e-4 * total, 'too many arg-max differences: %d of %d' % (flips, total)
+    # Two discontinuities sit on this path.  (1) ReLU (between the passes, and inside the readout MLP of `concat`): a
+    # pre-activation within fp32 rounding of zero lets the gradient through or not depending on the summation order.
+    # (2) The max readout routes each feature's gradient to the node attaining the maximum: where two nodes' values
+    # agree to rounding, a different (equally valid) choice moves O(1) of that feature's gradient to another node.
+    # At B = 4096 a handful of the ~15 M pre-activations / 3.7 M arg-maxes are such events.  They are FOUND here, not
+    # tolerated blindly: every ReLU sign and every arg-max that differs from the oracle's must be a near-tie (checked
+    # element by element), they must be a vanishing fraction, and only a batch set that has one is compared with the
+    # relaxed outer bound; without any, the tight bound applies.
+    events = 0
+    if B >= 4096:
+        events = discontinuity_events(case, B, batches, mode)
+    fro_tol, max_tol = (2e-3, 2e-2) if events else (None, None)
     for name, g in want.items():
         assert got.get(name) is not None, name
-        assert_grad_close(got[name].detach().cpu().numpy(), g, mode, '%s:B%d grad %s' % (case, B, name), fro_tol, max_tol,
-                          median_tol)
+        assert_grad_close(got[name].detach().cpu().numpy(), g, mode, '%s:B%d grad %s' % (case, B, name), fro_tol, max_tol)
 
 
 @pytest.mark.parametrize('case', sorted(CASES))
