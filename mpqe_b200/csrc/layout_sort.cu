@@ -330,90 +330,87 @@ __global__ void segment_starts_kernel(const uint32_t* __restrict__ sorted, const
   if (i == 0 || sorted[i] != sorted[i - 1]) seg_start[uid[i]] = (int32_t)i;
 }
 
+// Ordered segmented sum: unique row u = sum of the gradient rows of its pairs, in ascending pair index (the sort is
+// stable): a fixed summation order.  A warp serves SEG_PW consecutive unique rows: their segment bounds come from one
+// load, their first pair indices from one load, and the SEG_PW first rows are in flight together -- most rows have one
+// or two pairs, and one row per warp meant four dependent loads (count, bounds, pair index, row) for every 512 bytes.
+// Further pairs of a segment are requested four at a time (a remote row is a ~2 us round trip over NVLink).
+// PEERS: the pairs of `world` ranks are read IN PLACE from their buffers (peer-mapped memory): pair i lives in rank
+// i / per_rank, row i % per_rank -- gather and sum are one kernel, every remote row crosses NVLink once and is never
+// staged in local memory.
+struct PeerRows {
+  const float* rows[MPQE_MAX_PEERS];
+};
+constexpr int SEG_PW = 4;
+
+template <bool PEERS>
+__device__ __forceinline__ float4 pair_row(const float* rows, const PeerRows& P, uint32_t per_rank, uint32_t idx, int lane) {
+  if (PEERS) {
+    const uint32_t r = idx / per_rank, local = idx - r * per_rank;
+    return __ldcg(reinterpret_cast<const float4*>(P.rows[r] + (int64_t)local * D + lane * 4));
+  }
+  return *reinterpret_cast<const float4*>(rows + (int64_t)idx * D + lane * 4);
+}
+
+template <bool PEERS>
 __global__ void __launch_bounds__(256) segment_sum_kernel(const uint32_t* __restrict__ sorted_key,
                                                           const uint32_t* __restrict__ sorted_val,
                                                           const int32_t* __restrict__ seg_start,
                                                           const int64_t* __restrict__ num_unique, int64_t n,
                                                           const float* __restrict__ rows,
+                                                          const __grid_constant__ PeerRows P, uint32_t per_rank,
                                                           int64_t* __restrict__ unique_ids,
                                                           float* __restrict__ unique_rows, int64_t pad_id,
-                                                          uint32_t sentinel, float scale) {
+                                                          uint32_t sentinel, float scale, int64_t capacity) {
   const int lane = threadIdx.x & 31;
-  const int64_t u = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int64_t u0 = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * SEG_PW;
+  const int64_t limit = capacity < n ? capacity : n;
+  if (u0 >= limit) return;
   const int64_t nu = *num_unique;
-  if (u >= nu) {  // padding entries: a zero row with id `pad_id`, so fixed-size consumers need no host sync
-    if (u < n) {
-      *reinterpret_cast<float4*>(unique_rows + u * D + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (lane == 0) unique_ids[u] = pad_id;
-    }
-    return;
-  }
   // the sentinel (padding) keys sort last as one more segment: the last real row must stop where it starts
   const int64_t nu_all = nu + (sorted_key[n - 1] >= sentinel ? 1 : 0);
-  const int64_t i0 = seg_start[u];
-  const int64_t i1 = (u + 1 < nu_all) ? seg_start[u + 1] : n;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int64_t i = i0; i < i1; ++i) {  // ascending pair index (the sort is stable): fixed summation order
-    const float4 v = *reinterpret_cast<const float4*>(rows + (int64_t)sorted_val[i] * D + lane * 4);
-    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  int64_t bound = n;       // lane l: start of segment u0 + l (= end of segment u0 + l - 1)
+  if (lane <= SEG_PW && u0 + lane < nu_all) bound = seg_start[u0 + lane];
+  uint32_t first = 0, key = 0;
+  if (lane < SEG_PW && u0 + lane < nu) {
+    first = sorted_val[bound];
+    key = sorted_key[bound];
+    unique_ids[u0 + lane] = (int64_t)key;
+  } else if (lane < SEG_PW && u0 + lane < limit) {
+    unique_ids[u0 + lane] = pad_id;   // padding entries: a zero row with id `pad_id` (fixed-size consumers, no host sync)
   }
-  *reinterpret_cast<float4*>(unique_rows + u * D + lane * 4) =
-      make_float4(acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale);
-  if (lane == 0) unique_ids[u] = (int64_t)sorted_key[i0];
-}
-
-// The same summation with the pairs of `world` ranks read IN PLACE from their buffers (peer-mapped memory over NVLink):
-// pair i lives in rank i / per_rank, row i % per_rank.  Gather and sum are one kernel: every remote row crosses
-// NVLink once and is never staged in local memory.
-struct PeerRows {
-  const float* rows[MPQE_MAX_PEERS];
-};
-__global__ void __launch_bounds__(256) segment_sum_peers_kernel(const uint32_t* __restrict__ sorted_key,
-                                                                const uint32_t* __restrict__ sorted_val,
-                                                                const int32_t* __restrict__ seg_start,
-                                                                const int64_t* __restrict__ num_unique, int64_t n,
-                                                                const __grid_constant__ PeerRows P, uint32_t per_rank,
-                                                                int64_t* __restrict__ unique_ids,
-                                                                float* __restrict__ unique_rows, int64_t pad_id,
-                                                                uint32_t sentinel, float scale, int64_t capacity) {
-  const int lane = threadIdx.x & 31;
-  const int64_t u = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int64_t nu = *num_unique;
-  if (u >= capacity) return;
-  if (u >= nu) {
-    if (u < n) {
-      *reinterpret_cast<float4*>(unique_rows + u * D + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (lane == 0) unique_ids[u] = pad_id;
-    }
-    return;
-  }
-  const int64_t nu_all = nu + (sorted_key[n - 1] >= sentinel ? 1 : 0);
-  const int64_t i0 = seg_start[u];
-  const int64_t i1 = (u + 1 < nu_all) ? seg_start[u + 1] : n;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  // ascending pair index (rank-major, the sort is stable): fixed summation order.  Four rows are requested before the
-  // first is added: a remote row is a ~2 us round trip over NVLink, and a row with several pairs would otherwise pay
-  // it once per pair, one after the other.
-  for (int64_t i = i0; i < i1; i += 4) {
-    float4 v[4];
+  float4 acc[SEG_PW];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (i + k < i1) {
-        const uint32_t idx = sorted_val[i + k];
-        const uint32_t r = idx / per_rank, local = idx - r * per_rank;
-        v[k] = __ldcg(reinterpret_cast<const float4*>(P.rows[r] + (int64_t)local * D + lane * 4));
+  for (int k = 0; k < SEG_PW; ++k) {
+    const uint32_t idx = __shfl_sync(0xffffffffu, first, k);
+    acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (u0 + k < nu) {
+      const float4 v = pair_row<PEERS>(rows, P, per_rank, idx, lane);
+      acc[k].x += v.x; acc[k].y += v.y; acc[k].z += v.z; acc[k].w += v.w;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < SEG_PW; ++k) {
+    const int64_t i0 = __shfl_sync(0xffffffffu, bound, k), i1 = __shfl_sync(0xffffffffu, bound, k + 1);
+    if (u0 + k >= limit) break;
+    if (u0 + k < nu) {
+      for (int64_t i = i0 + 1; i < i1; i += 4) {
+        float4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i + j < i1) v[j] = pair_row<PEERS>(rows, P, per_rank, sorted_val[i + j], lane);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (i + j < i1) {
+            acc[k].x += v[j].x; acc[k].y += v[j].y; acc[k].z += v[j].z; acc[k].w += v[j].w;
+          }
       }
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (i + k < i1) {
-        acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w;
-      }
+    *reinterpret_cast<float4*>(unique_rows + (u0 + k) * D + lane * 4) =
+        make_float4(acc[k].x * scale, acc[k].y * scale, acc[k].z * scale, acc[k].w * scale);
   }
-  *reinterpret_cast<float4*>(unique_rows + u * D + lane * 4) =
-      make_float4(acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale);
-  if (lane == 0) unique_ids[u] = (int64_t)sorted_key[i0];
 }
 
 __global__ void __launch_bounds__(256) scatter_rows_kernel(const int64_t* __restrict__ ids,
@@ -562,8 +559,9 @@ static int sparse_rows_apply(const float* rows, int64_t count, int64_t table_row
   MPQE_CHECK_ARG(workspace && workspace_bytes >= mpqe_sparse_rows_workspace_bytes(count),
                  "mpqe_sparse_rows_apply: workspace too small");
   CombineBuffers c = carve_combine(workspace, count, table_rows, digit_bits);
-  segment_sum_kernel<<<blocks_for(count, 8), 256, 0, (cudaStream_t)stream>>>(
-      c.rk, c.rv, c.seg_start, num_unique, count, rows, unique_ids, unique_rows, pad_id, (uint32_t)table_rows, scale);
+  segment_sum_kernel<false><<<blocks_for((count + SEG_PW - 1) / SEG_PW, 8), 256, 0, (cudaStream_t)stream>>>(
+      c.rk, c.rv, c.seg_start, num_unique, count, rows, PeerRows(), 1u, unique_ids, unique_rows, pad_id,
+      (uint32_t)table_rows, scale, count);
   MPQE_CHECK_LAUNCH("segment_sum_kernel");
   return 0;
 }
@@ -600,10 +598,10 @@ extern "C" int mpqe_sparse_rows_apply_peers(const float* const* peer_rows_host, 
     MPQE_CHECK_ARG(P.rows[r] != nullptr, "mpqe_sparse_rows_apply_peers: null buffer of rank %d", r);
   CombineBuffers c = carve_combine(workspace, count, table_rows, PLAN_DIGIT_BITS);
   const int64_t cap = out_capacity < count ? out_capacity : count;
-  segment_sum_peers_kernel<<<blocks_for(cap, 8), 256, 0, (cudaStream_t)stream>>>(
-      c.rk, c.rv, c.seg_start, num_unique, count, P, (uint32_t)per_rank_count, unique_ids, unique_rows, pad_id,
+  segment_sum_kernel<true><<<blocks_for((cap + SEG_PW - 1) / SEG_PW, 8), 256, 0, (cudaStream_t)stream>>>(
+      c.rk, c.rv, c.seg_start, num_unique, count, nullptr, P, (uint32_t)per_rank_count, unique_ids, unique_rows, pad_id,
       (uint32_t)table_rows, scale, cap);
-  MPQE_CHECK_LAUNCH("segment_sum_peers_kernel");
+  MPQE_CHECK_LAUNCH("segment_sum_kernel<peers>");
   return 0;
 }
 

@@ -681,9 +681,10 @@ class Engine(object):
     # ---- backward -----------------------------------------------------------------------------------------
     def backward(self, jobs, W, dqs, G, defer_constant=False, side=None):
         """dqs[i] = d loss / d job.q.  Accumulates dense gradients into `G` (a Grads) and row gradients into G.rows.
-        `side` = (run, join): run(fn) executes fn() on a second stream forked from the current one, join() makes the
+        `side` = (run, join): run(fn) executes fn() on another stream forked from the current one, join() makes the
         current stream wait for it.  The weight-gradient launches of a pass then run next to its input-gradient
-        launch, which does not depend on them -- one kernel's write-bound tail overlaps the other's main loop."""
+        launch, which does not depend on them: one kernel's write-bound tail overlaps the other's main loop
+        (0.439 -> 0.400 ms per bench step).  Joined here, before the batch-constant tail."""
         readout = self.m.readout_str
         # gradient wrt the last pass output, as (tensor, slots, slot_map over outs[P-1])
         last = {}
@@ -810,7 +811,7 @@ class Engine(object):
                 else:
                     self.input_backward(job, dx, ins, G)
         G.flush()
-        if side is not None:    # the dense gradients below accumulate into the same matrices
+        if side is not None:    # the batch-constant tail accumulates into the same matrices as the weight gradients
             side[1]()
         if defer_constant:      # the caller runs it (e.g. on another stream, under independent work)
             G.finish = lambda: self.constant_backward(jobs, W, G)
@@ -1009,12 +1010,20 @@ class Grads(object):
         """Deferred dst += scale * column-sum(src): all of a backward's reductions run in one multi-item launch."""
         self.colsums.append(ops.ColsumItem(src, rows, stride, dst, scale))
 
-    def flush(self):
+    def flush_gathers(self):
         if self.gathers:
             ops.gather_multi(self.gathers, backward=True)
+        self.gathers = []
+
+    def flush_colsums(self):
         if self.colsums:
+            self.keep.append(self.colsums)
             ops.colsum_multi(self.colsums, self.device)
-        self.colsums, self.gathers = [], []
+        self.colsums = []
+
+    def flush(self):
+        self.flush_gathers()
+        self.flush_colsums()
 
 
 # ===============================================================================================================

@@ -176,6 +176,8 @@ class TrainStep(object):
         self._side.wait_stream(cur)
         with torch.cuda.stream(self._side):
             plan = make_plan()
+            self._plan_done = torch.cuda.Event()
+            self._plan_done.record(self._side)
         for t in keep:
             # read by the sort on the second stream: keep the caching allocator from handing the block to the main
             # stream's next allocation while those kernels are still pending
@@ -199,6 +201,10 @@ class TrainStep(object):
 
     def _join_side(self, dev):
         torch.cuda.current_stream(dev).wait_stream(self._side)
+
+    def _wait_plan(self, dev):
+        """The current stream waits for the plan only, not for what was put on the second stream after it."""
+        torch.cuda.current_stream(dev).wait_event(self._plan_done)
 
     def _on_side_stream(self, dev, fn):
         """Runs fn() on the second stream, ordered after everything enqueued on the current stream so far."""
@@ -378,22 +384,25 @@ class TrainStep(object):
         side = (lambda fn: self._on_wgrad_stream(dev, fn), lambda: self._join_wgrad(dev)) if self.overlap_wgrad else None
         G = loss_backward(m, jobs, W, tg, ng, self.margin, wts[1], self.table_offsets, rows=R,
                           defer_constant=not multi, flat=self._xflat if peer else None, side=side)
-        self._weight_decay(W, G, losses, sum(key))
-        mark('backward')
         if not multi:
-            self._join_side(dev)
-            # the batch-constant tail of the backward (five small latency-bound launches) runs on the second
-            # stream under the row summation, which does not depend on it
+            self._wait_plan(dev)
+            # the batch-constant tail of the backward (five small latency-bound launches) runs on another stream
+            # under the row summation, which does not depend on it
             self._on_side_stream(dev, G.finish)
             sparse = plan.apply(rows[:used], pad_id=self.total_rows)
             self._join_side(dev)
+            self._join_wgrad(dev)
+            self._weight_decay(W, G, losses, sum(key))
             return StepResult(losses, wts[1], G, sparse)
+        self._join_wgrad(dev)
+        self._weight_decay(W, G, losses, sum(key))
+        mark('backward')
         scale = 1.0 / self.world if self.average else 1.0
         owned = sum(hi - lo for _, lo, hi in self.owned_rows())     # bound of the distinct rows this rank can receive
         if peer:
             # the owner plan has finished reading the peers' ids before this rank signals B2: a rank that has passed B2
             # may start its next step and overwrite its ids
-            self._join_side(dev)
+            self._wait_plan(dev)
             mark('owner plan joined')
             self.peers.barrier()      # B2: every rank's gradient rows and dense bucket are final
             mark('B2')

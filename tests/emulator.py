@@ -308,6 +308,7 @@ def install(monkeypatch):
     monkeypatch.setattr(TrainStep, '_plan_on_side_stream', lambda self, make_plan, dev, keep=(): make_plan())
     monkeypatch.setattr(TrainStep, '_weights_on_side_stream', weights_now)
     monkeypatch.setattr(TrainStep, '_join_side', lambda self, dev: None)
+    monkeypatch.setattr(TrainStep, '_wait_plan', lambda self, dev: None)
     monkeypatch.setattr(TrainStep, '_on_side_stream', lambda self, dev, fn: fn())
     monkeypatch.setattr(TrainStep, '_on_wgrad_stream', lambda self, dev, fn: fn())
     monkeypatch.setattr(TrainStep, '_join_wgrad', lambda self, dev: None)
