@@ -391,8 +391,11 @@ def eval_bench(run, args, dev, world, barrier):
     index = mp_eval.RankIndex(run.model)
     eq = [None] * Q
 
-    def step():
-        return index.counts(ef, eq, et_d, anchor_ids=ea_d, var_ids=var_t, q_graphs=qg)
+    if args.no_graph:
+        def step():
+            return index.counts(ef, eq, et_d, anchor_ids=ea_d, var_ids=var_t, q_graphs=qg)
+    else:      # the batch as one CUDA graph (collectives included); ids stay in its device buffers
+        step = mp_eval.GraphedCounts(index, ef, ea_d, et_d, var_t, qg)
 
     for _ in range(3):
         l_, r_, _, n_ent = step()

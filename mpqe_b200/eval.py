@@ -103,6 +103,45 @@ class RankIndex(object):
         return both[0], both[1], pos, table.shape[0] - 1
 
 
+class GraphedCounts(object):
+    """`RankIndex.counts` for batches of one formula and one size as ONE CUDA graph: encoder, positive scores, rank
+    counts over this rank's table shard and -- with several ranks -- the all-gather of the embeddings and the integer
+    all-reduce of the counts (NCCL, captured).  A ranking batch on 1/N of the table is ~0.25 ms of kernels behind
+    ~30 launches and three collectives: issued one by one it is bound by the host.  Every rank must construct and call
+    it in step.  `anchor_ids` [B, anchors] / `target_nodes` [B]: the first batch (the graph is warmed up on it);
+    later batches are copied into the same device buffers."""
+
+    def __init__(self, index, formula, anchor_ids, target_nodes, var_ids, q_graphs):
+        model = index.model
+        dev = model.mode_embeddings.weight.device
+        self.index, self.formula = index, formula
+        self.anchors = anchor_ids.to(device=dev, dtype=torch.int64).contiguous().clone()
+        self.targets = model.enc.ids_on_device(target_nodes, dev).reshape(-1).contiguous().clone()
+        self._queries = [None] * self.anchors.shape[0]
+        self._args = dict(anchor_ids=self.anchors, var_ids=var_ids, q_graphs=q_graphs)
+        cur = torch.cuda.current_stream(dev)
+        warm = torch.cuda.Stream(device=dev)
+        warm.wait_stream(cur)
+        with torch.cuda.stream(warm):
+            for _ in range(2):
+                index.counts(formula, self._queries, self.targets, **self._args)
+        cur.wait_stream(warm)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = index.counts(formula, self._queries, self.targets, **self._args)
+
+    def __call__(self, anchor_ids=None, target_nodes=None):
+        """(count_lt, count_le, positive scores, N) -- views of the graph's output buffers, valid until the next call."""
+        if anchor_ids is not None:
+            self.anchors.copy_(anchor_ids, non_blocking=True)
+        if target_nodes is not None:
+            self.targets.copy_(self.index.model.enc.ids_on_device(target_nodes, self.targets.device).reshape(-1),
+                               non_blocking=True)
+        self.graph.replay()
+        return self.out
+
+
 @torch.no_grad()
 def full_rank_counts(model, formula, queries, target_nodes, anchor_ids=None, var_ids=None, q_graphs=None,
                      process_group=None, use_tensor_cores=None, index=None):

@@ -98,6 +98,26 @@ def test_full_rank_eval_counts_and_metrics(tc):
     assert torch.equal(l2, left) and torch.equal(r2, right)
 
 
+def test_graphed_rank_counts_equal_eager_counts():
+    """A ranking batch replayed as one CUDA graph gives the integers of the launch-by-launch path, also after new ids
+    were copied into its buffers."""
+    kg, cfg, params, model, qsets = setup(per_formula=48)
+    frm_rels, raw = qsets['3-inter'][0]
+    queries = [Query.deserialize(r) for r in raw]
+    formula = queries[0].formula
+    a_ids, var_ids, q_graphs = data_utils.RGCNQueryDataset.get_query_graph(formula, queries, model.rel_ids, model.mode_ids)
+    targets = torch.tensor([q.target_node for q in queries])
+    index = mp_eval.RankIndex(model, distributed=False)
+    first = slice(0, 24)
+    graphed = mp_eval.GraphedCounts(index, formula, a_ids[first], targets[first], var_ids,
+                                    data_utils.QueryGraphBatch(q_graphs.template, q_graphs.edge_rel_ids, 24))
+    for sl in (first, slice(24, 48), first):
+        l, r, pos, n = graphed(a_ids[sl], targets[sl])
+        want_l, want_r, want_pos, want_n = index.counts(formula, queries[sl], targets[sl])
+        torch.cuda.synchronize()
+        assert n == want_n and torch.equal(l, want_l) and torch.equal(r, want_r) and torch.equal(pos, want_pos)
+
+
 def test_training_loop_runs_and_loss_decreases():
     kg, cfg, params, model, qsets = setup(per_formula=64)
     train = {qt: {Query.deserialize(raw[0]).formula: [Query.deserialize(r) for r in raw]}
