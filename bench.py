@@ -218,6 +218,13 @@ def timed_steps(run, args, dev, world, barrier, flush):
     resident = [ts.to_device(hb) for hb in run.host]
     for _ in range(max(args.warmup, 3)):
         ts.forward_backward(resident)
+    if os.environ.get('MPQE_NCU_RANGE'):      # evidence capture: one eager step inside a profiler range
+        torch.cuda.synchronize()              # (ncu --profile-from-start off ...; profiles/capture_r02.sh)
+        torch.cuda.cudart().cudaProfilerStart()
+        flush.zero_()
+        ts.forward_backward(resident)
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
     launches_per_step = None
     if not args.no_graph:
         l0 = ops.launch_count
@@ -252,11 +259,13 @@ def timed_steps(run, args, dev, world, barrier, flush):
     # per-kernel timing for the roofline: the same step launched eagerly with CUDA events around the layer and
     # weight-gradient launches (events cannot be recorded inside a replayed graph)
     ops.profile = []
+    overlap, ts.overlap_wgrad = ts.overlap_wgrad, False      # every kernel timed alone, not next to another stream's
     barrier()
     for _ in range(min(args.steps, 10)):
         flush.zero_()
         ts.forward_backward(resident)
     barrier()
+    ts.overlap_wgrad = overlap
     prof, ops.profile = ops.profile, None
     if os.environ.get('MPQE_DP_TRACE'):      # phase times of the eager data-parallel step (diagnostic)
         ts.trace = []
@@ -391,6 +400,13 @@ def eval_bench(run, args, dev, world, barrier):
     index = mp_eval.RankIndex(run.model)
     eq = [None] * Q
 
+    if os.environ.get('MPQE_NCU_RANGE'):
+        index.counts(ef, eq, et_d, anchor_ids=ea_d, var_ids=var_t, q_graphs=qg)
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        index.counts(ef, eq, et_d, anchor_ids=ea_d, var_ids=var_t, q_graphs=qg)
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
     if args.no_graph:
         def step():
             return index.counts(ef, eq, et_d, anchor_ids=ea_d, var_ids=var_t, q_graphs=qg)

@@ -521,6 +521,7 @@ class Engine(object):
         tc = ops.tensor_cores_default()
         if W.need_grad:
             W.msumt = ops.transpose(W.msum)
+            W.dmsum = torch.empty_like(W.msum)
         if tc:
             packed = ops.pack_weights([W.msum[k] for k in range(len(W.msum_keys))] +
                                       ([W.msumt[k] for k in range(len(W.msum_keys))] if W.need_grad else []))
@@ -590,8 +591,9 @@ class Engine(object):
         """Runs every pass of every job; leaves job.q [B, D] (query embeddings)."""
         readout = self.m.readout_str
         self.build_inputs(jobs, W)
-        if getattr(W, 'prepared', None) is not jobs:
-            self.prepare(jobs, W)
+        prepared = getattr(W, 'prepared', None)
+        if prepared is not jobs and (prepared is None or not all(any(job is pj for pj in prepared) for job in jobs)):
+            self.prepare(jobs, W)      # (a subset of the prepared jobs -- one lane of a step -- is prepared)
         if getattr(W, 'ready_event', None) is not None:    # weights prepared on another stream
             torch.cuda.current_stream().wait_event(W.ready_event)
         max_p = max(job.P for job in jobs)
@@ -1204,7 +1206,12 @@ class RGCNEncoderDecoder(nn.Module):
         return tuple(by_param.get(id(p)) for p in self.parameters())
 
 
-def loss_forward(model, jobs, targets, negatives, margin, need_grad, grad_losses=None, W=None):
+def _one(x, i):
+    """Element i of a per-job device vector as a 1-element view; `x` may also be a list of such views."""
+    return x[i] if isinstance(x, (list, tuple)) else x[i:i + 1]
+
+
+def loss_forward(model, jobs, targets, negatives, margin, need_grad, grad_losses=None, W=None, losses_out=None):
     """Encodes every job once and scores it against its positives and negatives.
     Returns (per-job losses [len(jobs)] on the device, Weights).  With `grad_losses` (d total / d loss_i, known up
     front in a training step) and row slots reserved by `plan_rows`, the margin backward (job.dq and the target /
@@ -1213,17 +1220,18 @@ def loss_forward(model, jobs, targets, negatives, margin, need_grad, grad_losses
     if W is None:
         W = Weights(model, need_grad)
     model._engine.encode(jobs, W)
-    losses = torch.empty(len(jobs), dtype=torch.float32, device=device)
+    # losses_out: per-job 1-element views to write the losses to (a lane of a step writes into the step's vector)
+    losses = torch.empty(len(jobs), dtype=torch.float32, device=device) if losses_out is None else losses_out
     hinge = torch.empty(sum(job.B for job in jobs), dtype=torch.float32, device=device)
     items, off = [], 0
     for i, (job, tgt, neg) in enumerate(zip(jobs, targets, negatives)):
         it = ops.MarginItem(job.q, model.enc.table(job.target_mode), model.enc.node_maps, tgt, neg,
-                            hinge=hinge[off:off + job.B], loss=losses[i:i + 1])
+                            hinge=hinge[off:off + job.B], loss=_one(losses, i))
         job.dq = None
         if grad_losses is not None:
             rbuf, ids, roff, id_off = job.margin_res
             job.dq = torch.empty(job.B, D, dtype=torch.float32, device=device)
-            it.grad_loss, it.dq = grad_losses[i:i + 1], job.dq
+            it.grad_loss, it.dq = _one(grad_losses, i), job.dq
             it.rows_out, it.rows_id, it.rows_offset, it.id_offset = rbuf, ids, roff, id_off
         items.append(it)
         off += job.B
@@ -1278,7 +1286,7 @@ def loss_backward(model, jobs, W, targets, negatives, margin, grad_losses, table
         rbuf, ids, off, id_off = job.margin_res if G.rows.planned else G.rows.reserve(job.target_mode, 2 * job.B)
         dq = torch.empty(job.B, D, dtype=torch.float32, device=device)
         items.append(ops.MarginItem(job.q, model.enc.table(job.target_mode), model.enc.node_maps, tgt, neg,
-                                    grad_loss=grad_losses[i:i + 1], dq=dq, rows_out=rbuf, rows_id=ids, rows_offset=off,
+                                    grad_loss=_one(grad_losses, i), dq=dq, rows_out=rbuf, rows_id=ids, rows_offset=off,
                                     id_offset=id_off))
         dqs.append(dq)
     if items:
