@@ -178,6 +178,15 @@ typedef struct {
 } mpqe_matsum_item_t;
 MPQE_API int mpqe_matrix_sum_multi(const mpqe_matsum_item_t* items_host, int32_t n, void* stream);
 
+/* Basis decomposition of the relation weights (RGCNConv with num_bases > 0, reference model.py:281-284:
+ * w = torch.matmul(att, basis.view(num_bases, -1))) and its backward.
+ * mpqe_small_k_matmul: out[m, e] = sum_k a[m*a_row_stride + k*a_col_stride] * b[k, e], b [K, E], out [M, E], E % 4 == 0;
+ *   W = att @ basis is (a = att, strides (K, 1)); d basis = att^T @ dW is (a = att, strides (1, num_bases), b = dW).
+ * mpqe_rows_dot: out[m, k] = sum_e x[m, e] * y[k, e]  (d att = dW . basis).  Fixed summation orders. */
+MPQE_API int mpqe_small_k_matmul(const float* a, int64_t a_row_stride, int64_t a_col_stride, const float* b, int32_t M,
+                                 int32_t K, int64_t E, float* out, void* stream);
+MPQE_API int mpqe_rows_dot(const float* x, const float* y, int32_t M, int32_t K, int64_t E, float* out, void* stream);
+
 /* ---- a11: max readout (model.py:383-385; torch_scatter.scatter_max) -------------------------------------
  * q[b, c] = max_i z[b, i, c]; argmax[b, c] = smallest i attaining it (int64 node ROW b*n+i, like scatter_max). */
 MPQE_API int mpqe_max_readout_fwd(const float* z, int64_t B, int32_t n, float* q, int64_t* argmax, void* stream);
@@ -290,6 +299,11 @@ MPQE_API int mpqe_colsum_multi(const mpqe_colsum_item_t* items_host, int32_t n, 
  * ragged negatives: left[b] = #(neg < pos[b]), right[b] = #(neg <= pos[b]) over neg[offsets[b]:offsets[b+1]]. */
 MPQE_API int mpqe_rank_counts_ragged(const float* pos, const float* neg, const int64_t* offsets, int64_t B,
                             int64_t* left, int64_t* right, void* stream);
+/* ROC AUC pair counts (utils.py:34-36: roc_auc_score(labels, nan_to_num(predictions))): counts[0] += #(neg < pos),
+ * counts[1] += #(neg == pos) over all (positive, negative) score pairs after nan_to_num; counts is ACCUMULATED (zero it
+ * first).  AUC = (counts[0] + counts[1] / 2) / (num_pos * num_neg), the Mann-Whitney form of the same statistic. */
+MPQE_API int mpqe_auc_counts(const float* pos, int64_t num_pos, const float* neg, int64_t num_neg,
+                             unsigned long long* counts, void* stream);
 /* full-entity ranking against one table shard (new; north star "full-entity ranking eval"):
  * candidates = rows [row_begin, row_end) of `table`, score = cos(q[b], y(row)) as above;
  * left/right are ACCUMULATED (zero them first) so shards can be chained or merged with an integer allreduce. */

@@ -101,6 +101,8 @@ SIGNATURES = {
     'mpqe_colsum': (I32, [P, I64, I64, F32, P, I32, P, SZ, P]),
     'mpqe_transpose': (I32, [P, P, I64, I32, I32, P]),
     'mpqe_matrix_sum_multi': (I32, [P, I32, P]),
+    'mpqe_small_k_matmul': (I32, [P, I64, I64, P, I32, I32, I64, P, P]),
+    'mpqe_rows_dot': (I32, [P, P, I32, I32, I64, P, P]),
     'mpqe_max_readout_fwd': (I32, [P, I64, I32, P, P, P]),
     'mpqe_max_readout_bwd': (I32, [P, P, I64, I32, P, P]),
     'mpqe_margin_loss_workspace_bytes': (SZ, [I64]),
@@ -109,6 +111,7 @@ SIGNATURES = {
     'mpqe_cosine_scores': (I32, [P, I64, P, P, P, P, I64, P, P]),
     'mpqe_cosine_scores_bwd': (I32, [P, I64, P, P, P, P, I64, P, P, I32, P, P, P]),
     'mpqe_rank_counts_ragged': (I32, [P, P, P, I64, P, P, P]),
+    'mpqe_auc_counts': (I32, [P, I64, P, I64, P, P]),
     'mpqe_rank_counts_table_workspace_bytes': (SZ, [I64, I64]),
     'mpqe_rank_counts_table': (I32, [P, I64, P, P, I64, I64, P, P, P, SZ, I32, P]),
     'mpqe_rank_table_workspace_bytes': (SZ, [I64, I32]),

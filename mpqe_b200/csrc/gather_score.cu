@@ -236,6 +236,54 @@ __global__ void __launch_bounds__(ROW_THREADS) rank_counts_ragged_kernel(const f
   }
 }
 
+// AUC pair counts: counts[0] += #(neg < pos), counts[1] += #(neg == pos) over ALL (positive, negative) pairs after
+// nan_to_num (utils.py:34-36 -> sklearn roc_auc_score = the Mann-Whitney statistic (lt + eq/2) / (P*N)).  A CTA owns 256
+// positives (one per thread) and a slice of the negatives staged through shared memory; integer atomics only.
+__device__ __forceinline__ float nan_to_num(float v) {
+  if (v != v) return 0.f;
+  if (v > 3.402823466e38f) return 3.402823466e38f;
+  if (v < -3.402823466e38f) return -3.402823466e38f;
+  return v;
+}
+constexpr int AUC_NEG_TILE = 2048;
+__global__ void __launch_bounds__(256) auc_counts_kernel(const float* __restrict__ pos, int64_t P,
+                                                         const float* __restrict__ neg, int64_t N,
+                                                         unsigned long long* __restrict__ counts) {
+  __shared__ float tile[AUC_NEG_TILE];
+  __shared__ unsigned long long red[2][8];
+  const int64_t pi = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const float p = pi < P ? nan_to_num(pos[pi]) : 0.f;
+  const int64_t n0 = (int64_t)blockIdx.y * AUC_NEG_TILE;
+  const int cnt = (int)(N - n0 < AUC_NEG_TILE ? N - n0 : AUC_NEG_TILE);
+  for (int i = threadIdx.x; i < cnt; i += 256) tile[i] = nan_to_num(neg[n0 + i]);
+  __syncthreads();
+  unsigned lt = 0, eq = 0;
+  if (pi < P) {
+#pragma unroll 8
+    for (int i = 0; i < cnt; ++i) {
+      const float v = tile[i];
+      lt += v < p;
+      eq += v == p;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lt += __shfl_xor_sync(0xffffffffu, lt, o);
+    eq += __shfl_xor_sync(0xffffffffu, eq, o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    red[0][warp] = lt;
+    red[1][warp] = eq;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    unsigned long long s = 0;
+    for (int w = 0; w < 8; ++w) s += red[threadIdx.x][w];
+    if (s) atomicAdd(counts + threadIdx.x, s);
+  }
+}
+
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps, float bc1,
                             float bc2_sqrt) {
@@ -354,6 +402,18 @@ extern "C" int mpqe_cosine_scores_bwd(const float* q, int64_t B, const int64_t* 
   cosine_scores_bwd_kernel<<<row_blocks(B), ROW_THREADS, 0, (cudaStream_t)stream>>>(
       q, B, offsets, table, id2row, ids, grad_scores, dq, accumulate, rows_out, rows_id);
   MPQE_CHECK_LAUNCH("cosine_scores_bwd_kernel");
+  return 0;
+}
+
+extern "C" int mpqe_auc_counts(const float* pos, int64_t num_pos, const float* neg, int64_t num_neg,
+                               unsigned long long* counts, void* stream) {
+  MPQE_CHECK_ARG(pos && neg && counts && num_pos >= 1 && num_neg >= 1 && num_neg < (1ll << 40),
+                 "mpqe_auc_counts: bad argument");
+  const int64_t by = (num_neg + AUC_NEG_TILE - 1) / AUC_NEG_TILE;
+  MPQE_CHECK_ARG(by <= 65535, "mpqe_auc_counts: more than %lld negatives", (long long)65535 * AUC_NEG_TILE);
+  auc_counts_kernel<<<dim3((unsigned)((num_pos + 255) / 256), (unsigned)by), 256, 0, (cudaStream_t)stream>>>(
+      pos, num_pos, neg, num_neg, counts);
+  MPQE_CHECK_LAUNCH("auc_counts_kernel");
   return 0;
 }
 

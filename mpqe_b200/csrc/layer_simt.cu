@@ -651,8 +651,64 @@ __global__ void __launch_bounds__(256) matrix_sum_multi_kernel(const __grid_cons
   }
   *dst = s;
 }
+
+// ---- basis decomposition (RGCNConv num_bases > 0, model.py:281-284): W_r = sum_b att[r, b] * basis[b] --------------
+// out[m, e] = sum_k a[m*a_row + k*a_col] * b[k, e]   (K small: <= 64 bases / relations per pass of the loop).
+// One float4 of one output row per thread, k ascending: fixed order.  With (a_row, a_col) = (K, 1) this is
+// W = att @ basis, with (1, M) and b = dW it is d basis = att^T @ dW.
+__global__ void __launch_bounds__(256) small_k_matmul_kernel(const float* __restrict__ a, int64_t a_row, int64_t a_col,
+                                                             const float* __restrict__ b, int M, int K, int64_t E4,
+                                                             float* __restrict__ out) {
+  const int64_t e4 = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int m = blockIdx.y;
+  if (e4 >= E4) return;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < K; ++k) {
+    const float w = __ldg(a + m * a_row + k * a_col);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(b) + (int64_t)k * E4 + e4);
+    s.x += w * v.x; s.y += w * v.y; s.z += w * v.z; s.w += w * v.w;
+  }
+  reinterpret_cast<float4*>(out)[(int64_t)m * E4 + e4] = s;
+}
+
+// out[m, k] = sum_e x[m, e] * y[k, e]   (d att = dW . basis): one CTA per (m, k), fixed strided partials + fixed tree
+__global__ void __launch_bounds__(256) rows_dot_kernel(const float* __restrict__ x, const float* __restrict__ y, int K,
+                                                       int64_t E4, float* __restrict__ out) {
+  __shared__ float red[256];
+  const int m = blockIdx.y, k = blockIdx.x;
+  const float4* xr = reinterpret_cast<const float4*>(x) + (int64_t)m * E4;
+  const float4* yr = reinterpret_cast<const float4*>(y) + (int64_t)k * E4;
+  float acc = 0.f;
+  for (int64_t e = threadIdx.x; e < E4; e += 256) acc += dot4(__ldg(xr + e), __ldg(yr + e));
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[(int64_t)m * K + k] = red[0];
+}
 }  // namespace
 }  // namespace mpqe
+
+extern "C" int mpqe_small_k_matmul(const float* a, int64_t a_row_stride, int64_t a_col_stride, const float* b,
+                                   int32_t M, int32_t K, int64_t E, float* out, void* stream) {
+  MPQE_CHECK_ARG(a != nullptr && b != nullptr && out != nullptr && M >= 1 && M < 65536 && K >= 1 && E >= 4 && E % 4 == 0,
+                 "mpqe_small_k_matmul: bad argument");
+  const int64_t E4 = E / 4;
+  small_k_matmul_kernel<<<dim3((unsigned)((E4 + 255) / 256), (unsigned)M), 256, 0, (cudaStream_t)stream>>>(
+      a, a_row_stride, a_col_stride, b, M, K, E4, out);
+  MPQE_CHECK_LAUNCH("small_k_matmul_kernel");
+  return 0;
+}
+
+extern "C" int mpqe_rows_dot(const float* x, const float* y, int32_t M, int32_t K, int64_t E, float* out, void* stream) {
+  MPQE_CHECK_ARG(x != nullptr && y != nullptr && out != nullptr && M >= 1 && M < 65536 && K >= 1 && E >= 4 && E % 4 == 0,
+                 "mpqe_rows_dot: bad argument");
+  rows_dot_kernel<<<dim3((unsigned)K, (unsigned)M), 256, 0, (cudaStream_t)stream>>>(x, y, K, E / 4, out);
+  MPQE_CHECK_LAUNCH("rows_dot_kernel");
+  return 0;
+}
 
 extern "C" int mpqe_matrix_sum_multi(const mpqe_matsum_item_t* items_host, int32_t n, void* stream) {
   MPQE_CHECK_ARG(items_host != nullptr && n >= 1 && n <= MPQE_MAX_MATSUM_ITEMS,

@@ -34,6 +34,25 @@ def _uniform(size, tensor):
         tensor.data.uniform_(-bound, bound)
 
 
+class _BasisFn(torch.autograd.Function):
+    """W = att @ basis over the flattened [in, out] matrices (reference model.py:281-284) and its backward
+    (d att = dW . basis, d basis = att^T @ dW) on the library's small-inner-dimension kernels."""
+
+    @staticmethod
+    def forward(ctx, att, basis):
+        ctx.save_for_backward(att, basis)
+        with ops.device_guard(basis.device):
+            return ops.small_k_matmul(att.detach().contiguous(), basis.detach().contiguous())
+
+    @staticmethod
+    def backward(ctx, dw):
+        att, basis = ctx.saved_tensors
+        with ops.device_guard(basis.device):
+            dw = dw.contiguous()
+            return (ops.rows_dot(dw, basis.detach().contiguous()),
+                    ops.small_k_matmul(att.detach().contiguous(), dw, transpose_a=True))
+
+
 class RGCNConv(nn.Module):
     """Relational graph convolution  x'_i = x_i @ root + sum_{j ->r i} x_j @ W_r + bias  (aggr='add').
 
@@ -69,8 +88,7 @@ class RGCNConv(nn.Module):
         """[R, in, out] weights; with a basis decomposition W_r = sum_b att[r, b] * basis[b] (model.py:281-284)."""
         if self.att is None:
             return self.basis
-        return torch.matmul(self.att, self.basis.view(self.num_bases, -1)).view(
-            self.num_relations, self.in_channels, self.out_channels)
+        return _BasisFn.apply(self.att, self.basis)
 
     def forward(self, x, edge_index, edge_type=None, edge_norm=None, graph=None):
         if isinstance(edge_index, QueryGraphBatch):
@@ -1189,8 +1207,8 @@ class RGCNEncoderDecoder(nn.Module):
                 by_param[id(layer.basis)] = G.dw[li]
             else:  # W_r = sum_b att[r,b] basis[b]
                 dw = G.dw[li].view(layer.num_relations, -1)
-                by_param[id(layer.att)] = dw @ layer.basis.view(layer.num_bases, -1).t()
-                by_param[id(layer.basis)] = (layer.att.t() @ dw).view_as(layer.basis)
+                by_param[id(layer.att)] = ops.rows_dot(dw, layer.basis.detach())
+                by_param[id(layer.basis)] = ops.small_k_matmul(layer.att.detach(), dw, transpose_a=True).view_as(layer.basis)
             by_param[id(layer.root)] = G.droot[li]
             if layer.bias is not None:
                 by_param[id(layer.bias)] = G.dbias[li]

@@ -241,6 +241,36 @@ def layer_wgrad(groups, grad_operands, dests, ctas_hint=296, use_tensor_cores=No
     _count(1 if rows_only else 2)
 
 
+def small_k_matmul(a, b, transpose_a=False):
+    """out = a @ b (or a^T @ b) for a small inner dimension: a [M, K] ([K, M] with transpose_a), b [K, ...] -> [M, ...]
+    (mpqe_small_k_matmul: the basis decomposition of the relation weights and its d basis)."""
+    lib = _lib.load()
+    a, b = _chk(a, torch.float32, 'a'), _chk(b, torch.float32, 'b')
+    M, K = (a.shape[1], a.shape[0]) if transpose_a else (a.shape[0], a.shape[1])
+    if b.shape[0] != K:
+        raise _lib.MpqeError('small_k_matmul: inner dimensions differ (%d vs %d)' % (K, b.shape[0]))
+    E = b.numel() // K
+    out = torch.empty((M,) + tuple(b.shape[1:]), dtype=torch.float32, device=b.device)
+    rs, cs = (1, a.shape[1]) if transpose_a else (a.shape[1], 1)
+    _lib.check(lib.mpqe_small_k_matmul(_ptr(a), rs, cs, _ptr(b), M, K, E, _ptr(out), _stream()), 'mpqe_small_k_matmul')
+    _count()
+    return out
+
+
+def rows_dot(x, y):
+    """out[m, k] = <x[m], y[k]> over all trailing elements (mpqe_rows_dot: d att of the basis decomposition)."""
+    lib = _lib.load()
+    x, y = _chk(x, torch.float32, 'x'), _chk(y, torch.float32, 'y')
+    M, K = x.shape[0], y.shape[0]
+    E = x.numel() // M
+    if y.numel() // K != E:
+        raise _lib.MpqeError('rows_dot: row lengths differ')
+    out = torch.empty(M, K, dtype=torch.float32, device=x.device)
+    _lib.check(lib.mpqe_rows_dot(_ptr(x), _ptr(y), M, K, E, _ptr(out), _stream()), 'mpqe_rows_dot')
+    _count()
+    return out
+
+
 def matrix_sum_multi(items):
     """items: [(dst [D, D] view, [src [D, D] views], accumulate)]; dst (+)= sum(src) in order (mpqe_matrix_sum_multi).
     Destinations must be distinct within one call; a summand list longer than MPQE_MAX_MATSUM_SRCS is continued by
@@ -434,6 +464,18 @@ def rank_counts_ragged(pos, neg, offsets):
                                            _stream()), 'mpqe_rank_counts_ragged')
     _count()
     return left, right
+
+
+def auc_counts(pos, neg, counts=None):
+    """counts[0] += #(neg < pos), counts[1] += #(neg == pos) over all pairs (int64 [2] on the device, mpqe_auc_counts)."""
+    lib = _lib.load()
+    if counts is None:
+        counts = torch.zeros(2, dtype=torch.int64, device=pos.device)
+    _lib.check(lib.mpqe_auc_counts(_ptr(_chk(pos, torch.float32, 'pos')), pos.numel(),
+                                   _ptr(_chk(neg, torch.float32, 'neg')), neg.numel(), _ptr(counts), _stream()),
+               'mpqe_auc_counts')
+    _count()
+    return counts
 
 
 def rank_counts_table(q, pos, table, row_begin, row_end, left, right, use_tensor_cores=False):

@@ -52,6 +52,14 @@ def auc_from_scores(labels, scores):
     return (r[labels].sum() - npos * (npos + 1) / 2.0) / (npos * nneg)
 
 
+def auc_from_device_scores(pos, neg):
+    """The same statistic from device-resident scores of the positives and of the negatives, without sorting or copying
+    them: exact integer pair counts on the device (`ops.auc_counts`), one 16-byte read-back."""
+    with ops.device_guard(pos.device):
+        lt, eq = ops.auc_counts(pos.contiguous(), neg.contiguous()).tolist()
+    return (lt + 0.5 * eq) / (float(pos.numel()) * float(neg.numel()))
+
+
 def percentile_from_counts(left, right, lengths):
     """scipy.stats.percentileofscore(kind='rank'): (left + right + (left < right)) * 50 / n."""
     left = np.asarray(left, dtype=np.int64)
@@ -83,22 +91,28 @@ def _batches(formula_queries, batch_size):
 
 @torch.no_grad()
 def eval_auc_queries(test_queries, enc_dec, batch_size=128, hard_negatives=False, seed=0):
-    predictions, labels, formula_aucs = [], [], {}
+    all_pos, all_neg, formula_aucs = [], [], {}
     random.seed(seed)
     for formula, formula_queries in test_queries.items():
-        f_labels, f_scores = [], []
+        f_pos, f_neg = [], []
         for batch in _batches(formula_queries, batch_size):
             pool = (lambda q: q.hard_neg_samples) if hard_negatives else (lambda q: q.neg_samples)
             negatives = [random.choice(pool(q)) for q in batch]
             scores = enc_dec.forward(formula, batch, [q.target_node for q in batch], neg_nodes=negatives,
                                      neg_lengths=[1] * len(batch))
-            f_labels.extend([1] * len(batch) + [0] * len(negatives))
-            f_scores.append(scores)
-        f_scores = torch.cat(f_scores).cpu().numpy()
-        formula_aucs[formula] = auc_from_scores(f_labels, f_scores)
-        labels.extend(f_labels)
-        predictions.append(f_scores)
-    return auc_from_scores(labels, np.concatenate(predictions)), formula_aucs
+            f_pos.append(scores[:len(batch)])       # label 1 (utils.py:49-50)
+            f_neg.append(scores[len(batch):])       # label 0
+        f_pos, f_neg = torch.cat(f_pos), torch.cat(f_neg)
+        formula_aucs[formula] = _auc(f_pos, f_neg)
+        all_pos.append(f_pos)
+        all_neg.append(f_neg)
+    return _auc(torch.cat(all_pos), torch.cat(all_neg)), formula_aucs
+
+
+def _auc(pos, neg):
+    if not pos.is_cuda:
+        raise RuntimeError('AUC pair counts run on the device: pass CUDA scores (there is no CPU fallback)')
+    return auc_from_device_scores(pos, neg)
 
 
 @torch.no_grad()

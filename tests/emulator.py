@@ -291,7 +291,7 @@ def install(monkeypatch):
                  'broadcast_rows', 'max_readout', 'max_readout_bwd', 'cosine_margin', 'cosine_margin_bwd',
                  'cosine_scores', 'cosine_scores_bwd', 'rank_counts_ragged', 'rank_counts_table',
                  'build_query_graph', 'relation_sort', 'sparse_rows_combine', 'SparseRowsPlan', 'scatter_rows',
-                 'gather_multi', 'matrix_sum_multi',
+                 'gather_multi', 'matrix_sum_multi', 'small_k_matmul', 'rows_dot',
                  'cosine_margin_multi', 'colsum_multi', 'l2_reg', 'owner_plan'):
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(ops, 'device_guard', lambda device: contextlib.nullcontext())
@@ -360,6 +360,15 @@ def cosine_margin_multi(items, margin, backward=False):
             it.rows_id[it.rows_offset:it.rows_offset + 2 * B] += it.id_offset
         else:
             cosine_margin(it.q, it.table, it.id2row, it.ids_pos, it.ids_neg, margin, loss_out=it.loss)
+
+
+def small_k_matmul(a, b, transpose_a=False):
+    a2 = a.t() if transpose_a else a
+    return (a2 @ b.reshape(b.shape[0], -1)).reshape((a2.shape[0],) + tuple(b.shape[1:]))
+
+
+def rows_dot(x, y):
+    return x.reshape(x.shape[0], -1) @ y.reshape(y.shape[0], -1).t()
 
 
 def matrix_sum_multi(items):

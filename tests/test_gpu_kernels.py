@@ -510,3 +510,69 @@ def test_colsum_multi_shared_destinations():
         outs.append(cur.cpu())
     assert_close(outs[0].numpy(), want.numpy(), 1e-5, 1e-4, 'column sums')
     assert torch.equal(outs[0], outs[1])
+
+
+def test_basis_decomposition_kernels():
+    """W = att @ basis, d basis = att^T @ dW, d att = dW . basis (RGCNConv num_bases > 0, reference model.py:281-284)
+    against float64; relative error 1e-6 (plain fp32 sums of <= 38 / 16384 products in a fixed order)."""
+    att, basis, dw = rnd(38, 5, seed=1), rnd(5, D, D, seed=2), rnd(38, D, D, seed=3)
+    with torch.cuda.device(0):
+        w = ops.small_k_matmul(att.to(DEV), basis.to(DEV))
+        dbasis = ops.small_k_matmul(att.to(DEV), dw.to(DEV), transpose_a=True)
+        datt = ops.rows_dot(dw.to(DEV), basis.to(DEV))
+    want_w = (att.double() @ basis.double().view(5, -1)).view(38, D, D)
+    want_db = (att.double().t() @ dw.double().view(38, -1)).view(5, D, D)
+    want_da = dw.double().view(38, -1) @ basis.double().view(5, -1).t()
+    assert w.shape == (38, D, D) and dbasis.shape == (5, D, D) and datt.shape == (38, 5)
+    assert_close(w.cpu().numpy(), want_w.numpy(), 1e-6, 1e-6, 'att @ basis')
+    assert_close(dbasis.cpu().numpy(), want_db.numpy(), 1e-6, 2e-6, 'att^T @ dW')
+    assert_close(datt.cpu().numpy(), want_da.numpy(), 1e-5, 1e-4, 'dW . basis')
+
+
+def test_rgcn_conv_basis_decomposition_on_device():
+    """RGCNConv with num_bases > 0 on the GPU: output and the gradients of att / basis / root / bias / x against the
+    oracle's rgcn_conv."""
+    from mpqe_b200.data_utils import QueryGraphBatch, template_of
+    from mpqe_b200.model import RGCNConv
+    from oracle import mpqe_oracle as O
+    torch.manual_seed(1)
+    conv = RGCNConv(128, 128, 7, 3)
+    t = template_of('3-inter_chain')
+    g = QueryGraphBatch(t, [6, 2, 0], 37)
+    x = torch.randn(37 * t.num_nodes, 128)
+    pc = {k: v.detach().clone().requires_grad_(True) for k, v in conv.named_parameters()}
+    xc = x.clone().requires_grad_(True)
+    want = O.rgcn_conv(xc, g.edge_index, g.edge_type, pc['basis'], pc['root'], pc['bias'], att=pc['att'])
+    wgt = torch.randn_like(want)
+    (want * wgt).sum().backward()
+    conv = conv.to(DEV)
+    xd = x.to(DEV).requires_grad_(True)
+    out = conv(xd, g.to(DEV))
+    assert_close(out.detach().cpu().numpy(), want.detach().numpy(), 1e-5, 1e-5, 'conv out (bases)')
+    (out * wgt.to(DEV)).sum().backward()
+    assert_close(xd.grad.cpu().numpy(), xc.grad.numpy(), 1e-4, 1e-5, 'dx')
+    for k, prm in conv.named_parameters():
+        assert_close(prm.grad.cpu().numpy(), pc[k].grad.numpy(), 1e-4, 1e-4, 'd' + k)
+
+
+@pytest.mark.parametrize('P,N', [(1, 1), (300, 5000), (4097, 2049)])
+def test_auc_counts_match_sklearn(P, N):
+    """Exact integer pair counts -> the AUC of sklearn.metrics.roc_auc_score on the same scores (ties, NaN and inf
+    included: the reference applies nan_to_num first, utils.py:34-36)."""
+    from sklearn.metrics import roc_auc_score
+    from mpqe_b200 import utils
+    g = np.random.RandomState(P + N)
+    pos = np.round(g.randn(P).astype(np.float32), 2)        # rounding makes ties
+    neg = np.round(g.randn(N).astype(np.float32) - 0.3, 2)
+    if P > 10:
+        pos[3], pos[4], neg[5], neg[6] = np.nan, np.inf, np.nan, -np.inf
+    counts = ops.auc_counts(torch.from_numpy(pos).to(DEV), torch.from_numpy(neg).to(DEV)).cpu().numpy()
+    p64, n64 = np.nan_to_num(pos).astype(np.float64), np.nan_to_num(neg).astype(np.float64)
+    lt = int((n64[None, :] < p64[:, None]).sum())
+    eq = int((n64[None, :] == p64[:, None]).sum())
+    assert counts.tolist() == [lt, eq]
+    got = utils.auc_from_device_scores(torch.from_numpy(pos).to(DEV), torch.from_numpy(neg).to(DEV))
+    if lt + eq not in (0, P * N) or P * N > 1:
+        labels = np.concatenate([np.ones(P), np.zeros(N)])
+        want = roc_auc_score(labels, np.nan_to_num(np.concatenate([pos, neg])))
+        assert abs(got - want) < 1e-12
