@@ -348,11 +348,11 @@ class TrainStep(object):
         # the forward and backward; only the final row summation waits for the gradient rows.
         # The per-step weight preparation (transposes, tf32 tile images, summed matrices) goes to that stream too, ahead
         # of the sort: it overlaps the input gather; the first layer launch waits for its event.
-        # (single rank: the ids-only launch itself goes to that stream, in front of the sort, so the input gather
-        # does not wait for it; with several ranks the ids have to be in place before the first barrier)
+        # (the ids-only launch stays on this stream: moved in front of the sort it lets the input gather start at once,
+        # which then crowds out the small weight-preparation kernels the first layer launch waits for: +9 us per step)
         R = plan_rows(m, jobs, tg, ng, self.table_offsets,
                       rows_buffer=(lambda cap: self._xrows) if peer else None,
-                      ids_buffer=(lambda cap: self._xids) if peer else None, launch=multi)
+                      ids_buffer=(lambda cap: self._xids) if peer else None)
         rows, ids, used = R.shared
         if multi and used != self._xcap:
             raise ops._lib.MpqeError('data-parallel step: %d (row id, row) pairs, the exchange was set up for %d; call '
@@ -365,10 +365,7 @@ class TrainStep(object):
         W = self._weights_on_side_stream(jobs, dev)
         all_ids = None
         if not multi:
-            def ids_then_plan():
-                ops.gather_multi(R.id_items, backward='ids')
-                return ops.SparseRowsPlan(ids[:used], self.total_rows)
-            plan = self._plan_on_side_stream(ids_then_plan, dev, keep=(ids,))
+            plan = self._plan_on_side_stream(lambda: ops.SparseRowsPlan(ids[:used], self.total_rows), dev, keep=(ids,))
         else:
             if peer:
                 id_src = self._id_ptrs
