@@ -149,6 +149,10 @@ MPQE_API int mpqe_layer_forward(const mpqe_layer_group_t* groups_host, int32_t n
  * `count` device pointers; packed receives count * MPQE_PACKED_FLOATS floats.  Repack whenever the weights change. */
 #define MPQE_PACKED_FLOATS (2 * MPQE_D * MPQE_D)
 MPQE_API int mpqe_pack_weights(const float* const* mats_host, int32_t count, float* packed, void* stream);
+/* The same with an optional HOST array of per-matrix flags: transposed_host[i] != 0 packs the image of mats[i]^T (the
+ * matrix the input-gradient launches multiply by) straight from mats[i] -- no transposed copy has to exist first. */
+MPQE_API int mpqe_pack_weights_ex(const float* const* mats_host, const uint8_t* transposed_host, int32_t count,
+                                  float* packed, void* stream);
 
 /* Weight gradients of the same term lists (deterministic: fixed split over queries, ordered reduction). */
 MPQE_API size_t mpqe_layer_wgrad_workspace_bytes(int32_t num_dests, int32_t num_ctas_hint);

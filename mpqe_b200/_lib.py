@@ -131,6 +131,7 @@ SIGNATURES = {
     'mpqe_scatter_rows': (I32, [P, P, P, I64, P, I32, P]),
     'mpqe_adam_dense': (I32, [P, P, P, P, I64, F32, F32, F32, F32, I32, P]),
     'mpqe_pack_weights': (I32, [P, I32, P, P]),
+    'mpqe_pack_weights_ex': (I32, [P, P, I32, P, P]),
     'mpqe_gather_multi': (I32, [P, I32, I32, P]),
     'mpqe_cosine_margin_multi': (I32, [P, I32, F32, I32, P]),
     'mpqe_colsum_multi_workspace_bytes': (SZ, [P, I32]),

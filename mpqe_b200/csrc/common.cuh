@@ -59,7 +59,8 @@ int layer_forward_simt(const mpqe_layer_group_t* groups, int num_groups, cudaStr
 int layer_forward_tc(const mpqe_layer_group_t* groups, int num_groups, cudaStream_t stream);
 // second-generation tcgen05 layer kernel (layer_tc2.cu: queries on the N = 256 side) and its weight image
 int layer_forward_tc2(const mpqe_layer_group_t* groups, int num_groups, cudaStream_t stream);
-int pack_weights_tc2(const float* const* mats_host, int32_t count, float* packed, cudaStream_t stream);
+int pack_weights_tc2(const float* const* mats_host, const uint8_t* transposed_host, int32_t count, float* packed,
+                     cudaStream_t stream);
 // 1: layer_tc.cu (128-query units), 2: layer_tc2.cu (default); MPQE_LAYER_KERNEL selects, read once
 int tc_generation();
 int layer_wgrad_tc_launch(const WgradLaunch& launch, int total_chunks, cudaStream_t stream);

@@ -1154,8 +1154,17 @@ int mpqe::tc_generation() {
 }
 
 extern "C" int mpqe_pack_weights(const float* const* mats_host, int32_t count, float* packed, void* stream) {
+  return mpqe_pack_weights_ex(mats_host, nullptr, count, packed, stream);
+}
+
+extern "C" int mpqe_pack_weights_ex(const float* const* mats_host, const uint8_t* transposed_host, int32_t count,
+                                    float* packed, void* stream) {
   MPQE_CHECK_ARG(mats_host != nullptr && packed != nullptr && count >= 1, "mpqe_pack_weights: bad argument");
-  if (tc_generation() == 2) return pack_weights_tc2(mats_host, count, packed, (cudaStream_t)stream);
+  if (tc_generation() == 2) return pack_weights_tc2(mats_host, transposed_host, count, packed, (cudaStream_t)stream);
+  if (transposed_host != nullptr)
+    for (int i = 0; i < count; ++i)
+      MPQE_CHECK_ARG(!transposed_host[i], "mpqe_pack_weights_ex: the first-generation kernel's image has no transposed "
+                     "form (matrix %d); pass a transposed copy", i);
   for (int base = 0; base < count; base += PACK_MAX) {
     static thread_local PackLaunch P;
     const int n = count - base < PACK_MAX ? count - base : PACK_MAX;

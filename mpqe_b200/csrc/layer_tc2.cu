@@ -445,17 +445,25 @@ struct PackLaunch2 {
 
 __global__ void __launch_bounds__(256) pack_weights2_kernel(const __grid_constant__ PackLaunch2 P,
                                                             float* __restrict__ out) {
-  const float* M = P.m[blockIdx.y];
+  // bit 0 of the pointer: pack the image of M^T (what the input-gradient launches multiply by) straight from M, so the
+  // per-step weight preparation does not have to wait for a transposed copy
+  const uintptr_t tagged = reinterpret_cast<uintptr_t>(P.m[blockIdx.y]);
+  const bool transposed = (tagged & 1) != 0;
+  const float* M = reinterpret_cast<const float*>(tagged & ~(uintptr_t)1);
   const int c = blockIdx.x;                          // k chunk (16 k)
   float* hi_tile = out + ((int64_t)blockIdx.y * (D / KC) + c) * (2 * W_TILE / 4);
   float* lo_tile = hi_tile + W_TILE / 4;
   for (int e = threadIdx.x; e < 128 * 4; e += 256) {   // e -> (n, k quad): lanes run over n (coalesced reads of M rows)
     const int n = e & 127, q = e >> 7;
     float4 x;
-    x.x = M[(int64_t)(c * KC + q * 4 + 0) * D + n];
-    x.y = M[(int64_t)(c * KC + q * 4 + 1) * D + n];
-    x.z = M[(int64_t)(c * KC + q * 4 + 2) * D + n];
-    x.w = M[(int64_t)(c * KC + q * 4 + 3) * D + n];
+    if (transposed) {                                // operand element (n, k) = M^T[k][n] = M[n][k]: 16 contiguous bytes
+      x = *reinterpret_cast<const float4*>(M + (int64_t)n * D + c * KC + q * 4);
+    } else {
+      x.x = M[(int64_t)(c * KC + q * 4 + 0) * D + n];
+      x.y = M[(int64_t)(c * KC + q * 4 + 1) * D + n];
+      x.z = M[(int64_t)(c * KC + q * 4 + 2) * D + n];
+      x.w = M[(int64_t)(c * KC + q * 4 + 3) * D + n];
+    }
     float4 hi, lo;
     split_tf32(x, hi, lo);
     const int off = ((n >> 3) * 512 + q * 128 + (n & 7) * 16) / 4;
@@ -557,13 +565,17 @@ int layer_forward_tc2(const mpqe_layer_group_t* groups, int num_groups, cudaStre
   return 0;
 }
 
-int pack_weights_tc2(const float* const* mats_host, int32_t count, float* packed, cudaStream_t stream) {
+int pack_weights_tc2(const float* const* mats_host, const uint8_t* transposed_host, int32_t count, float* packed,
+                     cudaStream_t stream) {
   for (int base = 0; base < count; base += PACK_MAX) {
     static thread_local PackLaunch2 P;
     const int n = count - base < PACK_MAX ? count - base : PACK_MAX;
     for (int i = 0; i < n; ++i) {
       MPQE_CHECK_ARG(mats_host[base + i] != nullptr, "mpqe_pack_weights: matrix %d is null", base + i);
-      P.m[i] = mats_host[base + i];
+      const uintptr_t tag = transposed_host != nullptr && transposed_host[base + i] ? 1 : 0;
+      MPQE_CHECK_ARG((reinterpret_cast<uintptr_t>(mats_host[base + i]) & 15) == 0,
+                     "mpqe_pack_weights: matrix %d is not 16-byte aligned", base + i);
+      P.m[i] = reinterpret_cast<const float*>(reinterpret_cast<uintptr_t>(mats_host[base + i]) | tag);
     }
     pack_weights2_kernel<<<dim3(D / KC, n), 256, 0, stream>>>(P, packed + (int64_t)base * MPQE_PACKED_FLOATS);
     MPQE_CHECK_LAUNCH("pack_weights2_kernel");

@@ -349,8 +349,12 @@ class Job(object):
 class Weights(object):
     """Per-step views of the dense parameters in the layouts the kernels want."""
 
-    def __init__(self, model, need_grad):
+    def __init__(self, model, need_grad, defer_raw=False):
+        """defer_raw: with the tensor-core kernels the transposed matrices are only READ late in the backward (by the
+        one-row kernels of the batch-constant tail) -- their tile images are packed straight from the untransposed
+        parameters -- so a caller may run `raw_transposes()` itself, off the chain the first layer launch waits for."""
         self.w, self.root, self.bias = [], [], []
+        self.raw_pending, self.raw_event = False, None
         for layer in model.distinct_layers():
             self.w.append(layer.relation_weights().contiguous())
             self.root.append(layer.root)
@@ -367,9 +371,16 @@ class Weights(object):
             self.blocks = self.w1.shape[1] // D
             self.w1t = ops.transpose(self.w1.contiguous())                     # [blocks*D, D]: block p = W1[:, pD:(p+1)D]^T
             self.w2t = ops.transpose(self.w2.contiguous())
+        # second-generation tensor-core kernel: the images of the transposed matrices come from the pack kernel
+        self.pack_transposed = need_grad and ops.tensor_cores_default() and ops.layer_generation() == 2
         if need_grad:
-            self.wt = [ops.transpose(w) for w in self.w]
-            self.roott = [ops.transpose(r) for r in self.root]
+            if self.pack_transposed:
+                self.wt = [torch.empty_like(w) for w in self.w]
+                self.roott = [torch.empty_like(r) for r in self.root]
+                self.raw_pending = True
+            else:
+                self.wt = [ops.transpose(w) for w in self.w]
+                self.roott = [ops.transpose(r) for r in self.root]
             if ro is not None:
                 self.w1b = ops.transpose(self.w1t.view(self.blocks, D, D))     # [blocks, D(u), D(h)] contiguous
         # tcgen05 path: tf32 hi/lo tile images of every matrix, staged by the kernel with one bulk copy per tile;
@@ -377,12 +388,18 @@ class Weights(object):
         self.wp = self.rootp = self.wtp = self.roottp = None
         self.w1tp = self.w2tp = self.w2p = self.w1bp = None
         if ops.tensor_cores_default():
-            mats = []
+            mats, flags = [], []
             for li in range(len(self.w)):
-                mats += [self.w[li][r] for r in range(self.w[li].shape[0])] + [self.root[li]]
-                if need_grad:
+                fwd = [self.w[li][r] for r in range(self.w[li].shape[0])] + [self.root[li]]
+                mats += fwd
+                flags += [0] * len(fwd)
+                if need_grad and self.pack_transposed:
+                    mats += fwd
+                    flags += [1] * len(fwd)
+                elif need_grad:
                     mats += [self.wt[li][r] for r in range(self.wt[li].shape[0])] + [self.roott[li]]
-            packed = ops.pack_weights(mats)
+                    flags += [0] * len(fwd)
+            packed = ops.pack_weights(mats, flags)
             self.wp, self.rootp, self.wtp, self.roottp = [], [], [], []
             off = 0
             for li in range(len(self.w)):
@@ -405,6 +422,21 @@ class Weights(object):
                 self.w1tp, self.w2tp = packed[:self.blocks], packed[self.blocks]
                 if need_grad:
                     self.w2p, self.w1bp = packed[self.blocks + 1], packed[self.blocks + 2:]
+        self.msum = self.msumt = None
+        if not defer_raw:
+            self.raw_transposes()
+
+    def raw_transposes(self):
+        """Fills the transposed copies whose tile images were packed from the untransposed matrices."""
+        if not self.raw_pending:
+            return
+        for w, wt in zip(self.w, self.wt):
+            ops.transpose(w, wt)
+        for r, rt in zip(self.root, self.roott):
+            ops.transpose(r, rt)
+        if self.msum is not None and self.msumt is not None:
+            ops.transpose(self.msum, self.msumt)
+        self.raw_pending = False
 
 
 def _needed_slots(job, readout):
@@ -537,14 +569,19 @@ class Engine(object):
         ops.matrix_sum_multi([(W.msum[k], [self._pmat(W, li, key, 'm') for key in keys], False)
                               for k, (li, keys) in enumerate(W.msum_keys)])
         tc = ops.tensor_cores_default()
+        K = len(W.msum_keys)
+        deferred = W.need_grad and getattr(W, 'raw_pending', False)
         if W.need_grad:
-            W.msumt = ops.transpose(W.msum)
+            W.msumt = torch.empty_like(W.msum) if deferred else ops.transpose(W.msum)   # (filled by raw_transposes)
             W.dmsum = torch.empty_like(W.msum)
         if tc:
-            packed = ops.pack_weights([W.msum[k] for k in range(len(W.msum_keys))] +
-                                      ([W.msumt[k] for k in range(len(W.msum_keys))] if W.need_grad else []))
-            W.msump = packed[:len(W.msum_keys)]
-            W.msumtp = packed[len(W.msum_keys):] if W.need_grad else None
+            fwd = [W.msum[k] for k in range(K)]
+            if deferred:
+                packed = ops.pack_weights(fwd + fwd, [0] * K + [1] * K)
+            else:
+                packed = ops.pack_weights(fwd + ([W.msumt[k] for k in range(K)] if W.need_grad else []))
+            W.msump = packed[:K]
+            W.msumtp = packed[K:] if W.need_grad else None
 
     @staticmethod
     def _pgrad(G, li, key):
@@ -845,6 +882,8 @@ class Engine(object):
         cjobs = [job for job in jobs if getattr(job, 'const_fwd', None) is not None]
         if not cjobs:
             return
+        if getattr(W, 'raw_event', None) is not None:     # transposed copies filled on another stream (TrainStep)
+            torch.cuda.current_stream().wait_event(W.raw_event)
         by_layer = {}
         for job in cjobs:
             by_layer.setdefault(self.layer_index(0, job.P), []).append(job)

@@ -300,16 +300,25 @@ def matrix_sum_multi(items):
 PACKED_FLOATS = 2 * D * D
 
 
-def pack_weights(mats):
+def layer_generation():
+    """Which tcgen05 layer kernel the library dispatches to (MPQE_LAYER_KERNEL=1: the first-generation kernel)."""
+    import os
+    return 1 if os.environ.get('MPQE_LAYER_KERNEL') == '1' else 2
+
+
+def pack_weights(mats, transposed=None):
     """mats: [count, D, D] tensor (or list of [D, D] views) -> [count, PACKED_FLOATS] tf32 hi/lo tile images for the
-    tensor-core layer kernel (see mpqe_pack_weights)."""
+    tensor-core layer kernel (see mpqe_pack_weights).  transposed[i]: pack the image of mats[i]^T instead."""
     lib = _lib.load()
     views = [mats[i] for i in range(mats.shape[0])] if torch.is_tensor(mats) else list(mats)
     for v in views:
         _chk(v, torch.float32, 'matrix')
     out = torch.empty(len(views), PACKED_FLOATS, dtype=torch.float32, device=views[0].device)
     ptrs = (C.c_void_p * len(views))(*[v.data_ptr() for v in views])
-    _lib.check(lib.mpqe_pack_weights(ptrs, len(views), _ptr(out), _stream()), 'mpqe_pack_weights')
+    flags = None
+    if transposed is not None and any(transposed):
+        flags = (C.c_uint8 * len(views))(*[1 if f else 0 for f in transposed])
+    _lib.check(lib.mpqe_pack_weights_ex(ptrs, flags, len(views), _ptr(out), _stream()), 'mpqe_pack_weights')
     _count((len(views) + 255) // 256)
     return out
 

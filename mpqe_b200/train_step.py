@@ -193,10 +193,15 @@ class TrainStep(object):
             self._side = torch.cuda.Stream(device=dev)
         self._side.wait_stream(cur)
         with torch.cuda.stream(self._side):
-            W = Weights(self.model, True)
+            W = Weights(self.model, True, defer_raw=True)
             self.model._engine.prepare(jobs, W)
             W.ready_event = torch.cuda.Event()
             W.ready_event.record(self._side)
+            # the transposed copies themselves are read only by the one-row kernels at the end of the backward
+            if W.raw_pending:
+                W.raw_transposes()
+                W.raw_event = torch.cuda.Event()
+                W.raw_event.record(self._side)
         return W
 
     def _join_side(self, dev):

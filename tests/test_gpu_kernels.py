@@ -576,3 +576,13 @@ def test_auc_counts_match_sklearn(P, N):
         labels = np.concatenate([np.ones(P), np.zeros(N)])
         want = roc_auc_score(labels, np.nan_to_num(np.concatenate([pos, neg])))
         assert abs(got - want) < 1e-12
+
+
+def test_pack_weights_transposed_flag_equals_packing_a_transposed_copy():
+    """The tile image of M^T packed straight from M is bit-identical to the image packed from a transposed copy."""
+    m = rnd(5, D, D, seed=9).to(DEV)
+    with torch.cuda.device(0):
+        mt = ops.transpose(m)
+        want = ops.pack_weights([mt[i] for i in range(5)] + [m[i] for i in range(5)])
+        got = ops.pack_weights([m[i] for i in range(5)] * 2, [1] * 5 + [0] * 5)
+    assert torch.equal(got, want)
