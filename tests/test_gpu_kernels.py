@@ -542,12 +542,13 @@ def test_rgcn_conv_basis_decomposition_on_device():
     x = torch.randn(37 * t.num_nodes, 128)
     pc = {k: v.detach().clone().requires_grad_(True) for k, v in conv.named_parameters()}
     xc = x.clone().requires_grad_(True)
-    want = O.rgcn_conv(xc, g.edge_index, g.edge_type, pc['basis'], pc['root'], pc['bias'], att=pc['att'])
+    gd = g.to(DEV)       # (the edge list is materialised by a kernel)
+    want = O.rgcn_conv(xc, gd.edge_index.cpu(), gd.edge_type.cpu(), pc['basis'], pc['root'], pc['bias'], att=pc['att'])
     wgt = torch.randn_like(want)
     (want * wgt).sum().backward()
     conv = conv.to(DEV)
     xd = x.to(DEV).requires_grad_(True)
-    out = conv(xd, g.to(DEV))
+    out = conv(xd, gd)
     assert_close(out.detach().cpu().numpy(), want.detach().numpy(), 1e-5, 1e-5, 'conv out (bases)')
     (out * wgt.to(DEV)).sum().backward()
     assert_close(xd.grad.cpu().numpy(), xc.grad.numpy(), 1e-4, 1e-5, 'dx')
