@@ -21,6 +21,8 @@
 //                           no shared-memory transpose.  Two 256-column accumulators ping-pong (all 512 TMEM columns).
 #include <stdlib.h>
 
+#include <cuda.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -35,7 +37,9 @@ constexpr int PROD_WARPS = 8;
 constexpr int PROD_THREADS = PROD_WARPS * 32;
 constexpr int MMA_WARP = EPI_WARPS + PROD_WARPS;
 constexpr int TMA_WARP = MMA_WARP + 1;             // one thread of it stages the weight chunks (bulk copies)
+constexpr int XLOAD_WARP = TMA_WARP + 1;           // TMAX kernel: one thread of it loads the activation tiles (TMA)
 constexpr int THREADS = (TMA_WARP + 1) * 32;     // 448
+constexpr int THREADS_X = (XLOAD_WARP + 1) * 32; // 480
 constexpr int BQ = 256;                          // queries per unit = UMMA N
 constexpr int KC = 16;                           // k per pipeline stage = 2 UMMA k-steps of 8
 constexpr int STAGES = 3;
@@ -58,8 +62,25 @@ struct Shared2 {
   uint64_t empty[STAGES];
   uint64_t acc_full[2];
   uint64_t acc_empty[2];
+  uint64_t raw_full[RING];    // TMAX kernel: a raw activation tile has landed in its ring slot
+  uint64_t raw_empty[RING];   //              ... and has been read by every producer warp
   uint32_t tmem_base;
 };
+
+// TMAX kernel: the activation operands as 3-D tensor maps {128 k, slots, queries} (fp32, box {16 k, 1 slot, 256 queries},
+// 64-byte swizzle); of[group][term] = map of that term's operand
+constexpr int MAX_XMAPS = 24;
+struct alignas(64) XMaps {
+  CUtensorMap map[MAX_XMAPS];
+  uint8_t of[MPQE_MAX_GROUPS][MPQE_MAX_TERMS];
+};
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
 
 __device__ __forceinline__ uint8_t* align_1024(uint8_t* p) {
   return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023));
@@ -136,8 +157,12 @@ __device__ __forceinline__ uint32_t epi_block(const uint32_t (&v)[32], float bv,
   return pos;
 }
 
-__global__ void __launch_bounds__(THREADS, 1) layer_tc2_kernel(const __grid_constant__ LayerLaunch L,
-                                                               const __grid_constant__ Schedule S) {
+// TMAX: the raw activation tiles are brought into the ring by TMA tensor loads issued by one thread (warp XLOAD_WARP)
+// instead of by cp.async from the eight producer warps.
+template <bool TMAX>
+__global__ void __launch_bounds__(THREADS_X, 1) layer_tc2_kernel(const __grid_constant__ LayerLaunch L,
+                                                                 const __grid_constant__ Schedule S,
+                                                                 const __grid_constant__ XMaps XM) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ Shared2 sh;
   uint8_t* smem = align_1024(smem_raw);
@@ -154,6 +179,10 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc2_kernel(const __grid_cons
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(&sh.acc_full[b]), 1);
       mbar_init(smem_u32(&sh.acc_empty[b]), EPI_WARPS * 32);
+    }
+    for (int r = 0; r < RING; ++r) {
+      mbar_init(smem_u32(&sh.raw_full[r]), 1);
+      mbar_init(smem_u32(&sh.raw_empty[r]), PROD_WARPS);
     }
     fence_barrier_init();
   }
@@ -178,6 +207,53 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc2_kernel(const __grid_cons
     const int ptid = tid - EPI_WARPS * 32;                                // 0..255
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t my_off = pw * 4 * 512 + kq * 128 + (lane & 7) * 16;   // this thread's 16 bytes of row group 4 pw
+    if constexpr (TMAX) {
+      // the tiles arrive by TMA as [256 rows][64 bytes] with the 64-byte swizzle (16-byte chunk c of row r at chunk
+      // c ^ ((r >> 1) & 3)): with lane & 7 = row and lane >> 3 = chunk a quarter-warp's 16-byte reads fall into eight
+      // different bank groups, and the stores into the operand tiles are the same as in the cp.async version
+      uint32_t nst = 0;
+      {
+        Unit2 U0{0, 0, 0};
+        uint32_t m0;
+        for (int k = 0; next_unit(S, k, U0, m0); ++k) nst += __popc(m0) * (D / KC);
+      }
+      const uint32_t ring0 = smem_base + STAGES * STAGE_BYTES;
+      const uint32_t src_off = (uint32_t)(pw * 4 * 8 + (lane & 7)) * 64 + (uint32_t)((kq ^ ((lane >> 1) & 3)) * 16);
+      ST_DECL;
+#pragma unroll 1
+      for (uint32_t it = 0; it < nst; ++it) {
+        const int slot = it % RING;
+        ST_BEGIN();
+        mbar_wait(smem_u32(&sh.raw_full[slot]), (it / RING) & 1);
+        ST_END(3);   // waiting for the rows
+        const int s = it % STAGES;
+        const uint32_t use = it / STAGES;
+        ST_BEGIN();
+        if (use > 0) mbar_wait(smem_u32(&sh.empty[s]), (use - 1) & 1);
+        ST_END(0);   // waiting for a free stage
+        ST_BEGIN();
+        const uint32_t src = ring0 + slot * RING_SLOT + src_off;
+        const uint32_t xh = smem_base + s * STAGE_BYTES + 2 * W_TILE + my_off;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float4 x, hi, lo;
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                       : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
+                       : "r"(src + i * 512));
+          split_tf32_fast(x, hi, lo);
+          sts128(xh + i * 512, hi);
+          sts128(xh + i * 512 + X_TILE, lo);
+        }
+        ST_END(1);   // load back + split + stores
+        ST_BEGIN();
+        fence_proxy_async();
+        mbar_arrive(smem_u32(&sh.full[s]));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&sh.raw_empty[slot]));   // this warp has read its rows of the slot
+        ST_END(2);   // fence + arrive
+      }
+      if (pw == 0 && lane == 0) { ST_FLUSH(0, 4); }
+    } else {
     const uint32_t ring = smem_base + STAGES * STAGE_BYTES + ptid * 16;  // raw ring: [slot][i][thread] 16-byte pieces
     // load-side iterator over (unit, term, k chunk), LOADS_AHEAD stages ahead of the stores
     int uk = 0;
@@ -225,11 +301,19 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc2_kernel(const __grid_cons
     ST_DECL;
 #pragma unroll 1
     for (uint32_t it = 0;; ++it) {
+#ifdef MPQE_TC_STATS_FETCH                                                  // (debug: slot 3 = time in fetch_next)
+      ST_BEGIN();
+      fetch_next();
+      ST_END(3);
+      if (it >= issued) break;
+      asm volatile("cp.async.wait_group %0;" ::"n"(LOADS_AHEAD) : "memory");
+#else
       fetch_next();                                                        // stage it + LOADS_AHEAD
       if (it >= issued) break;                                             // nothing left: all issued stages stored
       ST_BEGIN();
       asm volatile("cp.async.wait_group %0;" ::"n"(LOADS_AHEAD) : "memory");   // stage `it` has landed (own pieces)
       ST_END(3);   // waiting for the rows
+#endif
       const int s = it % STAGES;
       const uint32_t use = it / STAGES;
       ST_BEGIN();
@@ -259,6 +343,31 @@ __global__ void __launch_bounds__(THREADS, 1) layer_tc2_kernel(const __grid_cons
       ST_END(2);   // fence + arrive
     }
     if (pw == 0 && lane == 0) { ST_FLUSH(0, 4); }
+    }   // !TMAX
+  } else if (TMAX && warp == XLOAD_WARP) {
+    // ===== activation loader (one thread): one 16 KB tensor load per stage, RING stages ahead =========================
+    if (lane == 0) {
+      uint32_t it = 0;
+      int uc = 0;
+      Unit2 U{0, 0, 0};
+      const uint32_t ring0 = smem_u32(smem) + STAGES * STAGE_BYTES;
+      for (uint32_t umask; next_unit(S, uc, U, umask); ++uc) {
+        const mpqe_layer_group_t& G = L.g[U.gi];
+        for (uint32_t m = umask; m != 0; m &= m - 1) {
+          const int t = __ffs(m) - 1;
+          const CUtensorMap* map = &XM.map[XM.of[U.gi][t]];
+          const int a_slot = G.terms[t].a_slot;
+          for (int c = 0; c < D / KC; ++c, ++it) {
+            const int slot = it % RING;
+            const uint32_t use = it / RING;
+            if (use > 0) mbar_wait(smem_u32(&sh.raw_empty[slot]), (use - 1) & 1);
+            const uint32_t bar = smem_u32(&sh.raw_full[slot]);
+            mbar_arrive_expect_tx(bar, X_TILE);
+            tma_load_3d(ring0 + slot * RING_SLOT, map, c * KC, a_slot, (int)U.q0, bar);
+          }
+        }
+      }
+    }
   } else if (warp == TMA_WARP) {
     // ===== weight stager (one thread): one 16 KB bulk copy of the pre-split chunk per stage ===========================
     // (a thread of its own: issued from a producer warp, the copy instruction held that warp -- and with it every
@@ -485,6 +594,60 @@ int sm_count() {
 
 }  // namespace
 
+// Tensor maps of the activation operands of one launch.  Returns false when the launch has to use the cp.async loader:
+// broadcast operands (a_slots == 0: a tensor map has no zero stride), more distinct operands than MAX_XMAPS, a driver
+// without cuTensorMapEncodeTiled, or MPQE_LAYER_LOADS=cpasync (A/B measurements).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static bool build_xmaps(const mpqe_layer_group_t* groups, int num_groups, XMaps& XM) {
+  static int mode = -1;   // 0: cp.async, 1: TMA
+  static EncodeTiledFn encode = nullptr;
+  if (mode < 0) {
+    const char* e = getenv("MPQE_LAYER_LOADS");
+    mode = (e != nullptr && strcmp(e, "cpasync") == 0) ? 0 : 1;
+    if (mode == 1) {
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult q;
+      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+          q != cudaDriverEntryPointSuccess || fn == nullptr) {
+        (void)cudaGetLastError();
+        mode = 0;
+      }
+      encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+  }
+  if (mode == 0) return false;
+  struct Key {
+    const float* a;
+    int32_t slots;
+    int64_t nq;
+  };
+  Key keys[MAX_XMAPS];
+  int n = 0;
+  for (int i = 0; i < num_groups; ++i)
+    for (int t = 0; t < groups[i].num_terms; ++t) {
+      const mpqe_term_t& T = groups[i].terms[t];
+      if (T.a_slots <= 0 || (reinterpret_cast<uintptr_t>(T.a) & 15) != 0) return false;
+      int k = 0;
+      while (k < n && !(keys[k].a == T.a && keys[k].slots == T.a_slots && keys[k].nq == groups[i].num_queries)) ++k;
+      if (k == n) {
+        if (n == MAX_XMAPS) return false;
+        keys[n++] = Key{T.a, T.a_slots, groups[i].num_queries};
+        const cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)T.a_slots, (cuuint64_t)groups[i].num_queries};
+        const cuuint64_t strides[2] = {(cuuint64_t)D * 4, (cuuint64_t)T.a_slots * D * 4};   // bytes, dims 1 and 2
+        const cuuint32_t box[3] = {(cuuint32_t)KC, 1u, (cuuint32_t)BQ};
+        const cuuint32_t estr[3] = {1u, 1u, 1u};
+        const CUresult r = encode(&XM.map[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(T.a), dims, strides,
+                                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return false;
+      }
+      XM.of[i][t] = (uint8_t)k;
+    }
+  return true;
+}
+
 static int launch_tc2(const mpqe_layer_group_t* groups, int num_groups, cudaStream_t stream) {
   static thread_local LayerLaunch L;
   memset(&L, 0, sizeof(L));
@@ -523,7 +686,12 @@ static int launch_tc2(const mpqe_layer_group_t* groups, int num_groups, cudaStre
     S.tile[pos] = tile_of[S.unit[pos]];
     S.gsm[pos] = gsm_of[S.unit[pos]];
   }
-  layer_tc2_kernel<<<grid, THREADS, TC2_SMEM, stream>>>(L, S);
+  static thread_local XMaps XM;
+  if (build_xmaps(groups, num_groups, XM)) {
+    layer_tc2_kernel<true><<<grid, THREADS_X, TC2_SMEM, stream>>>(L, S, XM);
+  } else {     // (operands a tensor map cannot describe, or MPQE_LAYER_LOADS=cpasync)
+    layer_tc2_kernel<false><<<grid, THREADS, TC2_SMEM, stream>>>(L, S, XM);
+  }
   MPQE_CHECK_LAUNCH("layer_tc2_kernel");
   return 0;
 }
@@ -531,7 +699,8 @@ static int launch_tc2(const mpqe_layer_group_t* groups, int num_groups, cudaStre
 int layer_forward_tc2(const mpqe_layer_group_t* groups, int num_groups, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    MPQE_CUDA(cudaFuncSetAttribute(layer_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC2_SMEM));
+    MPQE_CUDA(cudaFuncSetAttribute(layer_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC2_SMEM));
+    MPQE_CUDA(cudaFuncSetAttribute(layer_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC2_SMEM));
     configured = true;
   }
   int slots = 0;
