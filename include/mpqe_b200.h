@@ -263,9 +263,7 @@ MPQE_API int mpqe_gather_multi(const mpqe_gather_item_t* items_host, int32_t n, 
 /* One formula group of the margin loss (model.py:451-452, 483-485); fields as mpqe_cosine_margin_{fwd,bwd}.
  * hinge is a [B] scratch array; id_offset is added to the emitted table row ids.
  * backward: 0 = forward (hinge, loss), 1 = backward (dq, rows), 2 = both in one pass over q and the table rows --
- * usable when d total / d loss (grad_loss) is known before the forward, as in a training step; 3 = as 2 but without
- * the per-item mean (hinge is written, loss is not), 4 = only that mean (loss from hinge): lets a caller put the mean,
- * which nothing in the backward depends on, onto another stream. */
+ * usable when d total / d loss (grad_loss) is known before the forward, as in a training step. */
 typedef struct {
   const float* q;
   int64_t B;

@@ -302,17 +302,14 @@ extern "C" int mpqe_cosine_margin_multi(const mpqe_margin_item_t* items_host, in
   for (int i = 0; i < n; ++i) {
     const mpqe_margin_item_t& T = items_host[i];
     MPQE_CHECK_ARG(T.q && T.table && T.ids_pos && T.ids_neg && T.B >= 1, "mpqe_cosine_margin_multi: item %d: bad argument", i);
-    if (backward && backward != 4)
+    if (backward)
       MPQE_CHECK_ARG(T.grad_loss && T.dq && T.rows_out && T.rows_id, "mpqe_cosine_margin_multi: item %d: bad bwd argument", i);
     if (backward != 1)
       MPQE_CHECK_ARG(T.hinge && T.loss, "mpqe_cosine_margin_multi: item %d: bad fwd argument", i);
     L.it[i] = T;
     total += T.B;
   }
-  if (backward == 4) {     // the per-item means of a mode-3 call, e.g. on another stream (nothing in a step's backward
-    margin_mean_multi_kernel<<<n, 1024, 0, (cudaStream_t)stream>>>(L);   // depends on the loss values)
-    MPQE_CHECK_LAUNCH("margin_mean_multi_kernel");
-  } else if (backward) {
+  if (backward) {
     margin_bwd_multi_kernel<<<row_blocks(total), ROW_THREADS, 0, (cudaStream_t)stream>>>(L);
     MPQE_CHECK_LAUNCH("margin_bwd_multi_kernel");
     if (backward == 2) {   // fused: the gradient of the total wrt each loss is known up front (grad_loss)

@@ -1027,7 +1027,7 @@ class RowGrads(object):
 class Grads(object):
     """Dense gradient buffers (zero-initialised, kernels accumulate) + the row-gradient collector."""
 
-    def __init__(self, model, W, row_capacities, device, table_offsets=None, rows=None, flat=None, zero=True):
+    def __init__(self, model, W, row_capacities, device, table_offsets=None, rows=None, flat=None):
         self.device = device
         self.colsums, self.gathers, self.keep = [], [], []
         # one flat zeroed bucket: a single memset here, a single NCCL all-reduce in data-parallel training
@@ -1039,7 +1039,7 @@ class Grads(object):
         if flat is not None:       # caller-provided bucket (peer-visible memory in data-parallel training)
             if flat.numel() != sum(sizes):
                 raise ops._lib.MpqeError('dense gradient bucket has %d elements, need %d' % (flat.numel(), sum(sizes)))
-            self.flat = flat.zero_() if zero else flat      # (zero=False: the caller has zeroed it already)
+            self.flat = flat.zero_()
         else:
             self.flat = torch.zeros(sum(sizes), dtype=torch.float32, device=device)
         self._layout = (shapes, sizes, len(W.w), W.ro is not None)
@@ -1268,8 +1268,7 @@ def _one(x, i):
     return x[i] if isinstance(x, (list, tuple)) else x[i:i + 1]
 
 
-def loss_forward(model, jobs, targets, negatives, margin, need_grad, grad_losses=None, W=None, losses_out=None,
-                 later=None):
+def loss_forward(model, jobs, targets, negatives, margin, need_grad, grad_losses=None, W=None, losses_out=None):
     """Encodes every job once and scores it against its positives and negatives.
     Returns (per-job losses [len(jobs)] on the device, Weights).  With `grad_losses` (d total / d loss_i, known up
     front in a training step) and row slots reserved by `plan_rows`, the margin backward (job.dq and the target /
@@ -1293,13 +1292,7 @@ def loss_forward(model, jobs, targets, negatives, margin, need_grad, grad_losses
             it.rows_out, it.rows_id, it.rows_offset, it.id_offset = rbuf, ids, roff, id_off
         items.append(it)
         off += job.B
-    if grad_losses is not None and later is not None:
-        # `later`: a list that receives what nothing downstream waits for (the per-batch means of the hinge terms) as
-        # closures the caller runs where it likes, e.g. on another stream
-        ops.cosine_margin_multi(items, margin, backward='both-no-mean')
-        later.append(lambda: ops.cosine_margin_multi(items, margin, backward='mean'))
-    else:
-        ops.cosine_margin_multi(items, margin, backward='both' if grad_losses is not None else False)
+    ops.cosine_margin_multi(items, margin, backward='both' if grad_losses is not None else False)
     return losses, W
 
 
@@ -1334,14 +1327,14 @@ def plan_rows(model, jobs, targets, negatives, table_offsets, rows_buffer=None, 
 
 
 def loss_backward(model, jobs, W, targets, negatives, margin, grad_losses, table_offsets=None, rows=None,
-                  defer_constant=False, flat=None, side=None, zero_flat=True):
+                  defer_constant=False, flat=None, side=None):
     """Backward of `loss_forward` for d(total)/d(loss_i) = grad_losses[i] (device tensor [len(jobs)]).
     Returns the filled `Grads` (dense bucket + (row id, gradient row) pairs, not yet combined).  `rows`: a RowGrads
     from `plan_rows` (slots reserved and ids already emitted).  `defer_constant`: leave the batch-constant tail of the
     backward to the caller as `G.finish()` (the dense gradients are complete only after it)."""
     device = jobs[0].anchor_ids.device
     cap = model._row_capacities(jobs, [(job.target_mode, 2 * job.B) for job in jobs]) if rows is None else None
-    G = Grads(model, W, cap, device, table_offsets, rows, flat, zero_flat)
+    G = Grads(model, W, cap, device, table_offsets, rows, flat)
     dqs, items = [], []
     for i, (job, tgt, neg) in enumerate(zip(jobs, targets, negatives)):
         if G.rows.planned and getattr(job, 'dq', None) is not None:

@@ -741,16 +741,15 @@ class MarginItem(object):
 
 def cosine_margin_multi(items, margin, backward=False):
     """backward: False = forward (losses), True = backward (dq, table rows), 'both' = one pass doing both (needs
-    grad_loss before the forward: a training step knows d total / d loss_i up front), 'both-no-mean' / 'mean' = the
-    two halves of 'both' (the means can then run on another stream)."""
+    grad_loss before the forward: a training step knows d total / d loss_i up front)."""
     lib = _lib.load()
-    mode = {'both': 2, 'both-no-mean': 3, 'mean': 4}.get(backward, int(bool(backward)))
+    mode = 2 if backward == 'both' else int(bool(backward))
     for i in range(0, len(items), _lib.MAX_MARGIN_ITEMS):
         chunk = items[i:i + _lib.MAX_MARGIN_ITEMS]
         arr = (_lib.MarginItem * len(chunk))(*[it.to_c() for it in chunk])
         _lib.check(lib.mpqe_cosine_margin_multi(arr, len(chunk), margin, mode, _stream()),
                    'mpqe_cosine_margin_multi')
-        _count(2 if mode in (0, 2) else 1)
+        _count(1 if mode == 1 else 2)
 
 
 class ColsumItem(object):

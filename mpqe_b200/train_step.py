@@ -111,9 +111,6 @@ class TrainStep(object):
         self._side = None   # second stream for the id-only half of the row-gradient combine
         self._wgrad_stream = None   # third stream: weight gradients next to the input-gradient launches
         self.overlap_wgrad = os.environ.get('MPQE_OVERLAP_WGRAD', '1') != '0'
-        self.x_zero_side = os.environ.get('MPQE_X_ZERO_SIDE', '0') == '1'
-        self.x_mean_side = os.environ.get('MPQE_X_MEAN_SIDE', '0') == '1'
-        self.x_ids_side = os.environ.get('MPQE_X_IDS_SIDE', '0') == '1'
         self.rank = torch.distributed.get_rank(process_group) if self._dist() else 0
         self.peers = None        # PeerGroup (world > 1, peer-mapped memory available)
         self._xcap = None        # pairs per rank the exchange buffers were set up for
@@ -201,23 +198,11 @@ class TrainStep(object):
             W.ready_event = torch.cuda.Event()
             W.ready_event.record(self._side)
             # the transposed copies themselves are read only by the one-row kernels at the end of the backward
-            W.zeroed_flat = None
-            if W.raw_pending or self.x_zero_side:
+            if W.raw_pending:
                 W.raw_transposes()
-                if self.x_zero_side:      # the dense bucket is zeroed here too, off the main stream
-                    W.zeroed_flat = self._step_bucket(dev).zero_()
                 W.raw_event = torch.cuda.Event()
                 W.raw_event.record(self._side)
         return W
-
-    def _step_bucket(self, dev):
-        """The dense gradient bucket of a step: the peer-visible one with several ranks, else a persistent local one."""
-        if self.peers is not None and self._xflat is not None:
-            return self._xflat
-        n = sum(int(p.numel()) for p in self._dense_shapes())
-        if getattr(self, '_flat_local', None) is None or self._flat_local.numel() != n:
-            self._flat_local = torch.empty(n, dtype=torch.float32, device=dev)
-        return self._flat_local
 
     def _join_side(self, dev):
         torch.cuda.current_stream(dev).wait_stream(self._side)
@@ -372,7 +357,7 @@ class TrainStep(object):
         # which then crowds out the small weight-preparation kernels the first layer launch waits for: +9 us per step)
         R = plan_rows(m, jobs, tg, ng, self.table_offsets,
                       rows_buffer=(lambda cap: self._xrows) if peer else None,
-                      ids_buffer=(lambda cap: self._xids) if peer else None, launch=multi or not self.x_ids_side)
+                      ids_buffer=(lambda cap: self._xids) if peer else None)
         rows, ids, used = R.shared
         if multi and used != self._xcap:
             raise ops._lib.MpqeError('data-parallel step: %d (row id, row) pairs, the exchange was set up for %d; call '
@@ -385,11 +370,7 @@ class TrainStep(object):
         W = self._weights_on_side_stream(jobs, dev)
         all_ids = None
         if not multi:
-            def ids_then_plan():
-                if self.x_ids_side:
-                    ops.gather_multi(R.id_items, backward='ids')
-                return ops.SparseRowsPlan(ids[:used], self.total_rows)
-            plan = self._plan_on_side_stream(ids_then_plan, dev, keep=(ids,))
+            plan = self._plan_on_side_stream(lambda: ops.SparseRowsPlan(ids[:used], self.total_rows), dev, keep=(ids,))
         else:
             if peer:
                 id_src = self._id_ptrs
@@ -405,18 +386,11 @@ class TrainStep(object):
         if wts is None or wts[0] != key:
             wts = self._wts = (key, torch.tensor(key, dtype=torch.float32, device=dev))
         # d total / d loss_i = the batch weights, known now: the margin backward rides on the margin forward
-        later = [] if (self.x_mean_side and self.overlap_wgrad) else None
-        losses, W = loss_forward(m, jobs, tg, ng, self.margin, True, grad_losses=wts[1], W=W, later=later)
+        losses, W = loss_forward(m, jobs, tg, ng, self.margin, True, grad_losses=wts[1], W=W)
         mark('forward')
         side = (lambda fn: self._on_wgrad_stream(dev, fn), lambda: self._join_wgrad(dev)) if self.overlap_wgrad else None
-        if later:
-            self._on_wgrad_stream(dev, lambda: [fn() for fn in later])
-        flat, zero_flat = (self._xflat if peer else None), True
-        if W.zeroed_flat is not None:
-            torch.cuda.current_stream(dev).wait_event(W.raw_event)
-            flat, zero_flat = W.zeroed_flat, False
         G = loss_backward(m, jobs, W, tg, ng, self.margin, wts[1], self.table_offsets, rows=R,
-                          defer_constant=not multi, flat=flat, side=side, zero_flat=zero_flat)
+                          defer_constant=not multi, flat=self._xflat if peer else None, side=side)
         if not multi:
             self._wait_plan(dev)
             # the batch-constant tail of the backward (five small latency-bound launches) runs on another stream

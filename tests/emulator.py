@@ -303,7 +303,6 @@ def install(monkeypatch):
     def weights_now(self, jobs, dev):
         W = M.Weights(self.model, True)
         self.model._engine.prepare(jobs, W)
-        W.zeroed_flat = None
         return W
 
     monkeypatch.setattr(TrainStep, '_plan_on_side_stream', lambda self, make_plan, dev, keep=(): make_plan())
