@@ -24,6 +24,7 @@ buffers assembled with torch.distributed all_gather / all_reduce.
 """
 import os
 
+import numpy as np
 import torch
 
 from . import ops
@@ -149,6 +150,28 @@ class TrainStep(object):
         job = Job(t, rels, var_dev, hb.formula.anchor_modes, hb.formula.target_mode, device_ids[0], passes)
         job.var_rows_host = var_host
         return Batch(job, device_ids[1], device_ids[2], hb.weight)
+
+    def check_ids(self, hb):
+        """Raises IndexError (as the reference's nn.Embedding lookup would, data_utils.py:35) when a host batch holds an
+        entity id that is unknown or not of the mode its slot has.  The kernels do not validate ids -- an unknown id
+        would index its table at row -1 -- so loaders check the ids they are built from (`capture` does it for its
+        batches; a `replay` / `forward_backward` on ids from elsewhere should be preceded by this check)."""
+        maps = getattr(self, '_node_maps_host', None)
+        if maps is None:
+            maps = self._node_maps_host = self.model.enc.node_maps.cpu().numpy()
+        rows = {m: mod.weight.shape[0] - 1 for m, mod in self.model.enc.feature_modules.items()}
+        f = hb.formula
+        cols = [(hb.anchor_ids[:, i], m) for i, m in enumerate(f.anchor_modes)]
+        cols += [(hb.targets, f.target_mode), (hb.negatives, f.target_mode)]
+        for ids, mode in cols:
+            ids = np.asarray(ids).reshape(-1)
+            if ids.size == 0:
+                continue
+            if ids.min() < 0 or ids.max() >= maps.shape[0]:
+                raise IndexError('entity id out of range in a %s batch (mode %s)' % (f.query_type, mode))
+            r = maps[ids]
+            if (r < 0).any() or (r >= rows[mode]).any():
+                raise IndexError('entity id without a row in the %s table (batch of %s)' % (mode, f.query_type))
 
     def refresh(self, batch):
         """A Batch can be re-run: drop the activations of the previous step."""
@@ -481,6 +504,8 @@ class TrainStep(object):
         with ops.device_guard(dev):
             # all ids of a step live in ONE device buffer mirrored by ONE pinned host buffer: a step's input is a
             # single H2D copy instead of three small copies per formula batch
+            for hb in host_batches:
+                self.check_ids(hb)
             total = sum(hb.anchor_ids.numel() + hb.targets.numel() + hb.negatives.numel() for hb in host_batches)
             self._host_ids = torch.empty(total, dtype=torch.int64).pin_memory()
             self._dev_ids = torch.empty(total, dtype=torch.int64, device=dev)

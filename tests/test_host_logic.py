@@ -303,3 +303,28 @@ def test_readout_modules_forward_with_the_reference_signature(kind, op, monkeypa
     for name, prm in (('readout.layers.0.weight', mod.layers[0].weight), ('readout.layers.0.bias', mod.layers[0].bias),
                       ('readout.layers.2.weight', mod.layers[2].weight), ('readout.layers.2.bias', mod.layers[2].bias)):
         np.testing.assert_allclose(prm.grad.numpy(), p[name].grad.numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_train_step_check_ids_rejects_unknown_entities():
+    """The kernels index the tables without validating ids (the reference's nn.Embedding raises IndexError); the step's
+    host-side check does, and `capture` runs it on its batches."""
+    from mpqe_b200 import synthetic
+    from mpqe_b200.graph import Formula
+    from mpqe_b200.train_step import HostBatch, TrainStep
+    kg = synthetic.make_kg('tiny', seed=5)
+    rels, _, node_maps = kg.raw()
+    cfg = O.Config(readout='sum', num_layers=2)
+    params = O.init_params(rels, node_maps, cfg, d=128, seed=1)
+    model = build_model(kg.raw(), cfg, params, 'cpu', sparse_grad=True)
+    ts = TrainStep(model)
+    f = Formula('2-inter', kg.sample_formula('2-inter', np.random.RandomState(0)))
+    a, t, n = synthetic.sample_id_batch(kg, f, 8, np.random.RandomState(1))
+    ts.check_ids(HostBatch(f, torch.from_numpy(a), torch.from_numpy(t), torch.from_numpy(n)))
+    bad = a.copy()
+    bad[3, 1] = 10 ** 9
+    with pytest.raises(IndexError):
+        ts.check_ids(HostBatch(f, torch.from_numpy(bad), torch.from_numpy(t), torch.from_numpy(n)))
+    bad_t = t.copy()
+    bad_t[0] = -1
+    with pytest.raises(IndexError):
+        ts.check_ids(HostBatch(f, torch.from_numpy(a), torch.from_numpy(bad_t), torch.from_numpy(n)))
