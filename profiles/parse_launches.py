@@ -13,7 +13,8 @@ def load(path):
             v = float(row['Metric Value'].replace(',', ''))
             u = row['Metric Unit']
             v = v / 1000 if u == 'ns' else (v * 1000 if u == 'ms' else v)
-            rows.append((int(row['ID']), row['Kernel Name'].split('(')[0].replace('mpqe::<unnamed>::', ''), v,
+            rows.append((int(row['ID']), row['Kernel Name'].split('(')[0].replace('void ', '').replace('mpqe::<unnamed>::', '')
+                         .replace('unnamed>::', ''), v,
                          row['Grid Size']))
     return rows
 
@@ -26,7 +27,7 @@ def main(path):
     a = starts[-1]
     b = next((i for i in range(a + 1, len(rows)) if rows[i][1].startswith(('gather_ids_multi', 'cosine_scores'))),
              len(rows))
-    while b > a and rows[b - 1][1].startswith(('pack_weights', 'gather_fwd_multi', 'layer_', 'transpose')) and \
+    while b > a and rows[b - 1][1].startswith(('pack_weights', 'gather_fwd_multi', 'layer_', 'transpose', 'matrix_sum')) and \
             rows[b - 1][0] > rows[a][0] + 40:
         b -= 1     # forward launches of the evaluation that follows the last step
     tot = 0.0

@@ -26,7 +26,7 @@ def main(path):
         for i, ((c, n, w), k) in enumerate(zip(COLS, idx)):
             v = r[k] if k is not None else ''
             if n == 'kernel':
-                v = v.split('(')[0].replace('mpqe::<unnamed>::', '').replace('void ', '')[:w]
+                v = v.split('(')[0].replace('void ', '').replace('mpqe::<unnamed>::', '').replace('unnamed>::', '')[:w]
             elif n == 'us' and v:
                 x = float(v.replace(',', ''))
                 u = units[k]
