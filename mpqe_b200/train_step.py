@@ -438,20 +438,21 @@ class TrainStep(object):
             mark('B2')
             if self._dense_out is None:
                 self._dense_out = torch.empty_like(self._xflat)
-            if self.world < 4:        # one shot: every rank sums all buckets (N-1 buckets in, one kernel)
+            # the dense bucket is all-reduced on the second stream, next to the row combine on this one (both read over
+            # NVLink; the bucket is 1/10 of the rows).  Fewer than four ranks: one shot, every rank sums all buckets
+            # (N-1 buckets in, one kernel); else two shots: reduce this rank's slice, B3 (every slice is reduced),
+            # gather the slices
+            def one_shot():
                 ops.allreduce_peers(self._flat_ptrs, self._xdense, scale, self._dense_out)
-                sparse = plan.apply_peers(self._row_ptrs, used, pad_id=self.total_rows, scale=scale, capacity=owned)
-            else:
-                # two shots, on the second stream, next to the row combine on this one (both read over NVLink; the
-                # bucket is 1/10 of the rows): reduce this rank's slice, B3 (every slice is reduced), gather the slices
-                def two_shot():
-                    ops.reduce_scatter_peers(self._flat_ptrs, self.rank, self._xdense, scale)
-                    self.peers.barrier()
-                    ops.all_gather_peers(self._flat_ptrs, self._xdense, self._dense_out)
-                self._on_side_stream(dev, two_shot)
-                sparse = plan.apply_peers(self._row_ptrs, used, pad_id=self.total_rows, scale=scale, capacity=owned)
-                mark('row combine')
-                self._join_side(dev)
+
+            def two_shot():
+                ops.reduce_scatter_peers(self._flat_ptrs, self.rank, self._xdense, scale)
+                self.peers.barrier()
+                ops.all_gather_peers(self._flat_ptrs, self._xdense, self._dense_out)
+            self._on_side_stream(dev, one_shot if self.world < 4 else two_shot)
+            sparse = plan.apply_peers(self._row_ptrs, used, pad_id=self.total_rows, scale=scale, capacity=owned)
+            mark('row combine')
+            self._join_side(dev)
             mark('exchange done')
             return StepResult(losses, wts[1], G.over(self._dense_out), sparse)
         torch.distributed.all_reduce(G.flat, group=self.pg)
