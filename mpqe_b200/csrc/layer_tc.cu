@@ -16,6 +16,7 @@
 // The operands are staged by threads rather than by TMA because every element has to pass through registers once
 // anyway to be split into its hi/lo TF32 parts (and half of them need a transpose on the way).
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 
@@ -779,6 +780,211 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const __grid_const
   if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// The same weight gradient with a TMA loader (default; MPQE_WGRAD_LOADS=ldg selects the kernel above).
+// The kernel above has ONE stage of loads in flight per producer thread (two register sets; a third does not fit
+// into 128 registers) and issues 2048 16-byte requests per stage: its stage period was 2-3x the ~1700 cycles the
+// twelve N=128 MMAs of a stage need.  Here one thread issues two tensor loads per stage (box {128 features, 1 slot,
+// 32 queries} of each operand) into a two-slot raw ring, two stages ahead; the producers read the raw tiles back
+// (a warp reads one 512-byte row per instruction), transpose 4x4 in registers, split and store as before.
+// Shared memory: 2 operand stages x 64 KB + 2 raw slots x 32 KB.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int WG_STAGES = 2;
+constexpr int WG_RING = 2;
+constexpr int WG_RAW = 2 * TILE_BYTES;                 // A rows | G rows, [32 queries][128 features] each
+constexpr int WG_LOAD_WARP = MMA_WARP + 1;
+constexpr int WG_THREADS = (WG_LOAD_WARP + 1) * 32;    // 448
+constexpr size_t WG_SMEM = size_t(WG_STAGES) * STAGE_BYTES + size_t(WG_RING) * WG_RAW + 1024;
+constexpr int WG_MAX_MAPS = 24;
+struct alignas(64) WgradMaps {
+  CUtensorMap map[WG_MAX_MAPS];
+  uint8_t a_of[MPQE_MAX_GROUPS][MPQE_MAX_TERMS];   // map of term t's forward operand
+  uint8_t g_of[MPQE_MAX_GROUPS];                   // map of the group's gradient operand
+};
+struct WgShared {
+  uint64_t full[WG_STAGES];
+  uint64_t empty[WG_STAGES];
+  uint64_t acc_full[2];
+  uint64_t acc_empty[2];
+  uint64_t raw_full[WG_RING];
+  uint64_t raw_empty[WG_RING];
+  uint32_t tmem_base;
+};
+
+// iterator over the 32-query tiles of a CTA's units: (unit, matching (group, term), tile), crossing units
+struct WgWalk {
+  int uk = 0, j = 0, c = 0;
+  WgradIter wi{0, 0, 0, 0};
+  bool in_unit = false, alive = true;
+  // positions on the next tile; returns false when the CTA has no more work.  (g, t, q, valid) describe the tile.
+  __device__ __forceinline__ bool next(const WgradLaunch& L, const Schedule& S, int total_units, int& g, int& t,
+                                       int64_t& q, int& valid) {
+    if (!alive) return false;
+    while (!in_unit) {
+      const int unit = sched_unit(S, uk++, total_units);
+      if (unit < 0) {
+        alive = false;
+        return false;
+      }
+      decode_wgrad_unit(L, unit, j, c);
+      wi = WgradIter{0, 0, 0, 0};
+      in_unit = wgrad_seek(L, L.d[j].m_fwd, L.chunks[j], c, wi);
+    }
+    g = wi.g;
+    t = wi.t;
+    q = wi.q;
+    valid = (int)(wi.qe - wi.q < KC ? wi.qe - wi.q : KC);
+    wi.q += KC;
+    if (wi.q >= wi.qe) {
+      ++wi.t;
+      in_unit = wgrad_seek(L, L.d[j].m_fwd, L.chunks[j], c, wi);
+    }
+    return true;
+  }
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc2_kernel(const __grid_constant__ WgradLaunch L,
+                                                                  const __grid_constant__ Schedule S, int total_units,
+                                                                  const __grid_constant__ WgradMaps WM) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ WgShared sh;
+  __shared__ __align__(16) float epi_stage[EPI_WARPS][32][EPI_PITCH];
+  uint8_t* smem = align_1024(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < WG_STAGES; ++s) {
+      mbar_init(smem_u32(&sh.full[s]), PROD_THREADS);
+      mbar_init(smem_u32(&sh.empty[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&sh.acc_full[b]), 1);
+      mbar_init(smem_u32(&sh.acc_empty[b]), EPI_WARPS * 32);
+    }
+    for (int r = 0; r < WG_RING; ++r) {
+      mbar_init(smem_u32(&sh.raw_full[r]), 1);
+      mbar_init(smem_u32(&sh.raw_empty[r]), PROD_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32(&sh.tmem_base), TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sh.tmem_base;
+  const uint32_t base = smem_u32(smem);
+  const uint32_t ring0 = base + WG_STAGES * STAGE_BYTES;
+
+  if (warp >= EPI_WARPS && warp < MMA_WARP) {
+    // ===== producers: raw rows (ring) -> 4x4 register transpose -> hi / lo K-major tiles ============================
+    const int pw = warp - EPI_WARPS;
+    WgWalk walk;
+    int g, t, valid;
+    int64_t q;
+#pragma unroll 1
+    for (uint32_t it = 0; walk.next(L, S, total_units, g, t, q, valid); ++it) {
+      const int slot = it % WG_RING, s = it % WG_STAGES;
+      mbar_wait(smem_u32(&sh.raw_full[slot]), (it / WG_RING) & 1);
+      if (it >= WG_STAGES) mbar_wait(smem_u32(&sh.empty[s]), (it / WG_STAGES - 1) & 1);
+      const uint32_t raw = ring0 + slot * WG_RAW + lane * 16;
+      const uint32_t st = base + s * STAGE_BYTES;
+      Frag fa, fb;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int k = 4 * pw + r;                   // query row of the tile; rows >= valid belong to another chunk
+        fa.v[r] = fb.v[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < valid) {
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                       : "=f"(fa.v[r].x), "=f"(fa.v[r].y), "=f"(fa.v[r].z), "=f"(fa.v[r].w)
+                       : "r"(raw + k * 512));
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                       : "=f"(fb.v[r].x), "=f"(fb.v[r].y), "=f"(fb.v[r].z), "=f"(fb.v[r].w)
+                       : "r"(raw + TILE_BYTES + k * 512));
+        }
+      }
+      store_block4(fa, st, st + TILE_BYTES, pw, lane);
+      store_block4(fb, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, pw, lane);
+      fence_proxy_async();
+      mbar_arrive(smem_u32(&sh.full[s]));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&sh.raw_empty[slot]));
+    }
+  } else if (warp == WG_LOAD_WARP) {
+    // ===== loader (one thread): two tensor loads per stage ===========================================================
+    if (lane == 0) {
+      WgWalk walk;
+      int g, t, valid;
+      int64_t q;
+      for (uint32_t it = 0; walk.next(L, S, total_units, g, t, q, valid); ++it) {
+        const int slot = it % WG_RING;
+        if (it >= WG_RING) mbar_wait(smem_u32(&sh.raw_empty[slot]), (it / WG_RING - 1) & 1);
+        const uint32_t bar = smem_u32(&sh.raw_full[slot]);
+        const mpqe_term_t& T = L.g[g].terms[t];
+        mbar_arrive_expect_tx(bar, WG_RAW);
+        tma_load_3d(ring0 + slot * WG_RAW, &WM.map[WM.a_of[g][t]], 0, T.a_slot, (int)q, bar);
+        tma_load_3d(ring0 + slot * WG_RAW + TILE_BYTES, &WM.map[WM.g_of[g]], 0, L.go[g].slot_map[T.out_slot], (int)q, bar);
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      int uc = 0;
+      for (int unit; (unit = sched_unit(S, uc, total_units)) >= 0; ++uc) {
+        int j, c;
+        decode_wgrad_unit(L, unit, j, c);
+        const int nsteps = wgrad_unit_steps(L, j, c);
+        const int ab = uc & 1, use = uc >> 1;
+        if (use > 0) mbar_wait(smem_u32(&sh.acc_empty[ab]), (use - 1) & 1);
+        tc_fence_after();
+        for (int step = 0; step < nsteps; ++step, ++it) {
+          const int s = it % WG_STAGES;
+          mbar_wait(smem_u32(&sh.full[s]), (it / WG_STAGES) & 1);
+          tc_fence_after();
+          issue_stage(tmem + ab * 128, base + s * STAGE_BYTES, step == 0);
+          umma_commit(smem_u32(&sh.empty[s]));
+        }
+        umma_commit(smem_u32(&sh.acc_full[ab]));
+      }
+    }
+  } else if (warp < EPI_WARPS) {
+    int uc = 0;
+    for (int unit; (unit = sched_unit(S, uc, total_units)) >= 0; ++uc) {
+      int j, c;
+      decode_wgrad_unit(L, unit, j, c);
+      const int nsteps = wgrad_unit_steps(L, j, c);
+      const int ab = uc & 1;
+      mbar_wait(smem_u32(&sh.acc_full[ab]), (uc >> 1) & 1);
+      tc_fence_after();
+      float* P = L.partials + (int64_t)unit * D * D;   // units are numbered destination-major, chunk-minor
+      float* stage = &epi_stage[warp][0][0];
+      const int cq = (lane & 7) * 4;
+#pragma unroll 1
+      for (int c0 = 0; c0 < D; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + ab * 128 + c0, v);
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          *reinterpret_cast<float4*>(stage + lane * EPI_PITCH + i) =
+              make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
+                          __uint_as_float(v[i + 3]));
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = 4 * i + (lane >> 3);
+          float4 o = *reinterpret_cast<const float4*>(stage + rr * EPI_PITCH + cq);
+          if (nsteps == 0) o = make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(P + (warp * 32 + rr) * D + c0 + cq) = o;
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(&sh.acc_empty[ab]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+}
+
 // Pre-split weights for the layer kernel: out[m][k chunk] = [hi tile 16 KB | lo tile 16 KB] of B[n][k] = M[k][n],
 // i.e. byte-exact images of the shared-memory operand tiles, so that staging them is one bulk copy.
 constexpr int PACK_MAX = 256;
@@ -1055,11 +1261,51 @@ int layer_forward_tc(const mpqe_layer_group_t* groups, int num_groups, cudaStrea
   return 0;
 }
 
+// Tensor maps of the operands of a weight-gradient launch.  false: use the register-prefetch kernel (broadcast
+// operands, more distinct operands than WG_MAX_MAPS, no cuTensorMapEncodeTiled, or MPQE_WGRAD_LOADS=ldg).
+static bool build_wgrad_maps(const WgradLaunch& launch, WgradMaps& WM) {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("MPQE_WGRAD_LOADS");
+    mode = (e != nullptr && strcmp(e, "ldg") == 0) || tensor_map_encoder() == nullptr ? 0 : 1;
+  }
+  if (mode == 0) return false;
+  struct Key {
+    const float* p;
+    int32_t slots;
+    int64_t nq;
+  };
+  Key keys[WG_MAX_MAPS];
+  int n = 0;
+  auto find = [&](const float* p, int32_t slots, int64_t nq) -> int {
+    if (slots <= 0) return -1;
+    for (int k = 0; k < n; ++k)
+      if (keys[k].p == p && keys[k].slots == slots && keys[k].nq == nq) return k;
+    if (n == WG_MAX_MAPS) return -1;
+    if (!encode_rows_map(&WM.map[n], p, slots, nq, D, KC, CU_TENSOR_MAP_SWIZZLE_NONE)) return -1;
+    keys[n] = Key{p, slots, nq};
+    return n++;
+  };
+  for (int g = 0; g < launch.num_groups; ++g) {
+    const mpqe_layer_group_t& G = launch.g[g];
+    const int kg = find(launch.go[g].g, launch.go[g].g_slots, G.num_queries);
+    if (kg < 0) return false;
+    WM.g_of[g] = (uint8_t)kg;
+    for (int t = 0; t < G.num_terms; ++t) {
+      const int ka = find(G.terms[t].a, G.terms[t].a_slots, G.num_queries);
+      if (ka < 0) return false;
+      WM.a_of[g][t] = (uint8_t)ka;
+    }
+  }
+  return true;
+}
+
 // `launch` arrives fully prepared (groups, operands, dests, chunks, partials) from the host code in layer_simt.cu
 int layer_wgrad_tc_launch(const WgradLaunch& launch, int total_chunks, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     MPQE_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+    MPQE_CUDA(cudaFuncSetAttribute(wgrad_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM));
     configured = true;
   }
   const int grid = total_chunks < num_sms() ? total_chunks : num_sms();
@@ -1086,6 +1332,12 @@ int layer_wgrad_tc_launch(const WgradLaunch& launch, int total_chunks, cudaStrea
         cost[u++] = steps;
       }
     build_lpt(S, cost, total_chunks, grid);
+  }
+  static thread_local WgradMaps WM;
+  if (build_wgrad_maps(launch, WM)) {
+    wgrad_tc2_kernel<<<grid, WG_THREADS, WG_SMEM, stream>>>(launch, S, total_chunks, WM);
+    MPQE_CHECK_LAUNCH("wgrad_tc2_kernel");
+    return 0;
   }
   wgrad_tc_kernel<<<grid, THREADS, TC_SMEM, stream>>>(launch, S, total_chunks);
   MPQE_CHECK_LAUNCH("wgrad_tc_kernel");

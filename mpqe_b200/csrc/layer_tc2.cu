@@ -75,12 +75,6 @@ struct alignas(64) XMaps {
   uint8_t of[MPQE_MAX_GROUPS][MPQE_MAX_TERMS];
 };
 
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
-      : "memory");
-}
 
 __device__ __forceinline__ uint8_t* align_1024(uint8_t* p) {
   return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~uintptr_t(1023));
@@ -597,25 +591,11 @@ int sm_count() {
 // Tensor maps of the activation operands of one launch.  Returns false when the launch has to use the cp.async loader:
 // broadcast operands (a_slots == 0: a tensor map has no zero stride), more distinct operands than MAX_XMAPS, a driver
 // without cuTensorMapEncodeTiled, or MPQE_LAYER_LOADS=cpasync (A/B measurements).
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static bool build_xmaps(const mpqe_layer_group_t* groups, int num_groups, XMaps& XM) {
   static int mode = -1;   // 0: cp.async, 1: TMA
-  static EncodeTiledFn encode = nullptr;
   if (mode < 0) {
     const char* e = getenv("MPQE_LAYER_LOADS");
-    mode = (e != nullptr && strcmp(e, "cpasync") == 0) ? 0 : 1;
-    if (mode == 1) {
-      void* fn = nullptr;
-      cudaDriverEntryPointQueryResult q;
-      if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
-          q != cudaDriverEntryPointSuccess || fn == nullptr) {
-        (void)cudaGetLastError();
-        mode = 0;
-      }
-      encode = reinterpret_cast<EncodeTiledFn>(fn);
-    }
+    mode = (e != nullptr && strcmp(e, "cpasync") == 0) || tensor_map_encoder() == nullptr ? 0 : 1;
   }
   if (mode == 0) return false;
   struct Key {
@@ -634,14 +614,8 @@ static bool build_xmaps(const mpqe_layer_group_t* groups, int num_groups, XMaps&
       if (k == n) {
         if (n == MAX_XMAPS) return false;
         keys[n++] = Key{T.a, T.a_slots, groups[i].num_queries};
-        const cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)T.a_slots, (cuuint64_t)groups[i].num_queries};
-        const cuuint64_t strides[2] = {(cuuint64_t)D * 4, (cuuint64_t)T.a_slots * D * 4};   // bytes, dims 1 and 2
-        const cuuint32_t box[3] = {(cuuint32_t)KC, 1u, (cuuint32_t)BQ};
-        const cuuint32_t estr[3] = {1u, 1u, 1u};
-        const CUresult r = encode(&XM.map[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(T.a), dims, strides,
-                                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
-                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return false;
+        if (!encode_rows_map(&XM.map[k], T.a, T.a_slots, groups[i].num_queries, KC, BQ, CU_TENSOR_MAP_SWIZZLE_64B))
+          return false;
       }
       XM.of[i][t] = (uint8_t)k;
     }

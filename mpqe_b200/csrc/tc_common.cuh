@@ -1,6 +1,10 @@
 // PTX wrappers shared by the tcgen05 kernels (layer_tc.cu, layer_tc2.cu): mbarriers, bulk copies, tensor-memory
 // allocation, tcgen05.mma / .ld / .commit, shared-memory matrix descriptors and the tf32 hi/lo split.
 #pragma once
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -118,6 +122,48 @@ __device__ __forceinline__ void split_tf32(const float4& x, float4& hi, float4& 
 // (B = 4096: 224..768 units on 148 CTAs) round-robin leaves some CTAs with twice the work of others.
 constexpr int SCHED_MAX_UNITS = 2048;
 constexpr int SCHED_MAX_CTAS = 160;
+// ---- TMA tensor maps (host) -------------------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda); nullptr when
+// the driver does not have it.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    else
+      (void)cudaGetLastError();
+  }
+  return fn;
+}
+// An activation-like operand [queries][slots][128] fp32 as a 3-D map {128, slots, queries}; box {box_k, 1, box_q}.
+inline bool encode_rows_map(CUtensorMap* map, const float* base, int slots, int64_t queries, int box_k, int box_q,
+                            CUtensorMapSwizzle swizzle) {
+  EncodeTiledFn encode = tensor_map_encoder();
+  if (encode == nullptr || slots <= 0 || queries <= 0 || (reinterpret_cast<uintptr_t>(base) & 15) != 0) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)MPQE_D, (cuuint64_t)slots, (cuuint64_t)queries};
+  const cuuint64_t strides[2] = {(cuuint64_t)MPQE_D * 4, (cuuint64_t)slots * MPQE_D * 4};   // bytes, dims 1 and 2
+  const cuuint32_t box[3] = {(cuuint32_t)box_k, 1u, (cuuint32_t)box_q};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
+
 struct Schedule {
   int count;                                 // 0: round-robin (unit = blockIdx + k * gridDim)
   uint16_t start[SCHED_MAX_CTAS + 1];
