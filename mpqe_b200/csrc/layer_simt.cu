@@ -6,6 +6,8 @@
 //   :301-304  x @ root + bias                        -> one more term + epilogue
 //   :437      relu                                   -> epilogue
 // and, with transposed matrices / swapped slots, the input-gradient of the same (autograd of the above).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace mpqe {
@@ -593,15 +595,61 @@ extern "C" int mpqe_layer_wgrad(const mpqe_layer_group_t* groups_host, const mpq
         if (groups_host[i].terms[t].m == dests_host[j].m_fwd) weight[j] += (double)groups_host[i].num_queries;
     total += weight[j];
   }
-  const int64_t budget = max_parts - num_dests;
+  // Apportion the max_parts (destination, chunk) units so that the LARGEST unit is as small as possible, counted in
+  // the stages the kernels actually run: a chunk of destination j costs sum over groups of (matching terms) x (query
+  // tiles of the group's chunk range, chunk_range() on the device), and chunk ranges are whole tiles -- 4096 queries in
+  // 18 chunks are 16 chunks of 8 tiles and two empty ones.  Smallest feasible maximum by bisection; per destination the
+  // fewest chunks that reach it.  (The first version gave each destination 1 + floor(share * budget) chunks: with 18
+  // destinations the largest unit had 28 stages against a mean of 20.8 per CTA, and 8 of the 148 CTAs had none.)
+  const int64_t gran = use_tensor_cores ? 32 : KQ;
+  int terms_of[MPQE_MAX_DESTS][MPQE_MAX_GROUPS];
+  int64_t cap[MPQE_MAX_DESTS];
+  for (int j = 0; j < num_dests; ++j) {
+    cap[j] = (int64_t)(weight[j] / (4 * KQ)) + 1;  // at least ~64 query rows per chunk
+    if (cap[j] > 256) cap[j] = 256;
+    for (int i = 0; i < num_groups; ++i) {
+      terms_of[j][i] = 0;
+      for (int t = 0; t < groups_host[i].num_terms; ++t)
+        if (groups_host[i].terms[t].m == dests_host[j].m_fwd) ++terms_of[j][i];
+    }
+  }
+  auto unit_cost = [&](int j, int64_t c) {      // stages of the largest chunk of destination j split c ways
+    int64_t stages = 0;
+    for (int i = 0; i < num_groups; ++i) {
+      if (terms_of[j][i] == 0) continue;
+      const int64_t B = groups_host[i].num_queries;
+      int64_t per = (B + c - 1) / c;
+      per = (per + gran - 1) / gran * gran;
+      if (per > B) per = B;
+      stages += terms_of[j][i] * ((per + gran - 1) / gran);
+    }
+    return stages;
+  };
+  auto chunks_for = [&](int j, int64_t limit) {  // fewest chunks with unit_cost <= limit (cap[j] if none reaches it)
+    int64_t lo = 1, hi = cap[j];
+    if (unit_cost(j, hi) > limit) return hi;
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) / 2;
+      if (unit_cost(j, mid) <= limit) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+  };
+  int64_t lo = 1, hi = 1;
+  for (int j = 0; j < num_dests; ++j) hi = std::max(hi, unit_cost(j, 1));
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) / 2;
+    int64_t need = 0;
+    for (int j = 0; j < num_dests; ++j) need += chunks_for(j, mid);
+    if (need <= max_parts) hi = mid; else lo = mid + 1;
+  }
   int total_chunks = 0;
   for (int j = 0; j < num_dests; ++j) {
-    int64_t c = 1 + (total > 0 ? (int64_t)(budget * (weight[j] / total)) : 0);
-    const int64_t cap = (int64_t)(weight[j] / (4 * KQ)) + 1;  // at least ~64 query rows per chunk
-    if (c > cap) c = cap;
-    if (c > 256) c = 256;
-    L.chunks[j] = (int)c;
-    total_chunks += (int)c;
+    L.chunks[j] = (int)chunks_for(j, lo);
+    total_chunks += L.chunks[j];
+  }
+  if (total_chunks > max_parts) {    // (caps made the bound unreachable: shrink the largest counts)
+    for (int j = 0; j < num_dests && total_chunks > max_parts; ++j)
+      while (L.chunks[j] > 1 && total_chunks > max_parts) --L.chunks[j], --total_chunks;
   }
   if (use_tensor_cores) {
     if (layer_wgrad_tc_launch(L, total_chunks, (cudaStream_t)stream)) return 2;

@@ -229,9 +229,9 @@ def layer_wgrad(groups, grad_operands, dests, ctas_hint=296, use_tensor_cores=No
     tc = tensor_cores_default() if use_tensor_cores is None else bool(use_tensor_cores)
     if tc:
         import os
-        # persistent tcgen05 kernel: every destination gets 1 + its share of `ctas_hint` chunks, so with
-        # ctas_hint = SMs - destinations there is at most one (destination, chunk) unit per CTA (with 148 + destinations
-        # units a few CTAs ran two, twice as long as the rest: SMs active 56 % of the kernel's duration)
+        # persistent tcgen05 kernel: the workspace holds ctas_hint + destinations partial sums = the number of
+        # (destination, chunk) units the launch is split into: one per SM (with 148 + destinations units a few CTAs
+        # ran two, twice as long as the rest: SMs active 56 % of the kernel's duration)
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         ctas_hint = int(os.environ.get('MPQE_WGRAD_UNITS', str(max(sms - len(dests), sms // 2))))
     nbytes = lib.mpqe_layer_wgrad_workspace_bytes(len(dests), ctas_hint)
