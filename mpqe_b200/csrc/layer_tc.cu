@@ -1251,11 +1251,17 @@ int layer_forward_tc(const mpqe_layer_group_t* groups, int num_groups, cudaStrea
       S.gsm[pos] = gsm_of[S.unit[pos]];
     }
   }
-  static int dbg = -1;  // MPQE_TC_DEBUG: timing experiments only (bit0 no smem stores, bit1 no global loads,
-  if (dbg < 0) {        //                 bit2 no MMAs, bit3 no epilogue stores); results are wrong when non-zero
+  // MPQE_TC_DEBUG: timing experiments of debug builds only (-DMPQE_TC_STATS; bit0 no smem stores, bit1 no global loads,
+  // bit2 no MMAs, bit3 no epilogue stores: results are wrong when non-zero).  Release builds ignore the variable.
+#ifdef MPQE_TC_STATS
+  static int dbg = -1;
+  if (dbg < 0) {
     const char* e = getenv("MPQE_TC_DEBUG");
     dbg = e ? atoi(e) : 0;
   }
+#else
+  const int dbg = 0;
+#endif
   layer_tc_kernel<<<grid, THREADS, TC_SMEM, stream>>>(L, S, (int)units, dbg);
   MPQE_CHECK_LAUNCH("layer_tc_kernel");
   return 0;
